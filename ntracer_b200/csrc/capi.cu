@@ -1,0 +1,793 @@
+// capi.cu -- host side of the backend: C ABI of include/ntracer_b200.h, device arena builder
+// ("geom_allocator" in the north-star sense), stream / event / wavefront-queue management.
+// There is no CPU rendering path in this file or anywhere else in the library.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "arena_pack.h"
+#include "kernels.cuh"
+
+using namespace ntr;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? NTR_ERR_MEMORY : NTR_ERR_RUNTIME, "%s failed: %s", #expr, \
+                        cudaGetErrorString(e_));                                                         \
+    } while (0)
+
+constexpr int kMaxPasses = 64;          // upper bound on max_reflect_depth handled by the control block
+
+// control block layout (uint32 words)
+enum { CTL_TILE_CURSOR = 0, CTL_OVERFLOW = 1, CTL_COUNT0 = 2, CTL_CURSOR0 = CTL_COUNT0 + kMaxPasses + 1,
+       CTL_WORDS = CTL_CURSOR0 + kMaxPasses + 1 };
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__global__ void pack_kernel(const __grid_constant__ FrameDev f);
+
+}  // namespace
+
+struct ntr_scene {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing_valid = false;
+    SceneDev dev{};
+    CameraDev cam{};
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    float *d_lights = nullptr;
+    int base_flags = 0;
+    bool any_reflective = false;
+    bool instrumented = false;
+    int tree_depth = 0;
+    uint32_t *d_ctl = nullptr;
+    unsigned long long *d_counters = nullptr;
+    int *h_abort = nullptr;             // mapped pinned
+    int *d_abort = nullptr;
+    float *d_accum = nullptr; size_t accum_cap = 0;
+    unsigned char *d_packed = nullptr; size_t packed_cap = 0;
+    int32_t *d_ids = nullptr; float *d_dists = nullptr; size_t ids_cap = 0;
+    float4 *d_queue[2] = {nullptr, nullptr};
+    uint32_t queue_capacity = 0;
+    void *d_scratch = nullptr; size_t scratch_cap = 0;
+    ntr_counters counters{};
+    uint64_t launches = 0;
+    int grid_blocks[4] = {0, 0, 0, 0};
+    const KernelSet *(*kset)(int) = nullptr;
+    volatile bool busy = false;
+};
+
+namespace {
+
+const KernelSet *(*kernel_family(int dim))(int) {
+    switch (dim) {
+        case 3: return &kernel_set_d3;
+        case 4: return &kernel_set_d4;
+        case 5: return &kernel_set_d5;
+        case 6: return &kernel_set_d6;
+        case 7: return &kernel_set_d7;
+        case 8: return &kernel_set_d8;
+        default: return &kernel_set_dn;     // run-time dimension kernels (the reference's generic tracern)
+    }
+}
+
+int validate_desc(const ntr_scene_desc *d, int *tree_depth_out) {
+    if (!d) return fail(NTR_ERR_VALUE, "scene description is NULL");
+    if (d->dim < 3 || d->dim > NTR_MAX_DIM) return fail(NTR_ERR_VALUE, "dimension must be between 3 and %d", NTR_MAX_DIM);
+    if (d->kind != NTR_SCENE_BOX && d->kind != NTR_SCENE_COMPOSITE) return fail(NTR_ERR_VALUE, "unknown scene kind %d", d->kind);
+    *tree_depth_out = 0;
+    if (d->kind == NTR_SCENE_BOX) return NTR_OK;
+    if (d->batch_size < 1 || d->batch_size > 64) return fail(NTR_ERR_VALUE, "batch_size must be in 1..64");
+    if (!d->boundary) return fail(NTR_ERR_VALUE, "composite scene needs a boundary");
+    if (d->bg_gradient_axis < 0 || d->bg_gradient_axis >= d->dim) return fail(NTR_ERR_VALUE, "bg_gradient_axis out of range");
+    if (d->n_nodes && !d->nodes) return fail(NTR_ERR_VALUE, "nodes is NULL");
+    if (d->root != NTR_NULL_NODE && d->root >= d->n_nodes) return fail(NTR_ERR_VALUE, "root node out of range");
+    if (d->n_materials == 0 && (d->n_simplex || d->n_solids)) return fail(NTR_ERR_VALUE, "primitives without materials");
+    for (uint32_t i = 0; i < d->n_simplex; ++i)
+        if (d->simplex_mat[i] < 0 || (uint32_t)d->simplex_mat[i] >= d->n_materials)
+            return fail(NTR_ERR_VALUE, "simplex %u: material index out of range", i);
+    for (uint32_t i = 0; i < d->n_solids; ++i) {
+        if (d->solid_mat[i] < 0 || (uint32_t)d->solid_mat[i] >= d->n_materials)
+            return fail(NTR_ERR_VALUE, "solid %u: material index out of range", i);
+        const int type = (int)d->solids[(size_t)i * (1 + 2 * d->dim * d->dim + d->dim)];
+        if (type != NTR_SOLID_CUBE && type != NTR_SOLID_SPHERE) return fail(NTR_ERR_VALUE, "solid %u: unknown type", i);
+    }
+    for (uint32_t i = 0; i < d->n_nodes; ++i) {
+        const ntr_node &n = d->nodes[i];
+        if (n.meta & NTR_LEAF_FLAG) {
+            if ((uint64_t)n.w1 + n.w2 > d->n_leaf_refs) return fail(NTR_ERR_VALUE, "leaf %u: item range out of bounds", i);
+            for (uint32_t k = 0; k < n.w2; ++k) {
+                const uint32_t r = d->leaf_refs[n.w1 + k], kind = r >> 30, idx = r & NTR_IDX_MASK;
+                if (kind == NTR_REF_SIMPLEX) { if (idx >= d->n_simplex) return fail(NTR_ERR_VALUE, "leaf %u: simplex index out of range", i); }
+                else if (kind == NTR_REF_BATCH) { if ((uint64_t)idx + d->batch_size > d->n_simplex) return fail(NTR_ERR_VALUE, "leaf %u: batch out of range", i); }
+                else if (kind == NTR_REF_SOLID) { if (idx >= d->n_solids) return fail(NTR_ERR_VALUE, "leaf %u: solid index out of range", i); }
+                else return fail(NTR_ERR_VALUE, "leaf %u: bad item type", i);
+            }
+        } else {
+            if (n.meta >= (uint32_t)d->dim) return fail(NTR_ERR_VALUE, "branch %u: axis out of range", i);
+            if ((n.w2 != NTR_NULL_NODE && n.w2 >= d->n_nodes) || (n.w3 != NTR_NULL_NODE && n.w3 >= d->n_nodes))
+                return fail(NTR_ERR_VALUE, "branch %u: child out of range", i);
+        }
+    }
+    // depth (also rejects cycles: a path longer than the stack the kernels carry is an error either way)
+    int depth = 0;
+    if (d->root != NTR_NULL_NODE) {
+        std::vector<std::pair<uint32_t, int>> st;
+        st.push_back({d->root, 1});
+        size_t visited = 0;
+        while (!st.empty()) {
+            auto [n, dep] = st.back();
+            st.pop_back();
+            if (++visited > (size_t)d->n_nodes * 2 + 2) return fail(NTR_ERR_VALUE, "k-d tree is not a tree");
+            if (dep > NTR_MAX_TREE_DEPTH) return fail(NTR_ERR_VALUE, "k-d tree deeper than %d", NTR_MAX_TREE_DEPTH);
+            depth = std::max(depth, dep);
+            const ntr_node &nd = d->nodes[n];
+            if (nd.meta & NTR_LEAF_FLAG) continue;
+            if (nd.w2 != NTR_NULL_NODE) st.push_back({nd.w2, dep + 1});
+            if (nd.w3 != NTR_NULL_NODE) st.push_back({nd.w3, dep + 1});
+        }
+    }
+    *tree_depth_out = depth;
+    return NTR_OK;
+}
+
+void fill_params(SceneDev &dev, const ntr_scene_desc *d) { fill_scene_params(dev, d, kMaxPasses - 1); }
+
+int upload_lights(ntr_scene *sc, const ntr_scene_desc *d) {
+    const size_t stride = d->dim + 3;
+    const size_t n = ((size_t)d->n_point_lights + d->n_global_lights) * stride;
+    if (sc->d_lights) { cudaFree(sc->d_lights); sc->d_lights = nullptr; }
+    sc->dev.n_point = (int)d->n_point_lights;
+    sc->dev.n_global = (int)d->n_global_lights;
+    sc->dev.point_lights = sc->dev.global_lights = nullptr;
+    if (!n) return NTR_OK;
+    std::vector<float> h(n);
+    if (d->n_point_lights) memcpy(h.data(), d->point_lights, sizeof(float) * d->n_point_lights * stride);
+    if (d->n_global_lights) memcpy(h.data() + d->n_point_lights * stride, d->global_lights, sizeof(float) * d->n_global_lights * stride);
+    CUDA_TRY(cudaMalloc(&sc->d_lights, n * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(sc->d_lights, h.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    sc->dev.point_lights = sc->d_lights;
+    sc->dev.global_lights = sc->d_lights + d->n_point_lights * stride;
+    return NTR_OK;
+}
+
+// Builds the single device arena: nodes | leaf refs | simplex records | solid records | materials.
+int build_arena(ntr_scene *sc, const ntr_scene_desc *d) {
+    std::vector<unsigned char> h;
+    ArenaLayout L;
+    try { pack_arena(d, h, L); } catch (const std::bad_alloc &) { return fail(NTR_ERR_MEMORY, "out of host memory building the arena"); }
+    CUDA_TRY(cudaMalloc(&sc->arena, L.total));
+    sc->arena_bytes = L.total;
+    CUDA_TRY(cudaMemcpy(sc->arena, h.data(), L.total, cudaMemcpyHostToDevice));
+    bind_arena(sc->dev, d, L, static_cast<const unsigned char *>(sc->arena));
+    sc->any_reflective = L.any_reflective;
+    sc->base_flags = (L.any_transparent || d->n_solids) ? NTR_F_GENERAL : 0;
+    return NTR_OK;
+}
+
+int ensure(void **p, size_t *cap, size_t need) {
+    if (*cap >= need && *p) return NTR_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    const size_t n = align_up(need + need / 8, 256);
+    CUDA_TRY(cudaMalloc(p, n));
+    *cap = n;
+    return NTR_OK;
+}
+
+int ensure_queues(ntr_scene *sc, uint32_t capacity) {
+    if (sc->queue_capacity >= capacity && sc->d_queue[0]) return NTR_OK;
+    for (int i = 0; i < 2; ++i) if (sc->d_queue[i]) { cudaFree(sc->d_queue[i]); sc->d_queue[i] = nullptr; }
+    sc->queue_capacity = 0;
+    const uint32_t rec4 = 2 + 2 * ((sc->dev.dim + 3) / 4);
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMalloc(&sc->d_queue[i], (size_t)capacity * rec4 * sizeof(float4)));
+    sc->queue_capacity = capacity;
+    return NTR_OK;
+}
+
+int grid_for(ntr_scene *sc, int flags) {
+    if (!sc->grid_blocks[flags]) {
+        int per_sm = sc->kset(flags)->max_blocks_per_sm();
+        if (per_sm < 1) per_sm = 1;
+        sc->grid_blocks[flags] = per_sm * sc->sm_count;      // persistent: a whole number of CTAs per SM
+    }
+    return sc->grid_blocks[flags];
+}
+
+void fill_format(FormatDev &o, const ntr_image_format *f) {
+    memset(&o, 0, sizeof o);
+    o.n_channels = f->n_channels; o.bytes_per_pixel = f->bytes_per_pixel; o.reversed = f->reversed; o.pitch = f->pitch;
+    for (int i = 0; i < f->n_channels; ++i) {
+        o.f_r[i] = f->channels[i].f_r; o.f_g[i] = f->channels[i].f_g; o.f_b[i] = f->channels[i].f_b; o.f_c[i] = f->channels[i].f_c;
+        o.bits[i] = f->channels[i].bit_size; o.tfloat[i] = f->channels[i].tfloat;
+    }
+}
+
+int check_format(const ntr_image_format *f) {
+    if (!f) return fail(NTR_ERR_VALUE, "image format is NULL");
+    if (f->width < 1 || f->height < 1) return fail(NTR_ERR_VALUE, "width and height must be at least 1");
+    if (f->n_channels < 0 || f->n_channels > NTR_MAX_CHANNELS) return fail(NTR_ERR_VALUE, "too many channels");
+    int bits = 0;
+    for (int i = 0; i < f->n_channels; ++i) {
+        const ntr_channel &c = f->channels[i];
+        if (c.tfloat) { if (c.bit_size != 32) return fail(NTR_ERR_VALUE, "if \"tfloat\" is true, \"bit_size\" can only be 32"); }
+        else if (c.bit_size > 31) return fail(NTR_ERR_VALUE, "\"bit_size\" cannot be greater than 31 (unless \"tfloat\" is true)");
+        else if (c.bit_size < 1) return fail(NTR_ERR_VALUE, "\"bit_size\" cannot be less than 1");
+        bits += c.bit_size;
+    }
+    if (bits > 128) return fail(NTR_ERR_VALUE, "Too many bytes per pixel. The maximum is 16.");
+    if (f->bytes_per_pixel != (bits + 7) / 8) return fail(NTR_ERR_VALUE, "bytes_per_pixel does not match the channels");
+    if (f->pitch < f->width * f->bytes_per_pixel)
+        return fail(NTR_ERR_VALUE, "invalid image format: \"pitch\" must be at least \"width\" times the pixel size in bytes");
+    return NTR_OK;
+}
+
+struct RenderTarget {
+    int out_mode;               // what the caller wants
+    unsigned char *packed = nullptr;
+    float *accum = nullptr;
+    int32_t *ids = nullptr;
+    float *dists = nullptr;
+};
+
+// Enqueues every kernel of one frame on `st`.  view = (width,height), window = (x0,y0,w,h).
+int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0, int y0, int win_w, int win_h,
+                  const ntr_image_format *fmt, const RenderTarget &tgt, int tile_row_first, int tile_row_step,
+                  int compact, bool *used_passes) {
+    FrameDev f;
+    memset(&f, 0, sizeof f);
+    f.width = width; f.height = height;
+    // flat_origin_ray_source::set_params (tracer.hpp:65-69)
+    f.half_w = (float)width / 2.0f;
+    f.half_h = (float)height / 2.0f;
+    f.fovI = tanf(sc->dev.fov / 2) / f.half_w;
+    f.x0 = x0; f.y0 = y0; f.win_w = win_w; f.win_h = win_h;
+    f.tiles_x = (win_w + NTR_TILE - 1) / NTR_TILE;
+    f.tiles_y = (win_h + NTR_TILE - 1) / NTR_TILE;
+    f.tile_row_first = tile_row_first; f.tile_row_step = tile_row_step < 1 ? 1 : tile_row_step; f.compact = compact;
+    if (fmt) fill_format(f.fmt, fmt);
+
+    int flags = sc->base_flags | (sc->instrumented ? NTR_F_COUNT : 0);
+    const bool composite = sc->dev.kind == NTR_SCENE_COMPOSITE;
+    const bool passes = composite && tgt.out_mode != NTR_OUT_IDS && sc->any_reflective && sc->dev.max_depth > 0;
+    *used_passes = passes;
+
+    const size_t npix = (size_t)win_w * win_h;
+    f.packed = tgt.packed; f.accum = tgt.accum; f.ids = tgt.ids; f.dists = tgt.dists;
+    f.out_mode = tgt.out_mode;
+    if (passes && tgt.out_mode == NTR_OUT_PACKED) {
+        if (compact || tile_row_step != 1) return fail(NTR_ERR_VALUE, "internal: sharded render with passes must go through the accumulator");
+        int rc = ensure((void **)&sc->d_accum, &sc->accum_cap, npix * 3 * sizeof(float));
+        if (rc) return rc;
+        f.accum = sc->d_accum;
+        f.out_mode = NTR_OUT_ACCUM;
+    }
+    if (passes) {
+        // each pass can emit at most (1 + transparent layers) rays per input ray; start with 2 rays per pixel
+        // and let the overflow check regrow (ntr_counters.queue_overflows)
+        const uint64_t want = std::max<uint64_t>((uint64_t)npix * 2, 1u << 16);
+        if (sc->queue_capacity < want) {
+            int rc = ensure_queues(sc, (uint32_t)std::min<uint64_t>(want, 0x7FFFFFFFu));
+            if (rc) return rc;
+        }
+    }
+
+    ControlDev ctl;
+    ctl.tile_cursor = sc->d_ctl + CTL_TILE_CURSOR;
+    ctl.overflow = sc->d_ctl + CTL_OVERFLOW;
+    ctl.abort_flag = sc->d_abort;
+    ctl.counters = sc->d_counters;
+    CUDA_TRY(cudaMemsetAsync(sc->d_ctl, 0, CTL_WORDS * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(sc->d_counters, 0, 8 * sizeof(unsigned long long), st));
+
+    const KernelSet *ks = sc->kset(flags);
+    const int grid = grid_for(sc, flags);
+    const uint32_t rec4 = 2 + 2 * ((sc->dev.dim + 3) / 4);
+    QueueDev q;
+    memset(&q, 0, sizeof q);
+    q.capacity = sc->queue_capacity; q.rec4 = rec4;
+    q.in = nullptr;
+    q.out = sc->d_queue[0];
+    q.out_count = sc->d_ctl + CTL_COUNT0 + 1;
+    q.in_count = q.in_cursor = nullptr;
+    ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
+    ++sc->launches;
+    if (passes) {
+        for (int depth = 1; depth <= sc->dev.max_depth; ++depth) {
+            q.in = sc->d_queue[(depth - 1) & 1];
+            q.out = sc->d_queue[depth & 1];
+            q.in_count = sc->d_ctl + CTL_COUNT0 + depth;
+            q.out_count = sc->d_ctl + CTL_COUNT0 + depth + 1;
+            q.in_cursor = sc->d_ctl + CTL_CURSOR0 + depth;
+            ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
+            ++sc->launches;
+        }
+        if (tgt.out_mode == NTR_OUT_PACKED) {
+            f.out_mode = NTR_OUT_PACKED;
+            const long long groups = (long long)((win_w + 3) / 4) * win_h;
+            const int blocks = (int)std::min<long long>((groups + 255) / 256, (long long)sc->sm_count * 8);
+            pack_kernel<<<blocks, 256, 0, st>>>(f);
+            ++sc->launches;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return NTR_OK;
+}
+
+// Runs a frame on the scene's own stream, waits for it, handles queue overflow (regrow + retry) and abort.
+int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win_w, int win_h,
+                   const ntr_image_format *fmt, const RenderTarget &tgt, int trf, int trs, int compact,
+                   cudaStream_t st) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        bool passes = false;
+        CUDA_TRY(cudaEventRecord(sc->ev0, st));
+        int rc = enqueue_frame(sc, st, width, height, x0, y0, win_w, win_h, fmt, tgt, trf, trs, compact, &passes);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(sc->ev1, st));
+        sc->timing_valid = true;
+        uint32_t h_ctl[CTL_WORDS];
+        unsigned long long h_cnt[8];
+        CUDA_TRY(cudaMemcpyAsync(h_ctl, sc->d_ctl, sizeof h_ctl, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_cnt, sc->d_counters, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (*sc->h_abort) return fail(NTR_ERR_ABORTED, "render aborted");
+        const uint64_t overflows = sc->counters.queue_overflows;
+        sc->counters.primary_rays = (uint64_t)win_w * win_h;
+        if (trs > 1) {
+            const int tiles_y = (win_h + NTR_TILE - 1) / NTR_TILE;
+            uint64_t rows = 0;
+            for (int ty = trf; ty < tiles_y; ty += trs) rows += std::min(NTR_TILE, win_h - ty * NTR_TILE);
+            sc->counters.primary_rays = rows * (uint64_t)win_w;
+        }
+        sc->counters.reflection_rays = h_cnt[1]; sc->counters.shadow_rays = h_cnt[2]; sc->counters.node_steps = h_cnt[3];
+        sc->counters.simplex_tests = h_cnt[4]; sc->counters.solid_tests = h_cnt[5]; sc->counters.shaded_hits = h_cnt[6];
+        sc->counters.queue_overflows = overflows;
+        if (!passes || !h_ctl[CTL_OVERFLOW]) return NTR_OK;
+        // a wavefront queue was too small: the counters say how many records were wanted
+        uint32_t need = 0;
+        for (int d = 1; d <= kMaxPasses; ++d) need = std::max(need, h_ctl[CTL_COUNT0 + d]);
+        sc->counters.queue_overflows = overflows + 1;
+        rc = ensure_queues(sc, (uint32_t)std::min<uint64_t>((uint64_t)need * 2 + 1024, 0x7FFFFFFFu));
+        if (rc) return rc;
+    }
+    return fail(NTR_ERR_RUNTIME, "wavefront queue kept overflowing");
+}
+
+struct BusyGuard {
+    ntr_scene *sc;
+    bool ok;
+    explicit BusyGuard(ntr_scene *s) : sc(s), ok(!s->busy) { if (ok) { s->busy = true; *s->h_abort = 0; } }
+    ~BusyGuard() { if (ok) sc->busy = false; }
+};
+
+#define ENTER(sc)                                                                               \
+    if (!(sc)) return fail(NTR_ERR_VALUE, "scene is NULL");                                     \
+    CUDA_TRY(cudaSetDevice((sc)->device));                                                      \
+    BusyGuard guard_(sc);                                                                       \
+    if (!guard_.ok) return fail(NTR_ERR_RUNTIME, "the renderer is already running")
+
+// accum (3 floats per window pixel) -> packed image.  One thread packs 4 consecutive pixels of a row so the
+// 4*bpp bytes it owns are a whole number of 32-bit words.
+__global__ void pack_kernel(const __grid_constant__ FrameDev f) {
+    const int groups_x = (f.win_w + 3) / 4;
+    const long long total = (long long)groups_x * f.win_h;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(g / groups_x), x0 = (int)(g % groups_x) * 4;
+        const int n = min(4, f.win_w - x0);
+        const int bpp = f.fmt.bytes_per_pixel;
+        __align__(16) unsigned char buf[64];
+        for (int k = 0; k < n; ++k) {
+            const float *a = f.accum + ((size_t)y * f.win_w + x0 + k) * 3;
+            const float rgb[3] = {a[0], a[1], a[2]};
+            uint32_t w[4];
+            pack_pixel(f.fmt, rgb, w);
+            for (int j = 0; j < bpp; ++j) {
+                const int sj = f.fmt.reversed ? bpp - 1 - j : j;
+                buf[k * bpp + j] = (unsigned char)(w[sj >> 2] >> (8 * (3 - (sj & 3))));
+            }
+        }
+        unsigned char *dst = f.packed + (size_t)y * f.fmt.pitch + (size_t)x0 * bpp;
+        const int nb = n * bpp;
+        if (((size_t)dst & 3) == 0 && (nb & 3) == 0) {
+            for (int j = 0; j < nb; j += 4) *(uint32_t *)(dst + j) = *(const uint32_t *)(buf + j);
+        } else {
+            for (int j = 0; j < nb; ++j) dst[j] = buf[j];
+        }
+    }
+}
+
+__global__ void fma_peak_kernel(float *out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float b = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+        a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+    }
+    const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678f) out[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+NTR_API int ntr_abi_version(void) { return NTR_ABI_VERSION; }
+NTR_API const char *ntr_last_error(void) { return g_err.c_str(); }
+
+NTR_API int ntr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene **out) {
+    if (!out) return fail(NTR_ERR_VALUE, "out is NULL");
+    *out = nullptr;
+    int depth = 0;
+    int rc = validate_desc(desc, &depth);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(NTR_ERR_NO_DEVICE, "no CUDA device available: ntracer_b200 renders on sm_100a only and has no CPU fallback");
+    }
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    if (device >= ndev) return fail(NTR_ERR_VALUE, "device %d out of range", device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(NTR_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only (no fallback)", device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    ntr_scene *sc = new (std::nothrow) ntr_scene();
+    if (!sc) return fail(NTR_ERR_MEMORY, "out of memory");
+    sc->device = device;
+    sc->sm_count = prop.multiProcessorCount;
+    sc->tree_depth = depth;
+    sc->dev.dim = desc->dim;
+    sc->dev.kind = desc->kind;
+    sc->dev.root = NTR_NULL_NODE;
+    sc->dev.batch = 1;
+    sc->kset = kernel_family(desc->dim);
+    for (int i = 0; i < desc->dim; ++i) { sc->cam.right[i] = i == 0; sc->cam.up[i] = i == 1; sc->cam.fwd[i] = i == 2; }
+    auto bail = [&](int code) { ntr_scene_destroy(sc); return code; };
+    fill_params(sc->dev, desc);
+    if (desc->kind == NTR_SCENE_COMPOSITE) {
+        if ((rc = build_arena(sc, desc))) return bail(rc);
+        if ((rc = upload_lights(sc, desc))) return bail(rc);
+    }
+    auto cu = [&](cudaError_t e, const char *what) {
+        if (e == cudaSuccess) return 0;
+        return fail(e == cudaErrorMemoryAllocation ? NTR_ERR_MEMORY : NTR_ERR_RUNTIME, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    if ((rc = cu(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return bail(rc);
+    if ((rc = cu(cudaEventCreate(&sc->ev0), "cudaEventCreate"))) return bail(rc);
+    if ((rc = cu(cudaEventCreate(&sc->ev1), "cudaEventCreate"))) return bail(rc);
+    if ((rc = cu(cudaMalloc(&sc->d_ctl, CTL_WORDS * sizeof(uint32_t)), "cudaMalloc"))) return bail(rc);
+    if ((rc = cu(cudaMalloc(&sc->d_counters, 8 * sizeof(unsigned long long)), "cudaMalloc"))) return bail(rc);
+    if ((rc = cu(cudaHostAlloc(&sc->h_abort, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc"))) return bail(rc);
+    *sc->h_abort = 0;
+    if ((rc = cu(cudaHostGetDevicePointer(&sc->d_abort, sc->h_abort, 0), "cudaHostGetDevicePointer"))) return bail(rc);
+    *out = sc;
+    return NTR_OK;
+}
+
+NTR_API void ntr_scene_destroy(ntr_scene *sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    if (sc->stream) cudaStreamSynchronize(sc->stream);
+    cudaFree(sc->arena); cudaFree(sc->d_lights); cudaFree(sc->d_ctl); cudaFree(sc->d_counters);
+    cudaFree(sc->d_accum); cudaFree(sc->d_packed); cudaFree(sc->d_ids); cudaFree(sc->d_dists);
+    cudaFree(sc->d_queue[0]); cudaFree(sc->d_queue[1]); cudaFree(sc->d_scratch);
+    if (sc->h_abort) cudaFreeHost(sc->h_abort);
+    if (sc->ev0) cudaEventDestroy(sc->ev0);
+    if (sc->ev1) cudaEventDestroy(sc->ev1);
+    if (sc->stream) cudaStreamDestroy(sc->stream);
+    cudaGetLastError();
+    delete sc;
+}
+
+NTR_API int ntr_scene_set_camera(ntr_scene *sc, const float *origin, const float *axes) {
+    if (!sc || !origin || !axes) return fail(NTR_ERR_VALUE, "NULL argument");
+    if (sc->busy) return fail(NTR_ERR_RUNTIME, "the scene is locked while rendering");
+    const int D = sc->dev.dim;
+    for (int i = 0; i < D; ++i) {
+        sc->cam.origin[i] = origin[i];
+        sc->cam.right[i] = axes[i]; sc->cam.up[i] = axes[D + i]; sc->cam.fwd[i] = axes[2 * D + i];
+    }
+    return NTR_OK;
+}
+
+NTR_API int ntr_scene_set_params(ntr_scene *sc, const ntr_scene_desc *desc) {
+    if (!sc || !desc) return fail(NTR_ERR_VALUE, "NULL argument");
+    if (sc->busy) return fail(NTR_ERR_RUNTIME, "the scene is locked while rendering");
+    if (desc->dim != sc->dev.dim || desc->kind != sc->dev.kind) return fail(NTR_ERR_VALUE, "dimension / kind mismatch");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    if (desc->kind == NTR_SCENE_COMPOSITE) {
+        if (!desc->boundary) return fail(NTR_ERR_VALUE, "composite scene needs a boundary");
+        if (desc->bg_gradient_axis < 0 || desc->bg_gradient_axis >= desc->dim) return fail(NTR_ERR_VALUE, "bg_gradient_axis out of range");
+    }
+    fill_params(sc->dev, desc);
+    if (desc->kind == NTR_SCENE_COMPOSITE) return upload_lights(sc, desc);
+    return NTR_OK;
+}
+
+NTR_API int ntr_render_device(ntr_scene *sc, const ntr_image_format *fmt, void *dev_dst, size_t dst_len, void *stream,
+                              int tile_row_first, int tile_row_step, int compact) {
+    ENTER(sc);
+    int rc = check_format(fmt);
+    if (rc) return rc;
+    if (!dev_dst) return fail(NTR_ERR_VALUE, "destination is NULL");
+    if (tile_row_step < 1 || tile_row_first < 0 || tile_row_first >= tile_row_step) return fail(NTR_ERR_VALUE, "bad tile row interleave");
+    const int tiles_y = (fmt->height + NTR_TILE - 1) / NTR_TILE;
+    const int my_rows = tile_row_first < tiles_y ? (tiles_y - tile_row_first + tile_row_step - 1) / tile_row_step : 0;
+    const size_t need = compact ? (size_t)my_rows * NTR_TILE * fmt->pitch : (size_t)fmt->pitch * fmt->height;
+    if (dst_len < need) return fail(NTR_ERR_VALUE, "the buffer is too small for an image with the given dimensions");
+    cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
+    const bool composite = sc->dev.kind == NTR_SCENE_COMPOSITE;
+    const bool passes = composite && sc->any_reflective && sc->dev.max_depth > 0;
+    RenderTarget tgt;
+    tgt.out_mode = NTR_OUT_PACKED;
+    tgt.packed = static_cast<unsigned char *>(dev_dst);
+    if (!passes) {
+        // single persistent kernel, fully asynchronous on the caller's stream
+        bool p = false;
+        CUDA_TRY(cudaEventRecord(sc->ev0, st));
+        rc = enqueue_frame(sc, st, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, tile_row_first,
+                           tile_row_step, compact, &p);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(sc->ev1, st));
+        sc->timing_valid = true;
+        sc->counters = ntr_counters{};
+        sc->counters.primary_rays = (uint64_t)fmt->width * fmt->height;
+        return NTR_OK;
+    }
+    if (tile_row_step == 1 && !compact)
+        return run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, st);
+    // sharded + wavefront passes: render this rank's tile rows strip by strip is not needed -- the window
+    // mechanism renders exactly the rows of each owned tile row through the accumulator
+    for (int k = 0, ty = tile_row_first; ty < tiles_y; ty += tile_row_step, ++k) {
+        const int y0 = ty * NTR_TILE, h = std::min(NTR_TILE, fmt->height - y0);
+        ntr_image_format sub = *fmt;
+        sub.height = h;
+        RenderTarget t2 = tgt;
+        t2.packed = static_cast<unsigned char *>(dev_dst) + (compact ? (size_t)k * NTR_TILE * fmt->pitch : (size_t)y0 * fmt->pitch);
+        rc = run_frame_sync(sc, fmt->width, fmt->height, 0, y0, fmt->width, h, &sub, t2, 0, 1, 0, st);
+        if (rc) return rc;
+    }
+    return NTR_OK;
+}
+
+NTR_API int ntr_render(ntr_scene *sc, const ntr_image_format *fmt, void *dst, size_t dst_len) {
+    ENTER(sc);
+    int rc = check_format(fmt);
+    if (rc) return rc;
+    if (!dst) return fail(NTR_ERR_VALUE, "destination is NULL");
+    const size_t bytes = (size_t)fmt->pitch * fmt->height;
+    if (dst_len < bytes) return fail(NTR_ERR_VALUE, "the buffer is too small for an image with the given dimensions");
+    if ((rc = ensure((void **)&sc->d_packed, &sc->packed_cap, bytes))) return rc;
+    RenderTarget tgt;
+    tgt.out_mode = NTR_OUT_PACKED;
+    tgt.packed = sc->d_packed;
+    if ((rc = run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, sc->stream))) return rc;
+    // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
+    CUDA_TRY(cudaMemcpy2DAsync(dst, fmt->pitch, sc->d_packed, fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel,
+                               fmt->height, cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    return NTR_OK;
+}
+
+NTR_API int ntr_render_float(ntr_scene *sc, int width, int height, float *dst_rgb) {
+    ENTER(sc);
+    if (width < 1 || height < 1 || !dst_rgb) return fail(NTR_ERR_VALUE, "bad arguments");
+    const size_t bytes = (size_t)width * height * 3 * sizeof(float);
+    int rc = ensure((void **)&sc->d_accum, &sc->accum_cap, bytes);
+    if (rc) return rc;
+    RenderTarget tgt;
+    tgt.out_mode = NTR_OUT_ACCUM;
+    tgt.accum = sc->d_accum;
+    if ((rc = run_frame_sync(sc, width, height, 0, 0, width, height, nullptr, tgt, 0, 1, 0, sc->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst_rgb, sc->d_accum, bytes, cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    return NTR_OK;
+}
+
+NTR_API int ntr_calculate_color(ntr_scene *sc, int x, int y, int width, int height, float rgb_out[3]) {
+    ENTER(sc);
+    if (width < 1 || height < 1 || !rgb_out) return fail(NTR_ERR_VALUE, "bad arguments");
+    int rc = ensure((void **)&sc->d_accum, &sc->accum_cap, 3 * sizeof(float));
+    if (rc) return rc;
+    RenderTarget tgt;
+    tgt.out_mode = NTR_OUT_ACCUM;
+    tgt.accum = sc->d_accum;
+    if ((rc = run_frame_sync(sc, width, height, x, y, 1, 1, nullptr, tgt, 0, 1, 0, sc->stream))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(rgb_out, sc->d_accum, 3 * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    return NTR_OK;
+}
+
+NTR_API int ntr_primary_hit_ids(ntr_scene *sc, int width, int height, int32_t *ids_out, float *dist_out) {
+    ENTER(sc);
+    if (width < 1 || height < 1 || !ids_out) return fail(NTR_ERR_VALUE, "bad arguments");
+    const size_t n = (size_t)width * height;
+    if (sc->ids_cap < n) {
+        cudaFree(sc->d_ids); cudaFree(sc->d_dists);
+        sc->d_ids = nullptr; sc->d_dists = nullptr; sc->ids_cap = 0;
+        CUDA_TRY(cudaMalloc(&sc->d_ids, n * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc(&sc->d_dists, n * sizeof(float)));
+        sc->ids_cap = n;
+    }
+    RenderTarget tgt;
+    tgt.out_mode = NTR_OUT_IDS;
+    tgt.ids = sc->d_ids;
+    tgt.dists = sc->d_dists;
+    int rc = run_frame_sync(sc, width, height, 0, 0, width, height, nullptr, tgt, 0, 1, 0, sc->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ids_out, sc->d_ids, n * sizeof(int32_t), cudaMemcpyDeviceToHost, sc->stream));
+    if (dist_out) CUDA_TRY(cudaMemcpyAsync(dist_out, sc->d_dists, n * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    return NTR_OK;
+}
+
+static int ray_batch_scratch(ntr_scene *sc, uint32_t n, size_t *offs, const size_t *sizes, int count) {
+    size_t total = 0;
+    for (int i = 0; i < count; ++i) { offs[i] = total; total += align_up(sizes[i], 256); }
+    return ensure(&sc->d_scratch, &sc->scratch_cap, std::max<size_t>(total, 256));
+}
+
+NTR_API int ntr_trace_rays(ntr_scene *sc, uint32_t n, const float *origins, const float *dirs, float t_near, float t_far,
+                           const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids_out, float *dist_out,
+                           int32_t *n_transparent_out) {
+    ENTER(sc);
+    if (sc->dev.kind != NTR_SCENE_COMPOSITE) return fail(NTR_ERR_VALUE, "only composite scenes have a k-d tree");
+    if (!origins || !dirs || !ids_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    if (n == 0) return NTR_OK;
+    const size_t vb = (size_t)n * sc->dev.dim * sizeof(float), ib = (size_t)n * 4;
+    size_t offs[7];
+    const size_t sizes[7] = {vb, vb, ib, ib, ib, ib, ib};
+    int rc = ray_batch_scratch(sc, n, offs, sizes, 7);
+    if (rc) return rc;
+    unsigned char *b = static_cast<unsigned char *>(sc->d_scratch);
+    cudaStream_t st = sc->stream;
+    CUDA_TRY(cudaMemcpyAsync(b + offs[0], origins, vb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b + offs[1], dirs, vb, cudaMemcpyHostToDevice, st));
+    if (skip_ref) CUDA_TRY(cudaMemcpyAsync(b + offs[2], skip_ref, ib, cudaMemcpyHostToDevice, st));
+    if (skip_lane) CUDA_TRY(cudaMemcpyAsync(b + offs[3], skip_lane, ib, cudaMemcpyHostToDevice, st));
+    const int flags = sc->base_flags;
+    sc->kset(flags)->trace_rays(dim3((n + kCtaThreads - 1) / kCtaThreads), dim3(kCtaThreads), st, sc->dev, n,
+                                (const float *)(b + offs[0]), (const float *)(b + offs[1]), t_near, t_far,
+                                skip_ref ? (const uint32_t *)(b + offs[2]) : nullptr,
+                                skip_lane ? (const int32_t *)(b + offs[3]) : nullptr, (int32_t *)(b + offs[4]),
+                                (float *)(b + offs[5]), (int32_t *)(b + offs[6]));
+    ++sc->launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ids_out, b + offs[4], ib, cudaMemcpyDeviceToHost, st));
+    if (dist_out) CUDA_TRY(cudaMemcpyAsync(dist_out, b + offs[5], ib, cudaMemcpyDeviceToHost, st));
+    if (n_transparent_out) CUDA_TRY(cudaMemcpyAsync(n_transparent_out, b + offs[6], ib, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return NTR_OK;
+}
+
+NTR_API int ntr_occludes_rays(ntr_scene *sc, uint32_t n, const float *origins, const float *dirs, const float *distance,
+                              const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *occluded_out,
+                              int32_t *n_transparent_out) {
+    ENTER(sc);
+    if (sc->dev.kind != NTR_SCENE_COMPOSITE) return fail(NTR_ERR_VALUE, "only composite scenes have a k-d tree");
+    if (!origins || !dirs || !occluded_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    if (n == 0) return NTR_OK;
+    const size_t vb = (size_t)n * sc->dev.dim * sizeof(float), ib = (size_t)n * 4;
+    size_t offs[7];
+    const size_t sizes[7] = {vb, vb, ib, ib, ib, ib, ib};
+    int rc = ray_batch_scratch(sc, n, offs, sizes, 7);
+    if (rc) return rc;
+    unsigned char *b = static_cast<unsigned char *>(sc->d_scratch);
+    cudaStream_t st = sc->stream;
+    CUDA_TRY(cudaMemcpyAsync(b + offs[0], origins, vb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b + offs[1], dirs, vb, cudaMemcpyHostToDevice, st));
+    if (distance) CUDA_TRY(cudaMemcpyAsync(b + offs[2], distance, ib, cudaMemcpyHostToDevice, st));
+    if (skip_ref) CUDA_TRY(cudaMemcpyAsync(b + offs[3], skip_ref, ib, cudaMemcpyHostToDevice, st));
+    if (skip_lane) CUDA_TRY(cudaMemcpyAsync(b + offs[4], skip_lane, ib, cudaMemcpyHostToDevice, st));
+    const int flags = sc->base_flags;
+    sc->kset(flags)->occludes_rays(dim3((n + kCtaThreads - 1) / kCtaThreads), dim3(kCtaThreads), st, sc->dev, n,
+                                   (const float *)(b + offs[0]), (const float *)(b + offs[1]),
+                                   distance ? (const float *)(b + offs[2]) : nullptr,
+                                   skip_ref ? (const uint32_t *)(b + offs[3]) : nullptr,
+                                   skip_lane ? (const int32_t *)(b + offs[4]) : nullptr, (int32_t *)(b + offs[5]),
+                                   (int32_t *)(b + offs[6]));
+    ++sc->launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(occluded_out, b + offs[5], ib, cudaMemcpyDeviceToHost, st));
+    if (n_transparent_out) CUDA_TRY(cudaMemcpyAsync(n_transparent_out, b + offs[6], ib, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return NTR_OK;
+}
+
+NTR_API int ntr_abort(ntr_scene *sc) {
+    if (!sc) return fail(NTR_ERR_VALUE, "scene is NULL");
+    if (sc->busy) *sc->h_abort = 1;         // polled by every warp before it takes the next block of work
+    return NTR_OK;
+}
+
+NTR_API int ntr_get_counters(ntr_scene *sc, ntr_counters *out) {
+    if (!sc || !out) return fail(NTR_ERR_VALUE, "NULL argument");
+    *out = sc->counters;
+    return NTR_OK;
+}
+
+NTR_API int ntr_set_instrumented(ntr_scene *sc, int on) {
+    if (!sc) return fail(NTR_ERR_VALUE, "scene is NULL");
+    sc->instrumented = on != 0;
+    return NTR_OK;
+}
+
+NTR_API int ntr_last_kernel_ms(ntr_scene *sc, float *ms_out) {
+    if (!sc || !ms_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    if (!sc->timing_valid) return fail(NTR_ERR_RUNTIME, "nothing has been rendered yet");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    CUDA_TRY(cudaEventSynchronize(sc->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms_out, sc->ev0, sc->ev1));
+    return NTR_OK;
+}
+
+NTR_API uint64_t ntr_launch_count(ntr_scene *sc) { return sc ? sc->launches : 0; }
+
+NTR_API int ntr_measure_fp32_peak(int device, float *tflops_out) {
+    if (!tflops_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(NTR_ERR_NO_DEVICE, "no CUDA device"); }
+    if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    float *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 256));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    fma_peak_kernel<<<blocks, threads>>>(d, 1 << 10);
+    float best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        best = std::max(best, (float)(flops / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops_out = best;
+    return NTR_OK;
+}
+
+}  // extern "C"

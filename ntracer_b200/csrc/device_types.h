@@ -1,0 +1,100 @@
+// Plain-old-data types shared by the host side (arena builder, C ABI) and the device code.
+// Layouts are described in DESIGN.md section 3 ("data layout in HBM").
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>   // uint4 / float4 (plain C++ header of the CUDA toolkit)
+
+#include "../../include/ntracer_b200.h"
+
+#define NTR_MAXD NTR_MAX_DIM
+#define NTR_NONE_REF 0xFFFFFFFFu
+#define NTR_IDX_MASK 0x3FFFFFFFu
+#define NTR_TILE 32                 // RENDER_CHUNK_SIZE, reference src/render.cpp:43
+#define NTR_BLK_W 8                 // one warp renders an 8x4 pixel block
+#define NTR_BLK_H 4
+#define NTR_BLOCKS_PER_TILE ((NTR_TILE / NTR_BLK_W) * (NTR_TILE / NTR_BLK_H))
+
+#define NTR_THITS_CAP 16            // transparent hits kept per ray (reference is defined up to 10, tracer.hpp:26)
+#define NTR_MAILBOX_CAP 40          // mailbox entries kept per traversal (reference is defined up to 20, tracer.hpp:27)
+#define NTR_STACK_CAP (NTR_MAX_TREE_DEPTH + 2)
+
+// meta word stored in the last float slot of every simplex / solid record
+#define NTR_META_OPAQUE 0x80000000u
+
+// kernel variant flags (template parameter)
+enum : int {
+    NTR_F_GENERAL = 1,      // scene has transparent materials and/or solids: mailbox, transparent-hit list,
+                            // explicit normal mirroring (reference quirks)
+    NTR_F_COUNT = 2         // instrumented: node/primitive counters (never used for timing)
+};
+
+struct SceneDev {
+    const uint4 *nodes;             // ntr_node, 16 B
+    const uint32_t *leaf_refs;
+    const float *simplex;           // stride sstride floats: fn[D], d, p1[D], edges[D-1][D], pad.., meta
+    const float *solids;            // stride solstride floats: type, inv_orientation[D*D], position[D], orientation[D*D], pad.., meta
+    const float *materials;         // 12 floats per material (10 used)
+    const float *point_lights;      // stride D+3
+    const float *global_lights;     // stride D+3
+    uint32_t root;
+    uint32_t n_simplex;
+    int dim, batch, sstride, solstride;
+    int kind;
+    int n_point, n_global;
+    int shadows, camera_light, max_depth, bg_axis;
+    float fov;
+    float ambient[3], bg1[3], bg2[3], bg3[3];
+    float bmin[NTR_MAXD], bmax[NTR_MAXD];
+};
+
+struct CameraDev {
+    float origin[NTR_MAXD], right[NTR_MAXD], up[NTR_MAXD], fwd[NTR_MAXD];
+};
+
+struct FormatDev {
+    int n_channels, bytes_per_pixel, reversed, pitch;
+    float f_r[NTR_MAX_CHANNELS], f_g[NTR_MAX_CHANNELS], f_b[NTR_MAX_CHANNELS], f_c[NTR_MAX_CHANNELS];
+    unsigned char bits[NTR_MAX_CHANNELS], tfloat[NTR_MAX_CHANNELS];
+};
+
+// What a render pass writes.
+enum : int {
+    NTR_OUT_PACKED = 0,     // pack straight into the image format (no secondary passes needed)
+    NTR_OUT_ACCUM = 1,      // float RGB accumulator (secondary passes add to it, a pack kernel follows)
+    NTR_OUT_IDS = 2         // primary hit ids + distances (parity hook)
+};
+
+struct FrameDev {
+    int width, height;              // view size
+    float half_w, half_h, fovI;     // flat_origin_ray_source, reference src/tracer.hpp:60-69
+    int x0, y0;                     // window origin (calculate_color renders a 1x1 window)
+    int win_w, win_h;               // window size in pixels
+    int tiles_x, tiles_y;           // window size in 32x32 tiles
+    int tile_row_first, tile_row_step, compact;   // multi-GPU interleave (tile rows ty % step == first)
+    int out_mode;
+    unsigned char *packed;          // NTR_OUT_PACKED destination (device)
+    float *accum;                   // NTR_OUT_ACCUM: 3 floats per window pixel
+    int32_t *ids;                   // NTR_OUT_IDS
+    float *dists;
+    FormatDev fmt;
+};
+
+// One deferred ray of the wavefront (a reflection bounce): 16-byte aligned record.
+// layout: [0] pixel, [1] skip_ref, [2] skip_lane | depth<<16, [3] pad, [4..6] weight rgb, [7] pad,
+//         then origin[Dq], dir[Dq] with Dq = D rounded up to 4
+struct QueueDev {
+    float4 *in;                     // rays of this pass (nullptr for the primary pass)
+    float4 *out;                    // rays for the next pass
+    uint32_t *in_count;             // device counter written by the previous pass
+    uint32_t *out_count;
+    uint32_t *in_cursor;            // work-fetch cursor of this pass
+    uint32_t capacity;              // in records
+    uint32_t rec4;                  // record size in float4 units
+};
+
+struct ControlDev {
+    uint32_t *tile_cursor;          // atomic block queue of the primary pass
+    volatile int *abort_flag;       // host-mapped; renderer::state == CANCEL (reference src/render.cpp:333,412)
+    unsigned long long *counters;   // ntr_counters layout (8 x u64)
+    uint32_t *overflow;             // set when a wavefront queue was too small
+};

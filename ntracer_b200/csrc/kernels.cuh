@@ -1,0 +1,330 @@
+// kernels.cuh -- the __global__ kernels of the render path, templated on the dimension (DT = 3..8, 0 = run-time
+// dimension) and the variant flags; instantiated per dimension in kern_d*.cu so the translation units
+// compile in parallel.
+//
+//   render_pass_kernel  persistent warps; primary pass: atomic block queue over 32x32 tiles (reference
+//                       worker_draw, src/render.cpp:468-493) + ray generation + traversal + shading + pixel
+//                       packing epilogue; secondary passes: the same per-ray code over a wavefront queue of
+//                       reflection bounces written by the previous pass with warp-aggregated atomics.
+//   pack_kernel         float accumulator -> ImageFormat bytes (reference process_pixel, src/render.cpp:396-466)
+//   trace_rays_kernel / occludes_rays_kernel   KDNode.intersects / KDNode.occludes parity hooks
+#pragma once
+#include <cuda_runtime.h>
+
+#include "trace_core.cuh"
+
+namespace ntr {
+
+constexpr int kCtaThreads = 128;
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Deferred-ray sink: appends to the next pass's queue.  The slot index comes from ONE atomicAdd per
+// converged group of lanes (ballot of the active mask + prefix popcount), not one per ray.
+template <int DT> struct QueueEmit {
+    const QueueDev &q;
+    const ControlDev &ctl;
+    uint32_t pixel;
+    __device__ __forceinline__ void operator()(const Bounce<DT> &b) const {
+        const unsigned mask = __activemask();
+        const int leader = __ffs(mask) - 1;
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(q.out_count, (uint32_t)__popc(mask));
+        base = __shfl_sync(mask, base, leader);
+        const uint32_t idx = base + (uint32_t)__popc(mask & lanemask_lt());
+        if (idx >= q.capacity) { *ctl.overflow = 1u; return; }
+        float4 *rec = q.out + (size_t)idx * q.rec4;
+        rec[0] = make_float4(__uint_as_float(pixel), __uint_as_float(b.skip.ref),
+                             __int_as_float((b.skip.lane & 0xFFFF) | (b.depth << 16)), 0.0f);
+        rec[1] = make_float4(b.w[0], b.w[1], b.w[2], 0.0f);
+        constexpr int CAP = DimCap<DT>::value;
+        const int D4 = (int)(q.rec4 - 2) / 2;       // float4s per vector
+#pragma unroll
+        for (int k = 0; k < (CAP + 3) / 4; ++k) {
+            if (k < D4) {
+                float4 vo, vd;
+                vo.x = 4 * k + 0 < CAP ? b.o[4 * k + 0] : 0.f; vo.y = 4 * k + 1 < CAP ? b.o[4 * k + 1] : 0.f;
+                vo.z = 4 * k + 2 < CAP ? b.o[4 * k + 2] : 0.f; vo.w = 4 * k + 3 < CAP ? b.o[4 * k + 3] : 0.f;
+                vd.x = 4 * k + 0 < CAP ? b.d[4 * k + 0] : 0.f; vd.y = 4 * k + 1 < CAP ? b.d[4 * k + 1] : 0.f;
+                vd.z = 4 * k + 2 < CAP ? b.d[4 * k + 2] : 0.f; vd.w = 4 * k + 3 < CAP ? b.d[4 * k + 3] : 0.f;
+                rec[2 + k] = vo;
+                rec[2 + D4 + k] = vd;
+            }
+        }
+    }
+};
+struct NullEmit {
+    template <typename B> __device__ __forceinline__ void operator()(const B &) const {}
+};
+
+__device__ __forceinline__ void flush_counters(const ControlDev &ctl, const Counters &cnt) {
+    unsigned long long v[6] = {cnt.reflection_rays, cnt.shadow_rays, cnt.node_steps, cnt.simplex_tests,
+                               cnt.solid_tests, cnt.shaded_hits};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        unsigned long long x = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, off);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(ctl.counters + 1 + k, x);     // slot 0 = primary_rays (host)
+    }
+}
+
+// Warp-cooperative store of an 8x4 pixel block: pixels are staged in shared memory in memory byte order,
+// then every lane moves one 16-byte chunk of one row segment with the widest aligned store.
+__device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned char *stage /*512 B per warp*/,
+                                                   int px0, int py0, int ncols, int nrows, int out_row0,
+                                                   const uint32_t w[4], bool inside) {
+    const int lane = threadIdx.x & 31;
+    const int bpp = f.fmt.bytes_per_pixel;
+    const int r = lane >> 3, c = lane & 7;
+    if (inside) {
+        unsigned char *d = stage + r * 128 + c * bpp;
+        for (int j = 0; j < bpp; ++j) {
+            const int sj = f.fmt.reversed ? bpp - 1 - j : j;
+            d[j] = (unsigned char)(w[sj >> 2] >> (8 * (3 - (sj & 3))));
+        }
+    }
+    __syncwarp();
+    const int seg = ncols * bpp;
+    if (r < nrows) {
+        int off = c * 16;
+        int n = seg - off;
+        if (n > 16) n = 16;
+        if (n > 0) {
+            unsigned char *dst = f.packed + (size_t)(out_row0 + r) * f.fmt.pitch + (size_t)px0 * bpp + off;
+            const unsigned char *src = stage + r * 128 + off;
+            while (n > 0) {
+                const size_t a = (size_t)dst;
+                if (n >= 16 && (a & 15) == 0) { *(uint4 *)dst = *(const uint4 *)src; dst += 16; src += 16; n -= 16; }
+                else if (n >= 8 && (a & 7) == 0) { *(uint2 *)dst = *(const uint2 *)src; dst += 8; src += 8; n -= 8; }
+                else if (n >= 4 && (a & 3) == 0) { *(uint32_t *)dst = *(const uint32_t *)src; dst += 4; src += 4; n -= 4; }
+                else { *dst++ = *src++; --n; }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int DT, int FLAGS>
+__global__ void __launch_bounds__(kCtaThreads)
+render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ CameraDev cam,
+                   const __grid_constant__ FrameDev f, const __grid_constant__ QueueDev q,
+                   const __grid_constant__ ControlDev ctl) {
+    constexpr int CAP = DimCap<DT>::value;
+    __shared__ __align__(16) unsigned char stage_all[(kCtaThreads / 32) * 512];
+    unsigned char *stage = stage_all + (threadIdx.x >> 5) * 512;
+    const int lane = threadIdx.x & 31;
+    Counters cnt;
+    const float one[3] = {1.0f, 1.0f, 1.0f};
+
+    if (q.in == nullptr) {
+        // ---------------- primary pass: atomic block queue over the window's tiles ----------------
+        const int my_rows = f.tile_row_first < f.tiles_y
+                                ? (f.tiles_y - f.tile_row_first + f.tile_row_step - 1) / f.tile_row_step : 0;
+        const uint32_t total = (uint32_t)my_rows * (uint32_t)f.tiles_x * NTR_BLOCKS_PER_TILE;
+        for (;;) {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(ctl.tile_cursor, 1u);
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            if (b >= total) break;
+            // renderer::state poll (reference render.cpp:412).  The flag lives in mapped host memory, so only
+            // every 64th block looks at it; whoever sees it pushes the cursor past the end for everybody.
+            if ((b & 63u) == 0 && *ctl.abort_flag) { if (lane == 0) atomicAdd(ctl.tile_cursor, 0x40000000u); break; }
+            const uint32_t tile = b / NTR_BLOCKS_PER_TILE, sub = b % NTR_BLOCKS_PER_TILE;
+            const int tyi = (int)(tile / (uint32_t)f.tiles_x), tx = (int)(tile % (uint32_t)f.tiles_x);
+            const int ty = f.tile_row_first + tyi * f.tile_row_step;
+            const int bx = tx * NTR_TILE + (int)(sub % (NTR_TILE / NTR_BLK_W)) * NTR_BLK_W;     // window coords
+            const int by = ty * NTR_TILE + (int)(sub / (NTR_TILE / NTR_BLK_W)) * NTR_BLK_H;
+            if (bx >= f.win_w || by >= f.win_h) continue;
+            const int px = bx + (lane & 7), py = by + (lane >> 3);
+            const bool inside = px < f.win_w && py < f.win_h;
+            float acc[3] = {0.f, 0.f, 0.f};
+            HitRec prim;
+            prim.dist = 0; prim.ref = NTR_NONE_REF; prim.lane = -1;
+            if (inside) {
+                float o[CAP], dir[CAP];
+                primary_ray<DT>(s, cam, f, f.x0 + px, f.y0 + py, o, dir);
+                if (s.kind == NTR_SCENE_BOX) {
+                    box_color<DT>(s, o, dir, acc, &prim);
+                } else {
+                    const Skip none = {NTR_NONE_REF, 0};
+                    // output row index of this pixel in window coordinates (frame position or compacted strips)
+                    const uint32_t pix = (uint32_t)py * (uint32_t)f.win_w + (uint32_t)px;
+                    if (f.out_mode == NTR_OUT_ACCUM) {
+                        QueueEmit<DT> emit{q, ctl, pix};
+                        ray_color<DT, FLAGS>(s, o, dir, 0, none, one, acc, emit, cnt, &prim);
+                    } else {
+                        NullEmit emit;
+                        ray_color<DT, FLAGS>(s, o, dir, 0, none, one, acc, emit, cnt, &prim);
+                    }
+                }
+            }
+            __syncwarp();
+            const int out_row0 = f.compact ? (tyi * NTR_TILE + (by - ty * NTR_TILE)) : by;
+            if (f.out_mode == NTR_OUT_PACKED) {
+                uint32_t w[4] = {0, 0, 0, 0};
+                if (inside) pack_pixel(f.fmt, acc, w);
+                const int ncols = min(NTR_BLK_W, f.win_w - bx), nrows = min(NTR_BLK_H, f.win_h - by);
+                store_block_packed(f, stage, bx, by, ncols, nrows, out_row0, w, inside);
+            } else if (inside) {
+                const size_t pix = (size_t)py * f.win_w + px;
+                if (f.out_mode == NTR_OUT_ACCUM) {
+                    f.accum[pix * 3 + 0] = acc[0]; f.accum[pix * 3 + 1] = acc[1]; f.accum[pix * 3 + 2] = acc[2];
+                } else {
+                    f.ids[pix] = prim.ref == NTR_NONE_REF ? -1 : (s.kind == NTR_SCENE_BOX ? 0 : flat_prim_id(s, prim.ref, prim.lane));
+                    if (f.dists) f.dists[pix] = prim.dist;
+                }
+            }
+        }
+    } else {
+        // ---------------- secondary pass: reflection bounces queued by the previous pass ----------------
+        uint32_t n = *q.in_count;
+        if (n > q.capacity) n = q.capacity;
+        const int D = NTR_D(DT, s);
+        const int D4 = (int)(q.rec4 - 2) / 2;
+        for (;;) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(q.in_cursor, 32u);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base >= n) break;
+            if ((base & 2047u) == 0 && *ctl.abort_flag) { if (lane == 0) atomicAdd(q.in_cursor, 0x40000000u); break; }
+            const uint32_t idx = base + lane;
+            if (idx < n) {
+                const float4 *rec = q.in + (size_t)idx * q.rec4;
+                const float4 h = rec[0], wv = rec[1];
+                const uint32_t pix = __float_as_uint(h.x);
+                Skip skip;
+                skip.ref = __float_as_uint(h.y);
+                const int ld = __float_as_int(h.z);
+                skip.lane = (int)(short)(ld & 0xFFFF);
+                const int depth = ld >> 16;
+                float o[CAP], dir[CAP];
+#pragma unroll
+                for (int k = 0; k < (CAP + 3) / 4; ++k) {
+                    if (k < D4) {
+                        const float4 vo = rec[2 + k], vd = rec[2 + D4 + k];
+                        if (4 * k + 0 < CAP) { o[4 * k + 0] = vo.x; dir[4 * k + 0] = vd.x; }
+                        if (4 * k + 1 < CAP) { o[4 * k + 1] = vo.y; dir[4 * k + 1] = vd.y; }
+                        if (4 * k + 2 < CAP) { o[4 * k + 2] = vo.z; dir[4 * k + 2] = vd.z; }
+                        if (4 * k + 3 < CAP) { o[4 * k + 3] = vo.w; dir[4 * k + 3] = vd.w; }
+                    }
+                }
+                (void)D;
+                const float w[3] = {wv.x, wv.y, wv.z};
+                float acc[3] = {0.f, 0.f, 0.f};
+                QueueEmit<DT> emit{q, ctl, pix};
+                ray_color<DT, FLAGS>(s, o, dir, depth, skip, w, acc, emit, cnt, nullptr);
+                atomicAdd(f.accum + (size_t)pix * 3 + 0, acc[0]);
+                atomicAdd(f.accum + (size_t)pix * 3 + 1, acc[1]);
+                atomicAdd(f.accum + (size_t)pix * 3 + 2, acc[2]);
+            }
+        }
+    }
+    __syncwarp();
+    flush_counters(ctl, cnt);
+}
+
+// KDNode.intersects for a batch of rays (reference src/ntracer_body.hpp:1412-1458)
+template <int DT, int FLAGS>
+__global__ void __launch_bounds__(kCtaThreads)
+trace_rays_kernel(const __grid_constant__ SceneDev s, uint32_t n, const float *origins, const float *dirs,
+                  float t_near, float t_far, const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids,
+                  float *dist, int32_t *ntrans) {
+    constexpr int CAP = DimCap<DT>::value;
+    const int D = NTR_D(DT, s);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float o[CAP], dir[CAP];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { o[k] = origins[(size_t)i * D + k]; dir[k] = dirs[(size_t)i * D + k]; }
+    Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
+    GenState<DT> g;
+    g.th.clear();
+    HitRec oh;
+    oh.dist = FLT_MAX; oh.ref = NTR_NONE_REF; oh.lane = -1;
+    Counters cnt;
+    const bool hit = trace_nearest<DT, FLAGS>(s, o, dir, skip, t_near, t_far, oh, &g, cnt);
+    ids[i] = hit ? flat_prim_id(s, oh.ref, oh.lane) : -1;
+    if (dist) dist[i] = hit ? oh.dist : 0.0f;
+    if (ntrans) ntrans[i] = (FLAGS & NTR_F_GENERAL) ? g.th.n : 0;
+}
+
+// KDNode.occludes (reference src/ntracer_body.hpp:1460-1496)
+template <int DT, int FLAGS>
+__global__ void __launch_bounds__(kCtaThreads)
+occludes_rays_kernel(const __grid_constant__ SceneDev s, uint32_t n, const float *origins, const float *dirs,
+                     const float *distance, const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *occ,
+                     int32_t *ntrans) {
+    constexpr int CAP = DimCap<DT>::value;
+    const int D = NTR_D(DT, s);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float o[CAP], dir[CAP];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { o[k] = origins[(size_t)i * D + k]; dir[k] = dirs[(size_t)i * D + k]; }
+    Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
+    HitList hits;
+    hits.clear();
+    Counters cnt;
+    const bool r = trace_occludes<DT, FLAGS>(s, o, dir, distance ? distance[i] : FLT_MAX, skip, -FLT_MAX, FLT_MAX,
+                                            &hits, cnt);
+    occ[i] = r ? 1 : 0;
+    if (ntrans) ntrans[i] = (!r && (FLAGS & NTR_F_GENERAL)) ? hits.n : 0;
+}
+
+// ---- launch table -------------------------------------------------------------------------------------
+struct KernelSet {
+    void (*render_pass)(dim3, dim3, cudaStream_t, const SceneDev &, const CameraDev &, const FrameDev &,
+                        const QueueDev &, const ControlDev &);
+    void (*trace_rays)(dim3, dim3, cudaStream_t, const SceneDev &, uint32_t, const float *, const float *, float,
+                       float, const uint32_t *, const int32_t *, int32_t *, float *, int32_t *);
+    void (*occludes_rays)(dim3, dim3, cudaStream_t, const SceneDev &, uint32_t, const float *, const float *,
+                          const float *, const uint32_t *, const int32_t *, int32_t *, int32_t *);
+    int (*max_blocks_per_sm)();
+};
+
+template <int DT, int FLAGS> struct Launch {
+    static void render_pass(dim3 g, dim3 b, cudaStream_t st, const SceneDev &s, const CameraDev &cam,
+                            const FrameDev &f, const QueueDev &q, const ControlDev &ctl) {
+        render_pass_kernel<DT, FLAGS><<<g, b, 0, st>>>(s, cam, f, q, ctl);
+    }
+    static void trace_rays(dim3 g, dim3 b, cudaStream_t st, const SceneDev &s, uint32_t n, const float *o,
+                           const float *d, float tn, float tf, const uint32_t *sr, const int32_t *sl, int32_t *ids,
+                           float *dist, int32_t *nt) {
+        trace_rays_kernel<DT, FLAGS><<<g, b, 0, st>>>(s, n, o, d, tn, tf, sr, sl, ids, dist, nt);
+    }
+    static void occludes_rays(dim3 g, dim3 b, cudaStream_t st, const SceneDev &s, uint32_t n, const float *o,
+                              const float *d, const float *ld, const uint32_t *sr, const int32_t *sl, int32_t *occ,
+                              int32_t *nt) {
+        occludes_rays_kernel<DT, FLAGS><<<g, b, 0, st>>>(s, n, o, d, ld, sr, sl, occ, nt);
+    }
+    static int max_blocks_per_sm() {
+        int n = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_pass_kernel<DT, FLAGS>, kCtaThreads, 0);
+        return n;
+    }
+    static KernelSet get() { return KernelSet{&render_pass, &trace_rays, &occludes_rays, &max_blocks_per_sm}; }
+};
+
+// defined in kern_d*.cu: variant index = FLAGS (0..3)
+const KernelSet *kernel_set_d3(int flags);
+const KernelSet *kernel_set_d4(int flags);
+const KernelSet *kernel_set_d5(int flags);
+const KernelSet *kernel_set_d6(int flags);
+const KernelSet *kernel_set_d7(int flags);
+const KernelSet *kernel_set_d8(int flags);
+const KernelSet *kernel_set_dn(int flags);
+
+#define NTR_INSTANTIATE_DIM(NAME, DT)                                                                   \
+    const KernelSet *NAME(int flags) {                                                                  \
+        static const KernelSet sets[4] = {Launch<DT, 0>::get(), Launch<DT, 1>::get(), Launch<DT, 2>::get(), \
+                                          Launch<DT, 3>::get()};                                        \
+        return &sets[flags & 3];                                                                        \
+    }
+
+}  // namespace ntr

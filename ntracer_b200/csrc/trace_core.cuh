@@ -1,0 +1,1028 @@
+// trace_core.cuh -- per-ray device code of the ntracer_b200 render path (sm_100a).
+//
+// Everything in here is written against the *semantics* of the reference's per-pixel path
+// (Rouslan/NTracer src/tracer.hpp, cited per function as tracer.hpp:LINE) but shares none of its
+// structure: the reference is recursive, pointer-based and heap-list-based; this is an explicit
+// stack machine over a flat 16-byte-node arena with fixed-capacity per-ray lists, dimension as a
+// template parameter (DT = 3..8) or run time (DT = 0), and the recursive colour evaluation
+// linearised into RGB throughput weights so that reflection bounces can be deferred to wavefront
+// queues.
+//
+// The functions are __host__ __device__ so that tests/host_emul can run the very same state machine
+// on the CPU against the oracle without a GPU.  That harness is test-only; the product .so contains
+// only the __global__ kernels of kernels.cu and has no CPU path.
+#pragma once
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "device_types.h"
+
+#if defined(__CUDACC__)
+#define NTR_HD __host__ __device__ __forceinline__
+#else
+#define NTR_HD inline
+#endif
+
+// Loop unrolling policy of the translation unit: the fixed-dimension units (kern_d3..8.cu) unroll every
+// per-component loop completely; the run-time-dimension unit (kern_dn.cu) defines NTR_GENERIC_UNIT and keeps
+// them rolled (its trip counts are not compile-time constants and its vectors live in local memory).
+#if defined(NTR_GENERIC_UNIT)
+#define NTR_UNROLL _Pragma("unroll 1")
+#else
+#define NTR_UNROLL _Pragma("unroll")
+#endif
+
+namespace ntr {
+
+#define NTR_FUZZ (FLT_EPSILON * 10)            /* ROUNDING_FUZZ, tracer.hpp:25 */
+#define NTR_LIGHT_THRESHOLD (1.0f / 512)       /* tracer.hpp:31 */
+
+template <int DT> struct DimCap { static constexpr int value = DT > 0 ? DT : NTR_MAXD; };
+#define NTR_D(DT, s) (DT > 0 ? DT : (s).dim)
+
+NTR_HD float ldf(const float *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+NTR_HD uint32_t ldu(const uint32_t *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+NTR_HD float4 ld4(const float *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const float4 *>(p));
+#else
+    return *reinterpret_cast<const float4 *>(p);
+#endif
+}
+NTR_HD uint4 ldnode(const uint4 *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+NTR_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+NTR_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+
+// v[i] with a run-time i: a select chain for compile-time D (stays in registers), plain indexing otherwise
+template <int DT> NTR_HD float vsel(const float *v, int i) {
+    if (DT > 0) {
+        float r = v[0];
+    NTR_UNROLL
+        for (int k = 1; k < (DT > 0 ? DT : 1); ++k) r = (i == k) ? v[k] : r;
+        return r;
+    }
+    return v[i];
+}
+
+struct Counters {
+    unsigned long long node_steps = 0, simplex_tests = 0, solid_tests = 0, shadow_rays = 0, reflection_rays = 0,
+                       shaded_hits = 0;
+};
+
+struct Skip { uint32_t ref; int lane; };
+struct HitRec { float dist; uint32_t ref; int lane; };
+
+// ---- simplex records -------------------------------------------------------------------------------
+// Register-staged view of one simplex record: stage 1 brings face_normal and d (enough for the plane
+// test), stage 2 the rest.  DT == 0 reads through the pointer instead.
+template <int DT> struct SimplexRec {
+    static constexpr int S = (((DT + 1) * DT + 1) + 3) / 4 * 4;
+    static constexpr int N1 = (DT + 1 + 3) / 4;
+    float r[S];
+    const float *g;
+    NTR_HD void stage1(const float *rec) {
+        g = rec;
+    NTR_UNROLL
+        for (int k = 0; k < N1; ++k) {
+            float4 v = ld4(rec + 4 * k);
+            r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+        }
+    }
+    NTR_HD void stage2() {
+    NTR_UNROLL
+        for (int k = N1; k < S / 4; ++k) {
+            float4 v = ld4(g + 4 * k);
+            r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+        }
+    }
+    NTR_HD float at(int i) const { return r[i]; }
+    NTR_HD uint32_t meta(int sstride) const { return f2u(r[S - 1]); }
+};
+template <> struct SimplexRec<0> {
+    const float *g;
+    NTR_HD void stage1(const float *rec) { g = rec; }
+    NTR_HD void stage2() {}
+    NTR_HD float at(int i) const { return ldf(g + i); }
+    NTR_HD uint32_t meta(int sstride) const { return f2u(ldf(g + sstride - 1)); }
+};
+
+// triangle::intersects (tracer.hpp:411-440): the single-primitive n-simplex test.
+template <int DT>
+NTR_HD float simplex_single(const SceneDev &s, uint32_t idx, const float *o, const float *dir, float cutoff,
+                            uint32_t &meta) {
+    const int D = NTR_D(DT, s);
+    SimplexRec<DT> R;
+    R.stage1(s.simplex + (size_t)idx * s.sstride);
+    float denom = 0, od = 0;
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) { denom += R.at(i) * dir[i]; od += R.at(i) * o[i]; }
+    if (denom == 0) return 0;
+    float t = -(od + R.at(D)) / denom;
+    if (t <= 0 || t >= cutoff) return 0;
+    R.stage2();
+    float pside[DimCap<DT>::value];
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) pside[i] = R.at(D + 1 + i) - (o[i] + t * dir[i]);
+    float tot = 0;
+    NTR_UNROLL
+    for (int e = 0; e < D - 1; ++e) {
+        float area = 0;
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) area += R.at(2 * D + 1 + e * D + i) * pside[i];
+        if (area < -NTR_FUZZ || area > (1 + NTR_FUZZ)) return 0;
+        tot += area;
+    }
+    if (tot <= (1 + NTR_FUZZ)) { meta = R.meta(s.sstride); return t; }
+    return 0;
+}
+
+// One lane of triangle_batch::intersects (tracer.hpp:551-599): t >= 0 mask, lower edge bound only.
+// `best` is the running minimum of the lane scan (tracer.hpp:583-590); a lane that cannot beat it is
+// dropped before the edge tests -- same outcome, the reference simply evaluates every lane in SIMD.
+template <int DT>
+NTR_HD float simplex_lane(const SceneDev &s, uint32_t idx, const float *o, const float *dir, float best,
+                          uint32_t &meta) {
+    const int D = NTR_D(DT, s);
+    SimplexRec<DT> R;
+    R.stage1(s.simplex + (size_t)idx * s.sstride);
+    float denom = 0, od = 0;
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) { denom += R.at(i) * dir[i]; od += R.at(i) * o[i]; }
+    if (denom == 0) return 0;
+    float t = -(od + R.at(D)) / denom;
+    if (!(t >= 0)) return 0;
+    if (t == 0 || !(t < best)) return 0;
+    R.stage2();
+    float pside[DimCap<DT>::value];
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) pside[i] = R.at(D + 1 + i) - (o[i] + t * dir[i]);
+    float tot = 0;
+    NTR_UNROLL
+    for (int e = 0; e < D - 1; ++e) {
+        float area = 0;
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) area += R.at(2 * D + 1 + e * D + i) * pside[i];
+        if (!(area >= -NTR_FUZZ)) return 0;
+        tot += area;
+    }
+    if (!(tot <= (1 + NTR_FUZZ))) return 0;
+    meta = R.meta(s.sstride);
+    return t;
+}
+
+// triangle_batch::intersects lane scan (tracer.hpp:583-594): lowest lane with the strictly smallest t.
+template <int DT, int FLAGS>
+NTR_HD float batch_test(const SceneDev &s, uint32_t first, const float *o, const float *dir, int &index, float cutoff,
+                        uint32_t &meta, Counters &cnt) {
+    float min_t = cutoff;
+    int r_index = -1;
+    for (int l = 0; l < s.batch; ++l) {
+        if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
+        if (l == index) continue;
+        uint32_t m;
+        float t = simplex_lane<DT>(s, first + l, o, dir, min_t, m);
+        if (t) { min_t = t; r_index = l; meta = m; }
+    }
+    if (r_index == -1) return 0;
+    index = r_index;
+    return min_t;
+}
+
+// Geometry of a simplex hit: normal.origin = o + t*dir, normal.direction = +-unit(face_normal)
+// (tracer.hpp:434-436, 595-597).
+template <int DT>
+NTR_HD void simplex_normal(const SceneDev &s, uint32_t idx, const float *o, const float *dir, float t, float *P,
+                           float *N) {
+    const int D = NTR_D(DT, s);
+    const float *rec = s.simplex + (size_t)idx * s.sstride;
+    float fn[DimCap<DT>::value];
+    float denom = 0, sq = 0;
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) { fn[i] = ldf(rec + i); denom += fn[i] * dir[i]; sq += fn[i] * fn[i]; }
+    float len = sqrtf(sq);
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) {
+        P[i] = o[i] + t * dir[i];
+        float u = fn[i] / len;
+        N[i] = denom > 0 ? -u : u;
+    }
+}
+
+// ---- solids ----------------------------------------------------------------------------------------
+// solid::intersects (tracer.hpp:251-276) with hypercube_intersects (:126-152) / hypersphere_intersects
+// (:154-173).  P/N receive what the reference writes into `normal`; `wmask` has a bit per component of
+// normal.origin that was written (the cube test writes local-space coordinates into it even when it
+// misses -- DESIGN.md section 4, quirk Q12).
+template <int DT>
+NTR_HD float solid_test(const SceneDev &s, uint32_t idx, const float *o, const float *dir, float cutoff, float *P,
+                        float *N, uint32_t &wmask, uint32_t &meta) {
+    const int D = NTR_D(DT, s);
+    const float *rec = s.solids + (size_t)idx * s.solstride;
+    const int type = (int)ldf(rec);
+    const float *inv = rec + 1, *pos = rec + 1 + D * D, *orient = rec + 1 + D * D + D;
+    float to[DimCap<DT>::value], td[DimCap<DT>::value];
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) {
+        float a = 0, b = 0;
+    NTR_UNROLL
+        for (int j = 0; j < D; ++j) { float m = ldf(inv + i * D + j); a += m * o[j]; b += m * dir[j]; }
+        to[i] = a - ldf(pos + i);
+        td[i] = b;
+    }
+    wmask = 0;
+    float dist = 0;
+    float ln[DimCap<DT>::value];      // local-space normal.direction
+    if (type == NTR_SOLID_CUBE) {
+        bool found = false;
+        for (int i = 0; i < D && !found; ++i) {
+            float di = vsel<DT>(td, i);
+            if (di != 0) {
+                float face = di < 0 ? 1.0f : -1.0f;
+                float dd = (face - vsel<DT>(to, i)) / di;
+    NTR_UNROLL
+                for (int k = 0; k < D; ++k) if (k == i) P[k] = face;
+                wmask |= 1u << i;
+                if (dd > 0) {
+                    bool miss = false;
+    NTR_UNROLL
+                    for (int j = 0; j < D; ++j) {
+                        if (!miss && j != i) {
+                            float v = td[j] * dd + to[j];
+                            P[j] = v;
+                            wmask |= 1u << j;
+                            if (fabsf(v) > (1 + NTR_FUZZ)) miss = true;
+                        }
+                    }
+                    if (!miss) {
+                        if (dd >= cutoff) return 0;
+    NTR_UNROLL
+                        for (int k = 0; k < D; ++k) ln[k] = (k == i) ? face : 0.0f;
+                        dist = dd;
+                        found = true;
+                    }
+                }
+            }
+        }
+        if (!found) return 0;
+    } else {
+        float a = 0, b = 0, c = 0;
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) { a += td[i] * td[i]; b += td[i] * to[i]; c += to[i] * to[i]; }
+        b = 2 * b;
+        c = c - 1;
+        float disc = b * b - 4 * a * c;
+        if (disc < 0) return 0;
+        float dd = (-b - sqrtf(disc)) / (2 * a);
+        if (dd <= 0 || dd >= cutoff) return 0;
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) { P[i] = to[i] + td[i] * dd; ln[i] = P[i]; }
+        dist = dd;
+    }
+    // back-transform (tracer.hpp:273-274): origin = orientation*(origin + position), direction = orientation*direction
+    float tmp[DimCap<DT>::value];
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) tmp[i] = P[i] + ldf(pos + i);
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) {
+        float a = 0, b = 0;
+    NTR_UNROLL
+        for (int j = 0; j < D; ++j) { float m = ldf(orient + i * D + j); a += m * tmp[j]; b += m * ln[j]; }
+        P[i] = a;
+        N[i] = b;
+    }
+    wmask = 0xFFFFFFFFu;
+    meta = f2u(ldf(rec + s.solstride - 1));
+    return dist;
+}
+
+// material index / opacity bit of a hit target
+template <int DT> NTR_HD uint32_t target_meta(const SceneDev &s, uint32_t ref, int lane) {
+    uint32_t kind = ref >> 30, idx = ref & NTR_IDX_MASK;
+    if (kind == NTR_REF_SOLID) return f2u(ldf(s.solids + (size_t)idx * s.solstride + s.solstride - 1));
+    if (kind == NTR_REF_BATCH) idx += (uint32_t)lane;
+    return f2u(ldf(s.simplex + (size_t)idx * s.sstride + s.sstride - 1));
+}
+NTR_HD int flat_prim_id(const SceneDev &s, uint32_t ref, int lane) {
+    uint32_t kind = ref >> 30, idx = ref & NTR_IDX_MASK;
+    if (kind == NTR_REF_BATCH) return (int)(idx + (uint32_t)lane);
+    if (kind == NTR_REF_SIMPLEX) return (int)idx;
+    return (int)(s.n_simplex + idx);
+}
+
+// ---- per-ray lists of the general variant -------------------------------------------------------------
+struct HitList {                        // quick_list<ray_intersection>, tracer.hpp:663-729,781
+    float dist[NTR_THITS_CAP];
+    uint32_t ref[NTR_THITS_CAP];
+    signed char lane[NTR_THITS_CAP];
+    int n;
+    int dropped;
+    NTR_HD void clear() { n = 0; dropped = 0; }
+    NTR_HD void add(float d, uint32_t r, int l) {
+        if (n < NTR_THITS_CAP) { dist[n] = d; ref[n] = r; lane[n] = (signed char)l; ++n; }
+        else dropped = 1;
+    }
+    // trim_intersections (tracer.hpp:784-789) with quick_list::remove_at's swap-with-last (:723-728)
+    NTR_HD void trim(float d, int from) {
+        while (from < n) {
+            if (dist[from] >= d) {
+                --n;
+                if (from != n) { dist[from] = dist[n]; ref[from] = ref[n]; lane[from] = lane[n]; }
+            } else ++from;
+        }
+    }
+    // sort_and_unique (tracer.hpp:714-721): by distance, then drop adjacent entries with the same target
+    NTR_HD void sort_and_unique() {
+        for (int i = 1; i < n; ++i) {
+            float d = dist[i]; uint32_t r = ref[i]; signed char l = lane[i];
+            int j = i;
+            while (j > 0 && d < dist[j - 1]) { dist[j] = dist[j - 1]; ref[j] = ref[j - 1]; lane[j] = lane[j - 1]; --j; }
+            dist[j] = d; ref[j] = r; lane[j] = l;
+        }
+        if (n == 0) return;
+        int w = 0;
+        for (int i = 1; i < n; ++i) {
+            if (!(ref[i] == ref[w] && lane[i] == lane[w])) {
+                ++w;
+                dist[w] = dist[i]; ref[w] = ref[i]; lane[w] = lane[i];
+            }
+        }
+        n = w + 1;
+    }
+};
+
+struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,832-834
+    uint32_t v[NTR_MAILBOX_CAP];
+    int n;
+    NTR_HD void clear() { n = 0; }
+    NTR_HD bool has(uint32_t r) const {
+        for (int i = 0; i < n; ++i) if (v[i] == r) return true;
+        return false;
+    }
+    NTR_HD void add(uint32_t r) { if (n < NTR_MAILBOX_CAP) v[n++] = r; }
+};
+
+template <int DT> struct GenState {
+    float hitP[DimCap<DT>::value], hitN[DimCap<DT>::value];    // o_hit.normal as the reference leaves it
+    HitList th;
+    Mailbox mb;
+};
+
+// ---- leaves ----------------------------------------------------------------------------------------
+// kd_leaf::intersects for all-opaque, simplex-only scenes.  Without transparent hits and solids the
+// reference's mailbox, two-phase loop and final trim (tracer.hpp:977-1086) cannot influence the result:
+// a re-tested primitive misses its own cutoff, so only the running nearest hit matters.
+template <int DT, int FLAGS>
+NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, const float *dir, Skip skip, HitRec &oh,
+                        Counters &cnt) {
+    const uint32_t *items = s.leaf_refs + node.y;
+    const uint32_t size = node.z;
+    bool hit = false;
+    for (uint32_t i = 0; i < size; ++i) {
+        const uint32_t item = ldu(items + i);
+        uint32_t meta;
+        if ((item >> 30) == NTR_REF_BATCH) {
+            int index = skip.ref == item ? skip.lane : -1;
+            float dist = batch_test<DT, FLAGS>(s, item & NTR_IDX_MASK, o, dir, index, oh.dist, meta, cnt);
+            if (dist) { oh.dist = dist; oh.ref = item; oh.lane = index; hit = true; }
+        } else if (item != skip.ref) {
+            if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
+            float dist = simplex_single<DT>(s, item & NTR_IDX_MASK, o, dir, oh.dist, meta);
+            if (dist) { oh.dist = dist; oh.ref = item; oh.lane = -1; hit = true; }
+        }
+    }
+    return hit;
+}
+
+// One primitive test of the general variant; P/N/wmask as in solid_test.
+template <int DT, int FLAGS>
+NTR_HD float prim_test_general(const SceneDev &s, uint32_t item, const float *o, const float *dir, float cutoff,
+                               Skip skip, int &lane, float *P, float *N, uint32_t &wmask, uint32_t &meta,
+                               Counters &cnt) {
+    const uint32_t kind = item >> 30, idx = item & NTR_IDX_MASK;
+    wmask = 0;
+    float dist;
+    if (kind == NTR_REF_BATCH) {
+        lane = skip.ref == item ? skip.lane : -1;
+        dist = batch_test<DT, FLAGS>(s, idx, o, dir, lane, cutoff, meta, cnt);
+        if (dist) { simplex_normal<DT>(s, idx + (uint32_t)lane, o, dir, dist, P, N); wmask = 0xFFFFFFFFu; }
+    } else if (kind == NTR_REF_SIMPLEX) {
+        lane = -1;
+        if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
+        dist = simplex_single<DT>(s, idx, o, dir, cutoff, meta);
+        if (dist) { simplex_normal<DT>(s, idx, o, dir, dist, P, N); wmask = 0xFFFFFFFFu; }
+    } else {
+        lane = -1;
+        if (FLAGS & NTR_F_COUNT) cnt.solid_tests++;
+        dist = solid_test<DT>(s, idx, o, dir, cutoff, P, N, wmask, meta);
+    }
+    return dist;
+}
+
+// kd_leaf<Store,true>::intersects (tracer.hpp:977-1086), every observable behaviour kept:
+//   phase 0 (before the first opaque hit of this leaf): tests write straight into o_hit.normal;
+//   the first opaque hit switches to phase 1 WITHOUT marking the item checked, so the same item is
+//   tested again (and misses its own cutoff); in phase 1 a closer opaque hit replaces o_hit;
+//   finally transparent hits of this leaf at or beyond the LAST test's result are dropped.
+template <int DT, int FLAGS>
+NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, const float *dir, Skip skip, HitRec &oh,
+                         GenState<DT> &g, Counters &cnt) {
+    const int D = NTR_D(DT, s);
+    const uint32_t *items = s.leaf_refs + node.y;
+    const uint32_t size = node.z;
+    const int h_start = g.th.n;
+    float dist = 0;
+    bool phase1 = false;
+    float P[DimCap<DT>::value], N[DimCap<DT>::value];
+    for (uint32_t i = 0; i < size; ++i) {
+        const uint32_t item = ldu(items + i);
+        const bool is_batch = (item >> 30) == NTR_REF_BATCH;
+        if ((!is_batch && item == skip.ref) || g.mb.has(item)) continue;
+        int lane;
+        uint32_t wmask, meta;
+        dist = prim_test_general<DT, FLAGS>(s, item, o, dir, oh.dist, skip, lane, P, N, wmask, meta, cnt);
+        if (!phase1) {
+    NTR_UNROLL
+            for (int k = 0; k < D; ++k) if (wmask & (1u << k)) g.hitP[k] = P[k];
+            if (dist) {
+    NTR_UNROLL
+                for (int k = 0; k < D; ++k) g.hitN[k] = N[k];
+                if (meta & NTR_META_OPAQUE) {
+                    oh.dist = dist; oh.ref = item; oh.lane = lane;
+                    phase1 = true;
+                    --i;                // `goto hit` re-tests this item (tracer.hpp:1008,1041)
+                    continue;           // ... and skips checked.add
+                }
+                g.th.add(dist, item, lane);
+            }
+        } else if (dist) {
+            if (meta & NTR_META_OPAQUE) {
+                oh.dist = dist; oh.ref = item; oh.lane = lane;
+    NTR_UNROLL
+                for (int k = 0; k < D; ++k) { g.hitP[k] = P[k]; g.hitN[k] = N[k]; }
+            } else {
+                g.th.add(dist, item, lane);
+            }
+        }
+        g.mb.add(item);
+    }
+    if (!phase1) return false;
+    g.th.trim(dist, h_start);
+    return true;
+}
+
+// ---- nearest-hit traversal ----------------------------------------------------------------------------
+// kd_node_intersection::operator() (tracer.hpp:1179-1243) as an explicit stack machine.  Two frame
+// kinds reproduce the recursion exactly: AFTER_NEAR (pending far child, split distance t, the caller's
+// t_far, transparent-list size at entry) and AFTER_FAR (the near subtree hit beyond the split plane:
+// the call returns true whatever the far subtree finds, and trims on a far hit, :1225-1230).
+struct TravStack {
+    uint32_t node[NTR_STACK_CAP];       // far child | AFTER_FAR marker
+    float t[NTR_STACK_CAP];
+    float t_far[NTR_STACK_CAP];
+    unsigned char h_start[NTR_STACK_CAP];
+};
+#define NTR_FRAME_AFTER_FAR 0xFFFFFFFEu
+
+template <int DT, int FLAGS>
+NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, Skip skip, float t_near, float t_far,
+                          HitRec &oh, GenState<DT> *g, Counters &cnt) {
+    const int D = NTR_D(DT, s);
+    float invdir[DimCap<DT>::value];
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) invdir[i] = 1 / dir[i];            // tracer.hpp:1174
+    TravStack st;
+    int sp = 0;
+    uint32_t node = s.root;
+    if (FLAGS & NTR_F_GENERAL) { g->mb.clear(); }
+    for (;;) {
+        // ---- descend to a leaf (or fall off the tree) ----
+        bool result = false;
+        while (node != NTR_NULL_NODE) {
+            const uint4 n = ldnode(s.nodes + node);
+            if (n.x & NTR_LEAF_FLAG) {
+                if (FLAGS & NTR_F_GENERAL) result = leaf_general<DT, FLAGS>(s, n, o, dir, skip, oh, *g, cnt);
+                else result = leaf_opaque<DT, FLAGS>(s, n, o, dir, skip, oh, cnt);
+                break;
+            }
+            if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
+            const int axis = (int)n.x;
+            const float split = u2f(n.y);
+            const float da = vsel<DT>(dir, axis), oa = vsel<DT>(o, axis);
+            if (da != 0) {
+                if (oa == split) { node = da > 0 ? n.w : n.z; continue; }
+                const float t = (split - oa) * vsel<DT>(invdir, axis);
+                const uint32_t n_near = oa > split ? n.w : n.z;
+                const uint32_t n_far = oa > split ? n.z : n.w;
+                if (t < 0 || t > t_far) { node = n_near; continue; }
+                if (t < t_near) { node = n_far; continue; }
+                if (n_near != NTR_NULL_NODE) {
+                    if (n_far == NTR_NULL_NODE) { node = n_near; t_far = t; continue; }   // `|| !n_far) return hit`
+                    if (sp < NTR_STACK_CAP) {
+                        st.node[sp] = n_far; st.t[sp] = t; st.t_far[sp] = t_far;
+                        if (FLAGS & NTR_F_GENERAL) st.h_start[sp] = (unsigned char)g->th.n;
+                        ++sp;
+                    }
+                    node = n_near;
+                    t_far = t;
+                    continue;
+                }
+                node = n_far;
+                t_near = t;
+                continue;
+            }
+            node = oa >= split ? n.w : n.z;
+        }
+        // ---- unwind ----
+        for (;;) {
+            if (sp == 0) return result;
+            --sp;
+            const uint32_t fnode = st.node[sp];
+            if (fnode == NTR_FRAME_AFTER_FAR) {
+                if (FLAGS & NTR_F_GENERAL) { if (result) g->th.trim(oh.dist, st.h_start[sp]); }
+                result = true;
+                continue;
+            }
+            const float t = st.t[sp];
+            if (result && oh.dist <= t) continue;                   // tracer.hpp:1214
+            node = fnode;
+            t_near = t;
+            t_far = st.t_far[sp];
+            if (result) {                                           // tracer.hpp:1216-1231
+                st.node[sp] = NTR_FRAME_AFTER_FAR;                  // h_start[sp] stays
+                ++sp;
+            }
+            break;
+        }
+    }
+}
+
+// ---- occlusion (shadow) traversal ------------------------------------------------------------------------
+// kd_leaf::occludes (tracer.hpp:1088-1124): any opaque hit nearer than the light blocks; transparent
+// blockers are collected (no mailbox here).
+template <int DT, int FLAGS>
+NTR_HD bool leaf_occludes(const SceneDev &s, const uint4 node, const float *o, const float *dir, float ldistance,
+                          Skip skip, HitList *hits, Counters &cnt) {
+    const uint32_t *items = s.leaf_refs + node.y;
+    const uint32_t size = node.z;
+    for (uint32_t i = 0; i < size; ++i) {
+        const uint32_t item = ldu(items + i);
+        const uint32_t kind = item >> 30, idx = item & NTR_IDX_MASK;
+        uint32_t meta = 0;
+        float dist;
+        int lane = -1;
+        if (kind == NTR_REF_BATCH) {
+            lane = skip.ref == item ? skip.lane : -1;
+            dist = batch_test<DT, FLAGS>(s, idx, o, dir, lane, ldistance, meta, cnt);
+        } else {
+            if (item == skip.ref) continue;
+            if (kind == NTR_REF_SIMPLEX) {
+                if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
+                dist = simplex_single<DT>(s, idx, o, dir, ldistance, meta);
+            } else if (FLAGS & NTR_F_GENERAL) {
+                float P[DimCap<DT>::value], N[DimCap<DT>::value];
+                uint32_t wmask;
+                if (FLAGS & NTR_F_COUNT) cnt.solid_tests++;
+                dist = solid_test<DT>(s, idx, o, dir, ldistance, P, N, wmask, meta);
+            } else {
+                dist = 0;
+            }
+        }
+        if (dist) {
+            if (!(FLAGS & NTR_F_GENERAL) || (meta & NTR_META_OPAQUE)) return true;
+            hits->add(dist, item, lane);
+        }
+    }
+    return false;
+}
+
+// _occludes (tracer.hpp:1258-1307), including `if(t < ldistance) return false` (:1298): the far child is
+// only entered when the split plane is farther away than the light.
+template <int DT, int FLAGS>
+NTR_HD bool trace_occludes(const SceneDev &s, const float *o, const float *dir, float ldistance, Skip skip,
+                           float t_near, float t_far, HitList *hits, Counters &cnt) {
+    const int D = NTR_D(DT, s);
+    float invdir[DimCap<DT>::value];
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) invdir[i] = 1 / dir[i];
+    uint32_t st_node[NTR_STACK_CAP];
+    float st_t[NTR_STACK_CAP], st_tfar[NTR_STACK_CAP];
+    int sp = 0;
+    uint32_t node = s.root;
+    for (;;) {
+        while (node != NTR_NULL_NODE) {
+            const uint4 n = ldnode(s.nodes + node);
+            if (n.x & NTR_LEAF_FLAG) {
+                if (leaf_occludes<DT, FLAGS>(s, n, o, dir, ldistance, skip, hits, cnt)) return true;
+                break;
+            }
+            if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
+            const int axis = (int)n.x;
+            const float split = u2f(n.y);
+            const float da = vsel<DT>(dir, axis), oa = vsel<DT>(o, axis);
+            if (da != 0) {
+                if (oa == split) { node = da > 0 ? n.w : n.z; continue; }
+                const float t = (split - oa) * vsel<DT>(invdir, axis);
+                const uint32_t n_near = oa > split ? n.w : n.z;
+                const uint32_t n_far = oa > split ? n.z : n.w;
+                if (t < 0 || t > t_far) { node = n_near; continue; }
+                if (t < t_near) { node = n_far; continue; }
+                if (n_near != NTR_NULL_NODE) {
+                    if (n_far == NTR_NULL_NODE) { t_far = t; node = n_near; continue; }
+                    if (sp < NTR_STACK_CAP) { st_node[sp] = n_far; st_t[sp] = t; st_tfar[sp] = t_far; ++sp; }
+                    node = n_near;
+                    t_far = t;
+                    continue;
+                }
+                if (t < ldistance) break;           // near child null: falls to the same test (:1297-1298)
+                t_near = t;
+                node = n_far;
+                continue;
+            }
+            node = oa >= split ? n.w : n.z;
+        }
+        // the (sub)call returned false: resume the innermost pending far child
+        for (;;) {
+            if (sp == 0) return false;
+            --sp;
+            if (st_t[sp] < ldistance) continue;     // `return false` of that frame
+            node = st_node[sp];
+            t_near = st_t[sp];
+            t_far = st_tfar[sp];
+            break;
+        }
+    }
+}
+
+// ---- shading ------------------------------------------------------------------------------------------
+struct Mat { float c[3], spec[3], opacity, reflectivity, spec_int, spec_exp; };
+NTR_HD Mat load_mat(const SceneDev &s, uint32_t meta) {
+    const float *m = s.materials + (size_t)(meta & 0x7FFFFFFFu) * 12;
+    const float4 a = ld4(m), b = ld4(m + 4), c = ld4(m + 8);
+    Mat r;
+    r.c[0] = a.x; r.c[1] = a.y; r.c[2] = a.z; r.spec[0] = a.w; r.spec[1] = b.x; r.spec[2] = b.y;
+    r.opacity = b.z; r.reflectivity = b.w; r.spec_int = c.x; r.spec_exp = c.y;
+    return r;
+}
+
+// composite_scene::light_reaches (tracer.hpp:1750-1766): false when blocked, else multiplies `filtered`
+// by (1 - opacity) of every distinct transparent blocker.
+template <int DT, int FLAGS>
+NTR_HD bool light_reaches(const SceneDev &s, const float *o, const float *dir, float ldistance, Skip skip,
+                          float *filtered, Counters &cnt) {
+    HitList hits;
+    if (FLAGS & NTR_F_GENERAL) hits.clear();
+    cnt.shadow_rays++;
+    if (trace_occludes<DT, FLAGS>(s, o, dir, ldistance, skip, 0.0f, FLT_MAX, &hits, cnt)) return false;
+    if (FLAGS & NTR_F_GENERAL) {
+        if (hits.n) {
+            hits.sort_and_unique();
+            for (int i = hits.n - 1; i >= 0; --i) {
+                const Mat m = load_mat(s, target_meta<DT>(s, hits.ref[i], hits.lane[i]));
+                const float f = 1 - m.opacity;
+                filtered[0] *= f; filtered[1] *= f; filtered[2] *= f;
+            }
+        }
+    }
+    return true;
+}
+
+// append_specular (tracer.hpp:1701-1707), Blinn-Phong as written there (including `c *= a`).
+template <int DT>
+NTR_HD void append_specular(const SceneDev &s, float *spec, float &a, const Mat &m, const float *light_c,
+                            const float *view, const float *normal, const float *light_dir) {
+    const int D = NTR_D(DT, s);
+    float h[DimCap<DT>::value];
+    float sq = 0;
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) { h[i] = light_dir[i] - view[i]; sq += h[i] * h[i]; }
+    const float len = sqrtf(sq);
+    float dn = 0;
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) dn += normal[i] * (h[i] / len);
+    const float base = powf(dn, m.spec_exp) * m.spec_int;
+    const float k = base * (1 - a);
+    NTR_UNROLL
+    for (int c = 0; c < 3; ++c) spec[c] += m.spec[c] * light_c[c] * k;
+    a += k;
+    NTR_UNROLL
+    for (int c = 0; c < 3; ++c) spec[c] *= a;
+}
+
+// point_light::strength (tracer.hpp:1686-1688): 1/dist^(D-1), evaluated in double like std::pow(float,size_t)
+NTR_HD float light_strength(float dist, int D) {
+    double p = 1.0, d = (double)dist;
+    for (int i = 0; i < D - 1; ++i) p *= d;
+    return (float)(1.0 / p);
+}
+
+// A deferred reflection bounce (tracer.hpp:1842-1851 linearised: the recursive colour enters the parent
+// linearly, so the child ray carries the RGB weight c * reflectivity * (1 - spec_a) * parent weight).
+template <int DT> struct Bounce {
+    float o[DimCap<DT>::value], d[DimCap<DT>::value];
+    float w[3];
+    Skip skip;
+    int depth;
+};
+
+// composite_scene::base_color (tracer.hpp:1768-1854) for one hit (P, N) of primitive (ref, lane), with the
+// result multiplied by `w` and added to `acc`.  Returns true and fills `b` when a reflection ray follows.
+template <int DT, int FLAGS>
+NTR_HD bool shade_hit(const SceneDev &s, const float *view, const float *P, const float *N, uint32_t ref, int lane,
+                      int depth, const float *w, float *acc, Bounce<DT> &b, Counters &cnt) {
+    const int D = NTR_D(DT, s);
+    const Mat m = load_mat(s, target_meta<DT>(s, ref, lane));
+    const Skip source = {ref, lane};
+    float light[3] = {0, 0, 0}, spec[3] = {0, 0, 0};
+    float spec_a = 0;
+    cnt.shaded_hits++;
+
+    for (int li = 0; li < s.n_point; ++li) {
+        const float *pl = s.point_lights + (size_t)li * (D + 3);
+        const float lc[3] = {ldf(pl + D), ldf(pl + D + 1), ldf(pl + D + 2)};
+        float lv[DimCap<DT>::value];
+        float sq = 0;
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) { lv[i] = P[i] - ldf(pl + i); sq += lv[i] * lv[i]; }
+        const float dist = sqrtf(sq);
+        float sine = 0;
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) { lv[i] /= dist; sine += N[i] * lv[i]; }
+        if (sine > 0) {
+            const float strength = light_strength(dist, D);
+            if (s.shadows) {
+                if (fmaxf(lc[0], fmaxf(lc[1], lc[2])) * strength * sine > NTR_LIGHT_THRESHOLD) {
+                    float filtered[3] = {lc[0], lc[1], lc[2]};
+                    if (light_reaches<DT, FLAGS>(s, P, lv, dist, source, filtered, cnt)) {
+    NTR_UNROLL
+                        for (int c = 0; c < 3; ++c) { filtered[c] *= strength; light[c] += filtered[c] * sine; }
+                        if (m.spec_int != 0) append_specular<DT>(s, spec, spec_a, m, filtered, view, N, lv);
+                    }
+                }
+            } else {
+    NTR_UNROLL
+                for (int c = 0; c < 3; ++c) light[c] += lc[c] * strength * sine;
+            }
+        }
+    }
+    for (int li = 0; li < s.n_global; ++li) {
+        const float *gl = s.global_lights + (size_t)li * (D + 3);
+        const float lc[3] = {ldf(gl + D), ldf(gl + D + 1), ldf(gl + D + 2)};
+        float ld[DimCap<DT>::value];
+        float sine = 0;
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) { ld[i] = -ldf(gl + i); sine += N[i] * ld[i]; }
+        if (sine > 0) {
+            if (s.shadows) {
+                float filtered[3] = {lc[0], lc[1], lc[2]};
+                if (light_reaches<DT, FLAGS>(s, P, ld, FLT_MAX, source, filtered, cnt)) {
+    NTR_UNROLL
+                    for (int c = 0; c < 3; ++c) light[c] += filtered[c] * sine;
+                    if (m.spec_int != 0) append_specular<DT>(s, spec, spec_a, m, filtered, view, N, ld);
+                }
+            } else {
+    NTR_UNROLL
+                for (int c = 0; c < 3; ++c) light[c] += lc[c] * sine;
+            }
+        }
+    }
+
+    float sine = 0;
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) sine += view[i] * N[i];
+    sine = -sine;
+    if (s.camera_light && sine > 0) {
+    NTR_UNROLL
+        for (int c = 0; c < 3; ++c) light[c] += sine;
+        if (m.spec_int != 0) {
+            const float base = powf(sine, m.spec_exp) * m.spec_int;
+            const float k = base * (1 - spec_a);
+    NTR_UNROLL
+            for (int c = 0; c < 3; ++c) spec[c] += m.spec[c] * k;
+            spec_a += k;
+    NTR_UNROLL
+            for (int c = 0; c < 3; ++c) spec[c] *= spec_a;
+        }
+    }
+
+    const bool reflect = m.reflectivity != 0 && depth < s.max_depth;
+    const float keep = (reflect ? (1 - m.reflectivity) : 1.0f) * (1 - spec_a);
+    NTR_UNROLL
+    for (int c = 0; c < 3; ++c) {
+        const float local = s.ambient[c] + m.c[c] * light[c];
+        acc[c] += w[c] * (spec[c] + local * keep);
+    }
+    if (reflect) {
+        const float k = m.reflectivity * (1 - spec_a);
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) { b.o[i] = P[i]; b.d[i] = view[i] - N[i] * (-2 * sine); }
+    NTR_UNROLL
+        for (int c = 0; c < 3; ++c) b.w[c] = w[c] * m.c[c] * k;
+        b.skip = source;
+        b.depth = depth + 1;
+        cnt.reflection_rays++;
+    }
+    return reflect;
+}
+
+// composite_scene::aabb_distance (tracer.hpp:1892-1918)
+template <int DT> NTR_HD float aabb_distance(const SceneDev &s, const float *o, const float *dir) {
+    const int D = NTR_D(DT, s);
+    for (int i = 0; i < D; ++i) {
+        const float di = vsel<DT>(dir, i);
+        if (di != 0) {
+            const float oi = vsel<DT>(o, i);
+            const float plane = di > 0 ? vsel<DT>(s.bmin, i) : vsel<DT>(s.bmax, i);
+            float dist = (plane - oi) / di;
+            int skip = i;
+            if (dist < 0) { dist = 0; skip = -1; }
+            bool miss = false;
+    NTR_UNROLL
+            for (int j = 0; j < D; ++j) {
+                if (j != skip) {
+                    const float v = dir[j] * dist + o[j];
+                    if (v >= s.bmax[j] || v <= s.bmin[j]) miss = true;
+                }
+            }
+            if (!miss) return dist;
+        }
+    }
+    return -1;
+}
+
+// hit geometry for list entries and for the opaque hit of the fast variant
+template <int DT, int FLAGS>
+NTR_HD void hit_geometry(const SceneDev &s, uint32_t ref, int lane, float dist, const float *o, const float *dir,
+                         float *P, float *N) {
+    const uint32_t kind = ref >> 30, idx = ref & NTR_IDX_MASK;
+    if (kind == NTR_REF_SOLID) {
+        if (FLAGS & NTR_F_GENERAL) {
+            uint32_t wmask, meta;
+            solid_test<DT>(s, idx, o, dir, FLT_MAX, P, N, wmask, meta);
+        }
+        return;
+    }
+    simplex_normal<DT>(s, kind == NTR_REF_BATCH ? idx + (uint32_t)lane : idx, o, dir, dist, P, N);
+}
+
+// composite_scene::ray_color (tracer.hpp:1856-1883), linearised: the transparent layers (sorted near to
+// far) and the opaque hit / background each contribute base_color * op_i * prod_{j<i}(1 - op_j).
+// EMIT(const Bounce<DT>&) receives the deferred reflection rays.
+template <int DT, int FLAGS, typename EMIT>
+NTR_HD void ray_color(const SceneDev &s, const float *o, const float *dir, int depth, Skip source, const float *weight,
+                      float *acc, EMIT &emit, Counters &cnt, HitRec *primary_out) {
+    const int D = NTR_D(DT, s);
+    GenState<DT> g;
+    HitRec oh;
+    oh.dist = FLT_MAX; oh.ref = NTR_NONE_REF; oh.lane = -1;
+    if (FLAGS & NTR_F_GENERAL) {
+        g.th.clear();
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) { g.hitP[i] = 0; g.hitN[i] = 0; }
+    }
+    const float t0 = aabb_distance<DT>(s, o, dir);
+    const bool hit = t0 >= 0 && trace_nearest<DT, FLAGS>(s, o, dir, source, t0, FLT_MAX, oh, &g, cnt);
+    if (primary_out) { *primary_out = oh; if (!hit) { primary_out->ref = NTR_NONE_REF; primary_out->dist = 0; } }
+
+    float w[3] = {weight[0], weight[1], weight[2]};
+    float P[DimCap<DT>::value], N[DimCap<DT>::value];
+    Bounce<DT> b;
+    if (FLAGS & NTR_F_GENERAL) {
+        if (g.th.n) {
+            g.th.sort_and_unique();
+            for (int i = 0; i < g.th.n; ++i) {
+                const uint32_t ref = g.th.ref[i];
+                const int lane = g.th.lane[i];
+                const float op = load_mat(s, target_meta<DT>(s, ref, lane)).opacity;
+                hit_geometry<DT, FLAGS>(s, ref, lane, g.th.dist[i], o, dir, P, N);
+                const float wl[3] = {w[0] * op, w[1] * op, w[2] * op};
+                if (shade_hit<DT, FLAGS>(s, dir, P, N, ref, lane, depth, wl, acc, b, cnt)) emit(b);
+                w[0] *= 1 - op; w[1] *= 1 - op; w[2] *= 1 - op;
+            }
+        }
+    }
+    if (hit) {
+        if (FLAGS & NTR_F_GENERAL) {
+            if (shade_hit<DT, FLAGS>(s, dir, g.hitP, g.hitN, oh.ref, oh.lane, depth, w, acc, b, cnt)) emit(b);
+        } else {
+            hit_geometry<DT, FLAGS>(s, oh.ref, oh.lane, oh.dist, o, dir, P, N);
+            if (shade_hit<DT, FLAGS>(s, dir, P, N, oh.ref, oh.lane, depth, w, acc, b, cnt)) emit(b);
+        }
+    } else {
+        const float I = vsel<DT>(dir, s.bg_axis);       // tracer.hpp:1866-1867
+    NTR_UNROLL
+        for (int c = 0; c < 3; ++c) {
+            const float bg = I >= 0 ? s.bg1[c] * I + s.bg2[c] * (1 - I) : s.bg3[c] * -I + s.bg2[c] * (1 + I);
+            acc[c] += w[c] * bg;
+        }
+    }
+}
+
+// flat_origin_ray_source::operator() (tracer.hpp:71-75): integer pixel coordinates, no half-pixel offset
+template <int DT>
+NTR_HD void primary_ray(const SceneDev &s, const CameraDev &cam, const FrameDev &f, int x, int y, float *o, float *dir) {
+    const int D = NTR_D(DT, s);
+    const float fx = f.fovI * ((float)x - f.half_w), fy = f.fovI * ((float)y - f.half_h);
+    float sq = 0;
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) {
+        o[i] = cam.origin[i];
+        dir[i] = cam.fwd[i] + cam.right[i] * fx - cam.up[i] * fy;
+        sq += dir[i] * dir[i];
+    }
+    const float len = sqrtf(sq);
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) dir[i] /= len;
+}
+
+// box_scene::calculate_color (tracer.hpp:101-114) with hypercube_intersects (:126-152) inlined:
+// the unit hypercube at the origin, fixed shading, gradient background.
+template <int DT>
+NTR_HD void box_color(const SceneDev &s, const float *o, const float *dir, float *rgb, HitRec *primary_out) {
+    const int D = NTR_D(DT, s);
+    for (int i = 0; i < D; ++i) {
+        const float di = vsel<DT>(dir, i);
+        if (di != 0) {
+            const float face = di < 0 ? 1.0f : -1.0f;
+            const float dist = (face - vsel<DT>(o, i)) / di;
+            if (dist > 0) {
+                bool miss = false;
+    NTR_UNROLL
+                for (int j = 0; j < D; ++j) {
+                    if (j != i) { if (fabsf(dir[j] * dist + o[j]) > (1 + NTR_FUZZ)) miss = true; }
+                }
+                if (!miss) {
+                    const float sine = di * face;           // dot(view.direction, axis(i, face))
+                    const float k = sine <= 0 ? -sine : 0.0f;
+                    rgb[0] = k * 1.0f; rgb[1] = k * 0.5f; rgb[2] = k * 0.5f;
+                    if (primary_out) { primary_out->dist = dist; primary_out->ref = 0; primary_out->lane = -1; }
+                    return;
+                }
+            }
+        }
+    }
+    const float I = dir[0];
+    if (I > 0) { rgb[0] = I; rgb[1] = I; rgb[2] = I; }
+    else { rgb[0] = 0; rgb[1] = -I; rgb[2] = -I; }
+    if (primary_out) { primary_out->dist = 0; primary_out->ref = NTR_NONE_REF; primary_out->lane = -1; }
+}
+
+// ---- pixel packing ------------------------------------------------------------------------------------
+// process_pixel::operator() (reference src/render.cpp:421-462): channel = clamp(f_r*r+f_g*g+f_b*b+f_c,0,1);
+// integer channels lround(v * double(2^bits-1)), float channels raw IEEE bits; bits appended MSB-first into
+// a 128-bit big-endian accumulator.  out[0] holds the 4 most significant bytes (big-endian word order):
+// byte j of the pixel = (out[j/4] >> (8*(3 - j%4))) & 0xff.
+NTR_HD void pack_pixel(const FormatDev &f, const float *rgb, uint32_t out[4]) {
+    unsigned long long hi = 0, lo = 0;
+    int off = 0;
+    for (int ci = 0; ci < f.n_channels; ++ci) {
+        float v = f.f_r[ci] * rgb[0] + f.f_g[ci] * rgb[1] + f.f_b[ci] * rgb[2] + f.f_c[ci];
+        v = fminf(fmaxf(v, 0.0f), 1.0f);
+        const int bits = f.bits[ci];
+        unsigned long long ival;
+        if (f.tfloat[ci]) ival = f2u(v);
+        else {
+            // std::lround(val * double(0xffffffffu >> (32 - bit_size))), render.cpp:439
+            ival = (unsigned long long)llround((double)v * (double)(0xffffffffu >> (32 - bits)));
+        }
+        const int o = off >> 6, rm = off & 63;
+        const int sh = 64 - rm - bits;
+        const unsigned long long part = sh >= 0 ? ival << sh : ival >> -sh;
+        if (o == 0) hi |= part; else lo |= part;
+        if (rm + bits > 64) lo = ival << (128 - rm - bits);
+        off += bits;
+    }
+    out[0] = (uint32_t)(hi >> 32); out[1] = (uint32_t)hi; out[2] = (uint32_t)(lo >> 32); out[3] = (uint32_t)lo;
+}
+
+}  // namespace ntr

@@ -1,0 +1,229 @@
+// TEST INFRASTRUCTURE ONLY -- runs the product's per-ray state machine (ntracer_b200/csrc/trace_core.cuh,
+// the exact code the CUDA kernels inline) on the host, so that its logic can be checked against the
+// oracle in the CPU-only test tier (`-m "not gpu"`) where no B200 exists.  It is compiled into
+// tests/host_emul/libhostemul.so, which nothing under ntracer_b200/ loads: the product library
+// libntracer_b200.so contains no host rendering code at all.
+//
+// The frame driver below mimics the kernel's pass structure (primary pass, then one pass per
+// reflection depth over the queue written by the previous pass), single-threaded.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../ntracer_b200/csrc/arena_pack.h"
+#include "../../ntracer_b200/csrc/trace_core.cuh"
+
+using namespace ntr;
+
+namespace {
+
+template <int DT> struct VecEmit {
+    std::vector<Bounce<DT>> *out;
+    std::vector<uint32_t> *pix;
+    uint32_t pixel;
+    void operator()(const Bounce<DT> &b) { out->push_back(b); pix->push_back(pixel); }
+};
+
+struct Scene {
+    std::vector<unsigned char> arena;
+    std::vector<float> lights;
+    SceneDev dev;
+    CameraDev cam;
+    int flags;
+};
+
+void setup(Scene &S, const ntr_scene_desc *d, const float *cam_origin, const float *cam_axes) {
+    memset(&S.dev, 0, sizeof S.dev);
+    memset(&S.cam, 0, sizeof S.cam);
+    fill_scene_params(S.dev, d, 63);
+    S.dev.root = NTR_NULL_NODE;
+    S.dev.batch = 1;
+    S.flags = 0;
+    if (d->kind == NTR_SCENE_COMPOSITE) {
+        ArenaLayout L;
+        pack_arena(d, S.arena, L);
+        bind_arena(S.dev, d, L, S.arena.data());
+        S.flags = (L.any_transparent || d->n_solids) ? NTR_F_GENERAL : 0;
+        const size_t stride = d->dim + 3;
+        S.lights.resize(((size_t)d->n_point_lights + d->n_global_lights) * stride + 1);
+        if (d->n_point_lights) memcpy(S.lights.data(), d->point_lights, sizeof(float) * d->n_point_lights * stride);
+        if (d->n_global_lights) memcpy(S.lights.data() + d->n_point_lights * stride, d->global_lights, sizeof(float) * d->n_global_lights * stride);
+        S.dev.point_lights = S.lights.data();
+        S.dev.global_lights = S.lights.data() + d->n_point_lights * stride;
+        S.dev.n_point = (int)d->n_point_lights;
+        S.dev.n_global = (int)d->n_global_lights;
+    }
+    if (cam_origin && cam_axes) {
+        for (int i = 0; i < d->dim; ++i) {
+            S.cam.origin[i] = cam_origin[i];
+            S.cam.right[i] = cam_axes[i]; S.cam.up[i] = cam_axes[d->dim + i]; S.cam.fwd[i] = cam_axes[2 * d->dim + i];
+        }
+    }
+}
+
+template <int DT, int FLAGS>
+void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, unsigned long long *cnt_out) {
+    constexpr int CAP = DimCap<DT>::value;
+    FrameDev f;
+    memset(&f, 0, sizeof f);
+    f.width = w; f.height = h;
+    f.half_w = (float)w / 2.0f; f.half_h = (float)h / 2.0f;
+    f.fovI = tanf(S.dev.fov / 2) / f.half_w;
+    Counters cnt;
+    std::vector<Bounce<DT>> q, qn;
+    std::vector<uint32_t> qp, qpn;
+    const float one[3] = {1, 1, 1};
+    for (int y = 0; y < h; ++y) {
+        for (int x = 0; x < w; ++x) {
+            const uint32_t pix = (uint32_t)y * w + x;
+            float o[CAP], dir[CAP], acc[3] = {0, 0, 0};
+            HitRec prim;
+            prim.dist = 0; prim.ref = NTR_NONE_REF; prim.lane = -1;
+            primary_ray<DT>(S.dev, S.cam, f, x, y, o, dir);
+            if (S.dev.kind == NTR_SCENE_BOX) box_color<DT>(S.dev, o, dir, acc, &prim);
+            else {
+                VecEmit<DT> emit{&q, &qp, pix};
+                const Skip none = {NTR_NONE_REF, 0};
+                ray_color<DT, FLAGS>(S.dev, o, dir, 0, none, one, acc, emit, cnt, &prim);
+            }
+            if (rgb) { rgb[pix * 3] = acc[0]; rgb[pix * 3 + 1] = acc[1]; rgb[pix * 3 + 2] = acc[2]; }
+            if (ids) ids[pix] = prim.ref == NTR_NONE_REF ? -1 : (S.dev.kind == NTR_SCENE_BOX ? 0 : flat_prim_id(S.dev, prim.ref, prim.lane));
+            if (dists) dists[pix] = prim.dist;
+        }
+    }
+    while (!q.empty() && rgb) {
+        qn.clear(); qpn.clear();
+        for (size_t i = 0; i < q.size(); ++i) {
+            float acc[3] = {0, 0, 0};
+            VecEmit<DT> emit{&qn, &qpn, qp[i]};
+            ray_color<DT, FLAGS>(S.dev, q[i].o, q[i].d, q[i].depth, q[i].skip, q[i].w, acc, emit, cnt, nullptr);
+            rgb[(size_t)qp[i] * 3] += acc[0]; rgb[(size_t)qp[i] * 3 + 1] += acc[1]; rgb[(size_t)qp[i] * 3 + 2] += acc[2];
+        }
+        q.swap(qn); qp.swap(qpn);
+    }
+    if (cnt_out) {
+        cnt_out[0] = (unsigned long long)w * h; cnt_out[1] = cnt.reflection_rays; cnt_out[2] = cnt.shadow_rays;
+        cnt_out[3] = cnt.node_steps; cnt_out[4] = cnt.simplex_tests; cnt_out[5] = cnt.solid_tests; cnt_out[6] = cnt.shaded_hits;
+        cnt_out[7] = 0;
+    }
+}
+
+template <int DT> void render_d(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, unsigned long long *cnt) {
+    if (S.flags & NTR_F_GENERAL) render_t<DT, NTR_F_GENERAL | NTR_F_COUNT>(S, w, h, rgb, ids, dists, cnt);
+    else render_t<DT, NTR_F_COUNT>(S, w, h, rgb, ids, dists, cnt);
+}
+
+template <int DT, int FLAGS>
+void trace_t(Scene &S, uint32_t n, const float *origins, const float *dirs, float t_near, float t_far,
+             const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids, float *dist, int32_t *ntrans) {
+    const int D = S.dev.dim;
+    for (uint32_t i = 0; i < n; ++i) {
+        Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
+        GenState<DT> g;
+        g.th.clear();
+        HitRec oh;
+        oh.dist = FLT_MAX; oh.ref = NTR_NONE_REF; oh.lane = -1;
+        Counters cnt;
+        const bool hit = trace_nearest<DT, FLAGS>(S.dev, origins + (size_t)i * D, dirs + (size_t)i * D, skip, t_near, t_far, oh, &g, cnt);
+        ids[i] = hit ? flat_prim_id(S.dev, oh.ref, oh.lane) : -1;
+        if (dist) dist[i] = hit ? oh.dist : 0;
+        if (ntrans) ntrans[i] = (FLAGS & NTR_F_GENERAL) ? g.th.n : 0;
+    }
+}
+
+template <int DT, int FLAGS>
+void occl_t(Scene &S, uint32_t n, const float *origins, const float *dirs, const float *distance,
+            const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *occ, int32_t *ntrans) {
+    const int D = S.dev.dim;
+    for (uint32_t i = 0; i < n; ++i) {
+        Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
+        HitList hits;
+        hits.clear();
+        Counters cnt;
+        const bool r = trace_occludes<DT, FLAGS>(S.dev, origins + (size_t)i * D, dirs + (size_t)i * D,
+                                                distance ? distance[i] : FLT_MAX, skip, -FLT_MAX, FLT_MAX, &hits, cnt);
+        occ[i] = r;
+        if (ntrans) ntrans[i] = (!r && (FLAGS & NTR_F_GENERAL)) ? hits.n : 0;
+    }
+}
+
+#define DISPATCH_DIM(dim, CALL)            \
+    switch (dim) {                         \
+        case 3: { CALL(3); break; }        \
+        case 4: { CALL(4); break; }        \
+        case 5: { CALL(5); break; }        \
+        case 6: { CALL(6); break; }        \
+        case 7: { CALL(7); break; }        \
+        case 8: { CALL(8); break; }        \
+        default: { CALL(0); break; }       \
+    }
+
+}  // namespace
+
+extern "C" {
+
+// force_generic != 0 runs the run-time-dimension instantiation (DT = 0) whatever the dimension is
+__attribute__((visibility("default"))) int emul_render(const ntr_scene_desc *d, const float *cam_origin,
+                                                        const float *cam_axes, int w, int h, int force_generic,
+                                                        float *rgb, int32_t *ids, float *dists,
+                                                        unsigned long long *counters) {
+    Scene S;
+    setup(S, d, cam_origin, cam_axes);
+#define CALL(DT) render_d<DT>(S, w, h, rgb, ids, dists, counters)
+    DISPATCH_DIM(force_generic ? 0 : d->dim, CALL)
+#undef CALL
+    return 0;
+}
+
+__attribute__((visibility("default"))) int emul_trace_rays(const ntr_scene_desc *d, uint32_t n, const float *origins,
+                                                            const float *dirs, float t_near, float t_far,
+                                                            const uint32_t *skip_ref, const int32_t *skip_lane,
+                                                            int force_generic, int32_t *ids, float *dist, int32_t *ntrans) {
+    Scene S;
+    setup(S, d, nullptr, nullptr);
+#define CALL(DT)                                                                                                  \
+    if (S.flags & NTR_F_GENERAL) trace_t<DT, NTR_F_GENERAL>(S, n, origins, dirs, t_near, t_far, skip_ref, skip_lane, ids, dist, ntrans); \
+    else trace_t<DT, 0>(S, n, origins, dirs, t_near, t_far, skip_ref, skip_lane, ids, dist, ntrans)
+    DISPATCH_DIM(force_generic ? 0 : d->dim, CALL)
+#undef CALL
+    return 0;
+}
+
+__attribute__((visibility("default"))) int emul_occludes_rays(const ntr_scene_desc *d, uint32_t n, const float *origins,
+                                                               const float *dirs, const float *distance,
+                                                               const uint32_t *skip_ref, const int32_t *skip_lane,
+                                                               int force_generic, int32_t *occ, int32_t *ntrans) {
+    Scene S;
+    setup(S, d, nullptr, nullptr);
+#define CALL(DT)                                                                                              \
+    if (S.flags & NTR_F_GENERAL) occl_t<DT, NTR_F_GENERAL>(S, n, origins, dirs, distance, skip_ref, skip_lane, occ, ntrans); \
+    else occl_t<DT, 0>(S, n, origins, dirs, distance, skip_ref, skip_lane, occ, ntrans)
+    DISPATCH_DIM(force_generic ? 0 : d->dim, CALL)
+#undef CALL
+    return 0;
+}
+
+__attribute__((visibility("default"))) int emul_pack(const ntr_image_format *fmt, const float *rgb, unsigned char *dst) {
+    FormatDev f;
+    memset(&f, 0, sizeof f);
+    f.n_channels = fmt->n_channels; f.bytes_per_pixel = fmt->bytes_per_pixel; f.reversed = fmt->reversed; f.pitch = fmt->pitch;
+    for (int i = 0; i < fmt->n_channels; ++i) {
+        f.f_r[i] = fmt->channels[i].f_r; f.f_g[i] = fmt->channels[i].f_g; f.f_b[i] = fmt->channels[i].f_b; f.f_c[i] = fmt->channels[i].f_c;
+        f.bits[i] = fmt->channels[i].bit_size; f.tfloat[i] = fmt->channels[i].tfloat;
+    }
+    const int bpp = f.bytes_per_pixel;
+    for (int y = 0; y < fmt->height; ++y)
+        for (int x = 0; x < fmt->width; ++x) {
+            uint32_t w[4];
+            pack_pixel(f, rgb + ((size_t)y * fmt->width + x) * 3, w);
+            unsigned char *p = dst + (size_t)y * fmt->pitch + (size_t)x * bpp;
+            for (int j = 0; j < bpp; ++j) {
+                const int sj = f.reversed ? bpp - 1 - j : j;
+                p[j] = (unsigned char)(w[sj >> 2] >> (8 * (3 - (sj & 3))));
+            }
+        }
+    return 0;
+}
+
+}  // extern "C"

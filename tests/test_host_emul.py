@@ -1,0 +1,79 @@
+"""Runs the product's per-ray device code (ntracer_b200/csrc/trace_core.cuh: the stack-machine traversal,
+primitive tests, shading and pixel packing that the CUDA kernels inline) compiled for the HOST, and checks it
+against the oracle and the golden vectors.  This is how the kernel logic is exercised in the CPU-only tier;
+the `-m gpu` tests run the real kernels through the C ABI."""
+import numpy as np
+import pytest
+
+from ntracer_b200 import _capi
+from tests import emul_lib as el
+from tests import fixtures as fx
+from tests import oracle_lib as ol
+
+
+@pytest.mark.parametrize('name,variants', [
+    ('cell120', ['camlight', 'shadows', 'refl', 'refl_transp', 'transp', 'depth1_spec']),
+    ('ggs120', ['refl']),
+])
+def test_polytope_matches_oracle(name, variants):
+    sc, g = fx.load(name)
+    w, h = 96, 54
+    for v in variants:
+        s2 = fx.variant(sc, g, v)
+        a, cnt_o = ol.render_float(s2, w, h, with_counters=True)
+        b, cnt_e = el.render(s2, w, h)
+        assert np.abs(a - b).max() <= 2e-6, (name, v)
+        for k in ('primary_rays', 'reflection_rays', 'shadow_rays', 'node_steps', 'shaded_hits'):
+            assert cnt_o[k] == cnt_e[k], (name, v, k)
+
+
+@pytest.mark.parametrize('name', ['solids6', 'mixed3', 'soup9', 'box4', 'box9'])
+def test_scene_matches_oracle_and_golden(name):
+    sc, g = fx.load(name)
+    w, h = [int(v) for v in g['size']]
+    a = ol.render_float(sc, w, h)
+    b, ids, dist, cnt = el.render(sc, w, h, want_ids=True)
+    assert np.abs(a - b).max() <= 2e-6
+    if 'ids' in g:
+        assert fx.id_agreement(ids, g['ids'], dist, g['dist'])[0] >= 0.9999
+
+
+def test_runtime_dimension_variant_equals_fixed():
+    sc, g = fx.load('cell120')
+    a, _ = el.render(sc, 64, 36)
+    b, _ = el.render(sc, 64, 36, generic=True)
+    assert np.abs(a - b).max() <= 2e-6
+    sc, g = fx.load('solids6')
+    a, _ = el.render(sc, 64, 36)
+    b, _ = el.render(sc, 64, 36, generic=True)
+    assert np.abs(a - b).max() <= 2e-6
+
+
+def test_kdtree_known_answer_and_rays():
+    sc, g = fx.load('kdtree_kat')
+    ids, dist, nt = el.trace_rays(sc, g['origin'][None], g['direction'][None])
+    assert ids[0] == int(g['expected_id']) and nt[0] == 0
+    ids, dist, nt = el.trace_rays(sc, g['fan_origins'], g['fan_dirs'])
+    assert np.array_equal(ids, g['fan_ids'])
+    sc, g = fx.load('mixed3')
+    for generic in (False, True):
+        ids, dist, nt = el.trace_rays(sc, g['ray_origins'], g['ray_dirs'], generic=generic)
+        assert np.array_equal(ids, g['ray_ids'])
+        assert np.array_equal(nt, g['ray_ntrans'])
+        assert np.allclose(dist, g['ray_dists'], rtol=1e-5, atol=1e-5)
+    sc, g = fx.load('cell120')
+    occ, nt = el.occludes_rays(sc, g['occ_origins'], g['occ_dirs'], g['occ_dist'], g['occ_skip_ref'], g['occ_skip_lane'])
+    occ_o, _ = ol.occludes_rays(sc, g['occ_origins'], g['occ_dirs'], g['occ_dist'], g['occ_skip_ref'], g['occ_skip_lane'])
+    assert np.array_equal(occ, occ_o)
+    assert np.mean(occ == g['occ_result']) >= 0.995
+
+
+def test_pack_pixel_formats():
+    sc, g = fx.load('pack')
+    w, h = [int(v) for v in g['size']]
+    for n in g['names']:
+        n = str(n)
+        ch = [(int(c[0]), c[1], c[2], c[3], c[4], bool(c[5])) for c in g['fmt_' + n]]
+        pitch, rev = [int(v) for v in g['opt_' + n]]
+        fmt = _capi.make_image_format(w, h, ch, pitch, bool(rev))
+        assert np.array_equal(el.pack(fmt, g['float']), ol.pack(fmt, g['float'])), n
