@@ -1,0 +1,329 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the render path (BASELINE.json: Mrays/s and frame time).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c4|c1] [--impl ours|reference]
+
+A step = one frame of the workload.  At N=1 the workload is BASELINE.json configs[1]: the 4-D 120-cell
+{5,3,3} CompositeScene (the reference's own k-d tree, tests/golden/cell120.npz), 1920x1080, one PointLight
++ one GlobalLight, shadows on, RGB8 output.  N>1 (launched with torchrun, one rank per GPU): the same
+frame partitioned by interleaved 32-pixel tile rows, scene replicated, strips gathered with NCCL.
+
+One JSON line is printed by rank 0; see the prompt contract for the keys.  `value` = device-resident
+throughput (kernels only, CUDA events), `e2e` = the same metric through ntr_render with a HOST destination
+buffer (camera upload + D2H of the frame inside the timed region).  `cpu_baseline` / `--impl reference` time
+the reference's own multithreaded CPU renderer (oracle/_ref) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (fixture, width, height, description)
+    'c1': ('box4', 640, 480, "config 1: 4-D tesseract BoxScene 640x480"),
+    'c2': ('cell120', 1920, 1080, "config 2: 4-D 120-cell {5,3,3} CompositeScene 1920x1080, PointLight+GlobalLight, shadows on"),
+    'c4': ('ggs120', 3840, 2160, "config 4: great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4"),
+}
+METRIC = 'Mrays/s (primary+shadow+reflection)'
+
+
+def load_fixture(name):
+    from tests import fixtures as fx
+    return fx.load(name)
+
+
+def flops_per_frame(dim, cnt, n_lights):
+    """ALGORITHMIC flops of one frame from the reference
+    algorithm's counters (counting CPU restatement = the oracle)."""
+    D = dim
+    rays = cnt['primary_rays'] + cnt['reflection_rays']
+    return (cnt['primary_rays'] * (7 * D + 2) + rays * 2 * D * D + cnt['node_steps'] * 4 +
+            cnt['simplex_tests'] * (2 * D * D + 5 * D) + cnt['solid_tests'] * 8 * D * D +
+            cnt['shaded_hits'] * max(n_lights, 1) * (20 * D + 60))
+
+
+def bytes_per_frame(dim, cnt, frame_bytes):
+    """ALGORITHMIC bytes: 16 B per node step + one simplex record per simplex test + the frame."""
+    D = dim
+    return cnt['node_steps'] * 16 + cnt['simplex_tests'] * 4 * ((D + 1) * D + 1) + frame_bytes
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def reference_arm(args, sc, g, w, h, rays_per_frame):
+    """Times the reference's own CPU renderer (oracle/_ref: unmodified Rouslan/NTracer built by
+    oracle/build_ref.sh) on this box's host cores.  Falls back to the C port (oracle/ntr_oracle.c, OpenMP)."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    cores = os.cpu_count() or 1
+    import ref_bridge as rb
+    times = []
+    if rb.have_reference():
+        nt, scene, prims = rb.import_scene(sc)
+        rb.make_immortal(prims.values())     # see ref_bridge.make_immortal: the reference races on primitive refcounts
+        ntr = rb.load_reference()
+        fmt = ntr.ImageFormat(w, h, [ntr.Channel(8, 1, 0, 0), ntr.Channel(8, 0, 1, 0), ntr.Channel(8, 0, 0, 1)])
+        buf = bytearray(w * h * 3)
+        r = ntr.BlockingRenderer()          # threads=-1: hardware_concurrency() workers (render.cpp:829-838)
+        r.render(buf, fmt, scene)           # warm-up (late-starting workers)
+        budget = time.perf_counter() + 25.0
+        for _ in range(max(1, min(args.steps, 5))):
+            t = time.perf_counter()
+            r.render(buf, fmt, scene)
+            times.append(time.perf_counter() - t)
+            if time.perf_counter() > budget:
+                break
+        kind = 'reference'
+        sample = '%d full %dx%d frames, BlockingRenderer all cores, SSE4.2 build (AVX paths of the reference do not compile)' % (len(times), w, h)
+    else:
+        from tests import oracle_lib as ol
+        from ntracer_b200 import _capi
+        fmt = _capi.make_image_format(w, h, _capi.RGB8)
+        ol.render_packed(sc, _capi.make_image_format(64, 36, _capi.RGB8))
+        for _ in range(2):
+            t = time.perf_counter()
+            ol.render_packed(sc, fmt)
+            times.append(time.perf_counter() - t)
+        kind = 'port'
+        sample = '%d full %dx%d frames, oracle C port with OpenMP' % (len(times), w, h)
+    best = min(times)
+    return {'value': rays_per_frame / best / 1e6, 'unit': 'Mrays/s', 'cores': cores, 'kind': kind, 'sample': sample,
+            'sec_per_frame': best, 'median_sec_per_frame': statistics.median(times), 'Mpix_per_s': w * h / best / 1e6}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    fixture, w, h, desc = CONFIGS[args.config]
+    sc, g = load_fixture(fixture)
+    dim = int(sc['dim'])
+    frame_bytes = w * h * 3
+    n_lights = (len(sc.get('point_lights', [])) + len(sc.get('global_lights', []))) if int(sc['kind']) == 1 else 0
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        # ray counts of the frame from the counting CPU restatement (the reference does not count rays)
+        from tests import oracle_lib as ol
+        _, cnt = ol.render_float(sc, w, h, with_counters=True)
+        rays = cnt['primary_rays'] + cnt['shadow_rays'] + cnt['reflection_rays']
+        base = reference_arm(args, sc, g, w, h, rays)
+        line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'Mrays/s', 'n_gpus': args.gpus,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': base['sec_per_frame'] * 1e3,
+                'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': desc, 'rays_per_frame': rays},
+                'cpu_baseline': base,
+                'e2e': {'value': base['value'], 'unit': 'Mrays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from ntracer_b200 import _capi
+    from ntracer_b200.backend import DeviceScene, measure_fp32_peak
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    ds = DeviceScene(sc, local_rank)
+    fmt = _capi.make_image_format(w, h, _capi.RGB8)
+    tiles_y = (h + 31) // 32
+    my_rows = [ty for ty in range(tiles_y) if ty % world == rank]
+    max_rows = (tiles_y + world - 1) // world
+    strip_bytes = max_rows * 32 * fmt.pitch
+    strip = torch.zeros(strip_bytes, dtype=torch.uint8, device=dev)
+    gathered = torch.zeros(world * strip_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
+    host_frame = torch.zeros(world * strip_bytes if world > 1 else fmt.pitch * h, dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    cam_o = np.ascontiguousarray(sc['cam_origin'], np.float32)
+    cam_a = np.ascontiguousarray(sc['cam_axes'], np.float32)
+
+    # ray counts of this frame (device counters of a synchronous render)
+    ds.render_float(w, h)
+    cnt_gpu = ds.counters()
+    rays = cnt_gpu['primary_rays'] + cnt_gpu['shadow_rays'] + cnt_gpu['reflection_rays']
+
+    def step_device():
+        """one frame, inputs resident, output stays on the device; returns device ms (CUDA events on the
+        launching stream, ntr_last_kernel_ms)"""
+        ds.render_device(fmt, strip.data_ptr(), strip.numel(), 0, rank, world, world > 1)
+        ms = ds.last_kernel_ms()
+        if world > 1:
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            dist.all_gather_into_tensor(gathered, strip)
+            e1.record()
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms
+
+    def step_e2e():
+        """the same frame through the public host-buffer call: camera upload + render + D2H"""
+        ds.set_camera(cam_o, cam_a)
+        if world == 1:
+            ds.render(fmt, host_frame.numpy())
+        else:
+            ds.render_device(fmt, strip.data_ptr(), strip.numel(), 0, rank, world, True)
+            ds.last_kernel_ms()
+            dist.all_gather_into_tensor(gathered, strip)
+            if rank == 0:
+                host_frame.copy_(gathered, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+        step_e2e()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # ---- timed region 1: device-resident ----
+    barrier()
+    launches0 = ds.launch_count()
+    dev_ms = []
+    for _ in range(args.steps):
+        flush.zero_()                   # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        dev_ms.append(step_device())
+    barrier()
+    # ---- timed region 2: end to end through host buffers ----
+    e2e_s = []
+    for _ in range(args.steps):
+        flush.zero_()
+        barrier()
+        t = time.perf_counter()
+        step_e2e()
+        e2e_s.append(time.perf_counter() - t)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ds.launch_count() - launches0      # kernels of this library launched inside the two timed regions
+
+    tot_dev = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_dev, op=dist.ReduceOp.MAX)
+    dev_total_ms, e2e_total_ms = [float(v) for v in tot_dev.tolist()]
+
+    if rank == 0:
+        ms_per_step = dev_total_ms / args.steps
+        value = rays / (ms_per_step * 1e-3) / 1e6
+        e2e_ms = e2e_total_ms / args.steps
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'Mrays/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': desc, 'width': w, 'height': h, 'dim': dim, 'rays_per_frame': rays,
+                       'ray_counts': {k: cnt_gpu[k] for k in ('primary_rays', 'shadow_rays', 'reflection_rays')},
+                       'l2_flush_between_iterations': True, 'tree': 'reference k-d tree (exported, tests/golden)',
+                       'partition': 'interleaved 32-px tile rows over %d GPU(s)' % world,
+                       'frames_per_s': 1e3 / ms_per_step, 'Mpix_per_s': w * h / (ms_per_step * 1e-3) / 1e6},
+            'e2e': {'value': rays / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mrays/s', 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': int(4 * (dim + dim * dim)), 'd2h_bytes_per_step': int(frame_bytes)},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+        }
+        if world == 1:
+            # ---- roofline of the dominant kernel (render_pass_kernel: the only kernel of this frame) ----
+            from tests import oracle_lib as ol
+            _, cnt_ref = ol.render_float(sc, w, h, with_counters=True)     # reference-algorithm counts
+            flops = flops_per_frame(dim, cnt_ref, n_lights)
+            fp32_peak = measure_fp32_peak(local_rank)
+            achieved = flops / (ms_per_step * 1e-3) / 1e12
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+            except Exception:
+                pass
+            hbm_peak = peaks.get('hbm_gbs', 6650.0)
+            abytes = bytes_per_frame(dim, cnt_ref, frame_bytes)
+            line['roofline'] = {
+                'bound': 'fp32', 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp32_peak,
+                'traffic': None,
+                'peak_source': 'FP32 FMA micro-benchmark measured live in this run (ntr_measure_fp32_peak); MEASURED_PEAKS.json has HBM/BF16 only',
+                'algorithmic_flops_per_launch': flops, 'kernel': 'render_pass_kernel<4,0>', 'kernel_ms': ms_per_step,
+                'reference_algorithm_counts': cnt_ref,
+                'hbm': {'achieved': abytes / (ms_per_step * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                        'frac': abytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                        'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
+                        'algorithmic_bytes_per_launch': abytes,
+                        'note': 'working set (nodes+refs+simplexes, ~1.3 MB) is L2/L1-resident; DRAM traffic is the frame write'},
+            }
+            if not args.no_cpu_baseline:
+                line['cpu_baseline'] = reference_arm(args, sc, g, w, h, rays)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ds.close()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

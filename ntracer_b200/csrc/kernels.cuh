@@ -99,7 +99,7 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
             unsigned char *dst = f.packed + (size_t)(out_row0 + r) * f.fmt.pitch + (size_t)px0 * bpp + off;
             const unsigned char *src = stage + r * 128 + off;
             while (n > 0) {
-                const size_t a = (size_t)dst;
+                const size_t a = (size_t)dst | (size_t)src;      // both sides must be aligned for the unit
                 if (n >= 16 && (a & 15) == 0) { *(uint4 *)dst = *(const uint4 *)src; dst += 16; src += 16; n -= 16; }
                 else if (n >= 8 && (a & 7) == 0) { *(uint2 *)dst = *(const uint2 *)src; dst += 8; src += 8; n -= 8; }
                 else if (n >= 4 && (a & 3) == 0) { *(uint32_t *)dst = *(const uint32_t *)src; dst += 4; src += 4; n -= 4; }

@@ -288,6 +288,19 @@ def import_scene(sc, force_generic=False):
     return nt, scene, prims
 
 
+def make_immortal(objs):
+    """Workaround for a data race in the UNMODIFIED reference, applied from the outside: kd_leaf::occludes copies
+    a py::object per leaf item (src/tracer.hpp:1094 `auto item = this->items()[i];`), i.e. Py_INCREF/Py_DECREF on the
+    primitive from every render thread without the GIL.  The non-atomic updates get lost, the count eventually hits
+    zero and a primitive is freed under the renderer (ASAN: heap-use-after-free in a worker of BlockingRenderer;
+    seen as SIGSEGV / 'corrupted double-linked list' at 1280x720 and above with shadows on).  CPython 3.12 skips
+    reference counting for immortal objects, so marking the primitives immortal removes the racy writes without
+    touching the reference.  (It also removes cache-line ping-pong: if anything this favours the CPU baseline.)"""
+    import ctypes
+    for o in objs:
+        ctypes.c_uint32.from_address(id(o)).value = 0xFFFFFFFF     # _Py_IMMORTAL_REFCNT (64-bit builds)
+
+
 def polytope_scene(schlafli, cam_dist=4.0):
     """Run the reference's own scripts/polytope.py geometry + tree build for a Schlafli symbol
     (e.g. '5 3 3', '5/2 3 3') and return (nt, scene, camera).  pygame is stubbed (it is UI only) and
