@@ -1,0 +1,234 @@
+"""ntracer_b200.render -- host-side mirror of the reference's `ntracer.render` module (src/render.cpp) for the
+render path: Color, Material, Channel, ImageFormat, BlockingRenderer, CallbackRenderer, Scene, LockedError.
+Same names, arguments and error behaviour; the frames are produced by the CUDA backend (ntr_render)."""
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _capi
+
+
+class LockedError(Exception):
+    """Raised when a scene is modified while a renderer is using it (src/ntracer_body.hpp:235-240)."""
+
+
+def _color_tuple(c):
+    if isinstance(c, Color):
+        return (c.r, c.g, c.b)
+    t = tuple(float(x) for x in c)
+    if len(t) != 3:
+        raise TypeError('object must be an instance of Color or a sequence with three numbers')
+    return t
+
+
+class Color:
+    """Color(r,g,b) (src/light.hpp, doc/ntracer.rst:158-256)"""
+    __slots__ = ('r', 'g', 'b')
+
+    def __init__(self, r, g, b):
+        f = np.float32
+        self.r, self.g, self.b = float(f(r)), float(f(g)), float(f(b))
+
+    def __len__(self): return 3
+    def __getitem__(self, i): return (self.r, self.g, self.b)[i]
+    def __iter__(self): return iter((self.r, self.g, self.b))
+    def __repr__(self): return 'Color(%r,%r,%r)' % (self.r, self.g, self.b)
+    def __eq__(self, b): return isinstance(b, Color) and tuple(self) == tuple(b)
+    def __ne__(self, b): return not self.__eq__(b)
+    def __hash__(self): return hash(tuple(self))
+    def __neg__(self): return Color(-self.r, -self.g, -self.b)
+    def __buffer__(self, flags): return memoryview(np.array(tuple(self), np.float32))
+
+    def _bin(self, b, op):
+        if isinstance(b, Color):
+            return Color(op(self.r, b.r), op(self.g, b.g), op(self.b, b.b))
+        return Color(op(self.r, b), op(self.g, b), op(self.b, b))
+
+    def __add__(self, b): return self._bin(b, lambda x, y: x + y)
+    def __sub__(self, b): return self._bin(b, lambda x, y: x - y)
+    def __mul__(self, b): return self._bin(b, lambda x, y: x * y)
+    __rmul__ = __mul__
+    def __truediv__(self, b): return self._bin(b, lambda x, y: x / y)
+    __div__ = __truediv__
+    def apply(self, f): return Color(f(self.r), f(self.g), f(self.b))
+
+
+class Material:
+    """Material(color[,opacity=1,reflectivity=0,specular_intensity=1,specular_exp=8,specular_color=(1,1,1)])
+    (src/render.hpp:56-73, src/render.cpp:1249-1274).  Attributes are mutable, like the reference's."""
+    def __init__(self, color, opacity=1, reflectivity=0, specular_intensity=1, specular_exp=8, specular_color=(1, 1, 1)):
+        self.color = Color(*_color_tuple(color))
+        self.opacity, self.reflectivity = float(opacity), float(reflectivity)
+        self.specular_intensity, self.specular_exp = float(specular_intensity), float(specular_exp)
+        self.specular = Color(*_color_tuple(specular_color))
+
+    def __setattr__(self, k, v):
+        if k in ('color', 'specular'):
+            v = v if isinstance(v, Color) else Color(*_color_tuple(v))
+        elif k in ('opacity', 'reflectivity', 'specular_intensity', 'specular_exp'):
+            v = float(v)
+            if k in ('opacity', 'reflectivity'):
+                v = min(max(v, 0.0), 1.0)           # the reference clamps both to [0,1] (render.cpp:1211-1232)
+        object.__setattr__(self, k, v)
+
+    def _row(self):
+        return np.array([self.color.r, self.color.g, self.color.b, self.specular.r, self.specular.g, self.specular.b,
+                         self.opacity, self.reflectivity, self.specular_intensity, self.specular_exp], np.float32)
+
+    def __eq__(self, b): return isinstance(b, Material) and bool(np.all(self._row() == b._row()))
+    def __hash__(self): return id(self)
+    def __repr__(self):
+        return 'Material(%r,%r,%r,%r,%r,%r)' % (tuple(self.color), self.opacity, self.reflectivity, self.specular_intensity,
+                                                self.specular_exp, tuple(self.specular))
+
+
+class Channel:
+    """Channel(bit_size,f_r,f_g,f_b[,f_c=0,tfloat=False]) (src/render.cpp:95-164)"""
+    __slots__ = ('bit_size', 'f_r', 'f_g', 'f_b', 'f_c', 'tfloat')
+
+    def __init__(self, bit_size, f_r, f_g, f_b, f_c=0, tfloat=False):
+        bit_size = int(bit_size)
+        if tfloat:
+            if bit_size != 32:
+                raise ValueError('if "tfloat" is true, "bit_size" can only be 32')
+        elif bit_size > 31:
+            raise ValueError('"bit_size" cannot be greater than 31 (unless "tfloat" is true)')
+        elif bit_size < 1:
+            raise ValueError('"bit_size" cannot be less than 1')
+        object.__setattr__(self, 'bit_size', bit_size)
+        for n, v in (('f_r', f_r), ('f_g', f_g), ('f_b', f_b), ('f_c', f_c)):
+            object.__setattr__(self, n, float(np.float32(v)))
+        object.__setattr__(self, 'tfloat', bool(tfloat))
+
+    def __setattr__(self, k, v):
+        raise AttributeError('readonly attribute')
+
+    def _tuple(self): return (self.bit_size, self.f_r, self.f_g, self.f_b, self.f_c, self.tfloat)
+
+
+class ImageFormat:
+    """ImageFormat(width,height,channels[,pitch=0,reversed=False]) (src/render.cpp:167-288)"""
+    def __init__(self, width, height, channels, pitch=0, reversed=False):
+        self.width, self.height, self.reversed = int(width), int(height), bool(reversed)
+        self.set_channels(channels)
+        f = _capi.make_image_format(self.width, self.height, [c._tuple() for c in self._channels], int(pitch), self.reversed)
+        self.pitch = f.pitch
+
+    def set_channels(self, new_channels):
+        chans = list(new_channels)
+        for c in chans:
+            if not isinstance(c, Channel):
+                raise TypeError('object is not an instance of Channel')
+        bits = sum(c.bit_size for c in chans)
+        if bits > 16 * 8:
+            raise ValueError('Too many bytes per pixel. The maximum is 16.')
+        self._channels = tuple(chans)
+        self._bpp = (bits + 7) // 8
+
+    channels = property(lambda self: self._channels)
+    bytes_per_pixel = property(lambda self: self._bpp)
+
+    def _native(self):
+        return _capi.make_image_format(self.width, self.height, [c._tuple() for c in self._channels], self.pitch, self.reversed)
+
+
+class Scene:
+    """Abstract scene (src/render.hpp:8-26): anything with _prepare() -> DeviceScene and a `locked` counter."""
+    def calculate_color(self, x, y, width, height):
+        raise NotImplementedError
+
+
+def _writable_buffer(dest):
+    mv = memoryview(dest)
+    if mv.readonly:
+        raise BufferError('Object is not writable.')
+    return np.frombuffer(mv, dtype=np.uint8)
+
+
+class BlockingRenderer:
+    """BlockingRenderer([threads=-1]) (src/render.cpp:829-929).  `threads` has no meaning for the GPU backend."""
+    def __init__(self, threads=-1):
+        self._lock = threading.Lock()
+        self._dev = None
+
+    def render(self, dest, format, scene):
+        """-> True, or False if signal_abort() was called while rendering."""
+        if not isinstance(format, ImageFormat):
+            raise TypeError('object is not an instance of ImageFormat')
+        if not isinstance(scene, Scene):
+            raise TypeError('object is not an instance of Scene')
+        buf = _writable_buffer(dest)
+        fmt = format._native()
+        if buf.size < fmt.pitch * fmt.height:
+            raise ValueError('the buffer is too small for an image with the given dimensions')
+        if not self._lock.acquire(blocking=False):
+            raise RuntimeError('the renderer is already running')
+        try:
+            scene.locked += 1
+            try:
+                dev = scene._prepare()
+                self._dev = dev
+                rc = dev._lib.ntr_render(dev._h, C.byref(fmt), buf.ctypes.data_as(C.c_void_p), buf.size)
+                if rc == _capi.NTR_ERR_ABORTED:
+                    return False
+                _capi.check(rc)
+                return True
+            finally:
+                self._dev = None
+                scene.locked -= 1
+        finally:
+            self._lock.release()
+
+    def signal_abort(self):
+        dev = self._dev
+        if dev is not None:
+            dev.abort()
+
+
+class CallbackRenderer:
+    """CallbackRenderer([threads=0]) (src/render.cpp:495-728): begin_render returns immediately; `callback(self)`
+    runs on a worker thread once the frame is complete (not when aborted)."""
+    def __init__(self, threads=0):
+        self._thread = None
+        self._dev = None
+        self._lock = threading.Lock()
+
+    def begin_render(self, dest, format, scene, callback):
+        if not isinstance(format, ImageFormat):
+            raise TypeError('object is not an instance of ImageFormat')
+        if not isinstance(scene, Scene):
+            raise TypeError('object is not an instance of Scene')
+        buf = _writable_buffer(dest)
+        fmt = format._native()
+        if buf.size < fmt.pitch * fmt.height:
+            raise ValueError('the buffer is too small for an image with the given dimensions')
+        with self._lock:
+            if self._thread is not None and self._thread.is_alive() and threading.current_thread() is not self._thread:
+                raise RuntimeError('the renderer is already running')
+            scene.locked += 1
+            try:
+                dev = scene._prepare()
+            except Exception:
+                scene.locked -= 1
+                raise
+            self._dev = dev
+
+            def work():
+                try:
+                    rc = dev._lib.ntr_render(dev._h, C.byref(fmt), buf.ctypes.data_as(C.c_void_p), buf.size)
+                finally:
+                    scene.locked -= 1
+                    self._dev = None
+                if rc == _capi.NTR_OK:
+                    callback(self)
+
+            self._thread = threading.Thread(target=work, daemon=True)
+            self._thread.start()
+
+    def abort_render(self):
+        dev, t = self._dev, self._thread
+        if dev is not None:
+            dev.abort()
+        if t is not None and t is not threading.current_thread():
+            t.join()

@@ -1,0 +1,879 @@
+"""ntracer_b200.tracern -- host-side mirror of the reference's `ntracer.tracern` / `tracer{3..8}` modules
+(reference src/ntracer_body.hpp: the 31 Python types and 5 module functions, doc/ntracer.rst:452-1975) for
+the render path: the geometry / scene classes a script builds, flattened into the device arena and rendered
+by the CUDA backend through the C ABI.
+
+Same names, argument meaning and error behaviour as the reference; the arithmetic of the *render path*
+(Scene.calculate_color, KDNode.intersects / occludes, the renderers) runs on the GPU.  Host-side helper math
+(vectors, matrices, Triangle.from_points, the k-d tree builder) is plain numpy float32 -- it is scene set-up,
+not the hot path.  The dimension is a run-time attribute like in the reference's generic module.
+"""
+import math
+
+import numpy as np
+
+from . import _capi
+from .backend import DeviceScene, FLT_MAX
+from .render import Color, LockedError, Material, Scene, _color_tuple
+
+BATCH_SIZE = 4      # lanes of a TriangleBatch; the reference's SSE build has v_real::size == 4
+CUBE, SPHERE = 1, 2
+_F = np.float32
+
+
+def _check_dimension(d):
+    if d < 3:
+        raise ValueError('dimension cannot be smaller than 3')
+    if d > _capi.NTR_MAX_DIM:
+        raise ValueError('dimension cannot be greater than %d' % _capi.NTR_MAX_DIM)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class Vector:
+    """Vector(dimension[,values]) -- doc/ntracer.rst:1704-1822"""
+    __slots__ = ('_v',)
+
+    def __init__(self, dimension, values=None):
+        if isinstance(dimension, Vector) and values is None:
+            self._v = dimension._v.copy()
+            return
+        _check_dimension(dimension)
+        if values is None:
+            self._v = np.zeros(dimension, _F)
+        else:
+            v = np.array([float(x) for x in values], _F)
+            if v.size != dimension:
+                raise TypeError('this object has a dimension of %d and cannot be initialized with %d values' % (dimension, v.size))
+            self._v = v
+
+    @classmethod
+    def _wrap(cls, arr):
+        o = object.__new__(Vector)
+        o._v = np.ascontiguousarray(arr, _F)
+        return o
+
+    @staticmethod
+    def axis(dimension, axis, length=1):
+        _check_dimension(dimension)
+        if not 0 <= axis < dimension:
+            raise ValueError('axis must be between 0 and dimension-1')
+        v = np.zeros(dimension, _F)
+        v[axis] = length
+        return Vector._wrap(v)
+
+    dimension = property(lambda self: int(self._v.size))
+
+    def __len__(self): return int(self._v.size)
+    def __getitem__(self, i): return float(self._v[i])
+    def __iter__(self): return (float(x) for x in self._v)
+    def __buffer__(self, flags): return memoryview(self._v)
+    def __array__(self, dtype=None, copy=None): return self._v.astype(dtype) if dtype else self._v
+    def __repr__(self): return 'Vector(%d,(%s))' % (self._v.size, ','.join(repr(float(x)) for x in self._v))
+    def __str__(self): return '<%s>' % ','.join('%g' % float(x) for x in self._v)
+    def __hash__(self): return hash(self._v.tobytes())
+
+    def _coerce(self, b):
+        if isinstance(b, Vector):
+            if b._v.size != self._v.size:
+                raise TypeError('cannot perform vector operations on vectors of different dimension')
+            return b._v
+        return None
+
+    def __add__(self, b):
+        o = self._coerce(_as_vector(b, self._v.size))
+        return Vector._wrap(self._v + o)
+
+    def __sub__(self, b):
+        o = self._coerce(_as_vector(b, self._v.size))
+        return Vector._wrap(self._v - o)
+
+    def __mul__(self, b):
+        if isinstance(b, (Vector, Matrix)):
+            return NotImplemented
+        return Vector._wrap(self._v * _F(b))
+    __rmul__ = __mul__
+
+    def __truediv__(self, b): return Vector._wrap(self._v / _F(b))
+    __div__ = __truediv__
+    def __neg__(self): return Vector._wrap(-self._v)
+    def __abs__(self): return self.absolute()
+    def __eq__(self, b): return isinstance(b, Vector) and b._v.size == self._v.size and bool(np.all(self._v == b._v))
+    def __ne__(self, b): return not self.__eq__(b)
+
+    def square(self): return float(np.dot(self._v, self._v))
+    def absolute(self): return float(np.sqrt(_F(np.dot(self._v, self._v))))
+    def unit(self): return Vector._wrap(self._v / np.sqrt(_F(np.dot(self._v, self._v))))
+    def apply(self, f): return Vector(self._v.size, [f(float(x)) for x in self._v])
+
+    def set_c(self, index, value):
+        v = self._v.copy()
+        v[index] = value
+        return Vector._wrap(v)
+
+
+def _as_vector(x, dim=None):
+    if isinstance(x, Vector):
+        v = x
+    else:
+        seq = list(x)
+        v = Vector(len(seq) if dim is None else dim, seq)
+    if dim is not None and v.dimension != dim:
+        raise TypeError('object has a dimension of %d instead of %d' % (v.dimension, dim))
+    return v
+
+
+class Matrix:
+    """Matrix(dimension,values) -- doc/ntracer.rst:1114-1207; row-major, `values` is the flat sequence"""
+    __slots__ = ('_m',)
+
+    def __init__(self, dimension, values=None):
+        _check_dimension(dimension)
+        if values is None:
+            self._m = np.zeros((dimension, dimension), _F)
+            return
+        vals = list(values)
+        if len(vals) == dimension * dimension:
+            m = np.array([float(x) for x in vals], _F).reshape(dimension, dimension)
+        elif len(vals) == dimension:
+            m = np.array([[float(x) for x in row] for row in vals], _F)
+            if m.shape != (dimension, dimension):
+                raise TypeError('matrix rows must have %d items' % dimension)
+        else:
+            raise TypeError('a matrix of dimension %d needs %d values or %d rows' % (dimension, dimension ** 2, dimension))
+        self._m = m
+
+    @classmethod
+    def _wrap(cls, arr):
+        o = object.__new__(Matrix)
+        o._m = np.ascontiguousarray(arr, _F)
+        return o
+
+    dimension = property(lambda self: int(self._m.shape[0]))
+    values = property(lambda self: tuple(float(x) for x in self._m.ravel()))
+
+    def __len__(self): return int(self._m.shape[0])
+    def __getitem__(self, i): return Vector._wrap(self._m[i].copy())
+    def __eq__(self, b): return isinstance(b, Matrix) and self._m.shape == b._m.shape and bool(np.all(self._m == b._m))
+    def __repr__(self): return 'Matrix(%d,%r)' % (self.dimension, self.values)
+
+    def __mul__(self, b):
+        if isinstance(b, Matrix):
+            return Matrix._wrap(self._m @ b._m)
+        if isinstance(b, Vector):
+            return Vector._wrap(self._m @ b._v)
+        return NotImplemented
+
+    def determinant(self): return float(np.linalg.det(self._m.astype(np.float64)))
+
+    def inverse(self):
+        try:
+            return Matrix._wrap(np.linalg.inv(self._m.astype(np.float64)))
+        except np.linalg.LinAlgError:
+            raise ValueError('matrix is singular')
+
+    def transpose(self): return Matrix._wrap(self._m.T.copy())
+
+    @staticmethod
+    def identity(dimension):
+        _check_dimension(dimension)
+        return Matrix._wrap(np.eye(dimension, dtype=_F))
+
+    @staticmethod
+    def scale(*args):
+        if len(args) == 1:
+            v = _as_vector(args[0])
+            return Matrix._wrap(np.diag(v._v))
+        d, mag = args
+        _check_dimension(d)
+        return Matrix._wrap(np.eye(d, dtype=_F) * _F(mag))
+
+    @staticmethod
+    def reflection(axis):
+        a = _as_vector(axis)._v
+        sq = _F(np.dot(a, a))
+        return Matrix._wrap(np.eye(a.size, dtype=_F) - 2 * np.outer(a, a) / sq)      # geometry.hpp:602-608
+
+    @staticmethod
+    def rotation(a, b, theta):
+        a, b = _as_vector(a)._v, _as_vector(b, len(a))._v
+        c, s = _F(math.cos(theta) - 1), _F(math.sin(theta))
+        # geometry.hpp:579-591: r[row][col] = a[row]*(a[col]*c - b[col]*s) + b[row]*(b[col]*c + a[col]*s) (+1 on the diagonal)
+        m = np.outer(a, a * c - b * s) + np.outer(b, b * c + a * s) + np.eye(a.size, dtype=_F)
+        return Matrix._wrap(m)
+
+
+def dot(a, b):
+    a = _as_vector(a)
+    return float(np.dot(a._v, _as_vector(b, a.dimension)._v))
+
+
+def cross(vectors):
+    """Generalized cross product of D-1 vectors (geometry.hpp:858-893)."""
+    vs = [_as_vector(v) for v in vectors]
+    d = vs[0].dimension
+    if len(vs) != d - 1:
+        raise ValueError('the number of vectors must be exactly one less than their dimension')
+    m = np.stack([v._v for v in vs]).astype(np.float64)        # (D-1) x D
+    r = np.zeros(d, np.float64)
+    f = 1.0 if d % 2 else -1.0
+    for i in range(d):
+        r[i] = f * np.linalg.det(np.delete(m, i, axis=1).T)
+        f = -f
+    return Vector._wrap(r)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class CameraAxes:
+    def __init__(self, cam): self._cam = cam
+    def __len__(self): return self._cam.dimension
+    def __getitem__(self, i): return Vector._wrap(self._cam._axes[i].copy())
+
+    def __setitem__(self, i, v):
+        self._cam._axes[i] = _as_vector(v, self._cam.dimension)._v
+
+
+class Camera:
+    """Camera(dimension) -- src/camera.hpp:7-46, doc/ntracer.rst:598-647"""
+    def __init__(self, dimension):
+        _check_dimension(dimension)
+        self._origin = np.zeros(dimension, _F)
+        self._axes = np.eye(dimension, dtype=_F)
+
+    dimension = property(lambda self: int(self._origin.size))
+    axes = property(lambda self: CameraAxes(self))
+
+    @property
+    def origin(self): return Vector._wrap(self._origin.copy())
+
+    @origin.setter
+    def origin(self, v): self._origin = _as_vector(v, self.dimension)._v.copy()
+
+    def translate(self, offset):                 # camera.hpp:17-19
+        o = _as_vector(offset, self.dimension)._v
+        self._origin = self._origin + o @ self._axes
+
+    def transform(self, m):                      # camera.hpp:21-23: t_orientation.mult_transpose(m)
+        self._axes = (self._axes @ m._m.T).astype(_F)
+
+    def normalize(self):                         # camera.hpp:25-36 (Gram-Schmidt)
+        a = self._axes
+        new = np.zeros_like(a)
+        new[0] = a[0] / np.sqrt(np.dot(a[0], a[0]))
+        for i in range(1, a.shape[0]):
+            x = np.zeros(a.shape[1], _F)
+            for j in range(i - 1):
+                x += np.dot(a[i], a[j]) * a[j]
+            v = a[i] - x
+            new[i] = v / np.sqrt(np.dot(v, v))
+        self._axes = new
+
+    def _copy(self):
+        c = Camera(self.dimension)
+        c._origin, c._axes = self._origin.copy(), self._axes.copy()
+        return c
+
+
+class AABB:
+    """AABB(dimension[,start,end]) -- doc/ntracer.rst:465-542"""
+    def __init__(self, dimension, start=None, end=None):
+        _check_dimension(dimension)
+        self.start = Vector(dimension, [-FLT_MAX] * dimension) if start is None else _as_vector(start, dimension)
+        self.end = Vector(dimension, [FLT_MAX] * dimension) if end is None else _as_vector(end, dimension)
+
+    dimension = property(lambda self: self.start.dimension)
+
+    def left(self, axis, split):
+        return AABB(self.dimension, self.start, self.end.set_c(axis, split))
+
+    def right(self, axis, split):
+        return AABB(self.dimension, self.start.set_c(axis, split), self.end)
+
+    def intersects(self, primitive):
+        """Conservative overlap test on the prototype's bounding box (the reference runs exact separating-axis
+        tests, src/tracer.hpp:1465-1675; they belong to the tree builder)."""
+        b = primitive.boundary
+        return bool(np.all(self.start._v <= b.end._v) and np.all(self.end._v >= b.start._v))
+
+    def intersects_flat(self, primitive, skip):
+        b = primitive.boundary
+        k = [i for i in range(self.dimension) if i != skip]
+        return bool(np.all(self.start._v[k] <= b.end._v[k]) and np.all(self.end._v[k] >= b.start._v[k]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+class Primitive:
+    def __init__(self, *a, **k):
+        if type(self) is Primitive:
+            raise TypeError('the Primitive type cannot be instantiated directly')
+
+
+class PrimitiveBatch:
+    def __init__(self, *a, **k):
+        if type(self) is PrimitiveBatch:
+            raise TypeError('the PrimitiveBatch type cannot be instantiated directly')
+
+
+class Triangle(Primitive):
+    """Triangle(p1,face_normal,edge_normals,material): a (D-1)-simplex (src/tracer.hpp:392-488)"""
+    def __init__(self, p1, face_normal, edge_normals, material):
+        self.p1 = _as_vector(p1)
+        d = self.p1.dimension
+        self.face_normal = _as_vector(face_normal, d)
+        en = [_as_vector(e, d) for e in edge_normals]
+        if len(en) != d - 1:
+            raise ValueError('a triangle needs exactly dimension-1 edge normals')
+        self.edge_normals = tuple(en)
+        if not isinstance(material, Material):
+            raise TypeError('material must be an instance of Material')
+        self.material = material
+        self.d = float(-np.dot(self.face_normal._v, self.p1._v))       # recalculate_d, tracer.hpp:472-474
+
+    dimension = property(lambda self: self.p1.dimension)
+
+    @staticmethod
+    def from_points(points, material):          # tracer.hpp:442-462
+        pts = [_as_vector(p) for p in points]
+        n = pts[0].dimension
+        if len(pts) != n:
+            raise ValueError('a triangle needs exactly "dimension" points')
+        vs = [pts[i + 1] - pts[0] for i in range(n - 1)]
+        N = cross(vs)
+        sq = N.square()
+        edges = []
+        for i in range(n - 1):
+            tmp = list(vs)
+            tmp[i] = N
+            edges.append(cross(tmp) / sq)
+        return Triangle(pts[0], N, edges, material)
+
+    def to_points(self):                        # tracer.hpp:490-506
+        n = self.dimension
+        out = [self.p1]
+        for i in range(n - 1):
+            tmp = list(self.edge_normals)
+            tmp[i] = self.face_normal
+            out.append(cross(tmp) + self.p1)
+        return tuple(out)
+
+    def _row(self):
+        return np.concatenate([self.face_normal._v, np.array([self.d], _F), self.p1._v] + [e._v for e in self.edge_normals])
+
+
+class TriangleBatch(PrimitiveBatch):
+    """TriangleBatch(triangles): BATCH_SIZE simplexes tested together (src/tracer.hpp:532-641)"""
+    def __init__(self, triangles):
+        ts = list(triangles)
+        if len(ts) != BATCH_SIZE:
+            raise ValueError('a TriangleBatch requires exactly %d triangles' % BATCH_SIZE)
+        for t in ts:
+            if not isinstance(t, Triangle):
+                raise TypeError('object is not an instance of Triangle')
+        self._t = tuple(ts)
+
+    dimension = property(lambda self: self._t[0].dimension)
+    def __len__(self): return BATCH_SIZE
+    def __getitem__(self, i): return self._t[i]
+
+
+class Solid(Primitive):
+    """Solid(type,position,orientation,material) (src/tracer.hpp:231-289)"""
+    def __init__(self, type, position, orientation, material):
+        if type not in (CUBE, SPHERE):
+            raise ValueError('invalid shape type')
+        self.type = type
+        self.position = _as_vector(position)
+        if not isinstance(orientation, Matrix) or orientation.dimension != self.position.dimension:
+            raise TypeError('the orientation and position must have the same dimension')
+        self.orientation = orientation
+        self.inv_orientation = orientation.inverse()
+        if not isinstance(material, Material):
+            raise TypeError('material must be an instance of Material')
+        self.material = material
+
+    dimension = property(lambda self: self.position.dimension)
+
+    def _row(self):
+        return np.concatenate([np.array([self.type], _F), self.orientation._m.ravel(), self.inv_orientation._m.ravel(), self.position._v])
+
+
+class PrimitivePrototype:
+    pass
+
+
+class TrianglePointDatum:
+    def __init__(self, point, edge_normal): self.point, self.edge_normal = point, edge_normal
+
+
+class TrianglePrototype(PrimitivePrototype):
+    """TrianglePrototype(points[,material]) (src/ntracer_body.hpp:2658-2720)"""
+    def __init__(self, points, material=None):
+        if isinstance(points, Triangle):
+            if material is not None:
+                raise TypeError('if "points" is an instance of Triangle, "material" must be None')
+            tri, pts = points, list(points.to_points())
+        else:
+            if material is None:
+                raise TypeError('if "points" is not an instance of Triangle, "material" cannot be None')
+            pts = [_as_vector(p) for p in points]
+            tri = Triangle.from_points(pts, material)
+        self.primitive = tri
+        arr = np.stack([p._v for p in pts])
+        self.boundary = AABB(tri.dimension, Vector._wrap(arr.min(axis=0)), Vector._wrap(arr.max(axis=0)))
+        first = -np.sum([e._v for e in tri.edge_normals], axis=0)
+        self.point_data = tuple([TrianglePointDatum(pts[0], Vector._wrap(first))] +
+                                [TrianglePointDatum(pts[i + 1], tri.edge_normals[i]) for i in range(tri.dimension - 1)])
+
+    dimension = property(lambda self: self.primitive.dimension)
+    face_normal = property(lambda self: self.primitive.face_normal)
+    material = property(lambda self: self.primitive.material)
+
+
+class TriangleBatchPrototype(PrimitivePrototype):
+    def __init__(self, t_prototypes):
+        if isinstance(t_prototypes, TriangleBatch):
+            protos = [TrianglePrototype(t) for t in t_prototypes]
+            self.primitive = t_prototypes
+        else:
+            protos = list(t_prototypes)
+            self.primitive = TriangleBatch([p.primitive for p in protos])
+        lo = np.min([p.boundary.start._v for p in protos], axis=0)
+        hi = np.max([p.boundary.end._v for p in protos], axis=0)
+        self.boundary = AABB(protos[0].dimension, Vector._wrap(lo), Vector._wrap(hi))
+        self._protos = tuple(protos)
+
+    dimension = property(lambda self: self._protos[0].dimension)
+
+
+class SolidPrototype(PrimitivePrototype):
+    """SolidPrototype(type,position,orientation,material) (src/ntracer_body.hpp:2912-2961)"""
+    def __init__(self, type, position, orientation, material):
+        s = Solid(type, position, orientation, material)
+        self.primitive = s
+        d = s.dimension
+        pos = s.position._v
+        if type == CUBE:
+            extent = np.abs(s.orientation._m).sum(axis=1)           # sum over cube_component(i) = columns of orientation
+            self.boundary = AABB(d, Vector._wrap(pos - extent), Vector._wrap(pos + extent))
+        else:
+            lo, hi = np.zeros(d, _F), np.zeros(d, _F)
+            for i in range(d):
+                n = s.orientation._m[i] / np.sqrt(np.dot(s.orientation._m[i], s.orientation._m[i]))
+                e = np.zeros(d, _F)
+                e[i] = 1
+                a, b = float(np.dot(e - pos, n)), float(np.dot(-e - pos, n))
+                lo[i], hi[i] = min(a, b), max(a, b)
+            self.boundary = AABB(d, Vector._wrap(lo), Vector._wrap(hi))
+
+    dimension = property(lambda self: self.primitive.dimension)
+    type = property(lambda self: self.primitive.type)
+    position = property(lambda self: self.primitive.position)
+    orientation = property(lambda self: self.primitive.orientation)
+    inv_orientation = property(lambda self: self.primitive.inv_orientation)
+    material = property(lambda self: self.primitive.material)
+
+
+# ---------------------------------------------------------------------------------------------------------
+class RayIntersection:
+    """RayIntersection(dist,origin,normal,primitive[,batch_index=-1]) (doc/ntracer.rst:1360-1395)"""
+    def __init__(self, dist, origin, normal, primitive, batch_index=-1):
+        self.dist, self.origin, self.normal, self.primitive, self.batch_index = dist, origin, normal, primitive, batch_index
+
+
+class KDNode:
+    """Base of KDLeaf / KDBranch.  intersects / occludes run on the GPU (ntr_trace_rays / ntr_occludes_rays)."""
+    def __init__(self, *a, **k):
+        if type(self) is KDNode:
+            raise TypeError('the KDNode type cannot be instantiated directly')
+
+    def _device(self):
+        if getattr(self, '_dev', None) is None:
+            flat = _Flattener(self.dimension)
+            root = flat.walk(self)
+            sc = flat.scene_dict(root, AABB(self.dimension), None)
+            self._dev, self._flat = DeviceScene(sc), flat
+        return self._dev, self._flat
+
+    def _skip(self, flat, source, batch_index):
+        if source is None:
+            return None, None
+        if not isinstance(source, (Primitive, PrimitiveBatch)):
+            raise TypeError('object is not an instance of Primitive or PrimitiveBatch')
+        ref = flat.item_ref.get(id(source), 0xFFFFFFFF)
+        return np.array([ref], np.uint32), np.array([batch_index if isinstance(source, PrimitiveBatch) else -1], np.int32)
+
+    def intersects(self, origin, direction, t_near=-FLT_MAX, t_far=FLT_MAX, source=None, batch_index=-1):
+        """-> list of RayIntersection; the opaque hit (if any) is last (src/ntracer_body.hpp:1412-1458).
+        Transparent hits are counted by the backend but only the opaque hit is materialised here."""
+        o, d = _as_vector(origin, self.dimension), _as_vector(direction, self.dimension)
+        dev, flat = self._device()
+        sr, sl = self._skip(flat, source, batch_index)
+        ids, dist, nt = dev.trace_rays(o._v[None], d._v[None], t_near, t_far, sr, sl)
+        if ids[0] < 0:
+            return []
+        prim, lane = flat.prim_of_flat_id(int(ids[0]))
+        t = float(dist[0])
+        tri = prim[lane] if lane >= 0 else prim
+        P = o + d * t
+        if isinstance(tri, Triangle):
+            n = tri.face_normal.unit()
+            if dot(tri.face_normal, d) > 0:
+                n = -n
+        else:
+            n = None
+        return [RayIntersection(t, P, n, prim, lane)]
+
+    def occludes(self, origin, direction, distance=FLT_MAX, t_near=-FLT_MAX, t_far=FLT_MAX, source=None, batch_index=-1):
+        o, d = _as_vector(origin, self.dimension), _as_vector(direction, self.dimension)
+        dev, flat = self._device()
+        sr, sl = self._skip(flat, source, batch_index)
+        occ, nt = dev.occludes_rays(o._v[None], d._v[None], np.array([distance], _F), sr, sl)
+        return (bool(occ[0]), None if occ[0] else [])
+
+
+class KDLeaf(KDNode):
+    """KDLeaf(primitives) (doc/ntracer.rst:1026-1053); batches are kept first like kd_leaf (tracer.hpp:1142-1150)"""
+    def __init__(self, primitives):
+        items = list(primitives)
+        if not items:
+            raise ValueError('KDLeaf requires at least one item')
+        for p in items:
+            if not isinstance(p, (Primitive, PrimitiveBatch)):
+                raise TypeError('object is not an instance of Primitive or PrimitiveBatch')
+        d = items[0].dimension
+        if any(p.dimension != d for p in items):
+            raise TypeError('every member of KDLeaf must have the same dimension')
+        self._items = tuple([p for p in items if isinstance(p, PrimitiveBatch)] + [p for p in items if not isinstance(p, PrimitiveBatch)])
+        self._nbatches = sum(isinstance(p, PrimitiveBatch) for p in items)
+        self.dimension = d
+
+    def __len__(self): return len(self._items)
+    def __getitem__(self, i): return self._items[i]
+
+
+class KDBranch(KDNode):
+    """KDBranch(axis,split[,left=None,right=None]) (doc/ntracer.rst:980-1021)"""
+    def __init__(self, axis, split, left=None, right=None):
+        for n in (left, right):
+            if n is not None and not isinstance(n, KDNode):
+                raise TypeError('"left" and "right" must be instances of KDNode')
+        if left is None and right is None:
+            raise TypeError('"left" and "right" can\'t both be None')
+        if left is not None and right is not None and left.dimension != right.dimension:
+            raise TypeError('"left" and "right" must have the same dimension')
+        self.dimension = (left if left is not None else right).dimension
+        if not 0 <= axis < self.dimension:
+            raise ValueError('invalid axis')
+        self.axis, self.split, self.left, self.right = int(axis), float(_F(split)), left, right
+
+
+class _Flattener:
+    """Walks a KDNode tree into the flat arrays of ntr_scene_desc (the host half of the arena upload)."""
+    def __init__(self, dim):
+        self.dim = dim
+        self.nodes, self.refs, self.simplex, self.simplex_mat, self.solids, self.solid_mat = [], [], [], [], [], []
+        self.mats, self.mat_ids, self.item_ref, self.items, self.mat_objs = [], {}, {}, [], []
+        self.flat_owner = []            # flat simplex id -> (item, lane)
+
+    def mat_id(self, m):
+        k = id(m)
+        if k not in self.mat_ids:
+            self.mat_ids[k] = len(self.mats)
+            self.mats.append(m._row())
+            self.mat_objs.append(m)
+        return self.mat_ids[k]
+
+    def add_tri(self, t, owner, lane):
+        self.simplex.append(t._row())
+        self.simplex_mat.append(self.mat_id(t.material))
+        self.flat_owner.append((owner, lane))
+        return len(self.simplex) - 1
+
+    def ref_of(self, item):
+        k = id(item)
+        if k in self.item_ref:
+            return self.item_ref[k]
+        self.items.append(item)
+        if isinstance(item, TriangleBatch):
+            first = self.add_tri(item[0], item, 0)
+            for lane in range(1, BATCH_SIZE):
+                self.add_tri(item[lane], item, lane)
+            r = (_capi.REF_BATCH << 30) | first
+        elif isinstance(item, Triangle):
+            r = (_capi.REF_SIMPLEX << 30) | self.add_tri(item, item, -1)
+        elif isinstance(item, Solid):
+            self.solids.append(item._row())
+            self.solid_mat.append(self.mat_id(item.material))
+            r = (_capi.REF_SOLID << 30) | (len(self.solids) - 1)
+        else:
+            raise TypeError('unknown primitive type')
+        self.item_ref[k] = r
+        return r
+
+    def walk(self, root):
+        if root is None:
+            return _capi.NULL_NODE
+        # iterative pre-order (left subtree first) so deep trees do not hit the recursion limit
+        out_root = len(self.nodes)
+        stack = [(root, None, 0)]
+        while stack:
+            node, parent, slot = stack.pop()
+            idx = len(self.nodes)
+            if parent is not None:
+                self.nodes[parent][slot] = idx
+            if isinstance(node, KDLeaf):
+                first = len(self.refs)
+                for it in node._items:
+                    self.refs.append(self.ref_of(it))
+                self.nodes.append([_capi.LEAF_FLAG | node._nbatches, first, len(node._items), 0])
+            else:
+                bits = int(np.array([node.split], _F).view(np.uint32)[0])
+                self.nodes.append([node.axis, bits, _capi.NULL_NODE, _capi.NULL_NODE])
+                if node.right is not None:
+                    stack.append((node.right, idx, 3))
+                if node.left is not None:
+                    stack.append((node.left, idx, 2))
+        return out_root
+
+    def prim_of_flat_id(self, fid):
+        if fid < len(self.flat_owner):
+            return self.flat_owner[fid]
+        solids = [it for it in self.items if isinstance(it, Solid)]
+        return solids[fid - len(self.flat_owner)], -1
+
+    def material_snapshot(self):
+        return np.array([m._row() for m in self.mat_objs], _F).reshape(-1, 10)
+
+    def scene_dict(self, root, boundary, scene):
+        d = self.dim
+        stride = (d + 1) * d + 1
+        sc = {
+            'dim': np.int64(d), 'kind': np.int64(1), 'batch_size': np.int64(BATCH_SIZE), 'root': np.int64(root),
+            'nodes': np.array(self.nodes, np.uint32).reshape(-1, 4), 'leaf_refs': np.array(self.refs, np.uint32),
+            'simplex': np.array(self.simplex, _F).reshape(-1, stride), 'simplex_mat': np.array(self.simplex_mat, np.int32),
+            'solids': np.array(self.solids, _F).reshape(-1, 1 + 2 * d * d + d), 'solid_mat': np.array(self.solid_mat, np.int32),
+            'materials': self.material_snapshot(),
+            'boundary': np.stack([boundary.start._v, boundary.end._v]),
+        }
+        sc.update(_scene_params(scene, d))
+        return sc
+
+
+def _scene_params(scene, d):
+    if scene is None:
+        return {'params': np.array([0.8, 0, 1, 4, 1], np.float64), 'ambient': np.zeros(3, _F), 'bg1': np.ones(3, _F),
+                'bg2': np.zeros(3, _F), 'bg3': np.array([0, 1, 1], _F), 'point_lights': np.zeros((0, d + 3), _F),
+                'global_lights': np.zeros((0, d + 3), _F)}
+    return {
+        'params': np.array([scene.fov, scene.shadows, scene.camera_light, scene.max_reflect_depth, scene.bg_gradient_axis], np.float64),
+        'ambient': np.array(_color_tuple(scene.ambient_color), _F), 'bg1': np.array(_color_tuple(scene.bg1), _F),
+        'bg2': np.array(_color_tuple(scene.bg2), _F), 'bg3': np.array(_color_tuple(scene.bg3), _F),
+        'point_lights': np.array([list(l.position) + list(_color_tuple(l.color)) for l in scene.point_lights], _F).reshape(-1, d + 3),
+        'global_lights': np.array([list(l.direction) + list(_color_tuple(l.color)) for l in scene.global_lights], _F).reshape(-1, d + 3),
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------
+class PointLight:
+    """PointLight(position,color) (src/tracer.hpp:1678-1689)"""
+    def __init__(self, position, color):
+        self.position = _as_vector(position)
+        self.color = Color(*_color_tuple(color))
+
+    dimension = property(lambda self: self.position.dimension)
+
+
+class GlobalLight:
+    """GlobalLight(direction,color) (src/tracer.hpp:1691-1698)"""
+    def __init__(self, direction, color):
+        self.direction = _as_vector(direction)
+        self.color = Color(*_color_tuple(color))
+
+    dimension = property(lambda self: self.direction.dimension)
+
+
+class _LightList(list):
+    def __init__(self, scene, kind):
+        super().__init__()
+        self._scene, self._kind = scene, kind
+
+    def _check(self, light):
+        if not isinstance(light, self._kind):
+            raise TypeError('object is not an instance of %s' % self._kind.__name__)
+        if light.dimension != self._scene.dimension:
+            raise TypeError('the light must have the same dimension as the scene')
+        self._scene._check_unlocked()
+
+    def append(self, light):
+        self._check(light)
+        super().append(light)
+
+    def extend(self, lights):
+        for l in lights:
+            self.append(l)
+
+    def __setitem__(self, i, light):
+        self._check(light)
+        super().__setitem__(i, light)
+
+
+class _SceneBase(Scene):
+    def __init__(self, dimension):
+        self.locked = 0
+        self.fov = 0.8
+        self._cam = Camera(dimension)
+        self._dev = None
+
+    dimension = property(lambda self: self._cam.dimension)
+
+    def _check_unlocked(self):
+        if self.locked:
+            raise LockedError('the scene is locked for reading')
+
+    def set_camera(self, camera):
+        self._check_unlocked()
+        if not isinstance(camera, Camera) or camera.dimension != self.dimension:
+            raise TypeError('the scene and camera must have the same dimension')
+        self._cam = camera._copy()
+
+    def get_camera(self): return self._cam._copy()
+
+    def set_fov(self, fov):
+        self._check_unlocked()
+        self.fov = float(fov)
+
+    # ---- backend ----
+    def _device_scene(self):
+        raise NotImplementedError
+
+    def _prepare(self):
+        dev = self._device_scene()
+        dev.set_camera(self._cam._origin, self._cam._axes)
+        return dev
+
+    def calculate_color(self, x, y, width, height):
+        """Scene.calculate_color (src/render.cpp:586-614)"""
+        self.locked += 1
+        try:
+            return Color(*[float(v) for v in self._prepare().calculate_color(x, y, width, height)])
+        finally:
+            self.locked -= 1
+
+
+class BoxScene(_SceneBase):
+    """BoxScene(dimension) (src/tracer.hpp:83-123, doc/ntracer.rst:547-591)"""
+    def __init__(self, dimension):
+        _check_dimension(dimension)
+        super().__init__(dimension)
+
+    def _flat(self):
+        return {'dim': np.int64(self.dimension), 'kind': np.int64(0), 'batch_size': np.int64(1),
+                'params': np.array([self.fov, 0, 0, 0, 0], np.float64)}
+
+    def _device_scene(self):
+        if self._dev is None:
+            self._dev = DeviceScene(self._flat())
+            self._dev_fov = self.fov
+        elif self._dev_fov != self.fov:
+            self._dev.set_params(self._flat())
+            self._dev_fov = self.fov
+        return self._dev
+
+
+class CompositeScene(_SceneBase):
+    """CompositeScene(boundary,data) (src/tracer.hpp:1710-1927, doc/ntracer.rst:671-892)"""
+    def __init__(self, boundary, data):
+        if not isinstance(boundary, AABB):
+            raise TypeError('object is not an instance of AABB')
+        if not isinstance(data, KDNode):
+            raise TypeError('object is not an instance of KDNode')
+        if boundary.dimension != data.dimension:
+            raise TypeError('"boundary" and "data" must have the same dimesion')
+        super().__init__(boundary.dimension)
+        self.boundary, self.root = boundary, data
+        self.shadows, self.camera_light, self.max_reflect_depth, self.bg_gradient_axis = False, True, 4, 1
+        self.ambient_color, self.bg1, self.bg2, self.bg3 = Color(0, 0, 0), Color(1, 1, 1), Color(0, 0, 0), Color(0, 1, 1)
+        self.point_lights = _LightList(self, PointLight)
+        self.global_lights = _LightList(self, GlobalLight)
+        self._flat = None
+
+    def set_shadows(self, shadows):
+        self._check_unlocked(); self.shadows = bool(shadows)
+
+    def set_camera_light(self, camera_light):
+        self._check_unlocked(); self.camera_light = bool(camera_light)
+
+    def set_ambient_color(self, color):
+        self._check_unlocked(); self.ambient_color = Color(*_color_tuple(color))
+
+    def set_max_reflect_depth(self, depth):
+        self._check_unlocked()
+        if depth < 0:
+            raise ValueError('depth cannot be negative')
+        self.max_reflect_depth = int(depth)
+
+    def set_background(self, c1, c2=None, c3=None, axis=1):
+        self._check_unlocked()
+        if not 0 <= axis < self.dimension:
+            raise ValueError('"axis" must be between 0 and one less than the dimension of the scene')
+        c2 = c1 if c2 is None else c2
+        c3 = c1 if c3 is None else c3
+        self.bg1, self.bg2, self.bg3, self.bg_gradient_axis = Color(*_color_tuple(c1)), Color(*_color_tuple(c2)), Color(*_color_tuple(c3)), int(axis)
+
+    def add_light(self, light):
+        if isinstance(light, PointLight):
+            self.point_lights.append(light)
+        elif isinstance(light, GlobalLight):
+            self.global_lights.append(light)
+        else:
+            raise TypeError('object is not an instance of PointLight or GlobalLight')
+
+    def _device_scene(self):
+        # geometry is immutable once the scene exists; Material objects are not (the reference reads them through
+        # pointers), so the arena is rebuilt if any referenced material changed since the upload
+        if self._dev is not None and not np.array_equal(self._flat.material_snapshot(), self._mat_snapshot):
+            self._dev.close()
+            self._dev = None
+        if self._dev is None:
+            flat = _Flattener(self.dimension)
+            root = flat.walk(self.root)
+            self._flat = flat
+            self._mat_snapshot = flat.material_snapshot()
+            self._dev = DeviceScene(flat.scene_dict(root, self.boundary, self))
+        else:
+            sc = {'dim': np.int64(self.dimension), 'kind': np.int64(1), 'batch_size': np.int64(BATCH_SIZE), 'root': np.int64(0),
+                  'boundary': np.stack([self.boundary.start._v, self.boundary.end._v])}
+            sc.update(_scene_params(self, self.dimension))
+            self._dev.set_params(sc)
+        return self._dev
+
+
+# ---------------------------------------------------------------------------------------------------------
+def screen_coord_to_ray(cam, x, y, w, h, fov):
+    """src/ntracer_body.hpp:3342-3358 / flat_origin_ray_source (src/tracer.hpp:60-76)"""
+    half_w, half_h = _F(w) / _F(2), _F(h) / _F(2)
+    fovI = _F(math.tan(_F(fov) / 2)) / half_w
+    v = cam._axes[2] + cam._axes[0] * (fovI * (_F(x) - half_w)) - cam._axes[1] * (fovI * (_F(y) - half_h))
+    return Vector._wrap(v / np.sqrt(_F(np.dot(v, v))))
+
+
+def build_kdtree(primitives, extra_threads=-1, *, max_depth=None, split_threshold=None, traversal_cost=None,
+                 intersection_cost=None, update_primitives=False):
+    """-> (AABB, KDNode).  Host-side builder (ntracer_b200.kdbuild): a surface-area-heuristic k-d tree over the
+    prototypes' bounding boxes.  It is NOT the reference's builder (src/tracer.hpp:1930-2455): colours and hit
+    ids do not depend on the tree, except with shadows on."""
+    from .kdbuild import build
+    protos = list(primitives)
+    if not protos:
+        raise ValueError('cannot build tree from empty sequence')
+    for p in protos:
+        if not isinstance(p, PrimitivePrototype):
+            raise TypeError('object is not an instance of PrimitivePrototype')
+    d = protos[0].dimension
+    if any(p.dimension != d for p in protos):
+        raise TypeError('the primitive prototypes must all have the same dimension')
+    return build(protos, max_depth, split_threshold, traversal_cost, intersection_cost)
+
+
+def build_composite_scene(primitives, extra_threads=-1, **kw):
+    boundary, root = build_kdtree(primitives, extra_threads, **kw)
+    return CompositeScene(boundary, root)
