@@ -191,13 +191,9 @@ def main():
     dev = torch.device('cuda', local_rank)
     ds = DeviceScene(sc, local_rank)
     fmt = _capi.make_image_format(w, h, _capi.RGB8)
-    tiles_y = (h + 31) // 32
-    my_rows = [ty for ty in range(tiles_y) if ty % world == rank]
-    max_rows = (tiles_y + world - 1) // world
-    strip_bytes = max_rows * 32 * fmt.pitch
-    strip = torch.zeros(strip_bytes, dtype=torch.uint8, device=dev)
-    gathered = torch.zeros(world * strip_bytes, dtype=torch.uint8, device=dev) if world > 1 else None
-    host_frame = torch.zeros(world * strip_bytes if world > 1 else fmt.pitch * h, dtype=torch.uint8).pin_memory()
+    from ntracer_b200 import dist as ntd
+    dr = ntd.DistributedRenderer(ds, fmt)           # world == 1: the strip is the whole frame
+    host_frame = torch.zeros(fmt.pitch * h, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     cam_o = np.ascontiguousarray(sc['cam_origin'], np.float32)
     cam_a = np.ascontiguousarray(sc['cam_axes'], np.float32)
@@ -206,33 +202,27 @@ def main():
     ds.render_float(w, h)
     cnt_gpu = ds.counters()
     rays = cnt_gpu['primary_rays'] + cnt_gpu['shadow_rays'] + cnt_gpu['reflection_rays']
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def step_device():
-        """one frame, inputs resident, output stays on the device; returns device ms (CUDA events on the
-        launching stream, ntr_last_kernel_ms)"""
-        ds.render_device(fmt, strip.data_ptr(), strip.numel(), 0, rank, world, world > 1)
-        ms = ds.last_kernel_ms()
+        """one frame, inputs resident, output stays on the device (rank 0 ends up with the composed frame);
+        returns device ms between CUDA events on the launching stream"""
+        ev0.record(dr.stream)
+        dr.render_strip()
         if world > 1:
-            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-            e0.record()
-            dist.all_gather_into_tensor(gathered, strip)
-            e1.record()
-            e1.synchronize()
-            ms += e0.elapsed_time(e1)
-        return ms
+            dr.gather()
+            dr.frame_on_device()
+        ev1.record(dr.stream)
+        ev1.synchronize()
+        return ev0.elapsed_time(ev1)
 
     def step_e2e():
-        """the same frame through the public host-buffer call: camera upload + render + D2H"""
+        """the same frame through the host-buffer path: camera upload + render (+ gather) + D2H"""
         ds.set_camera(cam_o, cam_a)
         if world == 1:
             ds.render(fmt, host_frame.numpy())
         else:
-            ds.render_device(fmt, strip.data_ptr(), strip.numel(), 0, rank, world, True)
-            ds.last_kernel_ms()
-            dist.all_gather_into_tensor(gathered, strip)
-            if rank == 0:
-                host_frame.copy_(gathered, non_blocking=True)
-            torch.cuda.synchronize()
+            dr.render_to_host()
 
     def barrier():
         if world > 1:

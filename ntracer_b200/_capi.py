@@ -159,7 +159,7 @@ def make_desc(sc):
 
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libntracer_b200.so')
+_LIB_PATH = os.environ.get('NTR_B200_LIB') or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libntracer_b200.so')
 
 
 class BackendError(RuntimeError):

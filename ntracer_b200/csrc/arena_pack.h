@@ -1,10 +1,19 @@
 // arena_pack.h -- host-side packing of an ntr_scene_desc into the single device arena
-// (nodes | leaf refs | simplex records | solid records | materials; every section 256-byte aligned,
-// every record 16-byte aligned -- DESIGN.md section 3).  Header-only so that the test-only host
+// (nodes | leaf items | simplex records | batch blocks | solid records | materials; every section 256-byte
+// aligned, every record 16-byte aligned -- DESIGN.md section 3).
+//
+// Batch block (one per distinct triangle_batch item, B = batch_size lanes, B a multiple of 4):
+//   [ face_normal[c][lane] : D*B ][ d[lane] : B ]            "plane part", SoA across lanes: one float4 = one
+//                                                             component of 4 lanes, so the plane test of a lane group
+//                                                             is D+1 coalesced 16-byte loads
+//   [ lane 0: p1[D], edge_normals[D-1][D], pad to 4 ] ... [ lane B-1 ]   "edge parts", AoS: only read for lanes that
+//                                                             survive the plane test
+//   [ meta[lane] : B ]                                        material | opaque<<31  Header-only so that the test-only host
 // emulation harness (tests/host_emul) packs scenes exactly like the product does.
 #pragma once
 #include <string.h>
 
+#include <unordered_map>
 #include <vector>
 
 #include "device_types.h"
@@ -12,8 +21,8 @@
 namespace ntr {
 
 struct ArenaLayout {
-    size_t off_nodes = 0, off_refs = 0, off_simplex = 0, off_solids = 0, off_mats = 0, total = 0;
-    int sstride = 0, solstride = 0;
+    size_t off_nodes = 0, off_refs = 0, off_simplex = 0, off_batches = 0, off_solids = 0, off_mats = 0, total = 0;
+    int sstride = 0, solstride = 0, lane_part = 0, batch_block = 0;
     bool any_transparent = false, any_reflective = false;
 };
 
@@ -25,15 +34,38 @@ inline void pack_arena(const ntr_scene_desc *d, std::vector<unsigned char> &h, A
     L.sstride = (sin + 3) / 4 * 4;          // (D+1)*D+1 is odd: there is always a pad slot for the meta word
     const int solin = 1 + 2 * D * D + D;
     L.solstride = (solin + 1 + 3) / 4 * 4;
+    const int B = d->batch_size;
+    L.lane_part = (D * D + 3) / 4 * 4;
+    L.batch_block = (D + 1) * B + L.lane_part * B + B;          // floats; a multiple of 4 because B is
+    // distinct batch items (identity = leaf ref value) get one block each
+    std::vector<uint32_t> batch_first;                          // first simplex index of every distinct batch
+    std::unordered_map<uint32_t, uint32_t> batch_slot;
+    for (uint32_t i = 0; i < d->n_leaf_refs; ++i) {
+        const uint32_t r = d->leaf_refs[i];
+        if ((r >> 30) == NTR_REF_BATCH && batch_slot.emplace(r, (uint32_t)batch_first.size()).second)
+            batch_first.push_back(r & NTR_IDX_MASK);
+    }
     L.off_nodes = 0;
     L.off_refs = arena_align(L.off_nodes + (size_t)d->n_nodes * 16, 256);
-    L.off_simplex = arena_align(L.off_refs + (size_t)d->n_leaf_refs * 4, 256);
-    L.off_solids = arena_align(L.off_simplex + (size_t)d->n_simplex * L.sstride * 4, 256);
+    L.off_simplex = arena_align(L.off_refs + (size_t)d->n_leaf_refs * 8, 256);
+    L.off_batches = arena_align(L.off_simplex + (size_t)d->n_simplex * L.sstride * 4, 256);
+    L.off_solids = arena_align(L.off_batches + batch_first.size() * (size_t)L.batch_block * 4, 256);
     L.off_mats = arena_align(L.off_solids + (size_t)d->n_solids * L.solstride * 4, 256);
     L.total = arena_align(L.off_mats + (size_t)d->n_materials * 12 * 4, 256);
     h.assign(L.total, 0);
     if (d->n_nodes) memcpy(h.data() + L.off_nodes, d->nodes, (size_t)d->n_nodes * 16);
-    if (d->n_leaf_refs) memcpy(h.data() + L.off_refs, d->leaf_refs, (size_t)d->n_leaf_refs * 4);
+    {   // leaf items: {ref, float offset of the record inside its section}
+        uint32_t *it = reinterpret_cast<uint32_t *>(h.data() + L.off_refs);
+        for (uint32_t i = 0; i < d->n_leaf_refs; ++i) {
+            const uint32_t r = d->leaf_refs[i], kind = r >> 30, idx = r & NTR_IDX_MASK;
+            uint32_t off;
+            if (kind == NTR_REF_BATCH) off = batch_slot[r] * (uint32_t)L.batch_block;
+            else if (kind == NTR_REF_SIMPLEX) off = idx * (uint32_t)L.sstride;
+            else off = idx * (uint32_t)L.solstride;
+            it[2 * i] = r;
+            it[2 * i + 1] = off;
+        }
+    }
     auto mat_meta = [&](int32_t m) -> uint32_t {
         const float *mm = d->materials + (size_t)m * 10;
         const bool opaque = mm[6] >= 1.0f;              // primitive::opaque, reference src/tracer.hpp:187-189
@@ -46,6 +78,18 @@ inline void pack_arena(const ntr_scene_desc *d, std::vector<unsigned char> &h, A
         memcpy(sx + (size_t)i * L.sstride, d->simplex + (size_t)i * sin, sizeof(float) * sin);
         const uint32_t meta = mat_meta(d->simplex_mat[i]);
         memcpy(sx + (size_t)i * L.sstride + L.sstride - 1, &meta, 4);
+    }
+    float *bb = reinterpret_cast<float *>(h.data() + L.off_batches);
+    for (size_t k = 0; k < batch_first.size(); ++k) {
+        float *blk = bb + k * (size_t)L.batch_block;
+        float *edge = blk + (D + 1) * B, *meta = edge + (size_t)L.lane_part * B;
+        for (int l = 0; l < B; ++l) {
+            const float *src = d->simplex + (size_t)(batch_first[k] + l) * sin;     // fn[D], d, p1[D], edges
+            for (int c = 0; c <= D; ++c) blk[c * B + l] = src[c];
+            memcpy(edge + (size_t)l * L.lane_part, src + D + 1, sizeof(float) * (size_t)D * D);
+            const uint32_t m = mat_meta(d->simplex_mat[batch_first[k] + l]);
+            memcpy(meta + l, &m, 4);
+        }
     }
     float *so = reinterpret_cast<float *>(h.data() + L.off_solids);
     for (uint32_t i = 0; i < d->n_solids; ++i) {
@@ -66,7 +110,9 @@ inline void pack_arena(const ntr_scene_desc *d, std::vector<unsigned char> &h, A
 // Points a SceneDev at an arena that lives at `base` (device or, in the test harness, host memory).
 inline void bind_arena(SceneDev &dev, const ntr_scene_desc *d, const ArenaLayout &L, const unsigned char *base) {
     dev.nodes = reinterpret_cast<const uint4 *>(base + L.off_nodes);
-    dev.leaf_refs = reinterpret_cast<const uint32_t *>(base + L.off_refs);
+    dev.leaf_items = reinterpret_cast<const uint2 *>(base + L.off_refs);
+    dev.batches = reinterpret_cast<const float *>(base + L.off_batches);
+    dev.lane_part = L.lane_part;
     dev.simplex = reinterpret_cast<const float *>(base + L.off_simplex);
     dev.solids = reinterpret_cast<const float *>(base + L.off_solids);
     dev.materials = reinterpret_cast<const float *>(base + L.off_mats);

@@ -124,7 +124,10 @@ int validate_desc(const ntr_scene_desc *d, int *tree_depth_out) {
             for (uint32_t k = 0; k < n.w2; ++k) {
                 const uint32_t r = d->leaf_refs[n.w1 + k], kind = r >> 30, idx = r & NTR_IDX_MASK;
                 if (kind == NTR_REF_SIMPLEX) { if (idx >= d->n_simplex) return fail(NTR_ERR_VALUE, "leaf %u: simplex index out of range", i); }
-                else if (kind == NTR_REF_BATCH) { if ((uint64_t)idx + d->batch_size > d->n_simplex) return fail(NTR_ERR_VALUE, "leaf %u: batch out of range", i); }
+                else if (kind == NTR_REF_BATCH) {
+                    if ((uint64_t)idx + d->batch_size > d->n_simplex) return fail(NTR_ERR_VALUE, "leaf %u: batch out of range", i);
+                    if (d->batch_size % 4) return fail(NTR_ERR_VALUE, "batch items need a batch_size that is a multiple of 4");
+                }
                 else if (kind == NTR_REF_SOLID) { if (idx >= d->n_solids) return fail(NTR_ERR_VALUE, "leaf %u: solid index out of range", i); }
                 else return fail(NTR_ERR_VALUE, "leaf %u: bad item type", i);
             }
@@ -276,11 +279,14 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     const bool passes = composite && tgt.out_mode != NTR_OUT_IDS && sc->any_reflective && sc->dev.max_depth > 0;
     *used_passes = passes;
 
-    const size_t npix = (size_t)win_w * win_h;
+    {
+        const int my_rows = f.tile_row_first < f.tiles_y ? (f.tiles_y - f.tile_row_first + f.tile_row_step - 1) / f.tile_row_step : 0;
+        f.out_rows = compact ? my_rows * NTR_TILE : win_h;
+    }
+    const size_t npix = (size_t)win_w * f.out_rows;
     f.packed = tgt.packed; f.accum = tgt.accum; f.ids = tgt.ids; f.dists = tgt.dists;
     f.out_mode = tgt.out_mode;
     if (passes && tgt.out_mode == NTR_OUT_PACKED) {
-        if (compact || tile_row_step != 1) return fail(NTR_ERR_VALUE, "internal: sharded render with passes must go through the accumulator");
         int rc = ensure((void **)&sc->d_accum, &sc->accum_cap, npix * 3 * sizeof(float));
         if (rc) return rc;
         f.accum = sc->d_accum;
@@ -328,7 +334,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
         }
         if (tgt.out_mode == NTR_OUT_PACKED) {
             f.out_mode = NTR_OUT_PACKED;
-            const long long groups = (long long)((win_w + 3) / 4) * win_h;
+            const long long groups = (long long)((win_w + 3) / 4) * f.out_rows;
             const int blocks = (int)std::min<long long>((groups + 255) / 256, (long long)sc->sm_count * 8);
             pack_kernel<<<blocks, 256, 0, st>>>(f);
             ++sc->launches;
@@ -394,7 +400,7 @@ struct BusyGuard {
 // 4*bpp bytes it owns are a whole number of 32-bit words.
 __global__ void pack_kernel(const __grid_constant__ FrameDev f) {
     const int groups_x = (f.win_w + 3) / 4;
-    const long long total = (long long)groups_x * f.win_h;
+    const long long total = (long long)groups_x * f.out_rows;
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
         const int y = (int)(g / groups_x), x0 = (int)(g % groups_x) * 4;
         const int n = min(4, f.win_w - x0);
@@ -570,20 +576,9 @@ NTR_API int ntr_render_device(ntr_scene *sc, const ntr_image_format *fmt, void *
         sc->counters.primary_rays = (uint64_t)fmt->width * fmt->height;
         return NTR_OK;
     }
-    if (tile_row_step == 1 && !compact)
-        return run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, st);
-    // sharded + wavefront passes: render this rank's tile rows strip by strip is not needed -- the window
-    // mechanism renders exactly the rows of each owned tile row through the accumulator
-    for (int k = 0, ty = tile_row_first; ty < tiles_y; ty += tile_row_step, ++k) {
-        const int y0 = ty * NTR_TILE, h = std::min(NTR_TILE, fmt->height - y0);
-        ntr_image_format sub = *fmt;
-        sub.height = h;
-        RenderTarget t2 = tgt;
-        t2.packed = static_cast<unsigned char *>(dev_dst) + (compact ? (size_t)k * NTR_TILE * fmt->pitch : (size_t)y0 * fmt->pitch);
-        rc = run_frame_sync(sc, fmt->width, fmt->height, 0, y0, fmt->width, h, &sub, t2, 0, 1, 0, st);
-        if (rc) return rc;
-    }
-    return NTR_OK;
+    // wavefront passes: synchronous on `st` (the queue-overflow check needs the counters back)
+    return run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, tile_row_first,
+                          tile_row_step, compact, st);
 }
 
 NTR_API int ntr_render(ntr_scene *sc, const ntr_image_format *fmt, void *dst, size_t dst_len) {

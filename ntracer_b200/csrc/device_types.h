@@ -30,8 +30,9 @@ enum : int {
 
 struct SceneDev {
     const uint4 *nodes;             // ntr_node, 16 B
-    const uint32_t *leaf_refs;
+    const uint2 *leaf_items;        // {leaf ref (identity: (type<<30)|index), float offset of the item's record}
     const float *simplex;           // stride sstride floats: fn[D], d, p1[D], edges[D-1][D], pad.., meta
+    const float *batches;           // batch blocks (see arena_pack.h): SoA plane part + per-lane edge parts + metas
     const float *solids;            // stride solstride floats: type, inv_orientation[D*D], position[D], orientation[D*D], pad.., meta
     const float *materials;         // 12 floats per material (10 used)
     const float *point_lights;      // stride D+3
@@ -39,6 +40,7 @@ struct SceneDev {
     uint32_t root;
     uint32_t n_simplex;
     int dim, batch, sstride, solstride;
+    int lane_part;                  // floats per lane in a batch block's stage-2 part: D*D rounded up to 4
     int kind;
     int n_point, n_global;
     int shadows, camera_light, max_depth, bg_axis;
@@ -71,6 +73,7 @@ struct FrameDev {
     int win_w, win_h;               // window size in pixels
     int tiles_x, tiles_y;           // window size in 32x32 tiles
     int tile_row_first, tile_row_step, compact;   // multi-GPU interleave (tile rows ty % step == first)
+    int out_rows;                   // rows of the output / accumulator: win_h, or owned tile rows * 32 when compact
     int out_mode;
     unsigned char *packed;          // NTR_OUT_PACKED destination (device)
     float *accum;                   // NTR_OUT_ACCUM: 3 floats per window pixel

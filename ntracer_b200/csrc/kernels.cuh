@@ -153,8 +153,9 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                     box_color<DT>(s, o, dir, acc, &prim);
                 } else {
                     const Skip none = {NTR_NONE_REF, 0};
-                    // output row index of this pixel in window coordinates (frame position or compacted strips)
-                    const uint32_t pix = (uint32_t)py * (uint32_t)f.win_w + (uint32_t)px;
+                    // accumulator index of this pixel: frame position, or the compacted strip of this rank
+                    const int orow = f.compact ? (tyi * NTR_TILE + (py - ty * NTR_TILE)) : py;
+                    const uint32_t pix = (uint32_t)orow * (uint32_t)f.win_w + (uint32_t)px;
                     if (f.out_mode == NTR_OUT_ACCUM) {
                         QueueEmit<DT> emit{q, ctl, pix};
                         ray_color<DT, FLAGS>(s, o, dir, 0, none, one, acc, emit, cnt, &prim);
@@ -172,7 +173,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                 const int ncols = min(NTR_BLK_W, f.win_w - bx), nrows = min(NTR_BLK_H, f.win_h - by);
                 store_block_packed(f, stage, bx, by, ncols, nrows, out_row0, w, inside);
             } else if (inside) {
-                const size_t pix = (size_t)py * f.win_w + px;
+                const size_t pix = (size_t)(out_row0 + (lane >> 3)) * f.win_w + px;
                 if (f.out_mode == NTR_OUT_ACCUM) {
                     f.accum[pix * 3 + 0] = acc[0]; f.accum[pix * 3 + 1] = acc[1]; f.accum[pix * 3 + 2] = acc[2];
                 } else {
