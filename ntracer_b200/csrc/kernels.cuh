@@ -110,8 +110,11 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
     __syncwarp();
 }
 
+#ifndef NTR_MIN_CTAS
+#define NTR_MIN_CTAS 1
+#endif
 template <int DT, int FLAGS>
-__global__ void __launch_bounds__(kCtaThreads)
+__global__ void __launch_bounds__(kCtaThreads, NTR_MIN_CTAS)
 render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ CameraDev cam,
                    const __grid_constant__ FrameDev f, const __grid_constant__ QueueDev q,
                    const __grid_constant__ ControlDev ctl) {

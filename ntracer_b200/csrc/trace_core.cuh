@@ -1079,7 +1079,14 @@ NTR_HD void pack_pixel(const FormatDev &f, const float *rgb, uint32_t out[4]) {
     unsigned long long hi = 0, lo = 0;
     int off = 0;
     for (int ci = 0; ci < f.n_channels; ++ci) {
+        // ch.f_r*r + ch.f_g*g + ch.f_b*b + f_c (render.cpp:427), left to right and without FMA contraction: the
+        // packed bytes are integer work and must not depend on how the compiler fuses this expression
+#if defined(__CUDA_ARCH__)
+        float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.f_r[ci], rgb[0]), __fmul_rn(f.f_g[ci], rgb[1])),
+                                      __fmul_rn(f.f_b[ci], rgb[2])), f.f_c[ci]);
+#else
         float v = f.f_r[ci] * rgb[0] + f.f_g[ci] * rgb[1] + f.f_b[ci] * rgb[2] + f.f_c[ci];
+#endif
         v = fminf(fmaxf(v, 0.0f), 1.0f);
         const int bits = f.bits[ci];
         unsigned long long ival;
