@@ -482,7 +482,9 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->dev.kind = desc->kind;
     sc->dev.root = NTR_NULL_NODE;
     sc->dev.batch = 1;
-    sc->kset = kernel_family(desc->dim);
+    // the fixed-dimension kernels assume 4-lane batches (compile-time block offsets); other batch sizes of the
+    // reference's SIMD flavours (8, 16) go through the run-time-dimension kernels
+    sc->kset = kernel_family((desc->kind == NTR_SCENE_COMPOSITE && desc->batch_size != 4 && desc->batch_size != 1) ? 0 : desc->dim);
     for (int i = 0; i < desc->dim; ++i) { sc->cam.right[i] = i == 0; sc->cam.up[i] = i == 1; sc->cam.fwd[i] = i == 2; }
     auto bail = [&](int code) { ntr_scene_destroy(sc); return code; };
     fill_params(sc->dev, desc);

@@ -29,7 +29,9 @@ template <int DT> struct QueueEmit {
     const QueueDev &q;
     const ControlDev &ctl;
     uint32_t pixel;
+    bool enabled;       // false: the frame needs no secondary passes (nothing reflective) -- drop the bounce
     __device__ __forceinline__ void operator()(const Bounce<DT> &b) const {
+        if (!enabled) return;
         const unsigned mask = __activemask();
         const int leader = __ffs(mask) - 1;
         const int lane = threadIdx.x & 31;
@@ -111,7 +113,7 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 }
 
 #ifndef NTR_MIN_CTAS
-#define NTR_MIN_CTAS 1
+#define NTR_MIN_CTAS 6
 #endif
 template <int DT, int FLAGS>
 __global__ void __launch_bounds__(kCtaThreads, NTR_MIN_CTAS)
@@ -123,91 +125,69 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
     unsigned char *stage = stage_all + (threadIdx.x >> 5) * 512;
     const int lane = threadIdx.x & 31;
     Counters cnt;
-    const float one[3] = {1.0f, 1.0f, 1.0f};
 
-    if (q.in == nullptr) {
-        // ---------------- primary pass: atomic block queue over the window's tiles ----------------
-        const int my_rows = f.tile_row_first < f.tiles_y
-                                ? (f.tiles_y - f.tile_row_first + f.tile_row_step - 1) / f.tile_row_step : 0;
-        const uint32_t total = (uint32_t)my_rows * (uint32_t)f.tiles_x * NTR_BLOCKS_PER_TILE;
-        for (;;) {
-            uint32_t b = 0;
-            if (lane == 0) b = atomicAdd(ctl.tile_cursor, 1u);
-            b = __shfl_sync(0xFFFFFFFFu, b, 0);
-            if (b >= total) break;
-            // renderer::state poll (reference render.cpp:412).  The flag lives in mapped host memory, so only
-            // every 64th block looks at it; whoever sees it pushes the cursor past the end for everybody.
-            if ((b & 63u) == 0 && *ctl.abort_flag) { if (lane == 0) atomicAdd(ctl.tile_cursor, 0x40000000u); break; }
+    // One loop serves both kinds of pass so that the per-ray code (ray_color and everything it inlines) exists
+    // exactly once in the kernel: only the work fetch and the epilogue differ.
+    const bool primary = q.in == nullptr;
+    const int my_rows = f.tile_row_first < f.tiles_y
+                            ? (f.tiles_y - f.tile_row_first + f.tile_row_step - 1) / f.tile_row_step : 0;
+    uint32_t total = (uint32_t)my_rows * (uint32_t)f.tiles_x * NTR_BLOCKS_PER_TILE;
+    const int D4 = (int)(q.rec4 - 2) / 2;
+    if (!primary) {
+        total = *q.in_count;
+        if (total > q.capacity) total = q.capacity;
+    }
+    for (;;) {
+        // ---------------- fetch: an 8x4 pixel block of a tile (primary) or 32 queued bounces ----------------
+        uint32_t b = 0;
+        if (lane == 0) b = primary ? atomicAdd(ctl.tile_cursor, 1u) : atomicAdd(q.in_cursor, 32u);
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        if (b >= total) break;
+        // renderer::state poll (reference render.cpp:412).  The flag lives in mapped host memory, so only every
+        // 64th fetch looks at it; whoever sees it pushes the cursor past the end for everybody.
+        if ((b & (primary ? 63u : 2047u)) == 0 && *ctl.abort_flag) {
+            if (lane == 0) atomicAdd(primary ? ctl.tile_cursor : q.in_cursor, 0x40000000u);
+            break;
+        }
+        float o[CAP], dir[CAP];
+        float w[3] = {1.0f, 1.0f, 1.0f};
+        float acc[3] = {0.f, 0.f, 0.f};
+        Skip skip = {NTR_NONE_REF, 0};
+        int depth = 0;
+        uint32_t pix = 0;
+        bool active = false, inside = false;
+        int bx = 0, by = 0, px = 0, out_row0 = 0;
+        HitRec prim;
+        prim.dist = 0; prim.ref = NTR_NONE_REF; prim.lane = -1;
+        if (primary) {
             const uint32_t tile = b / NTR_BLOCKS_PER_TILE, sub = b % NTR_BLOCKS_PER_TILE;
             const int tyi = (int)(tile / (uint32_t)f.tiles_x), tx = (int)(tile % (uint32_t)f.tiles_x);
             const int ty = f.tile_row_first + tyi * f.tile_row_step;
-            const int bx = tx * NTR_TILE + (int)(sub % (NTR_TILE / NTR_BLK_W)) * NTR_BLK_W;     // window coords
-            const int by = ty * NTR_TILE + (int)(sub / (NTR_TILE / NTR_BLK_W)) * NTR_BLK_H;
+            bx = tx * NTR_TILE + (int)(sub % (NTR_TILE / NTR_BLK_W)) * NTR_BLK_W;       // window coordinates
+            by = ty * NTR_TILE + (int)(sub / (NTR_TILE / NTR_BLK_W)) * NTR_BLK_H;
             if (bx >= f.win_w || by >= f.win_h) continue;
-            const int px = bx + (lane & 7), py = by + (lane >> 3);
-            const bool inside = px < f.win_w && py < f.win_h;
-            float acc[3] = {0.f, 0.f, 0.f};
-            HitRec prim;
-            prim.dist = 0; prim.ref = NTR_NONE_REF; prim.lane = -1;
+            px = bx + (lane & 7);
+            const int py = by + (lane >> 3);
+            inside = px < f.win_w && py < f.win_h;
+            // output row of the block: frame position, or the compacted strip of this rank
+            out_row0 = f.compact ? (tyi * NTR_TILE + (by - ty * NTR_TILE)) : by;
+            pix = (uint32_t)(out_row0 + (lane >> 3)) * (uint32_t)f.win_w + (uint32_t)px;
             if (inside) {
-                float o[CAP], dir[CAP];
                 primary_ray<DT>(s, cam, f, f.x0 + px, f.y0 + py, o, dir);
-                if (s.kind == NTR_SCENE_BOX) {
-                    box_color<DT>(s, o, dir, acc, &prim);
-                } else {
-                    const Skip none = {NTR_NONE_REF, 0};
-                    // accumulator index of this pixel: frame position, or the compacted strip of this rank
-                    const int orow = f.compact ? (tyi * NTR_TILE + (py - ty * NTR_TILE)) : py;
-                    const uint32_t pix = (uint32_t)orow * (uint32_t)f.win_w + (uint32_t)px;
-                    if (f.out_mode == NTR_OUT_ACCUM) {
-                        QueueEmit<DT> emit{q, ctl, pix};
-                        ray_color<DT, FLAGS>(s, o, dir, 0, none, one, acc, emit, cnt, &prim);
-                    } else {
-                        NullEmit emit;
-                        ray_color<DT, FLAGS>(s, o, dir, 0, none, one, acc, emit, cnt, &prim);
-                    }
-                }
+                if (s.kind == NTR_SCENE_BOX) box_color<DT>(s, o, dir, acc, &prim);
+                else active = true;
             }
-            __syncwarp();
-            const int out_row0 = f.compact ? (tyi * NTR_TILE + (by - ty * NTR_TILE)) : by;
-            if (f.out_mode == NTR_OUT_PACKED) {
-                uint32_t w[4] = {0, 0, 0, 0};
-                if (inside) pack_pixel(f.fmt, acc, w);
-                const int ncols = min(NTR_BLK_W, f.win_w - bx), nrows = min(NTR_BLK_H, f.win_h - by);
-                store_block_packed(f, stage, bx, by, ncols, nrows, out_row0, w, inside);
-            } else if (inside) {
-                const size_t pix = (size_t)(out_row0 + (lane >> 3)) * f.win_w + px;
-                if (f.out_mode == NTR_OUT_ACCUM) {
-                    f.accum[pix * 3 + 0] = acc[0]; f.accum[pix * 3 + 1] = acc[1]; f.accum[pix * 3 + 2] = acc[2];
-                } else {
-                    f.ids[pix] = prim.ref == NTR_NONE_REF ? -1 : (s.kind == NTR_SCENE_BOX ? 0 : flat_prim_id(s, prim.ref, prim.lane));
-                    if (f.dists) f.dists[pix] = prim.dist;
-                }
-            }
-        }
-    } else {
-        // ---------------- secondary pass: reflection bounces queued by the previous pass ----------------
-        uint32_t n = *q.in_count;
-        if (n > q.capacity) n = q.capacity;
-        const int D = NTR_D(DT, s);
-        const int D4 = (int)(q.rec4 - 2) / 2;
-        for (;;) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(q.in_cursor, 32u);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (base >= n) break;
-            if ((base & 2047u) == 0 && *ctl.abort_flag) { if (lane == 0) atomicAdd(q.in_cursor, 0x40000000u); break; }
-            const uint32_t idx = base + lane;
-            if (idx < n) {
+        } else {
+            const uint32_t idx = b + lane;
+            if (idx < total) {
                 const float4 *rec = q.in + (size_t)idx * q.rec4;
                 const float4 h = rec[0], wv = rec[1];
-                const uint32_t pix = __float_as_uint(h.x);
-                Skip skip;
+                pix = __float_as_uint(h.x);
                 skip.ref = __float_as_uint(h.y);
                 const int ld = __float_as_int(h.z);
                 skip.lane = (int)(short)(ld & 0xFFFF);
-                const int depth = ld >> 16;
-                float o[CAP], dir[CAP];
+                depth = ld >> 16;
+                w[0] = wv.x; w[1] = wv.y; w[2] = wv.z;
 #pragma unroll
                 for (int k = 0; k < (CAP + 3) / 4; ++k) {
                     if (k < D4) {
@@ -218,14 +198,35 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                         if (4 * k + 3 < CAP) { o[4 * k + 3] = vo.w; dir[4 * k + 3] = vd.w; }
                     }
                 }
-                (void)D;
-                const float w[3] = {wv.x, wv.y, wv.z};
-                float acc[3] = {0.f, 0.f, 0.f};
-                QueueEmit<DT> emit{q, ctl, pix};
-                ray_color<DT, FLAGS>(s, o, dir, depth, skip, w, acc, emit, cnt, nullptr);
+                active = true;
+            }
+        }
+        // ---------------- the per-ray path ----------------
+        if (active) {
+            QueueEmit<DT> emit{q, ctl, pix, !primary || f.out_mode == NTR_OUT_ACCUM};
+            ray_color<DT, FLAGS>(s, o, dir, depth, skip, w, acc, emit, cnt, &prim);
+        }
+        // ---------------- epilogue ----------------
+        if (!primary) {
+            if (active) {
                 atomicAdd(f.accum + (size_t)pix * 3 + 0, acc[0]);
                 atomicAdd(f.accum + (size_t)pix * 3 + 1, acc[1]);
                 atomicAdd(f.accum + (size_t)pix * 3 + 2, acc[2]);
+            }
+            continue;
+        }
+        __syncwarp();
+        if (f.out_mode == NTR_OUT_PACKED) {
+            uint32_t pw[4] = {0, 0, 0, 0};
+            if (inside) pack_pixel(f.fmt, acc, pw);
+            const int ncols = min(NTR_BLK_W, f.win_w - bx), nrows = min(NTR_BLK_H, f.win_h - by);
+            store_block_packed(f, stage, bx, by, ncols, nrows, out_row0, pw, inside);
+        } else if (inside) {
+            if (f.out_mode == NTR_OUT_ACCUM) {
+                f.accum[(size_t)pix * 3 + 0] = acc[0]; f.accum[(size_t)pix * 3 + 1] = acc[1]; f.accum[(size_t)pix * 3 + 2] = acc[2];
+            } else {
+                f.ids[pix] = prim.ref == NTR_NONE_REF ? -1 : (s.kind == NTR_SCENE_BOX ? 0 : flat_prim_id(s, prim.ref, prim.lane));
+                if (f.dists) f.dists[pix] = prim.dist;
             }
         }
     }

@@ -76,6 +76,15 @@ NTR_HD uint4 ldnode(const uint4 *p) {
     return *p;
 #endif
 }
+NTR_HD float rcp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 NTR_HD float u2f(uint32_t u) {
 #if defined(__CUDA_ARCH__)
     return __uint_as_float(u);
@@ -212,7 +221,10 @@ template <int DT, int FLAGS>
 NTR_HD float batch_test(const SceneDev &s, uint32_t off, const float *o, const float *dir, int &index, float cutoff,
                         uint32_t &meta, Counters &cnt) {
     const int D = NTR_D(DT, s);
-    const int B = s.batch;
+    // fixed-dimension kernels are only used with 4-lane batches (the host routes anything else to the run-time
+    // dimension kernels), which makes every address below a compile-time offset from `blk`
+    const int B = DT > 0 ? 4 : s.batch;
+    const int LPART = DT > 0 ? (DT * DT + 3) / 4 * 4 : s.lane_part;
     const float *blk = s.batches + off;
     const float *edges = blk + (D + 1) * B;
     float min_t = cutoff;
@@ -227,31 +239,37 @@ NTR_HD float batch_test(const SceneDev &s, uint32_t off, const float *o, const f
         }
         const float4 dd = ld4(blk + D * B + g);
         const float dv[4] = {dd.x, dd.y, dd.z, dd.w};
-        float t4[4];
+        float num[4];
         unsigned viable = 0;
+        // Pre-filter with an approximate quotient (MUFU.RCP + FMUL instead of an IEEE division per lane).  It only
+        // ever REJECTS lanes the exact test below would reject as well: the approximate quotient is within 2^-21
+        // of the correctly rounded one (normal-range denominators only), its sign is exact, and the cutoff
+        // comparison leaves a 2^-20 margin; everything else falls through to the exact division.
+        const float cut = min_t * 1.000001f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float t = -(od[k] + dv[k]) / den[k];
-            t4[k] = t;
-            // mask = denom != 0 && t >= 0 (:562-565); t[i] && t[i] < min_t && i != index (:586)
-            const bool ok = (den[k] != 0) & (t >= 0) & (t != 0) & (t < min_t) & (g + k != index);
-            viable |= (ok ? 1u : 0u) << k;
+            num[k] = -(od[k] + dv[k]);
+            const float ta = num[k] * rcp_approx(den[k]);
+            const bool reject = (fabsf(den[k]) > 1e-30f) & ((ta < 0) | (ta > cut));
+            viable |= ((reject | (g + k == index)) ? 0u : 1u) << k;
         }
         if (FLAGS & NTR_F_COUNT) cnt.simplex_tests += 4;
         if (!viable) continue;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (!(viable & (1u << k))) continue;
-            const float t = t4[k];
-            if (!(t < min_t)) continue;
-            if (!batch_lane_edges<DT>(s, edges + (size_t)(g + k) * s.lane_part, o, dir, t)) continue;
+            if (den[k] == 0) continue;
+            // mask = denom != 0 && t >= 0 (:562-565); t[i] && t[i] < min_t (:586)
+            const float t = num[k] / den[k];
+            if (!(t >= 0) || t == 0 || !(t < min_t)) continue;
+            if (!batch_lane_edges<DT>(s, edges + (g + k) * LPART, o, dir, t)) continue;
             min_t = t;
             r_index = g + k;
         }
     }
     if (r_index == -1) return 0;
     index = r_index;
-    meta = f2u(ldf(edges + (size_t)B * s.lane_part + r_index));
+    meta = f2u(ldf(edges + B * LPART + r_index));
     return min_t;
 }
 
@@ -443,7 +461,7 @@ template <int DT> struct GenState {
 // most recently tested batch refs, kept as a shift register (0 = disabled).  Measured on config 2: 8 entries
 // remove 35 % of the simplex tests, 16 remove 42 % (the reference's unbounded list removes 39 %).
 #ifndef NTR_MINI_MAILBOX
-#define NTR_MINI_MAILBOX 8
+#define NTR_MINI_MAILBOX 16
 #endif
 struct MiniMailbox {
 #if NTR_MINI_MAILBOX > 0
@@ -840,53 +858,43 @@ NTR_HD bool shade_hit(const SceneDev &s, const float *view, const float *P, cons
     float spec_a = 0;
     cnt.shaded_hits++;
 
-    for (int li = 0; li < s.n_point; ++li) {
-        const float *pl = s.point_lights + (size_t)li * (D + 3);
-        const float lc[3] = {ldf(pl + D), ldf(pl + D + 1), ldf(pl + D + 2)};
+    // point lights first, then global lights (tracer.hpp:1776-1827), as ONE loop so that the shadow traversal
+    // (light_reaches) is instantiated once
+    const int n_lights = s.n_point + s.n_global;
+    for (int li = 0; li < n_lights; ++li) {
+        const bool is_point = li < s.n_point;
+        const float *L = is_point ? s.point_lights + (size_t)li * (D + 3) : s.global_lights + (size_t)(li - s.n_point) * (D + 3);
+        const float lc[3] = {ldf(L + D), ldf(L + D + 1), ldf(L + D + 2)};
         float lv[DimCap<DT>::value];
-        float sq = 0;
+        float dist = FLT_MAX, sine = 0, strength = 1.0f;
+        if (is_point) {
+            float sq = 0;
     NTR_UNROLL
-        for (int i = 0; i < D; ++i) { lv[i] = P[i] - ldf(pl + i); sq += lv[i] * lv[i]; }
-        const float dist = sqrtf(sq);
-        float sine = 0;
+            for (int i = 0; i < D; ++i) { lv[i] = P[i] - ldf(L + i); sq += lv[i] * lv[i]; }
+            dist = sqrtf(sq);
     NTR_UNROLL
-        for (int i = 0; i < D; ++i) { lv[i] /= dist; sine += N[i] * lv[i]; }
-        if (sine > 0) {
-            const float strength = light_strength(dist, D);
-            if (s.shadows) {
-                if (fmaxf(lc[0], fmaxf(lc[1], lc[2])) * strength * sine > NTR_LIGHT_THRESHOLD) {
-                    float filtered[3] = {lc[0], lc[1], lc[2]};
-                    if (light_reaches<DT, FLAGS>(s, P, lv, dist, source, filtered, cnt)) {
+            for (int i = 0; i < D; ++i) { lv[i] /= dist; sine += N[i] * lv[i]; }
+        } else {
     NTR_UNROLL
-                        for (int c = 0; c < 3; ++c) { filtered[c] *= strength; light[c] += filtered[c] * sine; }
-                        if (m.spec_int != 0) append_specular<DT>(s, spec, spec_a, m, filtered, view, N, lv);
-                    }
-                }
-            } else {
-    NTR_UNROLL
-                for (int c = 0; c < 3; ++c) light[c] += lc[c] * strength * sine;
-            }
+            for (int i = 0; i < D; ++i) { lv[i] = -ldf(L + i); sine += N[i] * lv[i]; }
         }
-    }
-    for (int li = 0; li < s.n_global; ++li) {
-        const float *gl = s.global_lights + (size_t)li * (D + 3);
-        const float lc[3] = {ldf(gl + D), ldf(gl + D + 1), ldf(gl + D + 2)};
-        float ld[DimCap<DT>::value];
-        float sine = 0;
+        if (!(sine > 0)) continue;
+        if (is_point) strength = light_strength(dist, D);
+        if (s.shadows) {
+            // LIGHT_THRESHOLD applies to point lights only, and drops the light entirely (tracer.hpp:1784-1803)
+            if (is_point && !(fmaxf(lc[0], fmaxf(lc[1], lc[2])) * strength * sine > NTR_LIGHT_THRESHOLD)) continue;
+            float filtered[3] = {lc[0], lc[1], lc[2]};
+            if (!light_reaches<DT, FLAGS>(s, P, lv, dist, source, filtered, cnt)) continue;
+            if (is_point) { filtered[0] *= strength; filtered[1] *= strength; filtered[2] *= strength; }
     NTR_UNROLL
-        for (int i = 0; i < D; ++i) { ld[i] = -ldf(gl + i); sine += N[i] * ld[i]; }
-        if (sine > 0) {
-            if (s.shadows) {
-                float filtered[3] = {lc[0], lc[1], lc[2]};
-                if (light_reaches<DT, FLAGS>(s, P, ld, FLT_MAX, source, filtered, cnt)) {
+            for (int c = 0; c < 3; ++c) light[c] += filtered[c] * sine;
+            if (m.spec_int != 0) append_specular<DT>(s, spec, spec_a, m, filtered, view, N, lv);
+        } else if (is_point) {
     NTR_UNROLL
-                    for (int c = 0; c < 3; ++c) light[c] += filtered[c] * sine;
-                    if (m.spec_int != 0) append_specular<DT>(s, spec, spec_a, m, filtered, view, N, ld);
-                }
-            } else {
+            for (int c = 0; c < 3; ++c) light[c] += lc[c] * strength * sine;
+        } else {
     NTR_UNROLL
-                for (int c = 0; c < 3; ++c) light[c] += lc[c] * sine;
-            }
+            for (int c = 0; c < 3; ++c) light[c] += lc[c] * sine;
         }
     }
 
@@ -990,28 +998,39 @@ NTR_HD void ray_color(const SceneDev &s, const float *o, const float *dir, int d
     float w[3] = {weight[0], weight[1], weight[2]};
     float P[DimCap<DT>::value], N[DimCap<DT>::value];
     Bounce<DT> b;
+    // layers near -> far: the surviving transparent hits (sorted, unique), then the opaque hit.  One loop, one
+    // shade_hit call site (keeps a single copy of the shading + shadow-traversal code in the kernel).
+    int n_layers = 0;
     if (FLAGS & NTR_F_GENERAL) {
-        if (g.th.n) {
-            g.th.sort_and_unique();
-            for (int i = 0; i < g.th.n; ++i) {
-                const uint32_t ref = g.th.ref[i];
-                const int lane = g.th.lane[i];
-                const float op = load_mat(s, target_meta<DT>(s, ref, lane)).opacity;
-                hit_geometry<DT, FLAGS>(s, ref, lane, g.th.dist[i], o, dir, P, N);
-                const float wl[3] = {w[0] * op, w[1] * op, w[2] * op};
-                if (shade_hit<DT, FLAGS>(s, dir, P, N, ref, lane, depth, wl, acc, b, cnt)) emit(b);
-                w[0] *= 1 - op; w[1] *= 1 - op; w[2] *= 1 - op;
+        if (g.th.n) g.th.sort_and_unique();
+        n_layers = g.th.n;
+    }
+    const int n_total = n_layers + (hit ? 1 : 0);
+    for (int i = 0; i < n_total; ++i) {
+        uint32_t ref;
+        int lane;
+        float wl[3];
+        if (i < n_layers) {
+            ref = g.th.ref[i];
+            lane = g.th.lane[i];
+            const float op = load_mat(s, target_meta<DT>(s, ref, lane)).opacity;
+            hit_geometry<DT, FLAGS>(s, ref, lane, g.th.dist[i], o, dir, P, N);
+            wl[0] = w[0] * op; wl[1] = w[1] * op; wl[2] = w[2] * op;
+            w[0] *= 1 - op; w[1] *= 1 - op; w[2] *= 1 - op;
+        } else {
+            ref = oh.ref;
+            lane = oh.lane;
+            wl[0] = w[0]; wl[1] = w[1]; wl[2] = w[2];
+            if (FLAGS & NTR_F_GENERAL) {
+    NTR_UNROLL
+                for (int k = 0; k < D; ++k) { P[k] = g.hitP[k]; N[k] = g.hitN[k]; }      // as the reference left it (Q12)
+            } else {
+                hit_geometry<DT, FLAGS>(s, ref, lane, oh.dist, o, dir, P, N);
             }
         }
+        if (shade_hit<DT, FLAGS>(s, dir, P, N, ref, lane, depth, wl, acc, b, cnt)) emit(b);
     }
-    if (hit) {
-        if (FLAGS & NTR_F_GENERAL) {
-            if (shade_hit<DT, FLAGS>(s, dir, g.hitP, g.hitN, oh.ref, oh.lane, depth, w, acc, b, cnt)) emit(b);
-        } else {
-            hit_geometry<DT, FLAGS>(s, oh.ref, oh.lane, oh.dist, o, dir, P, N);
-            if (shade_hit<DT, FLAGS>(s, dir, P, N, oh.ref, oh.lane, depth, w, acc, b, cnt)) emit(b);
-        }
-    } else {
+    if (!hit) {
         const float I = vsel<DT>(dir, s.bg_axis);       // tracer.hpp:1866-1867
     NTR_UNROLL
         for (int c = 0; c < 3; ++c) {
