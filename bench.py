@@ -31,14 +31,19 @@ CONFIGS = {
     # name: (fixture, width, height, description)
     'c1': ('box4', 640, 480, "config 1: 4-D tesseract BoxScene 640x480"),
     'c2': ('cell120', 1920, 1080, "config 2: 4-D 120-cell {5,3,3} CompositeScene 1920x1080, PointLight+GlobalLight, shadows on"),
-    'c4': ('ggs120', 3840, 2160, "config 4: great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4"),
+    'c4': ('ggs120:refl_transp', 3840, 2160, "config 4: great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4, 12 of 120 cells opacity 0.5"),
+    'c4o': ('ggs120', 3840, 2160, "config 4 (opaque variant): great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4"),
 }
 METRIC = 'Mrays/s (primary+shadow+reflection)'
 
 
 def load_fixture(name):
     from tests import fixtures as fx
-    return fx.load(name)
+    name, _, var = name.partition(':')
+    sc, g = fx.load(name)
+    if var:
+        sc = fx.variant(sc, g, var)
+    return sc, g
 
 
 def flops_per_frame(dim, cnt, n_lights):
@@ -113,19 +118,33 @@ def reference_arm(args, sc, g, w, h, rays_per_frame):
         nt, scene, prims = rb.import_scene(sc)
         rb.make_immortal(prims.values())     # see ref_bridge.make_immortal: the reference races on primitive refcounts
         ntr = rb.load_reference()
-        fmt = ntr.ImageFormat(w, h, [ntr.Channel(8, 1, 0, 0), ntr.Channel(8, 0, 1, 0), ntr.Channel(8, 0, 0, 1)])
-        buf = bytearray(w * h * 3)
+        def rfmt(ww, hh):
+            return ntr.ImageFormat(ww, hh, [ntr.Channel(8, 1, 0, 0), ntr.Channel(8, 0, 1, 0), ntr.Channel(8, 0, 0, 1)])
         r = ntr.BlockingRenderer()          # threads=-1: hardware_concurrency() workers (render.cpp:829-838)
-        r.render(buf, fmt, scene)           # warm-up (late-starting workers)
+        # probe at 1/8 resolution (also the warm-up: late-starting workers), then pick the largest
+        # frame of the same view (full, 1/2, 1/4 ... linear size) whose estimated cost fits ~6 s per frame
+        pw, ph = max(w // 8, 32), max(h // 8, 32)
+        pbuf = bytearray(pw * ph * 3)
+        r.render(pbuf, rfmt(pw, ph), scene)
+        t = time.perf_counter()
+        r.render(pbuf, rfmt(pw, ph), scene)
+        probe = (time.perf_counter() - t) / (pw * ph)
+        div = 1
+        while probe * (w // div) * (h // div) > 6.0 and div < 8:
+            div *= 2
+        sw, sh = w // div, h // div
+        fmt = rfmt(sw, sh)
+        buf = bytearray(sw * sh * 3)
         budget = time.perf_counter() + 25.0
         for _ in range(max(1, min(args.steps, 5))):
             t = time.perf_counter()
             r.render(buf, fmt, scene)
-            times.append(time.perf_counter() - t)
+            times.append((time.perf_counter() - t) * (w * h) / (sw * sh))    # scaled to the full frame's pixel count
             if time.perf_counter() > budget:
                 break
         kind = 'reference'
-        sample = '%d full %dx%d frames, BlockingRenderer all cores, SSE4.2 build (AVX paths of the reference do not compile)' % (len(times), w, h)
+        sample = ('%d frame(s) of the same view at %dx%d (1/%d linear size; times scaled by pixel count to %dx%d), BlockingRenderer '
+                  'all cores, SSE4.2 build (the AVX paths of the reference do not compile)' % (len(times), sw, sh, div, w, h))
     else:
         from tests import oracle_lib as ol
         from ntracer_b200 import _capi

@@ -47,11 +47,11 @@ typedef struct {
     const float *cam_o, *right, *up, *fwd;
     float half_w, half_h, fovI;
     ntr_counters cnt;
-    int undefined;      /* set when a quick_list outgrew its preallocation during the current pixel */
+    int undefined;      /* bit 0: a transparent-hit list, bit 1: the mailbox outgrew its preallocation during this pixel */
 } octx;
 
 static void hits_add(octx *c, ohits *l, const ohit *h) {
-    if (l->n >= QUICK_LIST_PREALLOC) c->undefined = 1;
+    if (l->n >= QUICK_LIST_PREALLOC) c->undefined |= 1;      /* transparent-hit list outgrew its 10 slots */
     if (l->n == l->cap) {
         l->cap = l->cap ? l->cap * 2 : 16;
         l->v = (ohit *)realloc(l->v, l->cap * sizeof(ohit));
@@ -63,7 +63,7 @@ static void hits_remove_at(ohits *l, size_t i) {             /* quick_list::remo
     if (i != l->n) l->v[i] = l->v[l->n];
 }
 static void mail_add(octx *c, omail *l, uint32_t ref) {
-    if (l->n >= ALL_HITS_LIST_PREALLOC) c->undefined = 1;
+    if (l->n >= ALL_HITS_LIST_PREALLOC) c->undefined |= 2;   /* mailbox outgrew its 20 slots */
     if (l->n == l->cap) {
         l->cap = l->cap ? l->cap * 2 : 32;
         l->v = (uint32_t *)realloc(l->v, l->cap * sizeof(uint32_t));

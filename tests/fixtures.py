@@ -24,6 +24,8 @@ def variant(sc, g, name):
     out = dict(sc)
     for k in VARIANT_KEYS:
         out[k] = g['v_%s_%s' % (name, k)]
+    if 'v_%s_simplex_mat' % name in g:
+        out['simplex_mat'] = g['v_%s_simplex_mat' % name]
     return out
 
 

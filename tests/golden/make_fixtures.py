@@ -288,8 +288,29 @@ def make_ggs120():
         golden['v_%s_float' % name] = ref_float(scene, w, h)
         for k, a in variant_arrays(s2).items():
             golden['v_%s_%s' % (name, k)] = a
-    golden['variants'] = np.array([n for n, _ in variants])
     sc = rb.export_scene(nt, scene)     # committed state: lights, shadows, reflectivity 0.3, depth 4
+    # config 4 proper: "reflections + transparency".  Every 10th of the 120 cells (cells = clusters of coplanar
+    # simplexes) gets opacity 0.5; with 12 transparent cells no ray collects more than 10 transparent hits, i.e. the
+    # reference's quick_list stays inside its preallocation.  The materials are assigned in the
+    # flat scene and the scene is rebuilt inside the reference through its public constructors.
+    S = sc['simplex']
+    nrm = np.linalg.norm(S[:, :4], axis=1, keepdims=True)
+    key = np.concatenate([S[:, :4] / nrm, S[:, 4:5] / nrm], axis=1)
+    key *= np.sign(key[np.arange(len(key)), np.argmax(np.abs(key[:, :4]), axis=1)])[:, None]
+    _, cell = np.unique(np.round(key, 3), axis=0, return_inverse=True)
+    assert cell.max() == 119
+    s2 = rb.strip_private(sc)
+    s2['simplex_mat'] = np.where(cell % 10 == 0, 1, 0).astype(np.int32)
+    m0 = sc['materials'][0].copy()
+    m1 = m0.copy()
+    m1[6] = 0.5
+    s2['materials'] = np.stack([m0, m1])
+    nt2, scene2, prims2 = rb.import_scene(s2)
+    golden['v_refl_transp_float'] = ref_float(scene2, w, h)
+    for k, a in variant_arrays(s2).items():
+        golden['v_refl_transp_' + k] = a
+    golden['v_refl_transp_simplex_mat'] = s2['simplex_mat']
+    golden['variants'] = np.array([n for n, _ in variants] + ['refl_transp'])
     save('ggs120', sc, **golden)
 
 

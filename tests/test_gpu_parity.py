@@ -86,13 +86,17 @@ def test_polytope_variants(name):
             with DeviceScene(s2) as dv:
                 img = dv.render_float(w, h)
                 cnt = dv.counters()
-            oimg, ocnt = ol.render_float(s2, w, h, with_counters=True)
-            # same algorithm, same inputs: only FMA contraction / libm differences remain
-            bad_o, _ = fx.lsb_stats(img, oimg, exclude=col)
-            bad_g, _ = fx.lsb_stats(img, g['v_%s_float' % v], exclude=col)
-            noisy = name == 'ggs120' and 'refl' in v
-            assert bad_o <= (0.012 if noisy else 0.001), (name, v, bad_o)
-            assert bad_g <= (0.012 if noisy else 0.001), (name, v, bad_g)
+            oimg, mask, ocnt = ol.render_float(s2, w, h, with_mask=True, with_counters=True)
+            # same algorithm, same inputs: only FMA contraction / libm differences remain.  Pixels where the reference
+            # itself is undefined (a quick_list outgrew its preallocation: mask != 0, see test_oracle_golden) are held
+            # to a loose bound only; the product's mailbox is bounded (40) where the oracle's is unbounded.
+            undefined = mask != 0
+            bad_o, _ = fx.lsb_stats(img, oimg, exclude=col | undefined)
+            bad_g, _ = fx.lsb_stats(img, g['v_%s_float' % v], exclude=col | undefined)
+            assert bad_o <= 0.001, (name, v, bad_o)
+            assert bad_g <= 0.001, (name, v, bad_g)
+            assert fx.lsb_stats(img, oimg, exclude=col)[0] <= 0.03, (name, v)
+            assert fx.lsb_stats(img, g['v_%s_float' % v], exclude=col)[0] <= 0.03, (name, v)
             assert cnt['primary_rays'] == w * h
             for k in ('reflection_rays', 'shadow_rays', 'shaded_hits'):
                 assert abs(cnt[k] - ocnt[k]) <= 0.01 * max(ocnt[k], 100), (name, v, k, cnt[k], ocnt[k])

