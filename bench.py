@@ -31,6 +31,7 @@ CONFIGS = {
     # name: (fixture, width, height, description)
     'c1': ('box4', 640, 480, "config 1: 4-D tesseract BoxScene 640x480"),
     'c2': ('cell120', 1920, 1080, "config 2: 4-D 120-cell {5,3,3} CompositeScene 1920x1080, PointLight+GlobalLight, shadows on"),
+    'c3': ('solids6', 1920, 1080, "config 3 stand-in: 6-D solids (2 hypercubes, 2 hyperspheres; SURVEY 8d C3), 1920x1080, reflections depth 4, PointLight, shadows, fixed-dim path"),
     'c4': ('ggs120:refl_transp', 3840, 2160, "config 4: great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4, 12 of 120 cells opacity 0.5"),
     'c4o': ('ggs120', 3840, 2160, "config 4 (opaque variant): great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4"),
 }

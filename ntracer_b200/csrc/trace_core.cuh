@@ -439,17 +439,108 @@ struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,8
     uint32_t v[NTR_MAILBOX_CAP];
     int n;
     NTR_HD void clear() { n = 0; }
+    // The reference's list is defined up to 20 entries (quick_list growth copies bytes, tracer.hpp:670-680: beyond
+    // that has() scans uninitialised slots).  This one is exact up to NTR_MAILBOX_CAP entries and then switches itself
+    // off -- in that regime the reference skips primitives at random, so there is nothing left to be faithful to, and
+    // a linear scan per item of a 1,600-item leaf would dominate the frame.
     NTR_HD bool has(uint32_t r) const {
+        if (n > NTR_MAILBOX_CAP) return false;
         for (int i = 0; i < n; ++i) if (v[i] == r) return true;
         return false;
     }
-    NTR_HD void add(uint32_t r) { if (n < NTR_MAILBOX_CAP) v[n++] = r; }
+    NTR_HD void add(uint32_t r) {
+        if (n < NTR_MAILBOX_CAP) v[n++] = r;
+        else n = NTR_MAILBOX_CAP + 1;
+    }
 };
 
 template <int DT> struct GenState {
     float hitP[DimCap<DT>::value], hitN[DimCap<DT>::value];    // o_hit.normal as the reference leaves it
     HitList th;
     Mailbox mb;
+};
+
+// ---- leaf index ---------------------------------------------------------------------------------------
+// Per-ray constants of the slab test.
+template <int DT> struct RaySlab {
+    float invdir[DimCap<DT>::value];
+    uint32_t zmask;                     // axes with direction == 0 (tested by containment instead of a slab)
+    NTR_HD void init(const SceneDev &s, const float *dir) {
+        const int D = NTR_D(DT, s);
+        zmask = 0;
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) { invdir[i] = 1 / dir[i]; zmask |= (dir[i] == 0 ? 1u : 0u) << i; }   // tracer.hpp:1174
+    }
+};
+
+// Walks the items of a leaf in their original order.  Big leaves carry an in-order bounding-box index
+// (arena_pack.h: build_leaf_index): subtrees whose (padded) box the ray segment (0, cutoff) misses are jumped over.
+// Skipping an item is only ever done when its test would have returned 0 (a miss), which has no side effect for
+// simplex items, so the sequential semantics of the reference's leaf loop are preserved.
+#ifndef NTR_USE_LEAF_INDEX
+#define NTR_USE_LEAF_INDEX 0      // see arena_pack.h: measured not to pay off on the benchmark scenes
+#endif
+template <int DT> struct LeafCursor {
+    const float *idx;
+    uint32_t i, n_nodes, size;
+    NTR_HD void begin(const SceneDev &s, const uint4 node) {
+        size = node.z;
+        i = 0;
+        idx = (NTR_USE_LEAF_INDEX && node.w) ? s.leaf_index + (size_t)(node.w - 1) * 4 : nullptr;
+        n_nodes = 2 * size - 1;
+    }
+    NTR_HD uint32_t next(const SceneDev &s, const float *o, const RaySlab<DT> &rs, float cutoff) {
+#if !NTR_USE_LEAF_INDEX
+        return i < size ? i++ : size;
+#else
+        if (!idx) return i < size ? i++ : size;
+        const int D = NTR_D(DT, s);
+        const int stride = DT > 0 ? (2 * DT + 2 + 3) / 4 * 4 : s.index_stride;
+        while (i < n_nodes) {
+            const float *nd = idx + (size_t)i * stride;
+            float tmin = 0.0f, tmax = cutoff;
+            bool out = false;
+            if (DT > 0) {
+                float r[(2 * (DT > 0 ? DT : 1) + 2 + 3) / 4 * 4];
+    NTR_UNROLL
+                for (int k = 0; k < stride / 4; ++k) {
+                    const float4 v = ld4(nd + 4 * k);
+                    r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+                }
+    NTR_UNROLL
+                for (int a = 0; a < D; ++a) {
+                    const float lo = r[a], hi = r[D + a];
+                    if (rs.zmask & (1u << a)) { out |= (o[a] < lo) | (o[a] > hi); }
+                    else {
+                        const float t1 = (lo - o[a]) * rs.invdir[a], t2 = (hi - o[a]) * rs.invdir[a];
+                        tmin = fmaxf(tmin, fminf(t1, t2));
+                        tmax = fminf(tmax, fmaxf(t1, t2));
+                    }
+                }
+                const uint32_t skip = f2u(r[2 * D]);
+                const int item = (int)f2u(r[2 * D + 1]);
+                if (out || tmin > tmax) { i = skip; continue; }
+                ++i;
+                if (item >= 0) return (uint32_t)item;
+            } else {
+                for (int a = 0; a < D; ++a) {
+                    const float lo = ldf(nd + a), hi = ldf(nd + D + a);
+                    if (rs.zmask & (1u << a)) { out |= (o[a] < lo) | (o[a] > hi); }
+                    else {
+                        const float t1 = (lo - o[a]) * rs.invdir[a], t2 = (hi - o[a]) * rs.invdir[a];
+                        tmin = fmaxf(tmin, fminf(t1, t2));
+                        tmax = fminf(tmax, fmaxf(t1, t2));
+                    }
+                }
+                if (out || tmin > tmax) { i = f2u(ldf(nd + 2 * D)); continue; }
+                const int item = (int)f2u(ldf(nd + 2 * D + 1));
+                ++i;
+                if (item >= 0) return (uint32_t)item;
+            }
+        }
+        return size;
+#endif
+    }
 };
 
 // ---- leaves ----------------------------------------------------------------------------------------
@@ -488,12 +579,16 @@ struct MiniMailbox {
 };
 
 template <int DT, int FLAGS>
-NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, const float *dir, Skip skip, HitRec &oh,
-                        MiniMailbox &mm, Counters &cnt) {
+NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, const float *dir, const RaySlab<DT> &rs,
+                        Skip skip, HitRec &oh, MiniMailbox &mm, Counters &cnt) {
     const uint2 *items = s.leaf_items + node.y;
     const uint32_t size = node.z;
     bool hit = false;
-    for (uint32_t i = 0; i < size; ++i) {
+    LeafCursor<DT> cur;
+    cur.begin(s, node);
+    for (;;) {
+        const uint32_t i = cur.next(s, o, rs, oh.dist);
+        if (i >= size) break;
         const uint2 it = lditem(items + i);
         const uint32_t item = it.x;
         uint32_t meta;
@@ -543,16 +638,24 @@ NTR_HD float prim_test_general(const SceneDev &s, uint2 it, const float *o, cons
 //   tested again (and misses its own cutoff); in phase 1 a closer opaque hit replaces o_hit;
 //   finally transparent hits of this leaf at or beyond the LAST test's result are dropped.
 template <int DT, int FLAGS>
-NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, const float *dir, Skip skip, HitRec &oh,
-                         GenState<DT> &g, Counters &cnt) {
+NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, const float *dir, const RaySlab<DT> &rs,
+                         Skip skip, HitRec &oh, GenState<DT> &g, Counters &cnt) {
     const int D = NTR_D(DT, s);
     const uint2 *items = s.leaf_items + node.y;
     const uint32_t size = node.z;
     const int h_start = g.th.n;
     float dist = 0;
-    bool phase1 = false;
+    bool phase1 = false, retest = false;
     float P[DimCap<DT>::value], N[DimCap<DT>::value];
-    for (uint32_t i = 0; i < size; ++i) {
+    LeafCursor<DT> cur;
+    cur.begin(s, node);
+    uint32_t i = 0, last_tested = 0;
+    for (;;) {
+        if (!retest) {
+            i = cur.next(s, o, rs, oh.dist);
+            if (i >= size) break;
+        }
+        retest = false;
         const uint2 it = lditem(items + i);
         const uint32_t item = it.x;
         const bool is_batch = (item >> 30) == NTR_REF_BATCH;
@@ -560,6 +663,7 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
         int lane;
         uint32_t wmask, meta;
         dist = prim_test_general<DT, FLAGS>(s, it, o, dir, oh.dist, skip, lane, P, N, wmask, meta, cnt);
+        last_tested = i;
         if (!phase1) {
     NTR_UNROLL
             for (int k = 0; k < D; ++k) if (wmask & (1u << k)) g.hitP[k] = P[k];
@@ -569,7 +673,7 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
                 if (meta & NTR_META_OPAQUE) {
                     oh.dist = dist; oh.ref = item; oh.lane = lane;
                     phase1 = true;
-                    --i;                // `goto hit` re-tests this item (tracer.hpp:1008,1041)
+                    retest = true;      // `goto hit` re-tests this item (tracer.hpp:1008,1041)
                     continue;           // ... and skips checked.add
                 }
                 g.th.add(dist, item, lane);
@@ -586,6 +690,9 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
         g.mb.add(item);
     }
     if (!phase1) return false;
+    // `dist` must be the result of the last test the reference performs.  When the index culled the tail of the
+    // leaf, those items would have been tested and missed (0).
+    if (cur.idx && last_tested + 1 < size) dist = 0;
     g.th.trim(dist, h_start);
     return true;
 }
@@ -606,10 +713,9 @@ struct TravStack {
 template <int DT, int FLAGS>
 NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, Skip skip, float t_near, float t_far,
                           HitRec &oh, GenState<DT> *g, Counters &cnt) {
-    const int D = NTR_D(DT, s);
-    float invdir[DimCap<DT>::value];
-    NTR_UNROLL
-    for (int i = 0; i < D; ++i) invdir[i] = 1 / dir[i];            // tracer.hpp:1174
+    RaySlab<DT> rs;
+    rs.init(s, dir);
+    const float *invdir = rs.invdir;
     TravStack st;
     int sp = 0;
     uint32_t node = s.root;
@@ -621,8 +727,8 @@ NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, S
         while (node != NTR_NULL_NODE) {
             const uint4 n = ldnode(s.nodes + node);
             if (n.x & NTR_LEAF_FLAG) {
-                if (FLAGS & NTR_F_GENERAL) result = leaf_general<DT, FLAGS>(s, n, o, dir, skip, oh, *g, cnt);
-                else result = leaf_opaque<DT, FLAGS>(s, n, o, dir, skip, oh, mm, cnt);
+                if (FLAGS & NTR_F_GENERAL) result = leaf_general<DT, FLAGS>(s, n, o, dir, rs, skip, oh, *g, cnt);
+                else result = leaf_opaque<DT, FLAGS>(s, n, o, dir, rs, skip, oh, mm, cnt);
                 break;
             }
             if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
@@ -681,11 +787,15 @@ NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, S
 // kd_leaf::occludes (tracer.hpp:1088-1124): any opaque hit nearer than the light blocks; transparent
 // blockers are collected (no mailbox here).
 template <int DT, int FLAGS>
-NTR_HD bool leaf_occludes(const SceneDev &s, const uint4 node, const float *o, const float *dir, float ldistance,
-                          Skip skip, HitList *hits, Counters &cnt) {
+NTR_HD bool leaf_occludes(const SceneDev &s, const uint4 node, const float *o, const float *dir, const RaySlab<DT> &rs,
+                          float ldistance, Skip skip, HitList *hits, Counters &cnt) {
     const uint2 *items = s.leaf_items + node.y;
     const uint32_t size = node.z;
-    for (uint32_t i = 0; i < size; ++i) {
+    LeafCursor<DT> cur;
+    cur.begin(s, node);
+    for (;;) {
+        const uint32_t i = cur.next(s, o, rs, ldistance);
+        if (i >= size) break;
         const uint2 it = lditem(items + i);
         const uint32_t item = it.x, off = it.y;
         const uint32_t kind = item >> 30;
@@ -722,10 +832,9 @@ NTR_HD bool leaf_occludes(const SceneDev &s, const uint4 node, const float *o, c
 template <int DT, int FLAGS>
 NTR_HD bool trace_occludes(const SceneDev &s, const float *o, const float *dir, float ldistance, Skip skip,
                            float t_near, float t_far, HitList *hits, Counters &cnt) {
-    const int D = NTR_D(DT, s);
-    float invdir[DimCap<DT>::value];
-    NTR_UNROLL
-    for (int i = 0; i < D; ++i) invdir[i] = 1 / dir[i];
+    RaySlab<DT> rs;
+    rs.init(s, dir);
+    const float *invdir = rs.invdir;
     uint32_t st_node[NTR_STACK_CAP];
     float st_t[NTR_STACK_CAP], st_tfar[NTR_STACK_CAP];
     int sp = 0;
@@ -734,7 +843,7 @@ NTR_HD bool trace_occludes(const SceneDev &s, const float *o, const float *dir, 
         while (node != NTR_NULL_NODE) {
             const uint4 n = ldnode(s.nodes + node);
             if (n.x & NTR_LEAF_FLAG) {
-                if (leaf_occludes<DT, FLAGS>(s, n, o, dir, ldistance, skip, hits, cnt)) return true;
+                if (leaf_occludes<DT, FLAGS>(s, n, o, dir, rs, ldistance, skip, hits, cnt)) return true;
                 break;
             }
             if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
