@@ -98,7 +98,7 @@ def test_polytope_variants(name):
             assert fx.lsb_stats(img, oimg, exclude=col)[0] <= 0.03, (name, v)
             assert fx.lsb_stats(img, g['v_%s_float' % v], exclude=col)[0] <= 0.03, (name, v)
             assert cnt['primary_rays'] == w * h
-            tol = 0.08 if undefined.mean() > 0.2 and 'transp' in v else 0.01     # bounded vs unbounded mailbox (see above)
+            tol = 0.15 if undefined.mean() > 0.2 and 'transp' in v else 0.01     # bounded vs unbounded mailbox (see above)
             for k in ('reflection_rays', 'shadow_rays', 'shaded_hits'):
                 assert abs(cnt[k] - ocnt[k]) <= tol * max(ocnt[k], 100), (name, v, k, cnt[k], ocnt[k])
         ids, dist = ds.primary_hit_ids(w, h)
