@@ -198,6 +198,21 @@ NTR_API int ntr_last_kernel_ms(ntr_scene *scene, float *ms_out);
 /* Number of kernel launches issued by this library on behalf of `scene` since creation. */
 NTR_API uint64_t ntr_launch_count(ntr_scene *scene);
 
+/* ---- scene construction next to the path (host-side, no GPU needed) ---------- */
+/* Triangle.from_points / TrianglePrototype for n simplexes at once (src/tracer.hpp:442-462: generalized cross
+ * products, src/geometry.hpp:858-893).  points: n x D x D (D vertices each); records: n x ((D+1)*D+1) in the
+ * ntr_scene_desc.simplex layout (face_normal[D], d, p1[D], edge_normals[D-1][D]). */
+NTR_API int ntr_simplex_from_points(int dim, uint32_t n, const float *points, float *records);
+/* k-d tree over n axis-aligned item bounds (lo/hi: n x D), replacing build_kdtree (src/tracer.hpp:1930-2455; kwargs
+ * max_depth, split_threshold, traversal_cost, intersection_cost of src/ntracer_body.hpp:3252-3298; <= 0 / < 0 select
+ * the defaults 25, 2, 1, 4).  Own algorithm (binned SAH, all axes, straddlers on both sides, empty children null).
+ * Outputs are malloc'ed, release them with ntr_free: nodes (leaf w1/w2 index into refs), refs = ITEM INDICES per
+ * leaf (0..n-1; the caller maps them to leaf refs), root (NTR_NULL_NODE if n == 0), boundary = 2 x D. */
+NTR_API int ntr_build_kdtree(int dim, uint32_t n, const float *lo, const float *hi, int max_depth, int split_threshold,
+                             float traversal_cost, float intersection_cost, ntr_node **nodes_out, uint32_t *n_nodes_out,
+                             uint32_t **refs_out, uint32_t *n_refs_out, uint32_t *root_out, float *boundary_out);
+NTR_API void ntr_free(void *p);
+
 /* FP32 FMA peak micro-benchmark (TFLOP/s) on the scene's device: the roofline denominator the
  * north star asks for (MEASURED_PEAKS.json has HBM and BF16 only). */
 NTR_API int ntr_measure_fp32_peak(int device, float *tflops_out);

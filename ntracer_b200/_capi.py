@@ -202,6 +202,10 @@ def load():
         'ntr_last_kernel_ms': (C.c_int, [vp, f32p]),
         'ntr_launch_count': (C.c_uint64, [vp]),
         'ntr_measure_fp32_peak': (C.c_int, [i32, f32p]),
+        'ntr_simplex_from_points': (C.c_int, [i32, u32, vp, vp]),
+        'ntr_build_kdtree': (C.c_int, [i32, u32, vp, vp, i32, i32, C.c_float, C.c_float, C.POINTER(vp), C.POINTER(u32),
+                                       C.POINTER(vp), C.POINTER(u32), C.POINTER(u32), vp]),
+        'ntr_free': (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError if the library does not export what the header declares
@@ -215,7 +219,7 @@ EXPORTED_SYMBOLS = (
     'ntr_scene_set_camera', 'ntr_scene_set_params', 'ntr_render', 'ntr_render_device', 'ntr_render_float',
     'ntr_calculate_color', 'ntr_primary_hit_ids', 'ntr_trace_rays', 'ntr_occludes_rays', 'ntr_abort',
     'ntr_get_counters', 'ntr_set_instrumented', 'ntr_last_kernel_ms', 'ntr_launch_count',
-    'ntr_measure_fp32_peak')
+    'ntr_measure_fp32_peak', 'ntr_simplex_from_points', 'ntr_build_kdtree', 'ntr_free')
 
 
 def check(status):

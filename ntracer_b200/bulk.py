@@ -1,0 +1,79 @@
+"""Bulk scene construction through the native host-side builder (csrc/builder.cpp): what a script does with
+TrianglePrototype + build_composite_scene, for sizes where one Python object per primitive is not an option
+(BASELINE config 5: 1 M ten-dimensional simplexes).  Produces flat scene dicts for DeviceScene.
+
+The arithmetic follows the reference (Triangle.from_points, src/tracer.hpp:442-462); the tree comes from this
+repo's own builder, not the reference's (nearest hits do not depend on the tree)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+
+def simplex_records(points):
+    """points: float32 [n, D, D] (n simplexes, D vertices of D coordinates) -> records float32 [n, (D+1)*D+1]"""
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    n, d, d2 = pts.shape
+    if d != d2:
+        raise ValueError('a simplex in D dimensions needs exactly D points')
+    rec = np.zeros((n, (d + 1) * d + 1), dtype=np.float32)
+    _capi.check(_capi.load().ntr_simplex_from_points(d, n, pts.ctypes.data_as(C.c_void_p), rec.ctypes.data_as(C.c_void_p)))
+    return rec
+
+
+def build_kdtree(lo, hi, max_depth=0, split_threshold=0, traversal_cost=-1.0, intersection_cost=-1.0):
+    """lo, hi: float32 [n, D] item bounds -> (nodes uint32 [m,4], item indices per leaf uint32 [k], root, boundary [2,D])"""
+    lo = np.ascontiguousarray(lo, dtype=np.float32)
+    hi = np.ascontiguousarray(hi, dtype=np.float32)
+    n, d = lo.shape
+    lib = _capi.load()
+    nodes_p, refs_p = C.c_void_p(), C.c_void_p()
+    n_nodes, n_refs, root = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    boundary = np.zeros((2, d), dtype=np.float32)
+    _capi.check(lib.ntr_build_kdtree(d, n, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), int(max_depth),
+                                     int(split_threshold), float(traversal_cost), float(intersection_cost),
+                                     C.byref(nodes_p), C.byref(n_nodes), C.byref(refs_p), C.byref(n_refs), C.byref(root),
+                                     boundary.ctypes.data_as(C.c_void_p)))
+    try:
+        nodes = np.ctypeslib.as_array(C.cast(nodes_p, C.POINTER(C.c_uint32)), shape=(max(n_nodes.value, 1) * 4,))[:n_nodes.value * 4].copy().reshape(-1, 4)
+        refs = np.ctypeslib.as_array(C.cast(refs_p, C.POINTER(C.c_uint32)), shape=(max(n_refs.value, 1),))[:n_refs.value].copy()
+    finally:
+        lib.ntr_free(nodes_p)
+        lib.ntr_free(refs_p)
+    return nodes, refs, int(root.value), boundary
+
+
+def simplex_scene(points, material_ids=None, materials=None, **tree_kw):
+    """Flat CompositeScene dict for n simplexes given by their vertices (float32 [n, D, D])."""
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    n, d, _ = pts.shape
+    rec = simplex_records(pts)
+    lo, hi = pts.min(axis=1), pts.max(axis=1)
+    nodes, refs, root, boundary = build_kdtree(lo, hi, **tree_kw)
+    if materials is None:
+        materials = np.array([[1, 0.5, 0.5, 1, 1, 1, 1, 0, 1, 8]], dtype=np.float32)      # Material((1,0.5,0.5))
+    if material_ids is None:
+        material_ids = np.zeros(n, dtype=np.int32)
+    cam_axes = np.eye(d, dtype=np.float32)
+    return {
+        'dim': np.int64(d), 'kind': np.int64(1), 'batch_size': np.int64(1), 'root': np.int64(root),
+        'nodes': nodes, 'leaf_refs': refs.astype(np.uint32),           # item index == simplex index, type 0 (single simplex)
+        'simplex': rec, 'simplex_mat': np.ascontiguousarray(material_ids, dtype=np.int32),
+        'solids': np.zeros((0, 1 + 2 * d * d + d), np.float32), 'solid_mat': np.zeros(0, np.int32),
+        'materials': np.ascontiguousarray(materials, dtype=np.float32).reshape(-1, 10), 'boundary': boundary,
+        'params': np.array([0.8, 0, 1, 4, 1], dtype=np.float64),
+        'ambient': np.zeros(3, np.float32), 'bg1': np.ones(3, np.float32), 'bg2': np.zeros(3, np.float32),
+        'bg3': np.array([0, 1, 1], np.float32),
+        'point_lights': np.zeros((0, d + 3), np.float32), 'global_lights': np.zeros((0, d + 3), np.float32),
+        'cam_origin': np.zeros(d, np.float32), 'cam_axes': cam_axes,
+    }
+
+
+def soup(dim, n, seed=1234, spread=0.05, thin=0.02):
+    """The synthetic simplex soup of BASELINE config 5: centres U(-1,1)^3 x U(-thin,thin)^(D-3),
+    vertices centre + U(-spread,spread)^D."""
+    rng = np.random.RandomState(seed)
+    c = np.concatenate([rng.uniform(-1, 1, (n, 3)), rng.uniform(-thin, thin, (n, dim - 3))], axis=1).astype(np.float32)
+    pts = c[:, None, :] + rng.uniform(-spread, spread, (n, dim, dim)).astype(np.float32)
+    return pts.astype(np.float32)

@@ -858,10 +858,11 @@ def screen_coord_to_ray(cam, x, y, w, h, fov):
 
 def build_kdtree(primitives, extra_threads=-1, *, max_depth=None, split_threshold=None, traversal_cost=None,
                  intersection_cost=None, update_primitives=False):
-    """-> (AABB, KDNode).  Host-side builder (ntracer_b200.kdbuild): a surface-area-heuristic k-d tree over the
-    prototypes' bounding boxes.  It is NOT the reference's builder (src/tracer.hpp:1930-2455): colours and hit
-    ids do not depend on the tree, except with shadows on."""
-    from .kdbuild import build
+    """-> (AABB, KDNode).  The tree comes from this backend's native host-side builder (csrc/builder.cpp,
+    ntr_build_kdtree: binned SAH over the prototypes' bounding boxes).  It is NOT the reference's builder
+    (src/tracer.hpp:1930-2455): colours and hit ids do not depend on the tree, except with shadows on
+    (DESIGN.md section 2)."""
+    from . import bulk
     protos = list(primitives)
     if not protos:
         raise ValueError('cannot build tree from empty sequence')
@@ -871,7 +872,24 @@ def build_kdtree(primitives, extra_threads=-1, *, max_depth=None, split_threshol
     d = protos[0].dimension
     if any(p.dimension != d for p in protos):
         raise TypeError('the primitive prototypes must all have the same dimension')
-    return build(protos, max_depth, split_threshold, traversal_cost, intersection_cost)
+    lo = np.stack([p.boundary.start._v for p in protos])
+    hi = np.stack([p.boundary.end._v for p in protos])
+    nodes, refs, root, boundary = bulk.build_kdtree(lo, hi, max_depth or 0, split_threshold or 0,
+                                                    -1.0 if traversal_cost is None else traversal_cost,
+                                                    -1.0 if intersection_cost is None else intersection_cost)
+    prims = [p.primitive for p in protos]
+    # children always follow their parent in the node array, so a reverse sweep builds the objects bottom-up
+    objs = [None] * len(nodes)
+    for i in range(len(nodes) - 1, -1, -1):
+        meta, a, b, c = (int(x) for x in nodes[i])
+        if meta & _capi.LEAF_FLAG:
+            objs[i] = KDLeaf([prims[j] for j in refs[a:a + b]])
+        else:
+            split = float(np.array([a], np.uint32).view(np.float32)[0])
+            objs[i] = KDBranch(meta, split, None if b == _capi.NULL_NODE else objs[b], None if c == _capi.NULL_NODE else objs[c])
+    if root == _capi.NULL_NODE:
+        raise ValueError('cannot build tree from empty sequence')
+    return AABB(d, Vector._wrap(boundary[0]), Vector._wrap(boundary[1])), objs[root]
 
 
 def build_composite_scene(primitives, extra_threads=-1, **kw):

@@ -1,0 +1,105 @@
+"""The native host-side builder (csrc/builder.cpp: SURVEY section 8f rows 1-2): Triangle.from_points in bulk and the
+k-d tree.  CPU only."""
+import numpy as np
+import pytest
+
+from ntracer_b200 import NTracer, Material, bulk, _capi
+from tests import oracle_lib as ol
+
+
+@pytest.mark.parametrize('dim', [3, 4, 5, 7, 10])
+def test_simplex_records_match_from_points(dim):
+    pts = bulk.soup(dim, 40, seed=dim, spread=0.5)
+    rec = bulk.simplex_records(pts)
+    nt = NTracer(dim)
+    for k in (0, 17, 39):
+        t = nt.Triangle.from_points([nt.Vector(*p) for p in pts[k]], Material((1, 1, 1)))
+        row = t._row()
+        assert np.abs(rec[k] - row).max() <= 2e-6 * np.abs(row).max()
+    # defining property (reference test_to_from_points, any dimension): edge_normal_i . (p_{j+1} - p_0) = -delta_ij
+    D = dim
+    E = rec[:, 2 * D + 1:].reshape(-1, D - 1, D)
+    V = pts[:, 1:, :] - pts[:, :1, :]
+    prod = np.einsum('nid,njd->nij', E.astype(np.float64), V.astype(np.float64))
+    assert np.abs(prod + np.eye(D - 1)).max() < 2e-3
+    assert np.abs(np.einsum('nd,njd->nj', rec[:, :D].astype(np.float64), V.astype(np.float64))).max() < 1e-4 * np.abs(rec[:, :D]).max()
+
+
+def walk(nodes, refs, root, lo, hi, fn):
+    stack = [(root, lo.copy(), hi.copy())]
+    while stack:
+        n, a, b = stack.pop()
+        if n == _capi.NULL_NODE:
+            fn(None, a, b)
+            continue
+        meta, w1, w2, w3 = (int(x) for x in nodes[n])
+        if meta & _capi.LEAF_FLAG:
+            fn(refs[w1:w1 + w2], a, b)
+        else:
+            split = float(np.array([w1], np.uint32).view(np.float32)[0])
+            lb, ra = b.copy(), a.copy()
+            lb[meta], ra[meta] = split, split
+            stack.append((w2, a, lb))
+            stack.append((w3, ra, b))
+
+
+@pytest.mark.parametrize('dim,n', [(3, 500), (5, 2000), (10, 3000)])
+def test_tree_is_complete(dim, n):
+    """Every item is listed in every leaf cell its box overlaps with positive measure, and empty (null) cells
+    overlap no item: then any ray finds every primitive it can hit."""
+    rng = np.random.RandomState(n)
+    c = rng.uniform(-1, 1, (n, dim))
+    e = rng.uniform(0.01, 0.2, (n, dim))
+    lo, hi = (c - e).astype(np.float32), (c + e).astype(np.float32)
+    nodes, refs, root, boundary = bulk.build_kdtree(lo, hi)
+    assert np.all(boundary[0] <= lo.min(axis=0)) and np.all(boundary[1] >= hi.max(axis=0))
+    seen = np.zeros(n, bool)
+    checked = [0]
+
+    def fn(items, a, b):
+        inside = np.all((lo < b) & (hi > a), axis=1)           # overlap with positive measure
+        if items is None:
+            assert not inside.any()
+            return
+        members = np.zeros(n, bool)
+        members[items] = True
+        seen[items] = True
+        assert not np.any(inside & ~members)
+        checked[0] += 1
+
+    walk(nodes, refs, root, boundary[0].astype(np.float64), boundary[1].astype(np.float64), fn)
+    assert seen.all() and checked[0] > 1
+    depth = _tree_depth(nodes, root)
+    assert depth <= 62
+
+
+def _tree_depth(nodes, root):
+    best, stack = 0, [(root, 1)]
+    while stack:
+        n, d = stack.pop()
+        if n == _capi.NULL_NODE:
+            continue
+        best = max(best, d)
+        meta, w1, w2, w3 = (int(x) for x in nodes[n])
+        if not meta & _capi.LEAF_FLAG:
+            stack += [(w2, d + 1), (w3, d + 1)]
+    return best
+
+
+def test_bulk_scene_equals_single_leaf_scene_under_the_oracle():
+    """config 5 in miniature: the images must not depend on which tree is used (no shadows)."""
+    dim, n = 10, 1500
+    pts = bulk.soup(dim, n, spread=0.5)
+    sc = bulk.simplex_scene(pts)
+    sc['cam_origin'] = np.array([0, 0, -3] + [0] * (dim - 3), np.float32)
+    one = dict(sc)
+    one['nodes'] = np.array([[_capi.LEAF_FLAG, 0, n, 0]], np.uint32)
+    one['leaf_refs'] = np.arange(n, dtype=np.uint32)
+    one['root'] = np.int64(0)
+    a = ol.render_float(sc, 48, 27)
+    b = ol.render_float(one, 48, 27)
+    ia, da = ol.primary_hit_ids(sc, 48, 27)
+    ib, db = ol.primary_hit_ids(one, 48, 27)
+    assert (ia >= 0).mean() > 0.02
+    assert np.mean(ia == ib) >= 0.999
+    assert np.abs(a - b).max() < 1e-4
