@@ -33,6 +33,8 @@ CONFIGS = {
     'c2': ('cell120', 1920, 1080, "config 2: 4-D 120-cell {5,3,3} CompositeScene 1920x1080, PointLight+GlobalLight, shadows on"),
     'c3': ('solids6', 1920, 1080, "config 3 stand-in: 6-D solids (2 hypercubes, 2 hyperspheres; SURVEY 8d C3), 1920x1080, reflections depth 4, PointLight, shadows, fixed-dim path"),
     'c4': ('ggs120:refl_transp', 3840, 2160, "config 4: great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4, 12 of 120 cells opacity 0.5"),
+    'c5': ('soup10:1000000', 3840, 2160, "config 5: 10-D synthetic simplex soup, 1,000,000 TrianglePrototypes (SURVEY 8d C5 generator, seed 1234), run-time-dimension kernels, 3840x2160, camera light only; tree from this repo's native builder (max_depth 17)"),
+    'c5s': ('soup10:16000', 3840, 2160, "config 5 reduced: the same 10-D soup generator with 16,000 simplexes (what the reference CPU renderer can be timed on), 3840x2160"),
     'c4o': ('ggs120', 3840, 2160, "config 4 (opaque variant): great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4"),
 }
 METRIC = 'Mrays/s (primary+shadow+reflection)'
@@ -41,6 +43,13 @@ METRIC = 'Mrays/s (primary+shadow+reflection)'
 def load_fixture(name):
     from tests import fixtures as fx
     name, _, var = name.partition(':')
+    if name == 'soup10':
+        # BASELINE config 5: generated here (no fixture can hold 1 M simplexes); scene construction (records + k-d
+        # tree) runs in the native host-side builder and is NOT part of any timed region
+        from ntracer_b200 import bulk
+        sc = bulk.simplex_scene(bulk.soup(10, int(var)), max_depth=17)
+        sc['cam_origin'] = np.array([0, 0, -3] + [0] * 7, np.float32)
+        return sc, {}
     sc, g = fx.load(name)
     if var:
         sc = fx.variant(sc, g, var)
@@ -115,6 +124,10 @@ def reference_arm(args, sc, g, w, h, rays_per_frame):
     cores = os.cpu_count() or 1
     import ref_bridge as rb
     times = []
+    if int(sc['simplex'].shape[0]) > 50000 if int(sc['kind']) == 1 else False:
+        return {'value': None, 'unit': 'Mrays/s', 'cores': cores, 'kind': 'reference',
+                'sample': 'not run: the reference cannot hold %d primitives (one Python object each, O(N^2) batch grouping); '
+                          'see config c5s for the same generator at 16,000 simplexes timed on both sides' % int(sc['simplex'].shape[0])}
     if rb.have_reference():
         nt, scene, prims = rb.import_scene(sc)
         rb.make_immortal(prims.values())     # see ref_bridge.make_immortal: the reference races on primitive refcounts
@@ -131,7 +144,7 @@ def reference_arm(args, sc, g, w, h, rays_per_frame):
         r.render(pbuf, rfmt(pw, ph), scene)
         probe = (time.perf_counter() - t) / (pw * ph)
         div = 1
-        while probe * (w // div) * (h // div) > 6.0 and div < 8:
+        while probe * (w // div) * (h // div) > 6.0 and div < 16:
             div *= 2
         sw, sh = w // div, h // div
         fmt = rfmt(sw, sh)
@@ -303,7 +316,17 @@ def main():
         if world == 1:
             # ---- roofline of the dominant kernel (render_pass_kernel: the only kernel of this frame) ----
             from tests import oracle_lib as ol
-            _, cnt_ref = ol.render_float(sc, w, h, with_counters=True)     # reference-algorithm counts
+            counts_from = 'counting CPU restatement of the reference algorithm (oracle) on the same tree'
+            if int(sc['kind']) == 1 and int(sc['simplex'].shape[0]) > 20000:
+                # far too slow for the scalar restatement at this size: the instrumented GPU build traverses the same
+                # tree with the same control flow (it only lacks the reference's mailbox for single simplexes)
+                ds.set_instrumented(True)
+                ds.render_float(w, h)
+                cnt_ref = ds.counters()
+                ds.set_instrumented(False)
+                counts_from = 'device counters of the instrumented kernels (NTR_F_COUNT) on the same tree'
+            else:
+                _, cnt_ref = ol.render_float(sc, w, h, with_counters=True)     # reference-algorithm counts
             flops = flops_per_frame(dim, cnt_ref, n_lights)
             fp32_peak = measure_fp32_peak(local_rank)
             achieved = flops / (ms_per_step * 1e-3) / 1e12
@@ -318,8 +341,8 @@ def main():
                 'bound': 'fp32', 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp32_peak,
                 'traffic': None,
                 'peak_source': 'FP32 FMA micro-benchmark measured live in this run (ntr_measure_fp32_peak); MEASURED_PEAKS.json has HBM/BF16 only',
-                'algorithmic_flops_per_launch': flops, 'kernel': 'render_pass_kernel<4,0>', 'kernel_ms': ms_per_step,
-                'reference_algorithm_counts': cnt_ref,
+                'algorithmic_flops_per_launch': flops, 'kernel': 'render_pass_kernel<%s,%d>' % (dim if 3 <= dim <= 8 else 0, 0), 'kernel_ms': ms_per_step,
+                'reference_algorithm_counts': cnt_ref, 'counts_from': counts_from,
                 'hbm': {'achieved': abytes / (ms_per_step * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                         'frac': abytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                         'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
