@@ -249,6 +249,21 @@ def main():
         ev1.synchronize()
         return ev0.elapsed_time(ev1)
 
+    def breakdown():
+        """per-phase device times of one step (diagnostic, NTR_BENCH_BREAKDOWN=1): render, gather, compose"""
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(dr.stream)
+        dr.render_strip()
+        e[1].record(dr.stream)
+        if world > 1:
+            dr.gather()
+        e[2].record(dr.stream)
+        if world > 1:
+            dr.frame_on_device()
+        e[3].record(dr.stream)
+        e[3].synchronize()
+        return [e[i].elapsed_time(e[i + 1]) for i in range(3)]
+
     def step_e2e():
         """the same frame through the host-buffer path: camera upload + render (+ gather) + D2H"""
         ds.set_camera(cam_o, cam_a)
@@ -266,6 +281,15 @@ def main():
         step_device()
         step_e2e()
 
+    if os.environ.get('NTR_BENCH_BREAKDOWN'):
+        rows = []
+        for _ in range(10):
+            flush.zero_()
+            barrier()
+            rows.append(breakdown())
+        if rank == 0:
+            med = [statistics.median(r[i] for r in rows) for i in range(3)]
+            print('breakdown ms (median of 10): render %.4f gather %.4f compose %.4f' % tuple(med), file=sys.stderr)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()

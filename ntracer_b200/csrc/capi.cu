@@ -75,6 +75,12 @@ struct ntr_scene {
     float4 *d_queue[2] = {nullptr, nullptr};
     uint32_t queue_capacity = 0;
     void *d_scratch = nullptr; size_t scratch_cap = 0;
+    // cost-sorted tile schedule (valid for one window / interleave geometry at a time)
+    unsigned long long *d_tile_cost = nullptr;
+    uint32_t *d_tile_order = nullptr;
+    size_t tile_cap = 0;
+    long long sched_key = -1;           // geometry the stored order belongs to
+    bool sched_ready = false;           // an order has been computed for sched_key
     ntr_counters counters{};
     uint64_t launches = 0;
     int grid_blocks[4] = {0, 0, 0, 0};
@@ -302,6 +308,28 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
         }
     }
 
+    // ---- tile schedule: reuse the order measured on the previous frame of the same geometry ----
+    const size_t n_tiles = (size_t)(f.out_rows ? (compact ? f.out_rows / NTR_TILE : (f.tiles_y - tile_row_first + f.tile_row_step - 1) / f.tile_row_step) : 0) * f.tiles_x;
+    const long long key = ((((long long)win_w * 65536 + win_h) * 64 + tile_row_first) * 64 + f.tile_row_step) * 4 + x0 % 2 * 2 + y0 % 2;
+    const bool use_sched = n_tiles >= 64 && composite && tgt.out_mode != NTR_OUT_IDS;
+    if (use_sched) {
+        if (sc->tile_cap < n_tiles) {
+            cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order);
+            sc->d_tile_cost = nullptr; sc->d_tile_order = nullptr; sc->tile_cap = 0;
+            CUDA_TRY(cudaMalloc(&sc->d_tile_cost, n_tiles * sizeof(unsigned long long)));
+            CUDA_TRY(cudaMalloc(&sc->d_tile_order, n_tiles * sizeof(uint32_t)));
+            sc->tile_cap = n_tiles;
+            sc->sched_key = -1;
+        }
+        if (sc->sched_key != key) {
+            CUDA_TRY(cudaMemsetAsync(sc->d_tile_cost, 0, n_tiles * sizeof(unsigned long long), st));
+            sc->sched_key = key;
+            sc->sched_ready = false;
+        }
+        f.tile_cost = sc->d_tile_cost;
+        f.tile_order = sc->sched_ready ? sc->d_tile_order : nullptr;
+    }
+
     ControlDev ctl;
     ctl.tile_cursor = sc->d_ctl + CTL_TILE_CURSOR;
     ctl.overflow = sc->d_ctl + CTL_OVERFLOW;
@@ -322,6 +350,14 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     q.in_count = q.in_cursor = nullptr;
     ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
     ++sc->launches;
+    if (use_sched) {
+        // schedule for the next frame of this view, computed on the device right behind the primary pass
+        const int tb = (int)((n_tiles + 127) / 128);
+        order_tiles_kernel<<<tb, 128, 0, st>>>(sc->d_tile_cost, sc->d_tile_order, (uint32_t)n_tiles);
+        decay_tile_cost_kernel<<<tb, 128, 0, st>>>(sc->d_tile_cost, (uint32_t)n_tiles);
+        sc->launches += 2;
+        sc->sched_ready = true;
+    }
     if (passes) {
         for (int depth = 1; depth <= sc->dev.max_depth; ++depth) {
             q.in = sc->d_queue[(depth - 1) & 1];
@@ -515,6 +551,7 @@ NTR_API void ntr_scene_destroy(ntr_scene *sc) {
     cudaFree(sc->arena); cudaFree(sc->d_lights); cudaFree(sc->d_ctl); cudaFree(sc->d_counters);
     cudaFree(sc->d_accum); cudaFree(sc->d_packed); cudaFree(sc->d_ids); cudaFree(sc->d_dists);
     cudaFree(sc->d_queue[0]); cudaFree(sc->d_queue[1]); cudaFree(sc->d_scratch);
+    cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order);
     if (sc->h_abort) cudaFreeHost(sc->h_abort);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);

@@ -77,6 +77,8 @@ struct FrameDev {
     int tile_row_first, tile_row_step, compact;   // multi-GPU interleave (tile rows ty % step == first)
     int out_rows;                   // rows of the output / accumulator: win_h, or owned tile rows * 32 when compact
     int out_mode;
+    const uint32_t *tile_order;     // cost-sorted tile schedule of the primary pass (nullptr = row-major)
+    unsigned long long *tile_cost;  // per owned tile: SM cycles spent on it this frame (feeds the next frame's order)
     unsigned char *packed;          // NTR_OUT_PACKED destination (device)
     float *accum;                   // NTR_OUT_ACCUM: 3 floats per window pixel
     int32_t *ids;                   // NTR_OUT_IDS

@@ -159,8 +159,16 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
         int bx = 0, by = 0, px = 0, out_row0 = 0;
         HitRec prim;
         prim.dist = 0; prim.ref = NTR_NONE_REF; prim.lane = -1;
+        long long t_start = 0;
+        uint32_t cost_tile = 0;
         if (primary) {
-            const uint32_t tile = b / NTR_BLOCKS_PER_TILE, sub = b % NTR_BLOCKS_PER_TILE;
+            // Longest-processing-time-first scheduling: tiles are handed out in the order of their measured cost
+            // in the previous frame of this view (order_tiles_kernel), so the kernel's tail consists of the cheapest
+            // blocks (background) instead of whatever happens to be last in row-major order.
+            const uint32_t slot = b / NTR_BLOCKS_PER_TILE, sub = b % NTR_BLOCKS_PER_TILE;
+            const uint32_t tile = f.tile_order ? __ldg(f.tile_order + slot) : slot;
+            cost_tile = tile;
+            if (f.tile_cost) t_start = clock64();
             const int tyi = (int)(tile / (uint32_t)f.tiles_x), tx = (int)(tile % (uint32_t)f.tiles_x);
             const int ty = f.tile_row_first + tyi * f.tile_row_step;
             bx = tx * NTR_TILE + (int)(sub % (NTR_TILE / NTR_BLK_W)) * NTR_BLK_W;       // window coordinates
@@ -206,6 +214,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
             QueueEmit<DT> emit{q, ctl, pix, !primary || f.out_mode == NTR_OUT_ACCUM};
             ray_color<DT, FLAGS>(s, o, dir, depth, skip, w, acc, emit, cnt, &prim);
         }
+        if (primary && f.tile_cost && lane == 0) atomicAdd(f.tile_cost + cost_tile, (unsigned long long)(clock64() - t_start));
         // ---------------- epilogue ----------------
         if (!primary) {
             if (active) {
@@ -232,6 +241,23 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
     }
     __syncwarp();
     flush_counters(ctl, cnt);
+}
+
+// Next frame's tile schedule: tiles sorted by decreasing cost (rank by counting; n <= a few thousand tiles), costs
+// halved so that the schedule follows a moving camera with some inertia.
+static __global__ void order_tiles_kernel(unsigned long long *cost, uint32_t *order, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long ci = cost[i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; ++j) {
+            const unsigned long long cj = cost[j];
+            rank += (cj > ci) || (cj == ci && j < i);
+        }
+        order[rank] = i;
+    }
+}
+static __global__ void decay_tile_cost_kernel(unsigned long long *cost, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cost[i] >>= 1;
 }
 
 // KDNode.intersects for a batch of rays (reference src/ntracer_body.hpp:1412-1458)

@@ -85,6 +85,13 @@ NTR_HD float rcp_approx(float x) {
     return 1.0f / x;
 #endif
 }
+NTR_HD void prefetch_l1(const void *p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 NTR_HD float u2f(uint32_t u) {
 #if defined(__CUDA_ARCH__)
     return __uint_as_float(u);
@@ -551,6 +558,9 @@ template <int DT> struct LeafCursor {
 // this ray can only miss its own cutoff again, see above), so false negatives are harmless.  The NTR_MINI_MAILBOX
 // most recently tested batch refs, kept as a shift register (0 = disabled).  Measured on config 2: 8 entries
 // remove 35 % of the simplex tests, 16 remove 42 % (the reference's unbounded list removes 39 %).
+#ifndef NTR_PREFETCH_NEXT_ITEM
+#define NTR_PREFETCH_NEXT_ITEM 0
+#endif
 #ifndef NTR_MINI_MAILBOX
 #define NTR_MINI_MAILBOX 16
 #endif
@@ -590,6 +600,14 @@ NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, con
         const uint32_t i = cur.next(s, o, rs, oh.dist);
         if (i >= size) break;
         const uint2 it = lditem(items + i);
+#if NTR_PREFETCH_NEXT_ITEM
+        // the traversal is latency bound (ncu: long-scoreboard stalls dominate): start fetching the next item's
+        // record while this one is being tested
+        if (i + 1 < size) {
+            const uint2 nx = lditem(items + i + 1);
+            prefetch_l1(((nx.x >> 30) == NTR_REF_BATCH ? s.batches : s.simplex) + nx.y);
+        }
+#endif
         const uint32_t item = it.x;
         uint32_t meta;
         if ((item >> 30) == NTR_REF_BATCH) {
