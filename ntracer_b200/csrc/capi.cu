@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -81,6 +82,10 @@ struct ntr_scene {
     size_t tile_cap = 0;
     long long sched_key = -1;           // geometry the stored order belongs to
     bool sched_ready = false;           // an order has been computed for sched_key
+    // diagnostic per-pass timing (NTR_PASS_TIMING=1): events between the passes of one frame
+    cudaEvent_t pass_ev[kMaxPasses + 4] = {};
+    int n_pass_ev = 0;
+    bool pass_timing = false;
     ntr_counters counters{};
     uint64_t launches = 0;
     int grid_blocks[4] = {0, 0, 0, 0};
@@ -311,7 +316,10 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     // ---- tile schedule: reuse the order measured on the previous frame of the same geometry ----
     const size_t n_tiles = (size_t)(f.out_rows ? (compact ? f.out_rows / NTR_TILE : (f.tiles_y - tile_row_first + f.tile_row_step - 1) / f.tile_row_step) : 0) * f.tiles_x;
     const long long key = ((((long long)win_w * 65536 + win_h) * 64 + tile_row_first) * 64 + f.tile_row_step) * 4 + x0 % 2 * 2 + y0 % 2;
-    const bool use_sched = n_tiles >= 64 && composite && tgt.out_mode != NTR_OUT_IDS;
+    // measured: the cost-sorted schedule pays when the frame is sharded over GPUs (8 GPUs, config 2: strip render
+    // 0.258 -> 0.203 ms) -- each rank then has only ~2 blocks per warp and the tail matters -- but costs ~8 % on a
+    // whole frame on one GPU (loss of row-major locality + the cost bookkeeping), so it is used for sharded renders only
+    const bool use_sched = n_tiles >= 64 && composite && tgt.out_mode != NTR_OUT_IDS && f.tile_row_step > 1;
     if (use_sched) {
         if (sc->tile_cap < n_tiles) {
             cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order);
@@ -348,8 +356,16 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     q.out = sc->d_queue[0];
     q.out_count = sc->d_ctl + CTL_COUNT0 + 1;
     q.in_count = q.in_cursor = nullptr;
+    auto mark = [&]() {
+        if (!sc->pass_timing || sc->n_pass_ev >= kMaxPasses + 4) return;
+        if (!sc->pass_ev[sc->n_pass_ev]) cudaEventCreate(&sc->pass_ev[sc->n_pass_ev]);
+        cudaEventRecord(sc->pass_ev[sc->n_pass_ev++], st);
+    };
+    sc->n_pass_ev = 0;
+    mark();
     ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
     ++sc->launches;
+    mark();
     if (use_sched) {
         // schedule for the next frame of this view, computed on the device right behind the primary pass
         const int tb = (int)((n_tiles + 127) / 128);
@@ -367,6 +383,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
             q.in_cursor = sc->d_ctl + CTL_CURSOR0 + depth;
             ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
             ++sc->launches;
+            mark();
         }
         if (tgt.out_mode == NTR_OUT_PACKED) {
             f.out_mode = NTR_OUT_PACKED;
@@ -396,6 +413,17 @@ int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win
         CUDA_TRY(cudaMemcpyAsync(h_ctl, sc->d_ctl, sizeof h_ctl, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(h_cnt, sc->d_counters, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        if (sc->pass_timing && sc->n_pass_ev > 1) {
+            fprintf(stderr, "ntr pass ms:");
+            for (int i = 0; i + 1 < sc->n_pass_ev; ++i) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, sc->pass_ev[i], sc->pass_ev[i + 1]);
+                fprintf(stderr, " %.3f", ms);
+            }
+            fprintf(stderr, "  rays:");
+            for (int d = 1; d <= sc->dev.max_depth + 1 && d <= kMaxPasses; ++d) fprintf(stderr, " %u", h_ctl[CTL_COUNT0 + d]);
+            fprintf(stderr, "\n");
+        }
         if (*sc->h_abort) return fail(NTR_ERR_ABORTED, "render aborted");
         const uint64_t overflows = sc->counters.queue_overflows;
         sc->counters.primary_rays = (uint64_t)win_w * win_h;
@@ -513,6 +541,7 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     if (!sc) return fail(NTR_ERR_MEMORY, "out of memory");
     sc->device = device;
     sc->sm_count = prop.multiProcessorCount;
+    sc->pass_timing = getenv("NTR_PASS_TIMING") != nullptr;
     sc->tree_depth = depth;
     sc->dev.dim = desc->dim;
     sc->dev.kind = desc->kind;

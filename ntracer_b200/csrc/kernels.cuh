@@ -210,9 +210,17 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
             }
         }
         // ---------------- the per-ray path ----------------
+#if NTR_COOP_LEAVES
+        if (s.kind != NTR_SCENE_BOX) {       // warp-uniform: every lane enters (cooperative leaves), `active` says who has a ray
+            if (!active) {
+#pragma unroll
+                for (int k = 0; k < CAP; ++k) { o[k] = 0.0f; dir[k] = 1.0f; }
+            }
+#else
         if (active) {
+#endif
             QueueEmit<DT> emit{q, ctl, pix, !primary || f.out_mode == NTR_OUT_ACCUM};
-            ray_color<DT, FLAGS>(s, o, dir, depth, skip, w, acc, emit, cnt, &prim);
+            ray_color<DT, FLAGS>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim);
         }
         if (primary && f.tile_cost && lane == 0) atomicAdd(f.tile_cost + cost_tile, (unsigned long long)(clock64() - t_start));
         // ---------------- epilogue ----------------

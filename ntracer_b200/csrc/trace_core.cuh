@@ -801,6 +801,168 @@ NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, S
     }
 }
 
+// ---- warp-cooperative nearest-hit traversal (device only, opaque variant) -----------------------------------------
+// Same state machine as trace_nearest, but leaves with at least NTR_COOP_LEAF_MIN items are evaluated by the WHOLE
+// warp for one ray at a time: the ray is broadcast, lane j tests items j, j+32, ..., and the winner is the
+// lexicographic minimum of (t, item index) -- exactly what the sequential scan with its strict `t < cutoff` rule
+// keeps (nearest hit, first-tested wins ties, tracer.hpp:1041-1082).  Why: rays that cross many of the 1,600-item
+// leaves of a star polytope take milliseconds each; in the wavefront passes a handful of such stragglers held a
+// whole pass hostage (measured: 1/8 of the rays took the same time as all of them).  With cooperation a straggler's
+// leaf costs 1/32 of the time whenever its warp-mates are idle, and nothing when they are busy too.
+// MUST be called by all 32 lanes of the warp (lanes without a ray pass enabled = false).
+// MEASURED (B200, config 4 opaque, 3840x2160): with cooperation enabled the frame went from 47.4 ms to 54.7 ms
+// (to 64.5 ms when every big leaf was served cooperatively): the extra ballots per leaf visit and the loss of the
+// shrinking per-lane cutoff cost more than the idle lanes give back, because the expensive wavefront passes turned
+// out to be throughput bound by INCOHERENT reflection rays (6-16 ns/ray against 1.5 ns/ray for primaries), not by a few
+// stragglers.  It is therefore compiled out by default (-DNTR_COOP_LEAVES=1 to enable); ray re-binning for
+// coherence is the lever that remains.
+#ifndef NTR_COOP_LEAVES
+#define NTR_COOP_LEAVES 0
+#endif
+#if defined(__CUDA_ARCH__) && NTR_COOP_LEAVES
+#ifndef NTR_COOP_LEAF_MIN
+#define NTR_COOP_LEAF_MIN 64
+#endif
+#ifndef NTR_COOP_MAX_LANES
+#define NTR_COOP_MAX_LANES 10       // cooperate only while at most this many lanes of the warp wait at big leaves
+#endif
+template <int DT, int FLAGS>
+__device__ __forceinline__ bool trace_nearest_coop(const SceneDev &s, bool enabled, const float *o, const float *dir,
+                                                   Skip skip, float t_near, float t_far, HitRec &oh, Counters &cnt) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const int D = NTR_D(DT, s);
+    const int lane = threadIdx.x & 31;
+    RaySlab<DT> rs;
+    rs.init(s, dir);
+    const float *invdir = rs.invdir;
+    TravStack st;
+    int sp = 0;
+    uint32_t node = s.root;
+    MiniMailbox mm;
+    mm.clear();
+    bool done = !enabled, pending = false, have_result = false, result = false, ret = false;
+    uint32_t pend_first = 0, pend_size = 0;
+    for (;;) {
+        if (!done) {
+            if (have_result) {                                      // ---- unwind (see trace_nearest) ----
+                have_result = false;
+                for (;;) {
+                    if (sp == 0) { done = true; ret = result; break; }
+                    --sp;
+                    const uint32_t fnode = st.node[sp];
+                    if (fnode == NTR_FRAME_AFTER_FAR) { result = true; continue; }
+                    const float t = st.t[sp];
+                    if (result && oh.dist <= t) continue;
+                    node = fnode;
+                    t_near = t;
+                    t_far = st.t_far[sp];
+                    if (result) { st.node[sp] = NTR_FRAME_AFTER_FAR; ++sp; }
+                    break;
+                }
+            }
+            if (!done) {                                            // ---- descend ----
+                result = false;
+                while (node != NTR_NULL_NODE) {
+                    const uint4 n = ldnode(s.nodes + node);
+                    if (n.x & NTR_LEAF_FLAG) {
+                        if (n.z >= NTR_COOP_LEAF_MIN) { pending = true; pend_first = n.y; pend_size = n.z; }
+                        else result = leaf_opaque<DT, FLAGS>(s, n, o, dir, rs, skip, oh, mm, cnt);
+                        break;
+                    }
+                    if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
+                    const int axis = (int)n.x;
+                    const float split = u2f(n.y);
+                    const float da = vsel<DT>(dir, axis), oa = vsel<DT>(o, axis);
+                    if (da != 0) {
+                        if (oa == split) { node = da > 0 ? n.w : n.z; continue; }
+                        const float t = (split - oa) * vsel<DT>(invdir, axis);
+                        const uint32_t n_near = oa > split ? n.w : n.z;
+                        const uint32_t n_far = oa > split ? n.z : n.w;
+                        if (t < 0 || t > t_far) { node = n_near; continue; }
+                        if (t < t_near) { node = n_far; continue; }
+                        if (n_near != NTR_NULL_NODE) {
+                            if (n_far == NTR_NULL_NODE) { node = n_near; t_far = t; continue; }
+                            if (sp < NTR_STACK_CAP) { st.node[sp] = n_far; st.t[sp] = t; st.t_far[sp] = t_far; ++sp; }
+                            node = n_near;
+                            t_far = t;
+                            continue;
+                        }
+                        node = n_far;
+                        t_near = t;
+                        continue;
+                    }
+                    node = oa >= split ? n.w : n.z;
+                }
+                if (!pending) have_result = true;
+            }
+        }
+        // ---- warp-synchronous part: serve the lanes that wait at a big leaf, one ray at a time ----
+        unsigned pm = __ballot_sync(FULL, pending);
+        if (!pm) {
+            if (__all_sync(FULL, done)) break;
+            continue;
+        }
+        if (__popc(pm) > NTR_COOP_MAX_LANES) {
+            // most of the warp sits at big leaves (coherent rays, typically the same leaf): the plain per-lane scan is
+            // the better schedule then -- every lane reads the same items (broadcast loads) and its own cutoff shrinks
+            // as it goes
+            if (pending) {
+                const uint4 n = make_uint4(NTR_LEAF_FLAG, pend_first, pend_size, 0u);
+                result = leaf_opaque<DT, FLAGS>(s, n, o, dir, rs, skip, oh, mm, cnt);
+                pending = false;
+                have_result = true;
+            }
+            continue;
+        }
+        while (pm) {
+            const int src = __ffs(pm) - 1;
+            pm &= pm - 1;
+            float bo[DimCap<DT>::value], bd[DimCap<DT>::value];
+    NTR_UNROLL
+            for (int i = 0; i < D; ++i) { bo[i] = __shfl_sync(FULL, o[i], src); bd[i] = __shfl_sync(FULL, dir[i], src); }
+            const uint32_t first = __shfl_sync(FULL, pend_first, src), size = __shfl_sync(FULL, pend_size, src);
+            const float cutoff = __shfl_sync(FULL, oh.dist, src);
+            const uint32_t sk_ref = __shfl_sync(FULL, skip.ref, src);
+            const int sk_lane = __shfl_sync(FULL, skip.lane, src);
+            const uint2 *items = s.leaf_items + first;
+            float best_t = cutoff;
+            uint32_t best_k = 0xFFFFFFFFu, best_ref = NTR_NONE_REF;
+            int best_lane = -1;
+            for (uint32_t k = lane; k < size; k += 32) {
+                const uint2 it = lditem(items + k);
+                uint32_t meta;
+                if ((it.x >> 30) == NTR_REF_BATCH) {
+                    int index = sk_ref == it.x ? sk_lane : -1;
+                    const float dist = batch_test<DT, FLAGS>(s, it.y, bo, bd, index, best_t, meta, cnt);
+                    if (dist) { best_t = dist; best_k = k; best_ref = it.x; best_lane = index; }
+                } else if (it.x != sk_ref) {
+                    if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
+                    const float dist = simplex_single<DT>(s, it.y, bo, bd, best_t, meta);
+                    if (dist) { best_t = dist; best_k = k; best_ref = it.x; best_lane = -1; }
+                }
+            }
+            // lexicographic minimum of (t, item index) over the warp
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ot = __shfl_xor_sync(FULL, best_t, off);
+                const uint32_t ok = __shfl_xor_sync(FULL, best_k, off), orf = __shfl_xor_sync(FULL, best_ref, off);
+                const int ol = __shfl_xor_sync(FULL, best_lane, off);
+                if (ok != 0xFFFFFFFFu && (best_k == 0xFFFFFFFFu || ot < best_t || (ot == best_t && ok < best_k))) {
+                    best_t = ot; best_k = ok; best_ref = orf; best_lane = ol;
+                }
+            }
+            if (lane == src) {
+                pending = false;
+                have_result = true;
+                result = best_k != 0xFFFFFFFFu;
+                if (result) { oh.dist = best_t; oh.ref = best_ref; oh.lane = best_lane; }
+            }
+        }
+    }
+    return ret;
+}
+#endif
+
 // ---- occlusion (shadow) traversal ------------------------------------------------------------------------
 // kd_leaf::occludes (tracer.hpp:1088-1124): any opaque hit nearer than the light blocks; transparent
 // blockers are collected (no mailbox here).
@@ -1107,8 +1269,8 @@ NTR_HD void hit_geometry(const SceneDev &s, uint32_t ref, int lane, float dist, 
 // far) and the opaque hit / background each contribute base_color * op_i * prod_{j<i}(1 - op_j).
 // EMIT(const Bounce<DT>&) receives the deferred reflection rays.
 template <int DT, int FLAGS, typename EMIT>
-NTR_HD void ray_color(const SceneDev &s, const float *o, const float *dir, int depth, Skip source, const float *weight,
-                      float *acc, EMIT &emit, Counters &cnt, HitRec *primary_out) {
+NTR_HD void ray_color(const SceneDev &s, bool enabled, const float *o, const float *dir, int depth, Skip source,
+                      const float *weight, float *acc, EMIT &emit, Counters &cnt, HitRec *primary_out) {
     const int D = NTR_D(DT, s);
     GenState<DT> g;
     HitRec oh;
@@ -1118,8 +1280,17 @@ NTR_HD void ray_color(const SceneDev &s, const float *o, const float *dir, int d
     NTR_UNROLL
         for (int i = 0; i < D; ++i) { g.hitP[i] = 0; g.hitN[i] = 0; }
     }
-    const float t0 = aabb_distance<DT>(s, o, dir);
+    // `enabled` = this lane has a ray.  (With NTR_COOP_LEAVES all 32 lanes of a warp enter so that big leaves can be
+    // evaluated cooperatively; everything after the traversal is per lane again.)
+    const float t0 = enabled ? aabb_distance<DT>(s, o, dir) : -1.0f;
+#if defined(__CUDA_ARCH__) && NTR_COOP_LEAVES
+    bool hit;
+    if (FLAGS & NTR_F_GENERAL) hit = t0 >= 0 && trace_nearest<DT, FLAGS>(s, o, dir, source, t0, FLT_MAX, oh, &g, cnt);
+    else hit = trace_nearest_coop<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, cnt);
+#else
     const bool hit = t0 >= 0 && trace_nearest<DT, FLAGS>(s, o, dir, source, t0, FLT_MAX, oh, &g, cnt);
+#endif
+    if (!enabled) return;
     if (primary_out) { *primary_out = oh; if (!hit) { primary_out->ref = NTR_NONE_REF; primary_out->dist = 0; } }
 
     float w[3] = {weight[0], weight[1], weight[2]};

@@ -53,6 +53,10 @@ class DistributedRenderer:
         self.ds, self.fmt, self.group = scene, fmt, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        # diagnostic: render only the share rank 0 of N would get, on one GPU (profiling the multi-GPU kernel shape
+        # without running ncu on a multi-rank job)
+        import os
+        self.fake_world = int(os.environ.get('NTR_FAKE_WORLD', '0')) if self.world == 1 else 0
         dev = torch.device('cuda', torch.cuda.current_device())
         # a dedicated (non-null) stream: the C ABI treats a NULL stream as "the scene's own stream"
         self.stream = torch.cuda.Stream(device=dev)
@@ -65,7 +69,7 @@ class DistributedRenderer:
     def render_strip(self):
         """Enqueue this rank's tile rows on self.stream (asynchronous for scenes without reflective materials)."""
         self.ds.render_device(self.fmt, self.strip.data_ptr(), self.strip.numel(), self.stream.cuda_stream,
-                              self.rank, self.world, True)
+                              self.rank, self.fake_world or self.world, True)
 
     def gather(self):
         if self.world > 1:

@@ -85,7 +85,7 @@ void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, un
             else {
                 VecEmit<DT> emit{&q, &qp, pix};
                 const Skip none = {NTR_NONE_REF, 0};
-                ray_color<DT, FLAGS>(S.dev, o, dir, 0, none, one, acc, emit, cnt, &prim);
+                ray_color<DT, FLAGS>(S.dev, true, o, dir, 0, none, one, acc, emit, cnt, &prim);
             }
             if (rgb) { rgb[pix * 3] = acc[0]; rgb[pix * 3 + 1] = acc[1]; rgb[pix * 3 + 2] = acc[2]; }
             if (ids) ids[pix] = prim.ref == NTR_NONE_REF ? -1 : (S.dev.kind == NTR_SCENE_BOX ? 0 : flat_prim_id(S.dev, prim.ref, prim.lane));
@@ -97,7 +97,7 @@ void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, un
         for (size_t i = 0; i < q.size(); ++i) {
             float acc[3] = {0, 0, 0};
             VecEmit<DT> emit{&qn, &qpn, qp[i]};
-            ray_color<DT, FLAGS>(S.dev, q[i].o, q[i].d, q[i].depth, q[i].skip, q[i].w, acc, emit, cnt, nullptr);
+            ray_color<DT, FLAGS>(S.dev, true, q[i].o, q[i].d, q[i].depth, q[i].skip, q[i].w, acc, emit, cnt, nullptr);
             rgb[(size_t)qp[i] * 3] += acc[0]; rgb[(size_t)qp[i] * 3 + 1] += acc[1]; rgb[(size_t)qp[i] * 3 + 2] += acc[2];
         }
         q.swap(qn); qp.swap(qpn);
