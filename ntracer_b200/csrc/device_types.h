@@ -95,6 +95,7 @@ struct QueueDev {
     uint32_t *in_count;             // device counter written by the previous pass
     uint32_t *out_count;
     uint32_t *in_cursor;            // work-fetch cursor of this pass
+    const uint32_t *in_perm;        // optional: coherence-sorted order of the input records (nullptr = as emitted)
     uint32_t capacity;              // in records
     uint32_t rec4;                  // record size in float4 units
 };
