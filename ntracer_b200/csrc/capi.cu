@@ -90,6 +90,7 @@ struct ntr_scene {
     uint32_t *d_keys[2] = {nullptr, nullptr}, *d_perm[2] = {nullptr, nullptr};
     void *d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0; uint32_t sort_cap = 0;
     bool sort_rays = true;
+    uint32_t queue_init = 0;            // NTR_QUEUE_INIT: initial queue capacity override (tests force the regrow path)
     float pass_ns_per_ray = 0.0f;       // measured cost of the wavefront passes of the previous frame (0 = unknown)
     // diagnostic per-pass timing (NTR_PASS_TIMING=1): events between the passes of one frame
     cudaEvent_t pass_ev[kMaxPasses + 4] = {};
@@ -315,7 +316,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     if (passes) {
         // each pass can emit at most (1 + transparent layers) rays per input ray; start with 2 rays per pixel
         // and let the overflow check regrow (ntr_counters.queue_overflows)
-        const uint64_t want = std::max<uint64_t>((uint64_t)npix * 2, 1u << 16);
+        const uint64_t want = sc->queue_init ? sc->queue_init : std::max<uint64_t>((uint64_t)npix * 2, 1u << 16);
         if (sc->queue_capacity < want) {
             int rc = ensure_queues(sc, (uint32_t)std::min<uint64_t>(want, 0x7FFFFFFFu));
             if (rc) return rc;
@@ -621,6 +622,7 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->sm_count = prop.multiProcessorCount;
     sc->pass_timing = getenv("NTR_PASS_TIMING") != nullptr;
     sc->sort_rays = getenv("NTR_NO_RAY_SORT") == nullptr;
+    if (const char *qi = getenv("NTR_QUEUE_INIT")) sc->queue_init = (uint32_t)strtoul(qi, nullptr, 10);
     sc->tree_depth = depth;
     sc->dev.dim = desc->dim;
     sc->dev.kind = desc->kind;

@@ -226,3 +226,57 @@ def test_abort_and_busy_semantics():
         assert ds.render(fmt).size == 64 * 48 * 3
         with pytest.raises(ValueError):
             ds.render(fmt, bytearray(10))
+
+
+def test_wavefront_queue_overflow_regrows_and_rerenders(monkeypatch):
+    """A queue that is too small must never drop bounces: the frame is re-rendered with a bigger one."""
+    sc, g = fx.load('cell120')
+    s2 = fx.variant(sc, g, 'refl_transp')
+    w, h = 160, 90
+    with DeviceScene(s2) as ds:
+        ref = ds.render_float(w, h)
+        assert ds.counters()['queue_overflows'] == 0
+    monkeypatch.setenv('NTR_QUEUE_INIT', '512')
+    with DeviceScene(s2) as ds:
+        img = ds.render_float(w, h)
+        assert ds.counters()['queue_overflows'] >= 1
+        assert np.abs(img - ref).max() <= 1e-5            # float atomics may land in a different order
+        fmt = _capi.make_image_format(w, h, _capi.RGB8)
+        a = ds.render(fmt)
+        assert np.abs(a.astype(np.int32) - ol.pack(fmt, ref).astype(np.int32)).max() <= 1
+
+
+def test_abort_stops_a_running_render():
+    """signal_abort / abort_render (reference src/render.cpp:702-722,911-923): a frame in flight ends early and the
+    call reports it (BlockingRenderer.render -> False)."""
+    import threading
+    import time
+    from ntracer_b200 import bulk
+    pts = bulk.soup(10, 60000)
+    sc = bulk.simplex_scene(pts, max_depth=14)
+    sc['cam_origin'] = np.array([0, 0, -3] + [0] * 7, np.float32)
+    with DeviceScene(sc) as ds:
+        fmt = _capi.make_image_format(3840, 2160, _capi.RGB8)
+        t0 = time.perf_counter()
+        ds.render(fmt)
+        full = time.perf_counter() - t0
+        result = {}
+
+        def run():
+            try:
+                ds.render(fmt)
+                result['rc'] = 'finished'
+            except RuntimeError as e:
+                result['rc'] = str(e)
+
+        th = threading.Thread(target=run)
+        t0 = time.perf_counter()
+        th.start()
+        time.sleep(min(0.05, full / 10))
+        ds.abort()
+        th.join()
+        aborted = time.perf_counter() - t0
+        if full > 0.3:                                    # only meaningful when the frame is long enough to interrupt
+            assert result['rc'] == 'render aborted'
+            assert aborted < 0.8 * full
+        assert ds.render(fmt).size == fmt.pitch * 2160    # and the scene is usable afterwards
