@@ -280,6 +280,65 @@ NTR_HD float batch_test(const SceneDev &s, uint32_t off, const float *o, const f
     return min_t;
 }
 
+// The same test split in two for 4-lane batches, so that the plane parts of TWO consecutive leaf items can be issued
+// back to back (independent loads and FFMA chains -> twice the instruction- and memory-level parallelism of a single
+// warp; ncu: the kernel is latency bound, issue slots 43 % busy).  Exactness: the plane part of the second item is
+// computed with the cutoff from BEFORE the first item's result, which is looser; the finish step re-checks every lane
+// against the cutoff current at that moment (`t < min_t`), which is precisely what the sequential scan does.
+struct BatchPlane { float num[4], den[4]; unsigned viable; };
+
+template <int DT>
+NTR_HD BatchPlane batch_plane4(const SceneDev &s, uint32_t off, const float *o, const float *dir, int index, float cutoff) {
+    const int D = NTR_D(DT, s);
+    const float *blk = s.batches + off;
+    float den[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) {
+        const float4 f = ld4(blk + i * 4);
+        den[0] += f.x * dir[i]; den[1] += f.y * dir[i]; den[2] += f.z * dir[i]; den[3] += f.w * dir[i];
+        od[0] += f.x * o[i]; od[1] += f.y * o[i]; od[2] += f.z * o[i]; od[3] += f.w * o[i];
+    }
+    const float4 dd = ld4(blk + D * 4);
+    const float dv[4] = {dd.x, dd.y, dd.z, dd.w};
+    BatchPlane r;
+    r.viable = 0;
+    const float cut = cutoff * 1.000001f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r.num[k] = -(od[k] + dv[k]);
+        r.den[k] = den[k];
+        const float ta = r.num[k] * rcp_approx(den[k]);
+        const bool reject = (fabsf(den[k]) > 1e-30f) & ((ta < 0) | (ta > cut));
+        r.viable |= ((reject | (k == index)) ? 0u : 1u) << k;
+    }
+    return r;
+}
+
+template <int DT>
+NTR_HD float batch_finish4(const SceneDev &s, uint32_t off, const BatchPlane &p, const float *o, const float *dir,
+                           int &index, float cutoff, uint32_t &meta) {
+    if (!p.viable) return 0;
+    const int D = NTR_D(DT, s);
+    const int LPART = DT > 0 ? (DT * DT + 3) / 4 * 4 : s.lane_part;
+    const float *edges = s.batches + off + (D + 1) * 4;
+    float min_t = cutoff;
+    int r_index = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!(p.viable & (1u << k))) continue;
+        if (p.den[k] == 0) continue;
+        const float t = p.num[k] / p.den[k];
+        if (!(t >= 0) || t == 0 || !(t < min_t)) continue;
+        if (!batch_lane_edges<DT>(s, edges + k * LPART, o, dir, t)) continue;
+        min_t = t;
+        r_index = k;
+    }
+    if (r_index == -1) return 0;
+    index = r_index;
+    meta = f2u(ldf(edges + 4 * LPART + r_index));
+    return min_t;
+}
+
 // Geometry of a simplex hit: normal.origin = o + t*dir, normal.direction = +-unit(face_normal)
 // (tracer.hpp:434-436, 595-597).
 template <int DT>
@@ -561,6 +620,10 @@ template <int DT> struct LeafCursor {
 #ifndef NTR_PREFETCH_NEXT_ITEM
 #define NTR_PREFETCH_NEXT_ITEM 0
 #endif
+#ifndef NTR_PAIR_BATCHES
+#define NTR_PAIR_BATCHES 0      // leaf_opaque testing two batch items per iteration (see batch_plane4): exact, but measured
+                                // slower on B200 (config 4 opaque 34.6 -> 38.7 ms, config 2 unchanged): off
+#endif
 #ifndef NTR_MINI_MAILBOX
 #define NTR_MINI_MAILBOX 16
 #endif
@@ -594,6 +657,49 @@ NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, con
     const uint2 *items = s.leaf_items + node.y;
     const uint32_t size = node.z;
     bool hit = false;
+#if !NTR_USE_LEAF_INDEX && NTR_PAIR_BATCHES
+    if (DT > 0) {
+        // two items per iteration: both plane parts first, then the finishes in leaf order
+        uint32_t i = 0;
+        while (i < size) {
+            const uint2 a = lditem(items + i);
+            const bool a_batch = (a.x >> 30) == NTR_REF_BATCH;
+            if (a_batch && i + 1 < size) {
+                const uint2 b = lditem(items + i + 1);
+                if ((b.x >> 30) == NTR_REF_BATCH) {
+                    const bool ta = !mm.test_and_set(a.x), tb = !mm.test_and_set(b.x);
+                    int ia = skip.ref == a.x ? skip.lane : -1, ib = skip.ref == b.x ? skip.lane : -1;
+                    BatchPlane pa, pb;
+                    pa.viable = pb.viable = 0;
+                    if (ta) pa = batch_plane4<DT>(s, a.y, o, dir, ia, oh.dist);
+                    if (tb) pb = batch_plane4<DT>(s, b.y, o, dir, ib, oh.dist);
+                    if (FLAGS & NTR_F_COUNT) cnt.simplex_tests += 4 * ((ta ? 1 : 0) + (tb ? 1 : 0));
+                    uint32_t meta;
+                    float dist = batch_finish4<DT>(s, a.y, pa, o, dir, ia, oh.dist, meta);
+                    if (dist) { oh.dist = dist; oh.ref = a.x; oh.lane = ia; hit = true; }
+                    dist = batch_finish4<DT>(s, b.y, pb, o, dir, ib, oh.dist, meta);
+                    if (dist) { oh.dist = dist; oh.ref = b.x; oh.lane = ib; hit = true; }
+                    i += 2;
+                    continue;
+                }
+            }
+            uint32_t meta;
+            if (a_batch) {
+                if (!mm.test_and_set(a.x)) {
+                    int index = skip.ref == a.x ? skip.lane : -1;
+                    const float dist = batch_test<DT, FLAGS>(s, a.y, o, dir, index, oh.dist, meta, cnt);
+                    if (dist) { oh.dist = dist; oh.ref = a.x; oh.lane = index; hit = true; }
+                }
+            } else if (a.x != skip.ref) {
+                if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
+                const float dist = simplex_single<DT>(s, a.y, o, dir, oh.dist, meta);
+                if (dist) { oh.dist = dist; oh.ref = a.x; oh.lane = -1; hit = true; }
+            }
+            ++i;
+        }
+        return hit;
+    }
+#endif
     LeafCursor<DT> cur;
     cur.begin(s, node);
     for (;;) {
