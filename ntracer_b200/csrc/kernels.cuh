@@ -113,7 +113,7 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 }
 
 #ifndef NTR_MIN_CTAS
-#define NTR_MIN_CTAS 6
+#define NTR_MIN_CTAS 8
 #endif
 template <int DT, int FLAGS>
 __global__ void __launch_bounds__(kCtaThreads, NTR_MIN_CTAS)

@@ -616,7 +616,8 @@ template <int DT> struct LeafCursor {
 // Small per-traversal mailbox of the opaque variant: purely an optimisation (a batch that was already tested against
 // this ray can only miss its own cutoff again, see above), so false negatives are harmless.  The NTR_MINI_MAILBOX
 // most recently tested batch refs, kept as a shift register (0 = disabled).  Measured on config 2: 8 entries
-// remove 35 % of the simplex tests, 16 remove 42 % (the reference's unbounded list removes 39 %).
+// remove 35 % of the simplex tests, 16 remove 42 % (the reference's unbounded list removes 39 %); 8 entries at 64
+// registers / 8 CTAs per SM beat 16 entries at 80 registers / 6 CTAs (config 2 -3.5 %, config 4 opaque -10 %).
 #ifndef NTR_PREFETCH_NEXT_ITEM
 #define NTR_PREFETCH_NEXT_ITEM 0
 #endif
@@ -625,7 +626,7 @@ template <int DT> struct LeafCursor {
                                 // slower on B200 (config 4 opaque 34.6 -> 38.7 ms, config 2 unchanged): off
 #endif
 #ifndef NTR_MINI_MAILBOX
-#define NTR_MINI_MAILBOX 16
+#define NTR_MINI_MAILBOX 8
 #endif
 struct MiniMailbox {
 #if NTR_MINI_MAILBOX > 0
