@@ -190,31 +190,42 @@ NTR_HD float simplex_single(const SceneDev &s, uint32_t off, const float *o, con
     return 0;
 }
 
-// Edge part of one batch lane (tracer.hpp:567-579): lower edge bound only, then the area sum.
-template <int DT>
-NTR_HD bool batch_lane_edges(const SceneDev &s, const float *lp, const float *o, const float *dir, float t) {
-    const int D = NTR_D(DT, s);
-    constexpr int LP = DT > 0 ? (DT * DT + 3) / 4 * 4 : 4;
+// Edge part of one batch lane (tracer.hpp:567-579): lower edge bound only, then the area sum.  The record is loaded
+// into registers by load(); issuing those loads BEFORE the exact division of the plane test (NTR_EARLY_EDGE_LOAD) was
+// tried and rejected.
+#ifndef NTR_EARLY_EDGE_LOAD
+#define NTR_EARLY_EDGE_LOAD 0      // measured: issuing the loads before the division is SLOWER (config 2 0.746 -> 0.82 ms,
+                                   // config 4 opaque 31.1 -> 34.5 ms): lanes rejected by the exact t test waste them
+#endif
+template <int DT> struct EdgeRec {
+    static constexpr int LP = DT > 0 ? (DT * DT + 3) / 4 * 4 : 4;
     float r[LP];
-    if (DT > 0) {
+    const float *g;
+    NTR_HD void load(const float *lp) {
+        g = lp;
+        if (DT > 0) {
     NTR_UNROLL
-        for (int k = 0; k < LP / 4; ++k) {
-            const float4 v = ld4(lp + 4 * k);
-            r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+            for (int k = 0; k < LP / 4; ++k) {
+                const float4 v = ld4(lp + 4 * k);
+                r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+            }
         }
     }
+    NTR_HD float at(int k) const { return DT > 0 ? r[k < LP ? k : 0] : ldf(g + k); }
+};
+
+template <int DT>
+NTR_HD bool batch_lane_edges(const SceneDev &s, const EdgeRec<DT> &er, const float *o, const float *dir, float t) {
+    const int D = NTR_D(DT, s);
     float pside[DimCap<DT>::value];
     NTR_UNROLL
-    for (int i = 0; i < D; ++i) pside[i] = (DT > 0 ? r[i < LP ? i : 0] : ldf(lp + i)) - (o[i] + t * dir[i]);
+    for (int i = 0; i < D; ++i) pside[i] = er.at(i) - (o[i] + t * dir[i]);
     float tot = 0;
     NTR_UNROLL
     for (int e = 0; e < D - 1; ++e) {
         float area = 0;
     NTR_UNROLL
-        for (int i = 0; i < D; ++i) {
-            const int k = D + e * D + i;
-            area += (DT > 0 ? r[k < LP ? k : 0] : ldf(lp + k)) * pside[i];
-        }
+        for (int i = 0; i < D; ++i) area += er.at(D + e * D + i) * pside[i];
         if (!(area >= -NTR_FUZZ)) return false;
         tot += area;
     }
@@ -267,9 +278,16 @@ NTR_HD float batch_test(const SceneDev &s, uint32_t off, const float *o, const f
             if (!(viable & (1u << k))) continue;
             if (den[k] == 0) continue;
             // mask = denom != 0 && t >= 0 (:562-565); t[i] && t[i] < min_t (:586)
+            EdgeRec<DT> er;
+#if NTR_EARLY_EDGE_LOAD
+            er.load(edges + (g + k) * LPART);       // in flight while the division below completes
+#endif
             const float t = num[k] / den[k];
             if (!(t >= 0) || t == 0 || !(t < min_t)) continue;
-            if (!batch_lane_edges<DT>(s, edges + (g + k) * LPART, o, dir, t)) continue;
+#if !NTR_EARLY_EDGE_LOAD
+            er.load(edges + (g + k) * LPART);
+#endif
+            if (!batch_lane_edges<DT>(s, er, o, dir, t)) continue;
             min_t = t;
             r_index = g + k;
         }
@@ -327,9 +345,11 @@ NTR_HD float batch_finish4(const SceneDev &s, uint32_t off, const BatchPlane &p,
     for (int k = 0; k < 4; ++k) {
         if (!(p.viable & (1u << k))) continue;
         if (p.den[k] == 0) continue;
+        EdgeRec<DT> er;
+        er.load(edges + k * LPART);
         const float t = p.num[k] / p.den[k];
         if (!(t >= 0) || t == 0 || !(t < min_t)) continue;
-        if (!batch_lane_edges<DT>(s, edges + k * LPART, o, dir, t)) continue;
+        if (!batch_lane_edges<DT>(s, er, o, dir, t)) continue;
         min_t = t;
         r_index = k;
     }
