@@ -365,7 +365,7 @@ def main():
                 'bound': 'fp32', 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp32_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
                 # (profiles/r01_c2_render_pass_ncu_full_summary.txt); only measured for the default workload
-                'traffic': 2.2e6 if args.config == 'c2' else None,
+                'traffic': 10.28e6 if args.config == 'c2' else None,
                 'peak_source': 'FP32 FMA micro-benchmark measured live in this run (ntr_measure_fp32_peak); MEASURED_PEAKS.json has HBM/BF16 only',
                 'algorithmic_flops_per_launch': flops, 'kernel': 'render_pass_kernel<%s,%d>' % (dim if 3 <= dim <= 8 else 0, 0), 'kernel_ms': ms_per_step,
                 'reference_algorithm_counts': cnt_ref, 'counts_from': counts_from,
