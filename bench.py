@@ -124,6 +124,7 @@ def reference_arm(args, sc, g, w, h, rays_per_frame):
     cores = os.cpu_count() or 1
     import ref_bridge as rb
     times = []
+    stream_ref = None
     if int(sc['simplex'].shape[0]) > 50000 if int(sc['kind']) == 1 else False:
         return {'value': None, 'unit': 'Mrays/s', 'cores': cores, 'kind': 'reference',
                 'sample': 'not run: the reference cannot hold %d primitives (one Python object each, O(N^2) batch grouping); '
@@ -156,6 +157,24 @@ def reference_arm(args, sc, g, w, h, rays_per_frame):
             times.append((time.perf_counter() - t) * (w * h) / (sw * sh))    # scaled to the full frame's pixel count
             if time.perf_counter() > budget:
                 break
+        if args.stream_frames >= 2 and div == 1 and min(times) < 0.5:
+            # the rotating-camera loop of polytope.py --benchmark on the same camera path as the GPU's stream leg:
+            # a bounded sample of its frames (every n-th camera), one BlockingRenderer.render per frame
+            from ntracer_b200 import stream as nts
+            cams = nts.rotation_cameras(sc['cam_origin'], sc['cam_axes'], args.stream_frames)
+            pick = cams[::max(1, len(cams) // 8)][:8]
+            st_times = []
+            for o, a in pick:
+                cam = nt.Camera()
+                cam.origin = nt.Vector(*[float(x) for x in o])
+                for i in range(int(sc['dim'])):
+                    cam.axes[i] = nt.Vector(*[float(x) for x in a[i]])
+                scene.set_camera(cam)
+                t = time.perf_counter()
+                r.render(buf, fmt, scene)
+                st_times.append(time.perf_counter() - t)
+            stream_ref = {'frames_sampled': len(pick), 'of': len(cams), 'ms_per_frame': 1e3 * sum(st_times) / len(st_times),
+                          'frames_per_s': len(st_times) / sum(st_times)}
         kind = 'reference'
         sample = ('%d frame(s) of the same view at %dx%d (1/%d linear size; times scaled by pixel count to %dx%d), BlockingRenderer '
                   'all cores, SSE4.2 build (the AVX paths of the reference do not compile)' % (len(times), sw, sh, div, w, h))
@@ -171,8 +190,11 @@ def reference_arm(args, sc, g, w, h, rays_per_frame):
         kind = 'port'
         sample = '%d full %dx%d frames, oracle C port with OpenMP' % (len(times), w, h)
     best = min(times)
-    return {'value': rays_per_frame / best / 1e6, 'unit': 'Mrays/s', 'cores': cores, 'kind': kind, 'sample': sample,
-            'sec_per_frame': best, 'median_sec_per_frame': statistics.median(times), 'Mpix_per_s': w * h / best / 1e6}
+    out = {'value': rays_per_frame / best / 1e6, 'unit': 'Mrays/s', 'cores': cores, 'kind': kind, 'sample': sample,
+           'sec_per_frame': best, 'median_sec_per_frame': statistics.median(times), 'Mpix_per_s': w * h / best / 1e6}
+    if stream_ref:
+        out['stream'] = stream_ref
+    return out
 
 
 def main():
@@ -183,6 +205,8 @@ def main():
     ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--stream-frames', type=int, default=160,
+                    help='frames of the rotating-camera loop (polytope.py --benchmark); 0 = skip that leg')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -314,6 +338,27 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = ds.launch_count() - launches0      # kernels of this library launched inside the two timed regions
 
+    # ---- the interactive loop: rotating camera, one frame per camera, two frames in flight, every
+    # frame copied into a pinned host buffer (ntr_render_begin / ntr_render_end); wall clock around the whole loop ----
+    stream_res = None
+    if world == 1 and args.stream_frames >= 2:
+        from ntracer_b200 import stream as nts
+        n_frames = int(max(8, min(args.stream_frames, 4000.0 / max(statistics.median(dev_ms), 1e-3))))
+        cams = nts.rotation_cameras(cam_o, cam_a, args.stream_frames)[:n_frames]
+        bufs = [host_frame.numpy(), torch.zeros(fmt.pitch * h, dtype=torch.uint8).pin_memory().numpy()]
+        nts.render_sequence(ds, fmt, cams[:4], bufs)                    # warm-up
+        torch.cuda.synchronize()
+        launches_s0 = ds.launch_count()
+        t = time.perf_counter()
+        nts.render_sequence(ds, fmt, cams, bufs)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t
+        stream_res = {'frames': n_frames, 'camera_path': 'polytope.py RotatingCamera, %d steps per turn' % args.stream_frames,
+                      'in_flight': 2, 'ms_per_frame': 1e3 * el / n_frames, 'frames_per_s': n_frames / el,
+                      'Mpix_per_s': w * h * n_frames / el / 1e6, 'd2h_bytes_per_frame': int(frame_bytes),
+                      'gpu_launches': int(ds.launch_count() - launches_s0)}
+        ds.set_camera(cam_o, cam_a)
+
     tot_dev = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot_dev, op=dist.ReduceOp.MAX)
@@ -337,6 +382,8 @@ def main():
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
+        if stream_res:
+            line['stream'] = stream_res
         if world == 1:
             # ---- roofline of the dominant kernel (render_pass_kernel: the only kernel of this frame) ----
             from tests import oracle_lib as ol

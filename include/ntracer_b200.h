@@ -165,6 +165,19 @@ NTR_API int ntr_render(ntr_scene *scene, const ntr_image_format *fmt, void *dst,
  * the multi-GPU gather uses; otherwise at their frame position. */
 NTR_API int ntr_render_device(ntr_scene *scene, const ntr_image_format *fmt, void *dev_dst, size_t dst_len,
                               void *stream, int tile_row_first, int tile_row_step, int compact);
+/* The interactive loop: CallbackRenderer.begin_render + completion (src/render.cpp:495-563,
+ * 651-700) as driven by scripts/polytope.py:505-557 (rotating camera, one frame after the other).
+ * ntr_render_begin enqueues the frame with the camera / parameters current at the call and returns a ticket
+ * without waiting; ntr_render_end(ticket) waits for that frame and completes the copy into the `dst` given
+ * to begin.  Up to NTR_FRAMES_IN_FLIGHT frames may be open: frame k+1 is traced while frame k crosses PCIe
+ * (double-buffered device frames + pinned staging; `dst` is written directly when it is itself pinned).
+ * The camera may be changed between begin and end (it is captured at begin).  `dst` must stay valid until end.
+ * Tickets must be ended in the order they were begun.  A third begin without an end -> NTR_ERR_RUNTIME
+ * ("already running", src/render.cpp:676).  ntr_render_end returns NTR_ERR_ABORTED if ntr_abort() hit the frame. */
+#define NTR_FRAMES_IN_FLIGHT 2
+NTR_API int ntr_render_begin(ntr_scene *scene, const ntr_image_format *fmt, void *dst, size_t dst_len,
+                             uint64_t *ticket_out);
+NTR_API int ntr_render_end(ntr_scene *scene, uint64_t ticket);
 /* Float RGB of every pixel (3 floats per pixel, row-major) = scene::calculate_color for the whole
  * view (src/render.hpp:12-13) before channel packing; host destination. */
 NTR_API int ntr_render_float(ntr_scene *scene, int width, int height, float *dst_rgb);

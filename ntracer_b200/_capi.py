@@ -191,6 +191,8 @@ def load():
         'ntr_scene_set_params': (C.c_int, [vp, C.POINTER(SceneDesc)]),
         'ntr_render': (C.c_int, [vp, C.POINTER(ImageFormat), vp, C.c_size_t]),
         'ntr_render_device': (C.c_int, [vp, C.POINTER(ImageFormat), vp, C.c_size_t, vp, i32, i32, i32]),
+        'ntr_render_begin': (C.c_int, [vp, C.POINTER(ImageFormat), vp, C.c_size_t, C.POINTER(C.c_uint64)]),
+        'ntr_render_end': (C.c_int, [vp, C.c_uint64]),
         'ntr_render_float': (C.c_int, [vp, i32, i32, vp]),
         'ntr_calculate_color': (C.c_int, [vp, i32, i32, i32, i32, f32p]),
         'ntr_primary_hit_ids': (C.c_int, [vp, i32, i32, vp, vp]),
@@ -216,10 +218,15 @@ def load():
 
 EXPORTED_SYMBOLS = (
     'ntr_abi_version', 'ntr_last_error', 'ntr_device_count', 'ntr_scene_create', 'ntr_scene_destroy',
-    'ntr_scene_set_camera', 'ntr_scene_set_params', 'ntr_render', 'ntr_render_device', 'ntr_render_float',
+    'ntr_scene_set_camera', 'ntr_scene_set_params', 'ntr_render', 'ntr_render_device', 'ntr_render_begin',
+    'ntr_render_end', 'ntr_render_float',
     'ntr_calculate_color', 'ntr_primary_hit_ids', 'ntr_trace_rays', 'ntr_occludes_rays', 'ntr_abort',
     'ntr_get_counters', 'ntr_set_instrumented', 'ntr_last_kernel_ms', 'ntr_launch_count',
     'ntr_measure_fp32_peak', 'ntr_simplex_from_points', 'ntr_build_kdtree', 'ntr_free')
+
+
+class AbortedError(RuntimeError):
+    """A render call ended early because ntr_abort() was called (NTR_ERR_ABORTED)."""
 
 
 def check(status):
@@ -234,4 +241,6 @@ def check(status):
         raise MemoryError(msg)
     if status == NTR_ERR_NO_DEVICE:
         raise BackendError(msg or 'no sm_100 CUDA device: ntracer_b200 has no CPU fallback')
+    if status == NTR_ERR_ABORTED:
+        raise AbortedError(msg)
     raise RuntimeError(msg)

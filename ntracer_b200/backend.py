@@ -25,6 +25,7 @@ class DeviceScene:
         self.dim = int(scene['dim'])
         self.kind = int(scene['kind'])
         self._scene = scene
+        self._open = {}
         desc, keep = _capi.make_desc(scene)
         _capi.check(self._lib.ntr_scene_create(C.byref(desc), device, C.byref(self._h)))
         if 'cam_origin' in scene and 'cam_axes' in scene:
@@ -76,6 +77,24 @@ class DeviceScene:
                 raise ValueError('the buffer is too small for an image with the given dimensions')
         _capi.check(self._lib.ntr_render(self._h, C.byref(fmt), _p(buf), buf.size))
         return out
+
+    def render_begin(self, fmt, dest):
+        """Enqueue one frame with the current camera and return a ticket (the interactive loop: frame k+1 is traced
+        while frame k is copied back; at most two frames open).  `dest` must stay alive until render_end(ticket)."""
+        buf = np.frombuffer(dest, dtype=np.uint8)
+        if buf.size < fmt.pitch * fmt.height:
+            raise ValueError('the buffer is too small for an image with the given dimensions')
+        ticket = C.c_uint64(0)
+        _capi.check(self._lib.ntr_render_begin(self._h, C.byref(fmt), _p(buf), buf.size, C.byref(ticket)))
+        self._open[ticket.value] = buf          # keeps the exported buffer alive while the copy engine writes it
+        return ticket.value
+
+    def render_end(self, ticket):
+        """Wait for the frame of `ticket` and finish the copy into its destination."""
+        try:
+            _capi.check(self._lib.ntr_render_end(self._h, C.c_uint64(ticket)))
+        finally:
+            self._open.pop(ticket, None)
 
     def render_device(self, fmt, dev_ptr, nbytes, stream=0, tile_row_first=0, tile_row_step=1, compact=False):
         """Asynchronous render into device memory (a torch tensor's data_ptr()) on a CUDA stream handle."""

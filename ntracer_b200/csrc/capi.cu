@@ -55,6 +55,19 @@ __global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, i
 
 }  // namespace
 
+// One open frame of the begin/end interface: its own device frame, a pinned staging buffer for pageable destinations
+// and the event that marks the end of its device->host copy.
+struct FrameSlot {
+    unsigned char *d_buf = nullptr; size_t d_cap = 0;
+    unsigned char *h_stage = nullptr; size_t h_cap = 0;
+    cudaEvent_t rendered = nullptr, copied = nullptr;
+    unsigned char *dst = nullptr;
+    size_t pitch = 0, row_bytes = 0;
+    int height = 0;
+    bool open = false, staged = false;
+    uint64_t ticket = 0;
+};
+
 struct ntr_scene {
     int device = 0;
     int sm_count = 0;
@@ -101,6 +114,10 @@ struct ntr_scene {
     int grid_blocks[4] = {0, 0, 0, 0};
     const KernelSet *(*kset)(int) = nullptr;
     volatile bool busy = false;
+    // begin/end frames (ntr_render_begin / ntr_render_end)
+    FrameSlot slots[NTR_FRAMES_IN_FLIGHT];
+    cudaStream_t copy_stream = nullptr;
+    uint64_t next_ticket = 0;
 };
 
 namespace {
@@ -442,10 +459,17 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     return NTR_OK;
 }
 
+// A device->host copy of the finished frame that run_frame_sync may enqueue right behind the kernels, so that frames
+// without wavefront passes need a single stream synchronisation.
+struct HostCopy {
+    void *dst; size_t dpitch; const void *src; size_t spitch, row_bytes; int rows;
+    bool done;
+};
+
 // Runs a frame on the scene's own stream, waits for it, handles queue overflow (regrow + retry) and abort.
 int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win_w, int win_h,
                    const ntr_image_format *fmt, const RenderTarget &tgt, int trf, int trs, int compact,
-                   cudaStream_t st) {
+                   cudaStream_t st, HostCopy *hc = nullptr) {
     for (int attempt = 0; attempt < 8; ++attempt) {
         bool passes = false;
         CUDA_TRY(cudaEventRecord(sc->ev0, st));
@@ -453,6 +477,10 @@ int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(sc->ev1, st));
         sc->timing_valid = true;
+        if (hc && !passes) {            // no overflow / retry possible: the frame in d_packed is final
+            CUDA_TRY(cudaMemcpy2DAsync(hc->dst, hc->dpitch, hc->src, hc->spitch, hc->row_bytes, hc->rows, cudaMemcpyDeviceToHost, st));
+            hc->done = true;
+        }
         uint32_t h_ctl[CTL_WORDS];
         unsigned long long h_cnt[8];
         CUDA_TRY(cudaMemcpyAsync(h_ctl, sc->d_ctl, sizeof h_ctl, cudaMemcpyDeviceToHost, st));
@@ -663,6 +691,13 @@ NTR_API void ntr_scene_destroy(ntr_scene *sc) {
     cudaFree(sc->d_queue[0]); cudaFree(sc->d_queue[1]); cudaFree(sc->d_scratch);
     cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order);
     cudaFree(sc->d_keys[0]); cudaFree(sc->d_keys[1]); cudaFree(sc->d_perm[0]); cudaFree(sc->d_perm[1]); cudaFree(sc->d_sort_tmp);
+    if (sc->copy_stream) { cudaStreamSynchronize(sc->copy_stream); cudaStreamDestroy(sc->copy_stream); }
+    for (FrameSlot &fs : sc->slots) {
+        cudaFree(fs.d_buf);
+        if (fs.h_stage) cudaFreeHost(fs.h_stage);
+        if (fs.rendered) cudaEventDestroy(fs.rendered);
+        if (fs.copied) cudaEventDestroy(fs.copied);
+    }
     if (sc->h_abort) cudaFreeHost(sc->h_abort);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
@@ -742,11 +777,99 @@ NTR_API int ntr_render(ntr_scene *sc, const ntr_image_format *fmt, void *dst, si
     RenderTarget tgt;
     tgt.out_mode = NTR_OUT_PACKED;
     tgt.packed = sc->d_packed;
-    if ((rc = run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, sc->stream))) return rc;
     // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
-    CUDA_TRY(cudaMemcpy2DAsync(dst, fmt->pitch, sc->d_packed, fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel,
-                               fmt->height, cudaMemcpyDeviceToHost, sc->stream));
-    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    HostCopy hc{dst, (size_t)fmt->pitch, sc->d_packed, (size_t)fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel, fmt->height, false};
+    if ((rc = run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, sc->stream, &hc))) return rc;
+    if (!hc.done) {
+        CUDA_TRY(cudaMemcpy2DAsync(hc.dst, hc.dpitch, hc.src, hc.spitch, hc.row_bytes, hc.rows, cudaMemcpyDeviceToHost, sc->stream));
+        CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    }
+    return NTR_OK;
+}
+
+NTR_API int ntr_render_begin(ntr_scene *sc, const ntr_image_format *fmt, void *dst, size_t dst_len, uint64_t *ticket_out) {
+    if (!sc) return fail(NTR_ERR_VALUE, "scene is NULL");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    if (sc->busy) return fail(NTR_ERR_RUNTIME, "the renderer is already running");
+    int rc = check_format(fmt);
+    if (rc) return rc;
+    if (!dst || !ticket_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    const size_t bytes = (size_t)fmt->pitch * fmt->height;
+    if (dst_len < bytes) return fail(NTR_ERR_VALUE, "the buffer is too small for an image with the given dimensions");
+    FrameSlot &fs = sc->slots[sc->next_ticket % NTR_FRAMES_IN_FLIGHT];
+    if (fs.open) return fail(NTR_ERR_RUNTIME, "the renderer is already running: %d frames are in flight, end one first", NTR_FRAMES_IN_FLIGHT);
+    bool any_open = false;
+    for (const FrameSlot &o : sc->slots) any_open |= o.open;
+    if (!any_open) *sc->h_abort = 0;           // a pending abort keeps hitting every frame that was open when it came
+    if (!sc->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
+    if (!fs.rendered) CUDA_TRY(cudaEventCreateWithFlags(&fs.rendered, cudaEventDisableTiming));
+    if (!fs.copied) CUDA_TRY(cudaEventCreateWithFlags(&fs.copied, cudaEventDisableTiming));
+    if ((rc = ensure((void **)&fs.d_buf, &fs.d_cap, bytes))) return rc;
+    // a pinned (or registered) destination is written by the copy engine directly; anything else goes through staging
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    fs.staged = !pinned;
+    if (fs.staged && fs.h_cap < bytes) {
+        if (fs.h_stage) { cudaFreeHost(fs.h_stage); fs.h_stage = nullptr; fs.h_cap = 0; }
+        CUDA_TRY(cudaHostAlloc((void **)&fs.h_stage, bytes + bytes / 8, cudaHostAllocDefault));
+        fs.h_cap = bytes + bytes / 8;
+    }
+    fs.dst = static_cast<unsigned char *>(dst);
+    fs.pitch = (size_t)fmt->pitch;
+    fs.row_bytes = (size_t)fmt->width * fmt->bytes_per_pixel;
+    fs.height = fmt->height;
+    RenderTarget tgt;
+    tgt.out_mode = NTR_OUT_PACKED;
+    tgt.packed = fs.d_buf;
+    const bool composite = sc->dev.kind == NTR_SCENE_COMPOSITE;
+    const bool passes = composite && sc->any_reflective && sc->dev.max_depth > 0;
+    sc->busy = true;
+    if (!passes) {
+        // one persistent kernel: fully asynchronous
+        bool p = false;
+        cudaEventRecord(sc->ev0, sc->stream);
+        rc = enqueue_frame(sc, sc->stream, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, &p);
+        cudaEventRecord(sc->ev1, sc->stream);
+        sc->timing_valid = rc == NTR_OK;
+        sc->counters = ntr_counters{};
+        sc->counters.primary_rays = (uint64_t)fmt->width * fmt->height;
+    } else {
+        // wavefront passes need their counters back between passes: traced synchronously, only the copy overlaps
+        rc = run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, sc->stream);
+        if (rc == NTR_ERR_ABORTED) rc = NTR_OK;     // reported by ntr_render_end
+    }
+    sc->busy = false;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(fs.rendered, sc->stream));
+    CUDA_TRY(cudaStreamWaitEvent(sc->copy_stream, fs.rendered, 0));
+    unsigned char *host = fs.staged ? fs.h_stage : fs.dst;
+    CUDA_TRY(cudaMemcpy2DAsync(host, fs.pitch, fs.d_buf, fs.pitch, fs.row_bytes, fs.height, cudaMemcpyDeviceToHost, sc->copy_stream));
+    CUDA_TRY(cudaEventRecord(fs.copied, sc->copy_stream));
+    fs.open = true;
+    fs.ticket = ++sc->next_ticket;
+    *ticket_out = fs.ticket;
+    return NTR_OK;
+}
+
+NTR_API int ntr_render_end(ntr_scene *sc, uint64_t ticket) {
+    if (!sc) return fail(NTR_ERR_VALUE, "scene is NULL");
+    FrameSlot *fs = nullptr;
+    for (FrameSlot &o : sc->slots) {
+        if (o.open && o.ticket == ticket) fs = &o;
+        else if (o.open && o.ticket < ticket) return fail(NTR_ERR_VALUE, "frames must be ended in the order they were begun");
+    }
+    if (!fs) return fail(NTR_ERR_VALUE, "no open frame with this ticket");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    const cudaError_t e = cudaEventSynchronize(fs->copied);
+    fs->open = false;
+    if (e != cudaSuccess) return fail(NTR_ERR_RUNTIME, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+    if (*sc->h_abort) return fail(NTR_ERR_ABORTED, "render aborted");
+    if (fs->staged) {
+        // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
+        if (fs->row_bytes == fs->pitch) memcpy(fs->dst, fs->h_stage, fs->pitch * (size_t)fs->height);
+        else for (int y = 0; y < fs->height; ++y) memcpy(fs->dst + (size_t)y * fs->pitch, fs->h_stage + (size_t)y * fs->pitch, fs->row_bytes);
+    }
     return NTR_OK;
 }
 
@@ -877,7 +1000,9 @@ NTR_API int ntr_occludes_rays(ntr_scene *sc, uint32_t n, const float *origins, c
 
 NTR_API int ntr_abort(ntr_scene *sc) {
     if (!sc) return fail(NTR_ERR_VALUE, "scene is NULL");
-    if (sc->busy) *sc->h_abort = 1;         // polled by every warp before it takes the next block of work
+    bool open = sc->busy;
+    for (const FrameSlot &fs : sc->slots) open |= fs.open;     // frames between ntr_render_begin and ntr_render_end
+    if (open) *sc->h_abort = 1;             // polled by every warp before it takes the next block of work
     return NTR_OK;
 }
 

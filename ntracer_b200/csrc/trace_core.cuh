@@ -842,6 +842,42 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
     return true;
 }
 
+// Per-ray axis tables of the traversal.  A k-d step needs o[axis], dir[axis] and 1/dir[axis] for a run-time axis; with
+// the vectors in registers that is a select chain per value (ncu, config 2: 7.4 % of all instructions).  With
+// NTR_SMEM_AXIS the fixed-dimension kernels keep the three vectors in a per-thread column of shared memory instead
+// (3*D floats per thread, column-major over the CTA: conflict-free for any mix of axes within a warp) and index it.
+// MEASURED (B200): slower everywhere -- config 2 0.740 -> 0.770 ms, config 3 0.551 -> 0.577 ms, config 4 opaque
+// 31.0 -> 32.7 ms: the shared-memory round trip sits on the node-to-node dependency chain, the selects do not.  Off.
+#ifndef NTR_SMEM_AXIS
+#define NTR_SMEM_AXIS 0
+#endif
+#if defined(__CUDA_ARCH__) && NTR_SMEM_AXIS
+#define NTR_AXIS_THREADS 128            // = kCtaThreads (kernels.cuh)
+template <int DT> __device__ __forceinline__ float *axis_slab() {
+    __shared__ float slab[3 * DimCap<DT>::value * NTR_AXIS_THREADS];
+    return slab + threadIdx.x;
+}
+#define NTR_AXIS_SETUP(DT, D, o, dir, invdir)                                                              \
+    float *axis_tab_ = nullptr;                                                                            \
+    if (DT > 0) {                                                                                          \
+        axis_tab_ = axis_slab<DT>();                                                                       \
+        _Pragma("unroll")                                                                                  \
+        for (int i_ = 0; i_ < (DT > 0 ? DT : 1); ++i_) {                                                   \
+            axis_tab_[i_ * NTR_AXIS_THREADS] = (o)[i_];                                                    \
+            axis_tab_[(DT + i_) * NTR_AXIS_THREADS] = (dir)[i_];                                           \
+            axis_tab_[(2 * DT + i_) * NTR_AXIS_THREADS] = (invdir)[i_];                                    \
+        }                                                                                                  \
+    }
+#define NTR_AXIS_O(DT, o, axis) (DT > 0 ? axis_tab_[(axis) * NTR_AXIS_THREADS] : (o)[axis])
+#define NTR_AXIS_DIR(DT, dir, axis) (DT > 0 ? axis_tab_[(DT + (axis)) * NTR_AXIS_THREADS] : (dir)[axis])
+#define NTR_AXIS_INV(DT, invdir, axis) (DT > 0 ? axis_tab_[(2 * DT + (axis)) * NTR_AXIS_THREADS] : (invdir)[axis])
+#else
+#define NTR_AXIS_SETUP(DT, D, o, dir, invdir)
+#define NTR_AXIS_O(DT, o, axis) vsel<DT>(o, axis)
+#define NTR_AXIS_DIR(DT, dir, axis) vsel<DT>(dir, axis)
+#define NTR_AXIS_INV(DT, invdir, axis) vsel<DT>(invdir, axis)
+#endif
+
 // ---- nearest-hit traversal ----------------------------------------------------------------------------
 // kd_node_intersection::operator() (tracer.hpp:1179-1243) as an explicit stack machine.  Two frame
 // kinds reproduce the recursion exactly: AFTER_NEAR (pending far child, split distance t, the caller's
@@ -861,6 +897,7 @@ NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, S
     RaySlab<DT> rs;
     rs.init(s, dir);
     const float *invdir = rs.invdir;
+    NTR_AXIS_SETUP(DT, NTR_D(DT, s), o, dir, invdir)
     TravStack st;
     int sp = 0;
     uint32_t node = s.root;
@@ -879,10 +916,10 @@ NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, S
             if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
             const int axis = (int)n.x;
             const float split = u2f(n.y);
-            const float da = vsel<DT>(dir, axis), oa = vsel<DT>(o, axis);
+            const float da = NTR_AXIS_DIR(DT, dir, axis), oa = NTR_AXIS_O(DT, o, axis);
             if (da != 0) {
                 if (oa == split) { node = da > 0 ? n.w : n.z; continue; }
-                const float t = (split - oa) * vsel<DT>(invdir, axis);
+                const float t = (split - oa) * NTR_AXIS_INV(DT, invdir, axis);
                 const uint32_t n_near = oa > split ? n.w : n.z;
                 const uint32_t n_far = oa > split ? n.z : n.w;
                 if (t < 0 || t > t_far) { node = n_near; continue; }
@@ -1142,6 +1179,7 @@ NTR_HD bool trace_occludes(const SceneDev &s, const float *o, const float *dir, 
     RaySlab<DT> rs;
     rs.init(s, dir);
     const float *invdir = rs.invdir;
+    NTR_AXIS_SETUP(DT, NTR_D(DT, s), o, dir, invdir)
     uint32_t st_node[NTR_STACK_CAP];
     float st_t[NTR_STACK_CAP], st_tfar[NTR_STACK_CAP];
     int sp = 0;
@@ -1156,10 +1194,10 @@ NTR_HD bool trace_occludes(const SceneDev &s, const float *o, const float *dir, 
             if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
             const int axis = (int)n.x;
             const float split = u2f(n.y);
-            const float da = vsel<DT>(dir, axis), oa = vsel<DT>(o, axis);
+            const float da = NTR_AXIS_DIR(DT, dir, axis), oa = NTR_AXIS_O(DT, o, axis);
             if (da != 0) {
                 if (oa == split) { node = da > 0 ? n.w : n.z; continue; }
-                const float t = (split - oa) * vsel<DT>(invdir, axis);
+                const float t = (split - oa) * NTR_AXIS_INV(DT, invdir, axis);
                 const uint32_t n_near = oa > split ? n.w : n.z;
                 const uint32_t n_far = oa > split ? n.z : n.w;
                 if (t < 0 || t > t_far) { node = n_near; continue; }

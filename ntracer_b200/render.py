@@ -232,3 +232,44 @@ class CallbackRenderer:
             dev.abort()
         if t is not None and t is not threading.current_thread():
             t.join()
+
+
+class StreamRenderer:
+    """Extension without a reference counterpart: the interactive loop of scripts/polytope.py:505-557 (begin_render ->
+    completion callback -> move the camera -> begin_render ...) with two frames in flight, so that frame k+1 is traced
+    while frame k crosses PCIe (ntr_render_begin / ntr_render_end).  The reference cannot overlap frames: its scene is
+    locked, camera included, until the frame is complete (src/tracer.hpp:1922-1926).
+
+        t0 = r.submit(buf0, fmt, scene); scene.set_camera(cam1)
+        t1 = r.submit(buf1, fmt, scene); r.wait(t0)  # buf0 is complete ...
+
+    The camera and scene parameters are captured by submit(); geometry must not change while frames are open."""
+    def __init__(self):
+        self._open = {}
+
+    def submit(self, dest, format, scene):
+        if not isinstance(format, ImageFormat):
+            raise TypeError('object is not an instance of ImageFormat')
+        if not isinstance(scene, Scene):
+            raise TypeError('object is not an instance of Scene')
+        buf = _writable_buffer(dest)
+        fmt = format._native()
+        if buf.size < fmt.pitch * fmt.height:
+            raise ValueError('the buffer is too small for an image with the given dimensions')
+        dev = scene._prepare()
+        ticket = dev.render_begin(fmt, buf)
+        self._open[ticket] = dev
+        return ticket
+
+    def wait(self, ticket):
+        """-> True, or False if abort() hit the frame."""
+        dev = self._open.pop(ticket)
+        try:
+            dev.render_end(ticket)
+        except _capi.AbortedError:
+            return False
+        return True
+
+    def abort(self):
+        for dev in set(self._open.values()):
+            dev.abort()
