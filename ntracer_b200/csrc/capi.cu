@@ -103,6 +103,7 @@ struct ntr_scene {
     uint32_t *d_keys[2] = {nullptr, nullptr}, *d_perm[2] = {nullptr, nullptr};
     void *d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0; uint32_t sort_cap = 0;
     bool sort_rays = true;
+    bool zero_copy = false;             // NTR_ZEROCOPY=1: ntr_render stores single-pass frames straight into pinned destinations
     uint32_t queue_init = 0;            // NTR_QUEUE_INIT: initial queue capacity override (tests force the regrow path)
     float pass_ns_per_ray = 0.0f;       // measured cost of the wavefront passes of the previous frame (0 = unknown)
     // diagnostic per-pass timing (NTR_PASS_TIMING=1): events between the passes of one frame
@@ -650,6 +651,7 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->sm_count = prop.multiProcessorCount;
     sc->pass_timing = getenv("NTR_PASS_TIMING") != nullptr;
     sc->sort_rays = getenv("NTR_NO_RAY_SORT") == nullptr;
+    if (const char *zc = getenv("NTR_ZEROCOPY")) sc->zero_copy = atoi(zc) != 0;
     if (const char *qi = getenv("NTR_QUEUE_INIT")) sc->queue_init = (uint32_t)strtoul(qi, nullptr, 10);
     sc->tree_depth = depth;
     sc->dev.dim = desc->dim;
@@ -773,9 +775,24 @@ NTR_API int ntr_render(ntr_scene *sc, const ntr_image_format *fmt, void *dst, si
     if (!dst) return fail(NTR_ERR_VALUE, "destination is NULL");
     const size_t bytes = (size_t)fmt->pitch * fmt->height;
     if (dst_len < bytes) return fail(NTR_ERR_VALUE, "the buffer is too small for an image with the given dimensions");
-    if ((rc = ensure((void **)&sc->d_packed, &sc->packed_cap, bytes))) return rc;
     RenderTarget tgt;
     tgt.out_mode = NTR_OUT_PACKED;
+    if (sc->zero_copy && !(sc->dev.kind == NTR_SCENE_COMPOSITE && sc->any_reflective && sc->dev.max_depth > 0)) {
+        // Single-pass frame into a pinned (mapped) destination: the packing epilogue of the kernel stores the pixels
+        // straight into host memory, so the PCIe transfer runs underneath the tracing instead of after it.
+        // MEASURED (B200, PCIe Gen5): byte-identical frames, but SLOWER end to end -- config 1 0.114 -> 0.186 ms,
+        // config 2 0.900 -> 0.983 ms, config 3 unchanged: the 24-byte row segments of the 8x4 pixel blocks make poor PCIe
+        // writes.  Off unless NTR_ZEROCOPY=1.
+        cudaPointerAttributes attr;
+        void *mapped = nullptr;
+        if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            cudaHostGetDevicePointer(&mapped, dst, 0) == cudaSuccess && mapped) {
+            tgt.packed = static_cast<unsigned char *>(mapped);
+            return run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, sc->stream);
+        }
+        cudaGetLastError();
+    }
+    if ((rc = ensure((void **)&sc->d_packed, &sc->packed_cap, bytes))) return rc;
     tgt.packed = sc->d_packed;
     // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
     HostCopy hc{dst, (size_t)fmt->pitch, sc->d_packed, (size_t)fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel, fmt->height, false};

@@ -1,16 +1,25 @@
 set -x
-timeout 600 python -m pytest tests/test_stream.py -m gpu -q -x 2>&1 | tail -5 > gpurun_out/stream_tests.txt
-python bench.py --steps 20 --warmup 5 > gpurun_out/v_base_c2.json 2>gpurun_out/v_base_c2.err
-python bench.py --config c4o --steps 5 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/v_base_c4o.json 2>gpurun_out/v_base_c4o.err
-NTR_B200_LIB=$PWD/variants/libntr_smemaxis.so python bench.py --steps 20 --warmup 5 --no-cpu-baseline --stream-frames 0 > gpurun_out/v_smem_c2.json 2>gpurun_out/v_smem_c2.err
-NTR_B200_LIB=$PWD/variants/libntr_smemaxis.so python bench.py --config c4o --steps 5 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/v_smem_c4o.json 2>gpurun_out/v_smem_c4o.err
-NTR_B200_LIB=$PWD/variants/libntr_smemaxis.so python bench.py --config c3 --steps 10 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/v_smem_c3.json 2>gpurun_out/v_smem_c3.err
-python bench.py --config c3 --steps 10 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/v_base_c3.json 2>gpurun_out/v_base_c3.err
-cat gpurun_out/stream_tests.txt
-for f in gpurun_out/v_*.json; do python - $f <<'P'
-import json,sys
-try:
-    d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); print(sys.argv[1], round(d['ms_per_step'],4), round(d['e2e']['ms_per_step'],4), d.get('stream'))
-except Exception as e: print(sys.argv[1],'ERR',e)
+python - <<'P' > gpurun_out/zc_check.txt 2>&1
+import os, numpy as np, torch
+import sys; sys.path.insert(0,'.')
+from tests import fixtures as fx
+from ntracer_b200 import _capi
+from ntracer_b200.backend import DeviceScene
+for name in ['cell120','box4','solids6']:
+    sc,g=fx.load(name)
+    w,h=1920,1080
+    fmt=_capi.make_image_format(w,h,_capi.RGB8,pitch=w*3+32)
+    os.environ['NTR_ZEROCOPY']='0'
+    with DeviceScene(sc) as ds:
+        a=ds.render(fmt, torch.full((fmt.pitch*h,),7,dtype=torch.uint8).pin_memory().numpy()).copy()
+    os.environ['NTR_ZEROCOPY']='1'
+    with DeviceScene(sc) as ds:
+        b=ds.render(fmt, torch.full((fmt.pitch*h,),7,dtype=torch.uint8).pin_memory().numpy()).copy()
+        c=ds.render(fmt, np.full(fmt.pitch*h,7,np.uint8)).copy()     # pageable: falls back to the copy
+    print(name,'zero-copy == copy:',np.array_equal(a,b),np.array_equal(a,c))
 P
-done
+for c in c2 c1 c3; do
+for z in 0 1; do
+NTR_ZEROCOPY=$z python bench.py --config $c --steps 20 --warmup 5 --no-cpu-baseline --stream-frames 0 > gpurun_out/zc${z}_$c.json 2>gpurun_out/zc${z}_$c.err
+done; done
+cat gpurun_out/zc_check.txt
