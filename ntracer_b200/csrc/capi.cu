@@ -44,6 +44,7 @@ int fail(int code, const char *fmt, ...) {
 constexpr int kMaxPasses = 64;          // upper bound on max_reflect_depth handled by the control block
 
 // control block layout (uint32 words)
+constexpr int kSlabMax = 4;
 enum { CTL_TILE_CURSOR = 0, CTL_OVERFLOW = 1, CTL_COUNT0 = 2, CTL_CURSOR0 = CTL_COUNT0 + kMaxPasses + 1,
        CTL_WORDS = CTL_CURSOR0 + kMaxPasses + 1 };
 
@@ -103,6 +104,12 @@ struct ntr_scene {
     uint32_t *d_keys[2] = {nullptr, nullptr}, *d_perm[2] = {nullptr, nullptr};
     void *d_sort_tmp = nullptr; size_t sort_tmp_bytes = 0; uint32_t sort_cap = 0;
     bool sort_rays = true;
+    // ntr_render of single-pass frames into pinned memory: the frame is cut into slabs of tile rows, one persistent
+    // kernel + copy per slab on its own stream, so that all but the last slab cross PCIe underneath the tracing
+    int ctl_slot = 0;
+    cudaStream_t slab_stream[kSlabMax] = {};
+    cudaEvent_t slab_done[kSlabMax] = {};
+    bool slabs = true;                  // NTR_NO_SLABS=1 switches it off
     bool zero_copy = false;             // NTR_ZEROCOPY=1: ntr_render stores single-pass frames straight into pinned destinations
     uint32_t queue_init = 0;            // NTR_QUEUE_INIT: initial queue capacity override (tests force the regrow path)
     float pass_ns_per_ray = 0.0f;       // measured cost of the wavefront passes of the previous frame (0 = unknown)
@@ -300,6 +307,8 @@ struct RenderTarget {
 int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0, int y0, int win_w, int win_h,
                   const ntr_image_format *fmt, const RenderTarget &tgt, int tile_row_first, int tile_row_step,
                   int compact, bool *used_passes) {
+    uint32_t *const d_ctl = sc->d_ctl + (size_t)sc->ctl_slot * CTL_WORDS;                 // one control block per slab
+    unsigned long long *const d_counters = sc->d_counters + (size_t)sc->ctl_slot * 8;
     FrameDev f;
     memset(&f, 0, sizeof f);
     f.width = width; f.height = height;
@@ -351,7 +360,6 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     if (use_sched) {
         if (sc->tile_cap < n_tiles) {
             cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order);
-    cudaFree(sc->d_keys[0]); cudaFree(sc->d_keys[1]); cudaFree(sc->d_perm[0]); cudaFree(sc->d_perm[1]); cudaFree(sc->d_sort_tmp);
             sc->d_tile_cost = nullptr; sc->d_tile_order = nullptr; sc->tile_cap = 0;
             CUDA_TRY(cudaMalloc(&sc->d_tile_cost, n_tiles * sizeof(unsigned long long)));
             CUDA_TRY(cudaMalloc(&sc->d_tile_order, n_tiles * sizeof(uint32_t)));
@@ -368,12 +376,12 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     }
 
     ControlDev ctl;
-    ctl.tile_cursor = sc->d_ctl + CTL_TILE_CURSOR;
-    ctl.overflow = sc->d_ctl + CTL_OVERFLOW;
+    ctl.tile_cursor = d_ctl + CTL_TILE_CURSOR;
+    ctl.overflow = d_ctl + CTL_OVERFLOW;
     ctl.abort_flag = sc->d_abort;
-    ctl.counters = sc->d_counters;
-    CUDA_TRY(cudaMemsetAsync(sc->d_ctl, 0, CTL_WORDS * sizeof(uint32_t), st));
-    CUDA_TRY(cudaMemsetAsync(sc->d_counters, 0, 8 * sizeof(unsigned long long), st));
+    ctl.counters = d_counters;
+    CUDA_TRY(cudaMemsetAsync(d_ctl, 0, CTL_WORDS * sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), st));
 
     const KernelSet *ks = sc->kset(flags);
     const int grid = grid_for(sc, flags);
@@ -383,7 +391,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     q.capacity = sc->queue_capacity; q.rec4 = rec4;
     q.in = nullptr;
     q.out = sc->d_queue[0];
-    q.out_count = sc->d_ctl + CTL_COUNT0 + 1;
+    q.out_count = d_ctl + CTL_COUNT0 + 1;
     q.in_count = q.in_cursor = nullptr;
     auto mark = [&]() {
         if (!(sc->pass_timing || passes) || sc->n_pass_ev >= kMaxPasses + 4) return;
@@ -407,9 +415,9 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
         for (int depth = 1; depth <= sc->dev.max_depth; ++depth) {
             q.in = sc->d_queue[(depth - 1) & 1];
             q.out = sc->d_queue[depth & 1];
-            q.in_count = sc->d_ctl + CTL_COUNT0 + depth;
-            q.out_count = sc->d_ctl + CTL_COUNT0 + depth + 1;
-            q.in_cursor = sc->d_ctl + CTL_CURSOR0 + depth;
+            q.in_count = d_ctl + CTL_COUNT0 + depth;
+            q.out_count = d_ctl + CTL_COUNT0 + depth + 1;
+            q.in_cursor = d_ctl + CTL_CURSOR0 + depth;
             q.in_perm = nullptr;
             // adaptive: the sort (one read-back + key kernel + radix sort per pass) only pays for expensive rays; cheap scenes
             // (config 3: 0.45 ns/ray) lose 20 % to it, star polytopes (6-16 ns/ray unsorted) gain 26-29 %
@@ -419,7 +427,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
                 // direction signs + quantised direction + quantised origin hands every warp 32 rays that walk the same
                 // part of the tree.  Needs the exact count on the host (CUB): one 4-byte read-back per pass.
                 uint32_t n = 0;
-                CUDA_TRY(cudaMemcpyAsync(&n, sc->d_ctl + CTL_COUNT0 + depth, 4, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaMemcpyAsync(&n, d_ctl + CTL_COUNT0 + depth, 4, cudaMemcpyDeviceToHost, st));
                 CUDA_TRY(cudaStreamSynchronize(st));
                 n = std::min(n, sc->queue_capacity);
                 if (n >= (1u << 15)) {
@@ -527,6 +535,57 @@ int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win
         if (rc) return rc;
     }
     return fail(NTR_ERR_RUNTIME, "wavefront queue kept overflowing");
+}
+
+// ntr_render for frames that need a single pass, into a pinned destination: slabs of tile rows, each with its own
+// persistent kernel and device->host copy on its own stream.  The kernels queue up behind each other on the device
+// (each fills the machine; the next one's CTAs move in as the previous one's retire, so no tail is added) and the copy
+// of slab k runs while slab k+1 is traced.  Returns 1 when it does not apply (the caller uses the plain path).
+int run_frame_slabs(ntr_scene *sc, const ntr_image_format *fmt, unsigned char *dst) {
+    const int tiles_y = (fmt->height + NTR_TILE - 1) / NTR_TILE;
+    const int S = std::min(kSlabMax, tiles_y / 4);
+    if (S < 2 || sc->instrumented) return 1;
+    for (int i = 1; i < S; ++i) {
+        if (!sc->slab_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&sc->slab_stream[i], cudaStreamNonBlocking));
+        if (!sc->slab_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&sc->slab_done[i], cudaEventDisableTiming));
+    }
+    const size_t pitch = (size_t)fmt->pitch, row_bytes = (size_t)fmt->width * fmt->bytes_per_pixel;
+    RenderTarget tgt;
+    tgt.out_mode = NTR_OUT_PACKED;
+    CUDA_TRY(cudaEventRecord(sc->ev0, sc->stream));
+    int rc = NTR_OK;
+    for (int i = 0; i < S && rc == NTR_OK; ++i) {
+        cudaStream_t st = i ? sc->slab_stream[i] : sc->stream;
+        if (i) CUDA_TRY(cudaStreamWaitEvent(st, sc->ev0, 0));
+        const int y0 = (int)((long long)tiles_y * i / S) * NTR_TILE;
+        const int y1 = std::min(fmt->height, (int)((long long)tiles_y * (i + 1) / S) * NTR_TILE);
+        tgt.packed = sc->d_packed + (size_t)y0 * pitch;
+        bool p = false;
+        sc->ctl_slot = i;
+        rc = enqueue_frame(sc, st, fmt->width, fmt->height, 0, y0, fmt->width, y1 - y0, fmt, tgt, 0, 1, 0, &p);
+        sc->ctl_slot = 0;
+        if (rc) break;
+        // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
+        CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)y0 * pitch, pitch, tgt.packed, pitch, row_bytes, y1 - y0, cudaMemcpyDeviceToHost, st));
+        if (i) CUDA_TRY(cudaEventRecord(sc->slab_done[i], st));
+    }
+    for (int i = 1; i < S; ++i) cudaStreamWaitEvent(sc->stream, sc->slab_done[i], 0);
+    if (rc) { cudaStreamSynchronize(sc->stream); return rc; }
+    CUDA_TRY(cudaEventRecord(sc->ev1, sc->stream));
+    sc->timing_valid = true;
+    unsigned long long h_cnt[kSlabMax * 8];
+    CUDA_TRY(cudaMemcpyAsync(h_cnt, sc->d_counters, sizeof(unsigned long long) * 8 * S, cudaMemcpyDeviceToHost, sc->stream));
+    CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    if (*sc->h_abort) return fail(NTR_ERR_ABORTED, "render aborted");
+    const uint64_t overflows = sc->counters.queue_overflows;
+    sc->counters = ntr_counters{};
+    sc->counters.queue_overflows = overflows;
+    sc->counters.primary_rays = (uint64_t)fmt->width * fmt->height;
+    for (int i = 0; i < S; ++i) {
+        sc->counters.reflection_rays += h_cnt[i * 8 + 1]; sc->counters.shadow_rays += h_cnt[i * 8 + 2];
+        sc->counters.shaded_hits += h_cnt[i * 8 + 6];
+    }
+    return NTR_OK;
 }
 
 struct BusyGuard {
@@ -652,6 +711,7 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->pass_timing = getenv("NTR_PASS_TIMING") != nullptr;
     sc->sort_rays = getenv("NTR_NO_RAY_SORT") == nullptr;
     if (const char *zc = getenv("NTR_ZEROCOPY")) sc->zero_copy = atoi(zc) != 0;
+    sc->slabs = getenv("NTR_NO_SLABS") == nullptr;
     if (const char *qi = getenv("NTR_QUEUE_INIT")) sc->queue_init = (uint32_t)strtoul(qi, nullptr, 10);
     sc->tree_depth = depth;
     sc->dev.dim = desc->dim;
@@ -675,8 +735,8 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     if ((rc = cu(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking), "cudaStreamCreate"))) return bail(rc);
     if ((rc = cu(cudaEventCreate(&sc->ev0), "cudaEventCreate"))) return bail(rc);
     if ((rc = cu(cudaEventCreate(&sc->ev1), "cudaEventCreate"))) return bail(rc);
-    if ((rc = cu(cudaMalloc(&sc->d_ctl, CTL_WORDS * sizeof(uint32_t)), "cudaMalloc"))) return bail(rc);
-    if ((rc = cu(cudaMalloc(&sc->d_counters, 8 * sizeof(unsigned long long)), "cudaMalloc"))) return bail(rc);
+    if ((rc = cu(cudaMalloc(&sc->d_ctl, kSlabMax * CTL_WORDS * sizeof(uint32_t)), "cudaMalloc"))) return bail(rc);
+    if ((rc = cu(cudaMalloc(&sc->d_counters, kSlabMax * 8 * sizeof(unsigned long long)), "cudaMalloc"))) return bail(rc);
     if ((rc = cu(cudaHostAlloc(&sc->h_abort, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc"))) return bail(rc);
     *sc->h_abort = 0;
     if ((rc = cu(cudaHostGetDevicePointer(&sc->d_abort, sc->h_abort, 0), "cudaHostGetDevicePointer"))) return bail(rc);
@@ -694,6 +754,10 @@ NTR_API void ntr_scene_destroy(ntr_scene *sc) {
     cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order);
     cudaFree(sc->d_keys[0]); cudaFree(sc->d_keys[1]); cudaFree(sc->d_perm[0]); cudaFree(sc->d_perm[1]); cudaFree(sc->d_sort_tmp);
     if (sc->copy_stream) { cudaStreamSynchronize(sc->copy_stream); cudaStreamDestroy(sc->copy_stream); }
+    for (int i = 0; i < kSlabMax; ++i) {
+        if (sc->slab_stream[i]) { cudaStreamSynchronize(sc->slab_stream[i]); cudaStreamDestroy(sc->slab_stream[i]); }
+        if (sc->slab_done[i]) cudaEventDestroy(sc->slab_done[i]);
+    }
     for (FrameSlot &fs : sc->slots) {
         cudaFree(fs.d_buf);
         if (fs.h_stage) cudaFreeHost(fs.h_stage);
@@ -794,6 +858,15 @@ NTR_API int ntr_render(ntr_scene *sc, const ntr_image_format *fmt, void *dst, si
     }
     if ((rc = ensure((void **)&sc->d_packed, &sc->packed_cap, bytes))) return rc;
     tgt.packed = sc->d_packed;
+    if (sc->slabs && !(sc->dev.kind == NTR_SCENE_COMPOSITE && sc->any_reflective && sc->dev.max_depth > 0)) {
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (pinned) {           // (a pageable destination would make every slab's copy block the host)
+            rc = run_frame_slabs(sc, fmt, static_cast<unsigned char *>(dst));
+            if (rc <= 0) return rc;
+        }
+    }
     // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
     HostCopy hc{dst, (size_t)fmt->pitch, sc->d_packed, (size_t)fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel, fmt->height, false};
     if ((rc = run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, sc->stream, &hc))) return rc;
