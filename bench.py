@@ -414,7 +414,7 @@ def main():
                 # (profiles/r01_c2_render_pass_ncu_full_summary.txt); only measured for the default workload
                 'traffic': 10.28e6 if args.config == 'c2' else None,
                 'peak_source': 'FP32 FMA micro-benchmark measured live in this run (ntr_measure_fp32_peak); MEASURED_PEAKS.json has HBM/BF16 only',
-                'algorithmic_flops_per_launch': flops, 'kernel': 'render_pass_kernel<%s,%d>' % (dim if 3 <= dim <= 8 else 0, 0), 'kernel_ms': ms_per_step,
+                'algorithmic_flops_per_launch': flops, 'kernel': 'render_pass_kernel<%s,%d>' % (dim if (3 <= dim <= 10 and not int(os.environ.get('NTR_FORCE_GENERIC', '0') or 0)) else 0, 0), 'kernel_ms': ms_per_step,
                 'reference_algorithm_counts': cnt_ref, 'counts_from': counts_from,
                 'hbm': {'achieved': abytes / (ms_per_step * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                         'frac': abytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,

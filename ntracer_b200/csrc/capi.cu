@@ -138,6 +138,8 @@ const KernelSet *(*kernel_family(int dim))(int) {
         case 6: return &kernel_set_d6;
         case 7: return &kernel_set_d7;
         case 8: return &kernel_set_d8;
+        case 9: return &kernel_set_d9;
+        case 10: return &kernel_set_d10;
         default: return &kernel_set_dn;     // run-time dimension kernels (the reference's generic tracern)
     }
 }
@@ -720,7 +722,9 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->dev.batch = 1;
     // the fixed-dimension kernels assume 4-lane batches (compile-time block offsets); other batch sizes of the
     // reference's SIMD flavours (8, 16) go through the run-time-dimension kernels
-    sc->kset = kernel_family((desc->kind == NTR_SCENE_COMPOSITE && desc->batch_size != 4 && desc->batch_size != 1) ? 0 : desc->dim);
+    // NTR_FORCE_GENERIC=1 is NTracer(dimension, force_generic=True) (lib/ntracer/wrapper.py:112-118): the run-time-dimension family
+    const bool force_generic = getenv("NTR_FORCE_GENERIC") != nullptr && atoi(getenv("NTR_FORCE_GENERIC")) != 0;
+    sc->kset = kernel_family((force_generic || (desc->kind == NTR_SCENE_COMPOSITE && desc->batch_size != 4 && desc->batch_size != 1)) ? 0 : desc->dim);
     for (int i = 0; i < desc->dim; ++i) { sc->cam.right[i] = i == 0; sc->cam.up[i] = i == 1; sc->cam.fwd[i] = i == 2; }
     auto bail = [&](int code) { ntr_scene_destroy(sc); return code; };
     fill_params(sc->dev, desc);

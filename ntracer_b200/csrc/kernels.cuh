@@ -115,8 +115,10 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 #ifndef NTR_MIN_CTAS
 #define NTR_MIN_CTAS 8
 #endif
+// above 8 dimensions the ray alone (origin, direction, hit point) is 30+ registers: 128 registers / 4 CTAs per SM
+template <int DT> struct MinCtas { static constexpr int value = DT > 8 ? 4 : NTR_MIN_CTAS; };
 template <int DT, int FLAGS>
-__global__ void __launch_bounds__(kCtaThreads, NTR_MIN_CTAS)
+__global__ void __launch_bounds__(kCtaThreads, MinCtas<DT>::value)
 render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ CameraDev cam,
                    const __grid_constant__ FrameDev f, const __grid_constant__ QueueDev q,
                    const __grid_constant__ ControlDev ctl) {
@@ -357,6 +359,8 @@ const KernelSet *kernel_set_d5(int flags);
 const KernelSet *kernel_set_d6(int flags);
 const KernelSet *kernel_set_d7(int flags);
 const KernelSet *kernel_set_d8(int flags);
+const KernelSet *kernel_set_d9(int flags);
+const KernelSet *kernel_set_d10(int flags);
 const KernelSet *kernel_set_dn(int flags);
 
 #define NTR_INSTANTIATE_DIM(NAME, DT)                                                                   \

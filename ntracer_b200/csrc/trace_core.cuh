@@ -132,7 +132,10 @@ struct HitRec { float dist; uint32_t ref; int lane; };
 template <int DT> struct SimplexRec {
     static constexpr int S = (((DT + 1) * DT + 1) + 3) / 4 * 4;
     static constexpr int N1 = (DT + 1 + 3) / 4;
-    float r[S];
+    // above 8 dimensions the record (>= 92 floats) is not staged in registers: stage 1 still brings face_normal and d
+    // as float4s, the rest is read element by element where it is used (the edge loop exits early on most records)
+    static constexpr bool STAGE_ALL = DT <= 8;
+    float r[STAGE_ALL ? S : 4 * N1];
     const float *g;
     NTR_HD void stage1(const float *rec) {
         g = rec;
@@ -143,14 +146,16 @@ template <int DT> struct SimplexRec {
         }
     }
     NTR_HD void stage2() {
+        if (STAGE_ALL) {
     NTR_UNROLL
-        for (int k = N1; k < S / 4; ++k) {
-            float4 v = ld4(g + 4 * k);
-            r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+            for (int k = N1; k < S / 4; ++k) {
+                float4 v = ld4(g + 4 * k);
+                r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+            }
         }
     }
-    NTR_HD float at(int i) const { return r[i]; }
-    NTR_HD uint32_t meta(int sstride) const { return f2u(r[S - 1]); }
+    NTR_HD float at(int i) const { return (STAGE_ALL || i < 4 * N1) ? r[i < (STAGE_ALL ? S : 4 * N1) ? i : 0] : ldf(g + i); }
+    NTR_HD uint32_t meta(int sstride) const { return STAGE_ALL ? f2u(r[(STAGE_ALL ? S : 4 * N1) - 1]) : f2u(ldf(g + S - 1)); }
 };
 template <> struct SimplexRec<0> {
     const float *g;
@@ -199,11 +204,12 @@ NTR_HD float simplex_single(const SceneDev &s, uint32_t off, const float *o, con
 #endif
 template <int DT> struct EdgeRec {
     static constexpr int LP = DT > 0 ? (DT * DT + 3) / 4 * 4 : 4;
-    float r[LP];
+    static constexpr bool STAGED = DT > 0 && DT <= 8;          // see SimplexRec
+    float r[STAGED ? LP : 4];
     const float *g;
     NTR_HD void load(const float *lp) {
         g = lp;
-        if (DT > 0) {
+        if (STAGED) {
     NTR_UNROLL
             for (int k = 0; k < LP / 4; ++k) {
                 const float4 v = ld4(lp + 4 * k);
@@ -211,7 +217,7 @@ template <int DT> struct EdgeRec {
             }
         }
     }
-    NTR_HD float at(int k) const { return DT > 0 ? r[k < LP ? k : 0] : ldf(g + k); }
+    NTR_HD float at(int k) const { return STAGED ? r[k < (STAGED ? LP : 4) ? k : 0] : ldf(g + k); }
 };
 
 template <int DT>

@@ -61,3 +61,64 @@ def center_column_mask(w, h):
     m = np.zeros((h, w), dtype=bool)
     m[:, w // 2] = True
     return m
+
+
+def batched_soup(dim, n_batches, seed=7, batch=4):
+    """Synthetic CompositeScene in `dim` dimensions made of `n_batches` 4-lane TriangleBatches (what the reference's SSE
+    flavour stores in its leaves) plus a few single simplexes, over a tree from this repo's builder, with two
+    materials (one reflective), a point light, a global light and shadows: exercises batch_test / simplex_single /
+    shading / shadow rays / one reflection pass of the fixed-dimension kernels for which the reference's own fixtures
+    (dimensions 3, 4, 6, 9) have no scene.  Not a reference golden: parity is against the oracle restatement."""
+    from ntracer_b200 import bulk
+    rng = np.random.RandomState(seed)
+    n_single = 5
+    n = n_batches * batch + n_single
+    # A random (D-1)-simplex almost never meets the camera's 3-flat inside its barycentric range once D > 5 (SURVEY 8d,
+    # C5), so each simplex is a triangle in the camera's 3-space (slightly below the flat in the extra axes) joined to
+    # one far vertex along every extra axis: its slice with the 3-flat is close to the triangle itself.
+    pts = np.zeros((n, dim, dim), np.float64)
+    c = rng.uniform(-1, 1, (n, 1, 3))
+    pts[:, :3, :3] = c + rng.uniform(-0.45, 0.45, (n, 3, 3))
+    pts[:, :3, 3:] = -rng.uniform(0.01, 0.05, (n, 3, dim - 3))
+    for k in range(3, dim):
+        pts[:, k, :3] = pts[:, :3, :3].mean(axis=1) + rng.uniform(-0.05, 0.05, (n, 3))
+        pts[:, k, 3:] = -rng.uniform(0.01, 0.05, (n, dim - 3))
+        pts[:, k, k] = rng.uniform(0.5, 1.5, n)
+    pts = pts.astype(np.float32)
+    rec = bulk.simplex_records(pts)
+    lo, hi = pts.min(axis=1), pts.max(axis=1)
+    # items: batches of `batch` consecutive records first, then the singles
+    ilo = [lo[k * batch:(k + 1) * batch].min(axis=0) for k in range(n_batches)] + [lo[n_batches * batch + k] for k in range(n_single)]
+    ihi = [hi[k * batch:(k + 1) * batch].max(axis=0) for k in range(n_batches)] + [hi[n_batches * batch + k] for k in range(n_single)]
+    refs_of_item = np.array([(1 << 30) | (k * batch) for k in range(n_batches)] +
+                            [n_batches * batch + k for k in range(n_single)], dtype=np.uint32)
+    nodes, item_idx, root, boundary = bulk.build_kdtree(np.array(ilo, np.float32), np.array(ihi, np.float32),
+                                                        max_depth=8, split_threshold=3)
+    # the reference keeps the batches of a leaf in front of its single primitives (tracer.hpp:1142-1150)
+    nodes = nodes.copy()
+    refs = refs_of_item[item_idx]
+    for k in range(len(nodes)):
+        if nodes[k, 0] & 0x80000000:
+            a, m = int(nodes[k, 1]), int(nodes[k, 2])
+            seg = refs[a:a + m]
+            isb = (seg >> 30) == 1
+            refs[a:a + m] = np.concatenate([seg[isb], seg[~isb]])
+            nodes[k, 0] = 0x80000000 | int(isb.sum())
+    mats = np.array([[1, 0.5, 0.5, 1, 1, 1, 1, 0, 1, 8],
+                     [0.4, 0.7, 1.0, 1, 1, 1, 1, 0.35, 0.8, 12]], dtype=np.float32)
+    light_pos = np.zeros(dim, np.float32); light_pos[1] = 4; light_pos[2] = -4
+    gdir = np.zeros(dim, np.float32); gdir[1] = -1
+    cam_origin = np.zeros(dim, np.float32); cam_origin[2] = -3.5
+    return {
+        'dim': np.int64(dim), 'kind': np.int64(1), 'batch_size': np.int64(batch), 'root': np.int64(root),
+        'nodes': nodes, 'leaf_refs': refs.astype(np.uint32), 'simplex': rec,
+        'simplex_mat': (rng.uniform(size=n) < 0.4).astype(np.int32),
+        'solids': np.zeros((0, 1 + 2 * dim * dim + dim), np.float32), 'solid_mat': np.zeros(0, np.int32),
+        'materials': mats, 'boundary': boundary,
+        'params': np.array([0.8, 1, 1, 2, 1], dtype=np.float64),            # fov, shadows, camera_light, max_reflect_depth, bg axis
+        'ambient': np.full(3, 0.05, np.float32), 'bg1': np.ones(3, np.float32), 'bg2': np.zeros(3, np.float32),
+        'bg3': np.array([0, 1, 1], np.float32),
+        'point_lights': np.concatenate([light_pos, [30, 30, 30]]).astype(np.float32)[None],
+        'global_lights': np.concatenate([gdir, [0.4, 0.4, 0.4]]).astype(np.float32)[None],
+        'cam_origin': cam_origin, 'cam_axes': np.eye(dim, dtype=np.float32),
+    }

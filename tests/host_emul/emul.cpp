@@ -156,6 +156,8 @@ void occl_t(Scene &S, uint32_t n, const float *origins, const float *dirs, const
         case 6: { CALL(6); break; }        \
         case 7: { CALL(7); break; }        \
         case 8: { CALL(8); break; }        \
+        case 9: { CALL(9); break; }        \
+        case 10: { CALL(10); break; }      \
         default: { CALL(0); break; }       \
     }
 

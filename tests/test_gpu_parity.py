@@ -280,3 +280,28 @@ def test_abort_stops_a_running_render():
             assert result['rc'] == 'render aborted'
             assert aborted < 0.8 * full
         assert ds.render(fmt).size == fmt.pitch * 2160    # and the scene is usable afterwards
+
+
+@pytest.mark.parametrize('dim', [3, 5, 7, 8, 9, 10, 12])
+def test_batched_soup_every_fixed_dimension_and_generic(dim, monkeypatch):
+    """Every fixed-dimension kernel family (3..10) and the run-time-dimension family (forced, and natively for 12)
+    on a lit, shadowed, reflective scene of 4-lane batches + single simplexes, against the oracle."""
+    sc = fx.batched_soup(dim, 60)
+    w, h = 160, 90
+    o, cnt_o = ol.render_float(sc, w, h, with_counters=True)
+    oids, odist = ol.primary_hit_ids(sc, w, h)
+    fmt = _capi.make_image_format(w, h, _capi.RGB8)
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv('NTR_FORCE_GENERIC', '1')
+        with DeviceScene(sc) as ds:
+            fl = ds.render_float(w, h)
+            cnt = ds.counters()
+            ids, dist = ds.primary_hit_ids(w, h)
+            img = ds.render(fmt)
+        bad, mx = fx.lsb_stats(fl, o)
+        assert bad <= 0.001, (dim, force, bad, mx)
+        assert fx.id_agreement(ids, oids, dist, odist)[0] >= 0.9999
+        for k in ('primary_rays', 'reflection_rays', 'shadow_rays'):
+            assert abs(cnt[k] - cnt_o[k]) <= 0.002 * max(cnt_o[k], 1) + 2, (dim, force, k, cnt[k], cnt_o[k])
+        assert np.abs(img.astype(np.int32) - ol.pack(fmt, fl).astype(np.int32)).max() <= 1

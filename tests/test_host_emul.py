@@ -83,3 +83,21 @@ def test_pack_pixel_formats():
         pitch, rev = [int(v) for v in g['opt_' + n]]
         fmt = _capi.make_image_format(w, h, ch, pitch, bool(rev))
         assert np.array_equal(el.pack(fmt, g['float']), ol.pack(fmt, g['float'])), n
+
+
+@pytest.mark.parametrize('dim', [3, 5, 7, 8, 9, 10, 12])
+def test_batched_soup_every_fixed_dimension_and_generic(dim):
+    """batch_test / simplex_single / shading / shadows / one reflection pass of every fixed-dimension instantiation
+    (3..10) and of the run-time-dimension one, on a synthetic scene with 4-lane batches (fixtures.batched_soup)."""
+    sc = fx.batched_soup(dim, 40)
+    w, h = 64, 36
+    a, cnt_o = ol.render_float(sc, w, h, with_counters=True)
+    assert cnt_o['shadow_rays'] > 500 and cnt_o['reflection_rays'] > 200          # the scene exercises both
+    b, ids, dist, cnt = el.render(sc, w, h, want_ids=True)
+    assert np.abs(a - b).max() <= 2e-6
+    oids, odist = ol.primary_hit_ids(sc, w, h)
+    assert fx.id_agreement(ids, oids, dist, odist)[0] >= 0.9999
+    for k in ('primary_rays', 'reflection_rays', 'shadow_rays', 'shaded_hits'):
+        assert cnt_o[k] == cnt[k], (dim, k)
+    g, _ = el.render(sc, w, h, generic=True)
+    assert np.abs(a - g).max() <= 2e-6
