@@ -115,8 +115,14 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 #ifndef NTR_MIN_CTAS
 #define NTR_MIN_CTAS 8
 #endif
-// above 8 dimensions the ray alone (origin, direction, hit point) is 30+ registers: 128 registers / 4 CTAs per SM
-template <int DT> struct MinCtas { static constexpr int value = DT > 8 ? 4 : NTR_MIN_CTAS; };
+// above 8 dimensions the ray alone (origin, direction, hit point) is 30+ registers: fewer CTAs per SM, more registers
+#ifndef NTR_MIN_CTAS_HI
+#define NTR_MIN_CTAS_HI 5          // measured on config 5 (16 k simplexes): 3 -> 31.7 ms, 4 -> 25.5, 5 -> 23.3, 6 -> 24.6, 8 -> 32.6
+#endif
+#ifndef NTR_MIN_CTAS_MID
+#define NTR_MIN_CTAS_MID 6         // dimensions 6..8; measured on config 3 (6-D): 8 -> 0.550 ms, 6 -> 0.536 ms
+#endif
+template <int DT> struct MinCtas { static constexpr int value = DT > 8 ? NTR_MIN_CTAS_HI : (DT >= 6 ? NTR_MIN_CTAS_MID : NTR_MIN_CTAS); };
 template <int DT, int FLAGS>
 __global__ void __launch_bounds__(kCtaThreads, MinCtas<DT>::value)
 render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ CameraDev cam,

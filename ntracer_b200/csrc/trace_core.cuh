@@ -165,7 +165,8 @@ template <> struct SimplexRec<0> {
     NTR_HD uint32_t meta(int sstride) const { return f2u(ldf(g + sstride - 1)); }
 };
 
-// triangle::intersects (tracer.hpp:411-440): the single-primitive n-simplex test.
+// triangle::intersects (tracer.hpp:411-440): the single-primitive n-simplex test.  (The approximate-quotient pre-filter of
+// batch_test was tried here too: config 5 got 3-4 % SLOWER -- one division per record is cheap next to the loads.)
 template <int DT>
 NTR_HD float simplex_single(const SceneDev &s, uint32_t off, const float *o, const float *dir, float cutoff,
                             uint32_t &meta) {
