@@ -197,6 +197,27 @@ def reference_arm(args, sc, g, w, h, rays_per_frame):
     return out
 
 
+TAIL_TIMEOUT_S = int(os.environ.get('NTR_BENCH_TAIL_TIMEOUT', '480'))
+REFERENCE_TIMEOUT_S = int(os.environ.get('NTR_BENCH_REFERENCE_TIMEOUT', '300'))
+
+
+def reference_arm_subprocess(args):
+    """cpu_baseline of the GPU arm: the reference arm in a process of its own (`bench.py --impl reference`), so that a
+    crash or hang of the reference's renderer (see ref_bridge.make_immortal) cannot take the measurement with it."""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--config', args.config, '--steps', str(args.steps),
+           '--warmup', str(args.warmup), '--stream-frames', str(args.stream_frames)]
+    env = dict(os.environ, RANK='0', WORLD_SIZE='1', LOCAL_RANK='0')
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=REFERENCE_TIMEOUT_S, env=env)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)['cpu_baseline']
+        why = 'no result (exit code %d): %s' % (out.returncode, out.stderr.strip()[-300:])
+    except subprocess.TimeoutExpired:
+        why = 'did not finish within %d s' % REFERENCE_TIMEOUT_S
+    return {'value': None, 'unit': 'Mrays/s', 'cores': os.cpu_count() or 1, 'kind': 'reference', 'sample': 'reference arm failed: ' + why}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -222,6 +243,14 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
+
+        def ref_watchdog():
+            print(json.dumps({'impl': 'reference', 'unavailable': 'the reference renderer did not finish within %d s '
+                              '(its worker threads race on Python refcounts, see oracle/ref_bridge.py)' % (2 * REFERENCE_TIMEOUT_S)}), flush=True)
+            os._exit(0)
+        rwd = threading.Timer(2 * REFERENCE_TIMEOUT_S, ref_watchdog)
+        rwd.daemon = True
+        rwd.start()
         # ray counts of the frame from the counting CPU restatement (the reference does not count rays)
         from tests import oracle_lib as ol
         _, cnt = ol.render_float(sc, w, h, with_counters=True)
@@ -233,7 +262,8 @@ def main():
                 'config': {'workload': desc, 'rays_per_frame': rays},
                 'cpu_baseline': base,
                 'e2e': {'value': base['value'], 'unit': 'Mrays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
+        rwd.cancel()
+        print(json.dumps(line), flush=True)
         return 0
 
     import torch
@@ -338,10 +368,9 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = ds.launch_count() - launches0      # kernels of this library launched inside the two timed regions
 
-    # ---- the interactive loop: rotating camera, one frame per camera, two frames in flight, every
-    # frame copied into a pinned host buffer (ntr_render_begin / ntr_render_end); wall clock around the whole loop ----
-    stream_res = None
-    if world == 1 and args.stream_frames >= 2:
+    def stream_leg():
+        """the interactive loop: rotating camera, one frame per camera, two frames in flight, every frame
+        copied into a pinned host buffer (ntr_render_begin / ntr_render_end); wall clock around the whole loop"""
         from ntracer_b200 import stream as nts
         n_frames = int(max(8, min(args.stream_frames, 4000.0 / max(statistics.median(dev_ms), 1e-3))))
         cams = nts.rotation_cameras(cam_o, cam_a, args.stream_frames)[:n_frames]
@@ -353,11 +382,11 @@ def main():
         nts.render_sequence(ds, fmt, cams, bufs)
         torch.cuda.synchronize()
         el = time.perf_counter() - t
-        stream_res = {'frames': n_frames, 'camera_path': 'polytope.py RotatingCamera, %d steps per turn' % args.stream_frames,
-                      'in_flight': 2, 'ms_per_frame': 1e3 * el / n_frames, 'frames_per_s': n_frames / el,
-                      'Mpix_per_s': w * h * n_frames / el / 1e6, 'd2h_bytes_per_frame': int(frame_bytes),
-                      'gpu_launches': int(ds.launch_count() - launches_s0)}
         ds.set_camera(cam_o, cam_a)
+        return {'frames': n_frames, 'camera_path': 'polytope.py RotatingCamera, %d steps per turn' % args.stream_frames,
+                'in_flight': 2, 'ms_per_frame': 1e3 * el / n_frames, 'frames_per_s': n_frames / el,
+                'Mpix_per_s': w * h * n_frames / el / 1e6, 'd2h_bytes_per_frame': int(frame_bytes),
+                'gpu_launches': int(ds.launch_count() - launches_s0)}
 
     tot_dev = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -382,8 +411,25 @@ def main():
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
-        if stream_res:
-            line['stream'] = stream_res
+        # The headline numbers are complete here.  The legs below (roofline counts, CPU baseline, interactive loop) run
+        # under a watchdog: if one of them hangs -- the reference's renderer has a refcount race that can corrupt its
+        # heap (oracle/ref_bridge.make_immortal) -- the line is printed without it instead of never.
+        emitted = threading.Lock()
+
+        def emit(note=None):
+            if not emitted.acquire(blocking=False):
+                return
+            if note:
+                line['incomplete'] = note
+            print(json.dumps(line), flush=True)
+
+        def watchdog():
+            emit('a post-measurement leg did not finish within %d s; keys present are valid' % TAIL_TIMEOUT_S)
+            os._exit(0)
+
+        wd = threading.Timer(TAIL_TIMEOUT_S, watchdog)
+        wd.daemon = True
+        wd.start()
         if world == 1:
             # ---- roofline of the dominant kernel (render_pass_kernel: the only kernel of this frame) ----
             from tests import oracle_lib as ol
@@ -423,8 +469,13 @@ def main():
                         'note': 'working set (nodes+refs+simplexes, ~1.3 MB) is L2/L1-resident; DRAM traffic is the frame write'},
             }
             if not args.no_cpu_baseline:
-                line['cpu_baseline'] = reference_arm(args, sc, g, w, h, rays)
-        print(json.dumps(line))
+                line['cpu_baseline'] = reference_arm_subprocess(args)
+            # single-pass scenes only: frames with wavefront passes are traced synchronously inside ntr_render_begin, so
+            # the loop adds nothing over `e2e` there
+            if args.stream_frames >= 2 and cnt_gpu['reflection_rays'] == 0:
+                line['stream'] = stream_leg()
+        wd.cancel()
+        emit()
     if world > 1:
         dist.destroy_process_group()
     ds.close()
