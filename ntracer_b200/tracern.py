@@ -288,16 +288,127 @@ class AABB:
     def right(self, axis, split):
         return AABB(self.dimension, self.start.set_c(axis, split), self.end)
 
+    def _center(self):
+        return (self.start._v + self.end._v) * _F(0.5)
+
+    @staticmethod
+    def _check_proto(self_dim, primitive, allowed, what):
+        if isinstance(primitive, (Primitive, PrimitiveBatch)):
+            raise TypeError('Instances of Primitive cannot be used directly. Use PrimitivePrototype instead.')
+        if not isinstance(primitive, allowed):
+            raise TypeError('object must be an instance of ' + what)
+        if primitive.dimension != self_dim:
+            raise TypeError('cannot perform intersection test on object with different dimension')
+
     def intersects(self, primitive):
-        """Conservative overlap test on the prototype's bounding box (the reference runs exact separating-axis
-        tests, src/tracer.hpp:1465-1675; they belong to the tree builder)."""
-        b = primitive.boundary
-        return bool(np.all(self.start._v <= b.end._v) and np.all(self.end._v >= b.start._v))
+        """Exact box/primitive overlap with non-zero volume (src/tracer.hpp:1459-1675): separating-axis tests for
+        simplexes (face normal, then every edge normal projected onto every coordinate hyperplane), for hypercubes
+        (cube normals and their projections) and a closest-point test for hyperspheres.  Touching does not count.
+        Arithmetic in float32 like the reference."""
+        AABB._check_proto(self.dimension, primitive, PrimitivePrototype, __name__ + '.PrimitivePrototype')
+        if isinstance(primitive, TriangleBatchPrototype):
+            b = primitive.boundary
+            if np.any(b.start._v >= self.end._v) or np.any(b.end._v <= self.start._v):
+                return False
+            return any(self._simplex_overlap(t) for t in primitive._protos)     # miss.all() -> False (:1559-1585)
+        if isinstance(primitive, TrianglePrototype):
+            b = primitive.boundary
+            if np.any(b.start._v >= self.end._v) or np.any(b.end._v <= self.start._v):
+                return False
+            return self._simplex_overlap(primitive)
+        return self._solid_overlap(primitive)
+
+    def _simplex_overlap(self, tp):
+        """the part of aabb::intersects(triangle_prototype) after the bounding-box rejection (:1470-1509)"""
+        d = self.dimension
+        half = (self.end._v - self.start._v) / _F(2)
+        origin = self._center()
+        fn = tp.face_normal._v
+        pts = np.stack([pd.point._v for pd in tp.point_data])           # D points
+        n_offset = _F(np.dot(fn, pts[0]))
+        po = _F(np.dot(origin, fn))
+        b_max = _F(np.sum(np.abs(half * fn)))
+        if po + b_max < n_offset or po - b_max > n_offset:
+            return False
+        for pd in tp.point_data:
+            axis = pd.edge_normal._v
+            for j in range(d):
+                keep = np.arange(d) != j
+                vals = pts[:, keep] @ axis[keep]
+                t_min, t_max = _F(vals.min()), _F(vals.max())
+                po = _F(np.dot(origin[keep], axis[keep]))
+                b_radius = _F(np.sum(np.abs(half[keep] * axis[keep])))
+                # a zero radius means the axis is parallel to the dropped coordinate: the test says nothing (:1503-1505)
+                if b_radius != 0 and (po + b_radius <= t_min or po - b_radius >= t_max):
+                    return False
+        return True
 
     def intersects_flat(self, primitive, skip):
+        """aabb::intersects_flat (:1512-1541, 1590-1625): the same test with coordinate `skip` ignored, used by the
+        builder for primitives lying in a split plane."""
+        AABB._check_proto(self.dimension, primitive, (TrianglePrototype, TriangleBatchPrototype),
+                          '%s.TrianglePrototype or %s.TriangleBatchPrototype' % (__name__, __name__))
+        d = self.dimension
         b = primitive.boundary
-        k = [i for i in range(self.dimension) if i != skip]
-        return bool(np.all(self.start._v[k] <= b.end._v[k]) and np.all(self.end._v[k] >= b.start._v[k]))
+        k = np.arange(d) != skip
+        if np.any(b.start._v[k] >= self.end._v[k]) or np.any(b.end._v[k] <= self.start._v[k]):
+            return False
+        protos = primitive._protos if isinstance(primitive, TriangleBatchPrototype) else (primitive,)
+        half = (self.end._v - self.start._v) / _F(2)
+        origin = self._center()
+
+        def lane(tp):
+            pts = [pd.point._v for pd in tp.point_data]
+            for i, pd in enumerate(tp.point_data):
+                axis = pd.edge_normal._v
+                t_max = _F(np.dot(pts[0][k], axis[k]))
+                t_min = _F(np.dot(pts[i if i else 1][k], axis[k]))
+                if t_min > t_max:
+                    t_min, t_max = t_max, t_min
+                po = _F(np.dot(origin[k], axis[k]))
+                b_max = _F(np.sum(np.abs(half[k] * axis[k])))
+                if po + b_max <= t_min or po - b_max >= t_max:
+                    return False
+            return True
+        return any(lane(t) for t in protos)
+
+    def _solid_overlap(self, sp):
+        """aabb::intersects(solid_prototype) (:1628-1675)"""
+        d = self.dimension
+        s = sp.primitive
+        half = (self.end._v - self.start._v) / _F(2)
+        center = self._center()
+        pos = s.position._v
+        if sp.type == CUBE:
+            b = sp.boundary
+            if np.any(self.end._v <= b.start._v) or np.any(self.start._v >= b.end._v):
+                return False
+            comps = s.orientation._m                                    # cube_component(i) = column i
+
+            def separated(axis):                                        # box_axis_test (:1628-1639)
+                a_po, b_po = _F(np.dot(pos, axis)), _F(np.dot(center, axis))
+                a_max = _F(np.sum(np.abs(comps.T @ axis)))
+                b_max = _F(np.sum(np.abs(half * axis)))
+                return b_po + b_max < a_po - a_max or b_po - b_max > a_po + a_max
+            for i in range(d):
+                normal = s.inv_orientation._m[i]                        # cube_normal(i) = row i of the inverse
+                if separated(normal):
+                    return False
+                sq = _F(np.dot(normal, normal))
+                for j in range(d):                                      # the normal projected onto each coordinate hyperplane
+                    axis = normal * -normal[j]
+                    axis[j] += sq
+                    if separated(axis):
+                        return False
+            return True
+        box_p = pos - s.inv_orientation._m @ center
+        closest = np.zeros(d, _F)
+        for i in range(d):
+            comp = s.orientation._m[i] * half[i]
+            x = _F(np.dot(box_p, comp)) / _F(np.dot(comp, comp))
+            closest = closest + _F(min(1.0, max(-1.0, float(x)))) * comp
+        diff = pos - closest
+        return bool(_F(np.dot(diff, diff)) < 1)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -404,6 +515,11 @@ class TrianglePointDatum:
     def __init__(self, point, edge_normal): self.point, self.edge_normal = point, edge_normal
 
 
+class TriangleBatchPointDatum:
+    """point / edge_normal of vertex j for every lane of a batch (indexable by lane)"""
+    def __init__(self, point, edge_normal): self.point, self.edge_normal = point, edge_normal
+
+
 class TrianglePrototype(PrimitivePrototype):
     """TrianglePrototype(points[,material]) (src/ntracer_body.hpp:2658-2720)"""
     def __init__(self, points, material=None):
@@ -442,6 +558,15 @@ class TriangleBatchPrototype(PrimitivePrototype):
         self._protos = tuple(protos)
 
     dimension = property(lambda self: self._protos[0].dimension)
+    # per-lane views of the SoA members (TriangleBatchPrototype.face_normal[i] etc., doc/ntracer.rst:1585-1650)
+    face_normal = property(lambda self: tuple(p.face_normal for p in self._protos))
+    material = property(lambda self: tuple(p.material for p in self._protos))
+
+    @property
+    def point_data(self):
+        return tuple(TriangleBatchPointDatum(tuple(p.point_data[j].point for p in self._protos),
+                                             tuple(p.point_data[j].edge_normal for p in self._protos))
+                     for j in range(self.dimension))
 
 
 class SolidPrototype(PrimitivePrototype):

@@ -165,3 +165,120 @@ def test_builder_tree_gives_reference_hit_ids():
     assert np.mean(out[0][0] == out[1][0]) >= 0.999
     assert np.abs(out[0][2] - out[1][2]).max() < 1e-4
     assert (out[0][0] >= 0).mean() > 0.1
+
+
+# ---- the builder-side geometry tests of the reference's own test-suite (lib/ntracer/tests/test.py), same vectors -------
+def test_aabb_reference_vectors():                   # test.py:132-140
+    nt = NTracer(5)
+    a = nt.AABB((1, 7, -5, 5, 4), (5, 13, -1, 6, 12))
+    assert a.dimension == 5
+    assert list(a.end) == [5, 13, -1, 6, 12] and list(a.start) == [1, 7, -5, 5, 4]
+    assert list(a.right(2, -3).start) == [1, 7, -3, 5, 4]
+    assert list(a.left(0, 2).end) == [2, 13, -1, 6, 12]
+
+
+def test_aabb_triangle_reference_vectors():          # test.py:142-203
+    nt = NTracer(3)
+    mat = Material((1, 1, 1))
+    box = nt.AABB((-1, -1, -1), (1, 1, 1))
+    tri = lambda pts: nt.TrianglePrototype(pts, mat)
+    assert not box.intersects(tri([(-2.092357, 0.1627209, 0.9231308), (0.274588, 0.8528936, 2.309217), (-1.212236, 1.855952, 0.3137006)]))
+    assert not box.intersects(tri([(2.048058, -3.022543, 1.447644), (1.961913, -0.5438575, -0.1552723), (0.3618142, -1.684767, 0.2162201)]))
+    assert not box.intersects(tri([(-4.335572, -1.690142, -1.302721), (0.8976227, 0.5090631, 4.6815), (-0.8176082, 4.334341, -1.763081)]))
+    assert box.intersects(tri([(0, 0, 0), (5, 5, 5), (1, 2, 3)]))
+    assert nt.AABB((-0.894424974918, -1.0, -0.850639998913), (0.0, -0.447214990854, 0.850639998913)).intersects(
+        tri([(0.0, -1.0, 0.0), (0.723599970341, -0.447214990854, 0.525720000267), (-0.276385009289, -0.447214990854, 0.850639998913)]))
+    rng = np.random.RandomState(3)
+    points = [[tuple(rng.uniform(-1, 1, 3)) for _ in range(3)] for _ in range(nt.BATCH_SIZE)]
+    flat = np.array(points, np.float32).reshape(-1, 3)
+    tbp = nt.TriangleBatchPrototype(tri(p) for p in points)
+    assert np.allclose(list(tbp.boundary.start), flat.min(axis=0)) and np.allclose(list(tbp.boundary.end), flat.max(axis=0))
+    assert nt.BATCH_SIZE == 4
+    assert box.intersects(nt.TriangleBatchPrototype([
+        tri([(5.8737568855285645, 0.0, 0.0), (2.362654209136963, 1.4457907676696777, 0.0), (-7.4159417152404785, -2.368093252182007, 5.305923938751221)]),
+        tri([(6.069871425628662, 0.0, 0.0), (8.298105239868164, 1.4387503862380981, 0.0), (-7.501928806304932, 4.3413987159729, 5.4995622634887695)]),
+        tri([(5.153589248657227, 0.0, 0.0), (-0.8880055546760559, 3.595335006713867, 0.0), (-0.14510761201381683, 6.0621466636657715, 1.7603594064712524)]),
+        tri([(1.9743329286575317, 0.0, 0.0), (-0.6579152345657349, 8.780682563781738, 0.0), (1.0433781147003174, 0.5538825988769531, 4.187061309814453)])]))
+
+
+def test_aabb_cube_and_sphere_reference_vectors():   # test.py:205-267
+    from ntracer_b200 import CUBE, SPHERE
+    nt = NTracer(3)
+    mat = Material((1, 1, 1))
+    box = nt.AABB((-1, -1, -1), (1, 1, 1))
+    cube = lambda pos, m: nt.SolidPrototype(CUBE, nt.Vector(*pos), nt.Matrix(*m), mat)
+    assert not box.intersects(cube((1.356136, 1.717844, 1.577731),
+                                   (-0.01922399, -0.3460019, 0.8615935, -0.03032121, -0.6326356, -0.5065715, 0.03728577, -0.6928598, 0.03227519)))
+    assert not box.intersects(cube((1.444041, 1.433598, 1.975453),
+                                   (0.3780299, -0.3535482, 0.8556266, -0.7643852, -0.6406123, 0.07301452, 0.5223108, -0.6816301, -0.5124177)))
+    assert not box.intersects(cube((-0.31218, -3.436678, 1.473133),
+                                   (0.8241131, -0.2224413, 1.540015, -1.461101, -0.7099018, 0.6793453, 0.5350775, -1.595884, -0.516849)))
+    assert not box.intersects(cube((0.7697315, -3.758033, 1.847144),
+                                   (0.6002195, -1.608681, -0.3900863, -1.461104, -0.7098908, 0.6793506, -0.7779449, 0.0921175, -1.576897)))
+    assert box.intersects(cube((0.4581598, -1.56134, 0.5541568),
+                               (0.3780299, -0.3535482, 0.8556266, -0.7643852, -0.6406123, 0.07301452, 0.5223108, -0.6816301, -0.5124177)))
+    assert not box.intersects(nt.SolidPrototype(SPHERE, nt.Vector(-1.32138, 1.6959, 1.729396), nt.Matrix.identity(), mat))
+    assert box.intersects(nt.SolidPrototype(SPHERE, nt.Vector(1.623511, -1.521197, -1.243952), nt.Matrix.identity(), mat))
+    with pytest.raises(TypeError):
+        box.intersects(nt.Solid(SPHERE, nt.Vector(0, 0, 0), nt.Matrix.identity(), mat))       # primitives need a prototype
+    with pytest.raises(TypeError):
+        NTracer(4).AABB().intersects(nt.SolidPrototype(SPHERE, nt.Vector(0, 0, 0), nt.Matrix.identity(), mat))
+
+
+def test_batch_and_buffer_interfaces():              # test.py:269-300
+    nt = NTracer(4)
+    rng = np.random.RandomState(11)
+    lo, hi = (lambda: float(rng.uniform(-1, 1))), (lambda: float(rng.uniform(9, 11)))
+    protos = [nt.TrianglePrototype([(lo(), lo(), lo(), lo()), (lo(), hi(), lo(), lo()), (hi(), lo(), lo(), lo()), (lo(), lo(), hi(), lo())],
+                                   Material((1, 1, 1.0 / (i + 1)))) for i in range(nt.BATCH_SIZE)]
+    bproto = nt.TriangleBatchPrototype(protos)
+    for i in range(nt.BATCH_SIZE):
+        assert protos[i].face_normal == bproto.face_normal[i]
+        for j in range(nt.dimension):
+            assert protos[i].point_data[j].point == bproto.point_data[j].point[i]
+            assert protos[i].point_data[j].edge_normal == bproto.point_data[j].edge_normal[i]
+        assert protos[i].material == bproto.material[i]
+    v = NTracer(7).Vector(1, 2, 3, 4, 5, 6, 7)
+    assert list(v) == list(memoryview(v))
+    c = Color(0.5, 0.1, 0)
+    assert list(c) == list(memoryview(c))
+
+
+def test_aabb_tests_agree_with_the_reference_on_random_input():
+    """AABB.intersects / intersects_flat for simplexes, batches, cubes and spheres against the compiled reference."""
+    import os, sys, random
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+    import ref_bridge as rb
+    if not rb.have_reference():
+        pytest.skip('oracle/_ref not built')
+    rb.load_reference()
+    import ntracer as R
+    import ntracer_b200 as M
+    random.seed(5)
+    seen = set()
+    for dim in (3, 4, 6):
+        rn, mn = R.NTracer(dim), M.NTracer(dim)
+        rmat, mmat = R.Material((1, 1, 1)), M.Material((1, 1, 1))
+        for trial in range(120):
+            lo = tuple(random.uniform(-2, 1) for _ in range(dim))
+            hi = tuple(l + random.uniform(0.1, 2.5) for l in lo)
+            rbx, mbx = rn.AABB(lo, hi), mn.AABB(lo, hi)
+            pts = [tuple(random.uniform(-3, 3) for _ in range(dim)) for _ in range(dim)]
+            rp, mp = rn.TrianglePrototype(pts, rmat), mn.TrianglePrototype(pts, mmat)
+            sk = random.randrange(dim)
+            pos = tuple(random.uniform(-3, 3) for _ in range(dim))
+            ori = [tuple(random.uniform(-1.5, 1.5) for _ in range(dim)) for _ in range(dim)]
+            got = [mbx.intersects(mp), mbx.intersects_flat(mp, sk)]
+            want = [rbx.intersects(rp), rbx.intersects_flat(rp, sk)]
+            for typ_r, typ_m in ((R.CUBE, M.CUBE), (R.SPHERE, M.SPHERE)):
+                want.append(rbx.intersects(rn.SolidPrototype(typ_r, rn.Vector(pos), rn.Matrix(ori), rmat)))
+                got.append(mbx.intersects(mn.SolidPrototype(typ_m, mn.Vector(pos), mn.Matrix(ori), mmat)))
+            if trial % 4 == 0:
+                ptss = [[tuple(random.uniform(-3, 3) for _ in range(dim)) for _ in range(dim)] for _ in range(rn.BATCH_SIZE)]
+                rb_, mb_ = (rn.TriangleBatchPrototype([rn.TrianglePrototype(p, rmat) for p in ptss]),
+                            mn.TriangleBatchPrototype([mn.TrianglePrototype(p, mmat) for p in ptss]))
+                want += [rbx.intersects(rb_), rbx.intersects_flat(rb_, sk)]
+                got += [mbx.intersects(mb_), mbx.intersects_flat(mb_, sk)]
+            assert got == want, (dim, trial)
+            seen.update(want)
+    assert seen == {True, False}
