@@ -610,6 +610,10 @@ class KDNode:
         if type(self) is KDNode:
             raise TypeError('the KDNode type cannot be instantiated directly')
 
+    def __getstate__(self):
+        # the device copy (a handle into the CUDA library) is a cache: it never travels with a pickle
+        return {k: v for k, v in self.__dict__.items() if k not in ('_dev', '_flat')}
+
     def _device(self):
         if getattr(self, '_dev', None) is None:
             flat = _Flattener(self.dimension)
@@ -816,10 +820,19 @@ class GlobalLight:
     dimension = property(lambda self: self.direction.dimension)
 
 
+def _restore_light_list(scene, kind, items):
+    lst = _LightList(scene, kind)
+    list.extend(lst, items)                 # already validated when they were added
+    return lst
+
+
 class _LightList(list):
     def __init__(self, scene, kind):
         super().__init__()
         self._scene, self._kind = scene, kind
+
+    def __reduce__(self):
+        return _restore_light_list, (self._scene, self._kind, list(self))
 
     def _check(self, light):
         if not isinstance(light, self._kind):
@@ -849,6 +862,13 @@ class _SceneBase(Scene):
         self._dev = None
 
     dimension = property(lambda self: self._cam.dimension)
+
+    def __getstate__(self):
+        # device copy and lock count belong to this process (pickle codecs of the reference: src/render.cpp:1391-1657)
+        st = {k: v for k, v in self.__dict__.items() if k not in ('_dev', '_flat', '_mat_snapshot')}
+        st['_dev'] = None
+        st['locked'] = 0
+        return st
 
     def _check_unlocked(self):
         if self.locked:

@@ -24,50 +24,25 @@ class NTracer:
         obj.dimension = dim
         obj.base = mod
 
-        class Vector(mod.Vector):
-            __slots__ = ()
+        # Like the reference's wrappers (lib/ntracer/wrapper.py:10-66) the curried classes hand back instances of the
+        # BASE classes -- `nt.Vector(1,2,3)` is a tracern.Vector -- so objects made through different NTracer instances
+        # mix freely and pickle by their module-level type.
+        def curried(base, make, **statics):
+            ns = {'__slots__': (), '__new__': lambda cls, *a, **k: make(*a, **k)}
+            ns.update({k: staticmethod(v) for k, v in statics.items()})
+            return type(base.__name__, (base,), ns)
 
-            def __init__(self, *values):
-                if len(values) > 1:
-                    mod.Vector.__init__(self, dim, values)
-                else:
-                    mod.Vector.__init__(self, dim, *values)
+        def spread(base):
+            # Vector / Matrix accept their values as separate arguments as well as one sequence
+            return lambda *values: base(dim, values) if len(values) > 1 else base(dim, *values)
 
-            @staticmethod
-            def axis(axis, length=1):
-                return mod.Vector.axis(dim, axis, length)
-
-        class Matrix(mod.Matrix):
-            __slots__ = ()
-
-            def __init__(self, *values):
-                if len(values) > 1:
-                    mod.Matrix.__init__(self, dim, values)
-                else:
-                    mod.Matrix.__init__(self, dim, *values)
-
-            @staticmethod
-            def scale(factor):
-                if isinstance(factor, mod.Vector):
-                    return mod.Matrix.scale(factor)
-                return mod.Matrix.scale(dim, factor)
-
-            @staticmethod
-            def identity():
-                return mod.Matrix.identity(dim)
-
-        class Camera(mod.Camera):
-            def __init__(self):
-                mod.Camera.__init__(self, dim)
-
-        class BoxScene(mod.BoxScene):
-            def __init__(self):
-                mod.BoxScene.__init__(self, dim)
-
-        class AABB(mod.AABB):
-            def __init__(self, *args, **kwds):
-                mod.AABB.__init__(self, dim, *args, **kwds)
-
+        Vector = curried(mod.Vector, spread(mod.Vector), axis=lambda axis, length=1: mod.Vector.axis(dim, axis, length))
+        Matrix = curried(mod.Matrix, spread(mod.Matrix),
+                         scale=lambda factor: mod.Matrix.scale(factor) if isinstance(factor, mod.Vector) else mod.Matrix.scale(dim, factor),
+                         identity=lambda: mod.Matrix.identity(dim))
+        Camera = curried(mod.Camera, lambda: mod.Camera(dim))
+        BoxScene = curried(mod.BoxScene, lambda: mod.BoxScene(dim))
+        AABB = curried(mod.AABB, lambda *a, **k: mod.AABB(dim, *a, **k))
         obj.Vector, obj.Matrix, obj.Camera, obj.BoxScene, obj.AABB = Vector, Matrix, Camera, BoxScene, AABB
         for n in ['CompositeScene', 'KDNode', 'KDLeaf', 'KDBranch', 'Primitive', 'PrimitiveBatch', 'PrimitivePrototype',
                   'Solid', 'SolidPrototype', 'Triangle', 'TriangleBatch', 'TrianglePrototype', 'TriangleBatchPrototype',
