@@ -655,10 +655,43 @@ template <int DT> struct LeafCursor {
 #ifndef NTR_MINI_MAILBOX
 #define NTR_MINI_MAILBOX 8
 #endif
+// Optional mailbox for SINGLE simplexes (leaf items that are not batches: scenes from bulk.simplex_scene, config 5).
+// The register mailbox above is useless there (76 items per leaf on the 1 M soup), and without any mailbox the kernels
+// re-test a simplex in every leaf it was duplicated into: 12,500 tests per ray against the 4,591 the reference
+// algorithm performs with its unbounded list (oracle counters).  NTR_SINGLE_MAILBOX = N (a power of two) keeps a
+// direct-mapped table of the N most recently tested ids per ray in local memory; a false negative only costs a
+// repeated test.  Exact for the same reason as the batch mailbox.  Host emulation, 200 k ten-dimensional simplexes,
+// tests per ray: none 2,859 | 64 entries 2,319 | 256 entries 1,727 | 1,024 entries 1,487 | unbounded (oracle) 1,395,
+// images identical.  Default 0 (off): written at the end of round 1 when no GPU time was left -- whether the
+// local-memory traffic (N*4 bytes per thread) costs less than the tests it saves is still to be measured.
+#ifndef NTR_SINGLE_MAILBOX
+#define NTR_SINGLE_MAILBOX 0
+#endif
+struct SingleMailbox {
+#if NTR_SINGLE_MAILBOX > 0
+    static_assert((NTR_SINGLE_MAILBOX & (NTR_SINGLE_MAILBOX - 1)) == 0, "NTR_SINGLE_MAILBOX must be a power of two");
+    uint32_t v[NTR_SINGLE_MAILBOX];
+    NTR_HD void clear() {
+        for (int i = 0; i < NTR_SINGLE_MAILBOX; ++i) v[i] = NTR_NONE_REF;
+    }
+    NTR_HD bool test_and_set(uint32_t r) {
+        const uint32_t h = ((r * 2654435761u) >> 16) & (uint32_t)(NTR_SINGLE_MAILBOX - 1);       // Fibonacci hash, middle bits
+        if (v[h] == r) return true;
+        v[h] = r;
+        return false;
+    }
+#else
+    NTR_HD void clear() {}
+    NTR_HD bool test_and_set(uint32_t) { return false; }
+#endif
+};
+
 struct MiniMailbox {
+    SingleMailbox single;
 #if NTR_MINI_MAILBOX > 0
     uint32_t v[NTR_MINI_MAILBOX];       // most recent first; constant indices only, so it lives in registers
     NTR_HD void clear() {
+        single.clear();
 #pragma unroll
         for (int i = 0; i < NTR_MINI_MAILBOX; ++i) v[i] = NTR_NONE_REF;
     }
@@ -674,7 +707,7 @@ struct MiniMailbox {
         return f;
     }
 #else
-    NTR_HD void clear() {}
+    NTR_HD void clear() { single.clear(); }
     NTR_HD bool test_and_set(uint32_t) { return false; }
 #endif
 };
@@ -750,6 +783,7 @@ NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, con
             float dist = batch_test<DT, FLAGS>(s, it.y, o, dir, index, oh.dist, meta, cnt);
             if (dist) { oh.dist = dist; oh.ref = item; oh.lane = index; hit = true; }
         } else if (item != skip.ref) {
+            if (mm.single.test_and_set(item)) continue;
             if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
             float dist = simplex_single<DT>(s, it.y, o, dir, oh.dist, meta);
             if (dist) { oh.dist = dist; oh.ref = item; oh.lane = -1; hit = true; }
