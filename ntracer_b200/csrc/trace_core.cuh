@@ -667,8 +667,8 @@ template <int DT> struct LeafCursor {
 #ifndef NTR_SINGLE_MAILBOX
 #define NTR_SINGLE_MAILBOX 0
 #endif
-struct SingleMailbox {
 #if NTR_SINGLE_MAILBOX > 0
+struct SingleMailbox {
     static_assert((NTR_SINGLE_MAILBOX & (NTR_SINGLE_MAILBOX - 1)) == 0, "NTR_SINGLE_MAILBOX must be a power of two");
     uint32_t v[NTR_SINGLE_MAILBOX];
     NTR_HD void clear() {
@@ -680,18 +680,19 @@ struct SingleMailbox {
         v[h] = r;
         return false;
     }
-#else
-    NTR_HD void clear() {}
-    NTR_HD bool test_and_set(uint32_t) { return false; }
-#endif
 };
+#endif
 
 struct MiniMailbox {
+#if NTR_SINGLE_MAILBOX > 0
     SingleMailbox single;
+#endif
 #if NTR_MINI_MAILBOX > 0
     uint32_t v[NTR_MINI_MAILBOX];       // most recent first; constant indices only, so it lives in registers
     NTR_HD void clear() {
+#if NTR_SINGLE_MAILBOX > 0
         single.clear();
+#endif
 #pragma unroll
         for (int i = 0; i < NTR_MINI_MAILBOX; ++i) v[i] = NTR_NONE_REF;
     }
@@ -707,7 +708,11 @@ struct MiniMailbox {
         return f;
     }
 #else
-    NTR_HD void clear() { single.clear(); }
+    NTR_HD void clear() {
+#if NTR_SINGLE_MAILBOX > 0
+        single.clear();
+#endif
+    }
     NTR_HD bool test_and_set(uint32_t) { return false; }
 #endif
 };
@@ -783,7 +788,9 @@ NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, con
             float dist = batch_test<DT, FLAGS>(s, it.y, o, dir, index, oh.dist, meta, cnt);
             if (dist) { oh.dist = dist; oh.ref = item; oh.lane = index; hit = true; }
         } else if (item != skip.ref) {
+#if NTR_SINGLE_MAILBOX > 0
             if (mm.single.test_and_set(item)) continue;
+#endif
             if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
             float dist = simplex_single<DT>(s, it.y, o, dir, oh.dist, meta);
             if (dist) { oh.dist = dist; oh.ref = item; oh.lane = -1; hit = true; }
