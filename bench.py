@@ -47,7 +47,7 @@ def load_fixture(name):
         # BASELINE config 5: generated here (no fixture can hold 1 M simplexes); scene construction (records + k-d
         # tree) runs in the native host-side builder and is NOT part of any timed region
         from ntracer_b200 import bulk
-        sc = bulk.simplex_scene(bulk.soup(10, int(var)), max_depth=17)
+        sc = bulk.simplex_scene(bulk.soup(10, int(var)), max_depth=int(os.environ.get('NTR_BENCH_SOUP_DEPTH', '17')))
         sc['cam_origin'] = np.array([0, 0, -3] + [0] * 7, np.float32)
         return sc, {}
     sc, g = fx.load(name)
