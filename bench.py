@@ -136,6 +136,11 @@ def reference_arm(args, sc, g, w, h, rays_per_frame):
         def rfmt(ww, hh):
             return ntr.ImageFormat(ww, hh, [ntr.Channel(8, 1, 0, 0), ntr.Channel(8, 0, 1, 0), ntr.Channel(8, 0, 0, 1)])
         r = ntr.BlockingRenderer()          # threads=-1: hardware_concurrency() workers (render.cpp:829-838)
+        # The reference's workers check `busy_threads` WITHOUT the lock when they start (render.cpp:773-777): a worker
+        # caught between that check and its first wait when render() posts a job is counted in busy_threads but sleeps
+        # through the job, and render() then waits forever (seen as a hang of the first frame on a busy box).  Give
+        # the workers time to reach their wait before the first job; every later job is posted under the lock.
+        time.sleep(1.0)
         # probe at 1/8 resolution (also the warm-up: late-starting workers), then pick the largest
         # frame of the same view (full, 1/2, 1/4 ... linear size) whose estimated cost fits ~6 s per frame
         pw, ph = max(w // 8, 32), max(h // 8, 32)

@@ -15,6 +15,8 @@ import os
 import random
 import sys
 
+import time
+
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -43,7 +45,9 @@ def ref_float(scene, w, h):
 def ref_packed(scene, w, h, channels=RGB8, pitch=0, reversed=False, fill=0xAB):
     fmt = ref_format(w, h, channels, pitch, reversed)
     buf = bytearray([fill]) * (fmt.pitch * h)
-    assert ntracer.BlockingRenderer().render(buf, fmt, scene)
+    renderer = ntracer.BlockingRenderer()
+    time.sleep(0.5)      # reference start-up race: workers must be waiting before the first job (see bench.reference_arm)
+    assert renderer.render(buf, fmt, scene)
     return np.frombuffer(bytes(buf), dtype=np.uint8).copy()
 
 
