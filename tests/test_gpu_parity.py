@@ -246,12 +246,13 @@ def test_wavefront_queue_overflow_regrows_and_rerenders(monkeypatch):
         assert np.abs(a.astype(np.int32) - ol.pack(fmt, ref).astype(np.int32)).max() <= 1
 
 
-def test_abort_stops_a_running_render():
+def test_abort_stops_a_running_render(monkeypatch):
     """signal_abort / abort_render (reference src/render.cpp:702-722,911-923): a frame in flight ends early and the
     call reports it (BlockingRenderer.render -> False)."""
     import threading
     import time
     from ntracer_b200 import bulk
+    monkeypatch.setenv('NTR_FORCE_GENERIC', '1')      # the slower run-time-dimension kernels: a frame long enough to interrupt
     pts = bulk.soup(10, 60000)
     sc = bulk.simplex_scene(pts, max_depth=14)
     sc['cam_origin'] = np.array([0, 0, -3] + [0] * 7, np.float32)
