@@ -432,8 +432,43 @@ def make_soup9():
     save('soup9', sc, size=np.array([w, h]), float=ref_float(scene, w, h), ids=ids, dist=dist)
 
 
+def make_rotation():
+    """The interactive loop: frames of the reference itself along the camera path of
+    scripts/polytope.py:522-557 (RotatingCamera), computed with the reference's own Camera / Matrix classes, for the
+    exported cell120 (single-pass) and solids6 (reflective, wavefront passes) scenes.  40 steps per turn, 160x90."""
+    import math
+    from tests import fixtures as fx
+    frames, w, h = 40, 160, 90
+    out = {'frames': np.array(frames), 'size': np.array([w, h]), 'steps': np.array([5, 17, 29])}
+    for name in ('cell120', 'solids6'):
+        sc, g = fx.load(name)
+        nt, scene, prims = rb.import_scene(sc)
+        rb.make_immortal(prims.values())
+        d = int(sc['dim'])
+        cam = scene.get_camera()
+        cam_distance = nt.dot(cam.origin, cam.axes[2])
+        hh, incr = 1 / math.sqrt(d - 1), 2 * math.pi / frames
+        cams_o, cams_a, packed = [], [], []
+        for k in range(1, frames):
+            a2 = cam.axes[0] * hh + cam.axes[1] * hh
+            for i in range(d - 3):
+                a2 += cam.axes[i + 3] * hh
+            cam.transform(nt.Matrix.rotation(cam.axes[2], a2, incr))
+            cam.normalize()
+            cam.origin = cam.axes[2] * cam_distance
+            if k in (5, 17, 29):
+                scene.set_camera(cam)
+                cams_o.append(np.array(list(cam.origin), np.float32))
+                cams_a.append(np.array([list(cam.axes[i]) for i in range(d)], np.float32))
+                packed.append(ref_packed(scene, w, h))
+        out[name + '_origin'], out[name + '_axes'], out[name + '_packed'] = np.stack(cams_o), np.stack(cams_a), np.stack(packed)
+    path = os.path.join(HERE, 'rotation.npz')
+    np.savez_compressed(path, **out)
+    print('wrote %s (%.1f KiB)' % (path, os.path.getsize(path) / 1024))
+
+
 ALL = {'box': make_box, 'pack': make_pack, 'kdtree_kat': make_kdtree_kat, 'cell120': make_cell120,
-       'ggs120': make_ggs120, 'solids6': make_solids6, 'mixed3': make_mixed3, 'soup9': make_soup9}
+       'ggs120': make_ggs120, 'solids6': make_solids6, 'mixed3': make_mixed3, 'soup9': make_soup9, 'rotation': make_rotation}
 
 if __name__ == '__main__':
     random.seed(1)

@@ -123,3 +123,46 @@ def test_stream_pinned_destination_ticket_rules_and_abort():
         t4 = ds.render_begin(fmt, pinned[0].numpy())            # the next frame starts clean
         ds.render_end(t4)
         assert np.array_equal(pinned[0].numpy(), ref)
+
+
+def _rotation_golden():
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'rotation.npz'))
+
+
+@pytest.mark.parametrize('name', ['cell120', 'solids6'])
+def test_oracle_and_camera_path_match_reference_frames_of_the_rotation(name):
+    """tests/golden/rotation.npz: frames rendered by the reference itself along its RotatingCamera path
+    (make_fixtures.py: make_rotation)."""
+    g = _rotation_golden()
+    sc, _ = fx.load(name)
+    frames = int(g['frames'])
+    w, h = [int(v) for v in g['size']]
+    cams = stream.rotation_cameras(sc['cam_origin'], sc['cam_axes'], frames)
+    fmt = _capi.make_image_format(w, h, _capi.RGB8)
+    for j, k in enumerate(int(v) for v in g['steps']):
+        ro, ra = g[name + '_origin'][j], g[name + '_axes'][j]
+        assert np.abs(cams[k][0] - ro).max() <= 3e-5 * max(1.0, float(np.abs(ro).max()))
+        assert np.abs(cams[k][1] - ra).max() <= 3e-5
+        gold = g[name + '_packed'][j].reshape(h, w, 3).astype(np.int32)
+        mine = ol.render_packed(sc, fmt, cam=(ro, ra)).reshape(h, w, 3).astype(np.int32)     # the reference's own camera
+        assert np.mean(np.abs(mine - gold).max(axis=2) > 1) <= 0.001, (name, k)
+        assert len(np.unique(gold.reshape(-1, 3), axis=0)) > 20                                # a real picture
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['cell120', 'solids6'])
+def test_streamed_frames_match_reference_frames_of_the_rotation(name):
+    from ntracer_b200.backend import DeviceScene
+    g = _rotation_golden()
+    sc, _ = fx.load(name)
+    w, h = [int(v) for v in g['size']]
+    fmt = _capi.make_image_format(w, h, _capi.RGB8)
+    cams = [(g[name + '_origin'][j], g[name + '_axes'][j]) for j in range(len(g['steps']))]
+    got = {}
+    with DeviceScene(sc) as ds:
+        bufs = [np.zeros(fmt.pitch * h, np.uint8), np.zeros(fmt.pitch * h, np.uint8)]
+        stream.render_sequence(ds, fmt, cams, bufs, sink=lambda k, b: got.__setitem__(k, b.copy()))
+    for j in range(len(cams)):
+        gold = g[name + '_packed'][j].reshape(h, w, 3).astype(np.int32)
+        d = np.abs(got[j].reshape(h, w, 3).astype(np.int32) - gold).max(axis=2)
+        assert np.mean(d > 1) <= 0.001, (name, j)
