@@ -67,6 +67,9 @@ class FakeDR:
     def frame_on_device(self): pass
     def render_to_host(self): self.ds.render_device()
 ntd.DistributedRenderer = FakeDR
+import torch.distributed as _dist
+_real_init = _dist.init_process_group
+_dist.init_process_group = lambda backend=None, **k: _real_init('gloo')      # NCCL needs GPUs; the flow is the same
 import bench
 sys.argv = ['bench.py'] + %(argv)r
 sys.exit(bench.main())
@@ -119,3 +122,20 @@ def test_reference_arm_line():
     assert line['impl'] == 'reference' and line['value'] > 0 and line['e2e']['value'] == line['value']
     assert line['cpu_baseline']['kind'] in ('reference', 'port')
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
+
+
+def test_two_rank_flow_prints_one_line_from_rank_0(tmp_path):
+    """The launcher the driver uses for N > 1 (torch.distributed.run, one process per GPU), with gloo standing in for
+    NCCL: both ranks run the timed regions, the maxima are reduced, rank 0 alone prints the line, nobody hangs."""
+    script = tmp_path / 'stub_bench.py'
+    script.write_text(STUB % {'root': ROOT, 'refl': 0, 'hang': 0,
+                              'argv': ['--gpus', '2', '--config', 'c1', '--steps', '3', '--warmup', '1']})
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1')
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29731', str(script)],
+                         capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert out.returncode == 0 and len(lines) == 1, (out.stdout[-1500:], out.stderr[-1500:])
+    line = json.loads(lines[0])
+    assert line['n_gpus'] == 2 and line['scaling'] == 'strong' and line['value'] > 0 and line['e2e']['value'] > 0
+    assert 'roofline' not in line and 'cpu_baseline' not in line and 'stream' not in line     # N = 1 only
