@@ -27,6 +27,10 @@ def build_kdtree(lo, hi, max_depth=0, split_threshold=0, traversal_cost=-1.0, in
     lo = np.ascontiguousarray(lo, dtype=np.float32)
     hi = np.ascontiguousarray(hi, dtype=np.float32)
     n, d = lo.shape
+    if hi.shape != lo.shape:
+        raise ValueError('lo and hi must have the same shape')
+    if n and not (np.all(np.isfinite(lo)) and np.all(np.isfinite(hi)) and np.all(lo <= hi)):
+        raise ValueError('item bounds must be finite with lo <= hi on every axis')
     lib = _capi.load()
     nodes_p, refs_p = C.c_void_p(), C.c_void_p()
     n_nodes, n_refs, root = C.c_uint32(), C.c_uint32(), C.c_uint32()

@@ -211,6 +211,8 @@ NTR_API int ntr_build_kdtree(int dim, uint32_t n, const float *lo, const float *
         return NTR_ERR_VALUE;
     if (n && (!lo || !hi)) return NTR_ERR_VALUE;
     const int D = dim;
+    for (size_t k = 0; k < (size_t)n * D; ++k)             // NaN, infinite or inverted bounds would poison the SAH sweep
+        if (!(lo[k] <= hi[k]) || !(lo[k] > -3e38f) || !(hi[k] < 3e38f)) return NTR_ERR_VALUE;
     Builder b;
     b.D = D; b.lo = lo; b.hi = hi;
     b.max_depth = max_depth > 0 ? std::min(max_depth, NTR_MAX_TREE_DEPTH - 2) : 25;

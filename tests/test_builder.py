@@ -103,3 +103,27 @@ def test_bulk_scene_equals_single_leaf_scene_under_the_oracle():
     assert (ia >= 0).mean() > 0.02
     assert np.mean(ia == ib) >= 0.999
     assert np.abs(a - b).max() < 1e-4
+
+
+def test_builder_edge_cases_and_input_validation():
+    import ctypes as C
+    from ntracer_b200 import _capi
+    one = np.array([[0, 0, 0]], np.float32)
+    nodes, refs, root, bnd = bulk.build_kdtree(one, one + 1)
+    assert nodes.shape == (1, 4) and refs.tolist() == [0] and root == 0 and np.all(bnd[0] < 0) and np.all(bnd[1] > 1)
+    nodes, refs, root, bnd = bulk.build_kdtree(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert nodes.shape == (0, 4) and refs.size == 0 and root == 0xFFFFFFFF            # an empty scene: no root
+    flat_lo = np.array([[0, 0, 0], [2, 0, 0]], np.float32)                            # zero extent on one axis
+    nodes, refs, root, bnd = bulk.build_kdtree(flat_lo, flat_lo + np.array([1, 1, 0], np.float32))
+    assert sorted(refs.tolist()) == [0, 1]
+    for bad_lo, bad_hi in (([[0, 0, np.nan]], [[1, 1, 1]]), ([[1, 1, 1]], [[0, 0, 0]]), ([[0, 0, 0]], [[1, np.inf, 1]])):
+        with pytest.raises(ValueError):
+            bulk.build_kdtree(np.array(bad_lo, np.float32), np.array(bad_hi, np.float32))
+    # the C entry point refuses the same input on its own (NTR_ERR_VALUE), whatever the caller checked
+    lib = _capi.load()
+    lo, hi = np.array([[1, 1, 1]], np.float32), np.array([[0, 0, 0]], np.float32)
+    p1, p2, a, b, c = C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    bnd = np.zeros((2, 3), np.float32)
+    rc = lib.ntr_build_kdtree(3, 1, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), 0, 0, -1.0, -1.0,
+                              C.byref(p1), C.byref(a), C.byref(p2), C.byref(b), C.byref(c), bnd.ctypes.data_as(C.c_void_p))
+    assert rc == _capi.NTR_ERR_VALUE
