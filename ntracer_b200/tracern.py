@@ -19,6 +19,7 @@ from .render import Color, LockedError, Material, Scene, _color_tuple
 BATCH_SIZE = 4      # lanes of a TriangleBatch; the reference's SSE build has v_real::size == 4
 CUBE, SPHERE = 1, 2
 _F = np.float32
+ROUNDING_FUZZ = _F(10) * np.finfo(np.float32).eps        # src/tracer.hpp:25
 
 
 def _check_dimension(d):
@@ -412,16 +413,52 @@ class AABB:
 
 
 # ---------------------------------------------------------------------------------------------------------
+_PROBE_MATERIAL = Material((1, 1, 1))       # opaque: KDNode.intersects materialises opaque hits only
+
+
 class Primitive:
     def __init__(self, *a, **k):
         if type(self) is Primitive:
             raise TypeError('the Primitive type cannot be instantiated directly')
+
+    def __getstate__(self):
+        return {k: v for k, v in self.__dict__.items() if k != '_probe'}
+
+    def _probe_leaf(self):
+        """A one-item tree around a copy of this primitive's geometry: the single-primitive ray test runs on the GPU
+        through the same kernels as everything else (there is no CPU path).  Geometry is immutable, so it is cached."""
+        leaf = self.__dict__.get('_probe')
+        if leaf is None:
+            leaf = self._probe = KDLeaf([self._twin()])
+        return leaf
+
+    def intersects(self, origin, direction):
+        """-> RayIntersection or None (src/ntracer_body.hpp:1002-1019): triangle::intersects / solid::intersects for one
+        ray, whatever the material's opacity."""
+        hits = self._probe_leaf().intersects(origin, direction)
+        if not hits:
+            return None
+        h = hits[-1]
+        return RayIntersection(h.dist, h.origin, h.normal, self)
 
 
 class PrimitiveBatch:
     def __init__(self, *a, **k):
         if type(self) is PrimitiveBatch:
             raise TypeError('the PrimitiveBatch type cannot be instantiated directly')
+
+    __getstate__ = Primitive.__getstate__
+    _probe_leaf = Primitive._probe_leaf
+
+    def intersects(self, origin, direction, index=-1):
+        """-> RayIntersection (batch_index = the lane that was hit) or None; lane `index` is ignored
+        (src/ntracer_body.hpp:1038-1056, triangle_batch::intersects tracer.hpp:551-599)."""
+        leaf = self._probe_leaf()
+        hits = leaf.intersects(origin, direction, source=leaf[0] if index >= 0 else None, batch_index=index)
+        if not hits:
+            return None
+        h = hits[-1]
+        return RayIntersection(h.dist, h.origin, h.normal, self, h.batch_index)
 
 
 class Triangle(Primitive):
@@ -440,6 +477,9 @@ class Triangle(Primitive):
         self.d = float(-np.dot(self.face_normal._v, self.p1._v))       # recalculate_d, tracer.hpp:472-474
 
     dimension = property(lambda self: self.p1.dimension)
+
+    def _twin(self):
+        return Triangle(self.p1, self.face_normal, self.edge_normals, _PROBE_MATERIAL)
 
     @staticmethod
     def from_points(points, material):          # tracer.hpp:442-462
@@ -485,6 +525,9 @@ class TriangleBatch(PrimitiveBatch):
     def __len__(self): return BATCH_SIZE
     def __getitem__(self, i): return self._t[i]
 
+    def _twin(self):
+        return TriangleBatch([t._twin() for t in self._t])
+
 
 class Solid(Primitive):
     """Solid(type,position,orientation,material) (src/tracer.hpp:231-289)"""
@@ -502,6 +545,44 @@ class Solid(Primitive):
         self.material = material
 
     dimension = property(lambda self: self.position.dimension)
+
+    def _twin(self):
+        return Solid(self.type, self.position, self.orientation, _PROBE_MATERIAL)
+
+    def _hit_frame(self, o, d):
+        """What solid::intersects leaves in `normal` for a ray that hits (src/tracer.hpp:126-173, 251-276), recomputed on
+        the host for RayIntersection.origin / .normal: the hit is found in the solid's frame and carried back with
+        `orientation` -- the normal is NOT renormalised and the origin follows the reference's frame
+        arithmetic as written (Q5).  -> (origin, normal) as float32 arrays, or None if this arithmetic finds no hit."""
+        n = self.dimension
+        lo = (self.inv_orientation._m @ o - self.position._v).astype(_F)
+        ld = (self.inv_orientation._m @ d).astype(_F)
+        if self.type == CUBE:
+            for i in range(n):
+                if ld[i] == 0:
+                    continue
+                face = _F(1) if ld[i] < 0 else _F(-1)
+                dist = (face - lo[i]) / ld[i]
+                if not dist > 0:
+                    continue
+                p = (ld * dist + lo).astype(_F)
+                p[i] = face
+                others = np.arange(n) != i
+                if np.any(np.abs(p[others]) > 1 + ROUNDING_FUZZ):
+                    continue
+                nd = np.zeros(n, _F)
+                nd[i] = face
+                return (self.orientation._m @ (p + self.position._v)).astype(_F), (self.orientation._m @ nd).astype(_F)
+            return None
+        a = _F(np.dot(ld, ld))
+        b = _F(2) * _F(np.dot(ld, lo))
+        c = _F(np.dot(lo, lo)) - _F(1)
+        disc = b * b - _F(4) * a * c
+        if disc < 0:
+            return None
+        dist = (-b - np.sqrt(disc)) / (_F(2) * a)
+        p = (lo + ld * dist).astype(_F)
+        return (self.orientation._m @ (p + self.position._v)).astype(_F), (self.orientation._m @ p).astype(_F)
 
     def _row(self):
         return np.concatenate([np.array([self.type], _F), self.orientation._m.ravel(), self.inv_orientation._m.ravel(), self.position._v])
@@ -648,7 +729,10 @@ class KDNode:
             if dot(tri.face_normal, d) > 0:
                 n = -n
         else:
+            frame = tri._hit_frame(o._v, d._v)
             n = None
+            if frame is not None:
+                P, n = Vector._wrap(frame[0]), Vector._wrap(frame[1])
         return [RayIntersection(t, P, n, prim, lane)]
 
     def occludes(self, origin, direction, distance=FLT_MAX, t_near=-FLT_MAX, t_far=FLT_MAX, source=None, batch_index=-1):

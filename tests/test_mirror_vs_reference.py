@@ -109,3 +109,79 @@ def test_triangles_and_prototype_bounds(dim):
             assert close(arr(ms.boundary.start), arr(rs.boundary.start), 1e-3), (tr, trial)
             assert close(arr(ms.boundary.end), arr(rs.boundary.end), 1e-3)
             assert close(marr(ms.inv_orientation, dim), marr(rs.inv_orientation, dim), 1e-3)
+
+
+class _EmulatedDevice:
+    """Test double for backend.DeviceScene: the same flat scene, rays traced by the host-emulated device code
+    (tests/emul_lib.py).  The product always talks to the CUDA library; this only lets the Python half of
+    Primitive.intersects (twins, skip lanes, hit frames of solids) be checked against the reference without a GPU."""
+    def __init__(self, sc, device=-1):
+        self.sc = sc
+
+    def trace_rays(self, origins, dirs, t_near, t_far, skip_ref=None, skip_lane=None):
+        from tests import emul_lib as el
+        return el.trace_rays(self.sc, origins, dirs, t_near, t_far, skip_ref, skip_lane)
+
+    def close(self):
+        pass
+
+
+@pytest.mark.parametrize('device', ['emulated', pytest.param('cuda', marks=pytest.mark.gpu)])
+@pytest.mark.parametrize('dim', [3, 4, 6])
+def test_single_primitive_ray_tests(dim, device, monkeypatch):
+    """Triangle.intersects / TriangleBatch.intersects / Solid.intersects (src/ntracer_body.hpp:1002-1056) against the
+    reference's; once with the host-emulated device code behind the mirror (no GPU), once through the CUDA library."""
+    rb.load_reference()
+    import ntracer as R
+    from ntracer_b200 import tracern
+    if device == 'emulated':
+        monkeypatch.setattr(tracern, 'DeviceScene', _EmulatedDevice)
+    rnd = random.Random(300 + dim)
+    rn, mn = R.NTracer(dim), M.NTracer(dim)
+    rmat, mmat = R.Material((1, 1, 1), 0.5), M.Material((1, 1, 1), 0.5)           # transparent: still reported
+    hits = misses = 0
+
+    def rays(target, n):
+        for _ in range(n):
+            o = [rnd.uniform(-4, 4) for _ in range(dim)]
+            aim = [t + rnd.uniform(-0.6, 0.6) for t in target]
+            yield o, [a - b for a, b in zip(aim, o)]
+
+    def same(mh, rh):
+        nonlocal hits, misses
+        assert (mh is None) == (rh is None)
+        if rh is None:
+            misses += 1
+            return
+        hits += 1
+        assert close(mh.dist, rh.dist, 1e-4) and close(arr(mh.origin), arr(rh.origin), 1e-3)
+        assert close(arr(mh.normal), arr(rh.normal), 1e-3)
+        assert mh.batch_index == rh.batch_index
+
+    for trial in range(6):
+        pts = [tuple(rnd.uniform(-2, 2) for _ in range(dim)) for _ in range(dim)]
+        rt, mt = rn.Triangle.from_points([rn.Vector(p) for p in pts], rmat), mn.Triangle.from_points([mn.Vector(p) for p in pts], mmat)
+        centre = [sum(p[i] for p in pts) / dim for i in range(dim)]
+        for o, d in rays(centre, 12):
+            mh, rh = mt.intersects(mn.Vector(o), mn.Vector(d)), rt.intersects(rn.Vector(o), rn.Vector(d))
+            same(mh, rh)
+            if mh is not None:
+                assert mh.primitive is mt
+        # a batch: 4 simplexes around the same centre; skipping the winner exposes the next lane
+        ptss = [[tuple(c + rnd.uniform(-1.5, 1.5) for c in centre) for _ in range(dim)] for _ in range(rn.BATCH_SIZE)]
+        rbt = rn.TriangleBatch([rn.Triangle.from_points([rn.Vector(p) for p in ps], rmat) for ps in ptss])
+        mbt = mn.TriangleBatch([mn.Triangle.from_points([mn.Vector(p) for p in ps], mmat) for ps in ptss])
+        for o, d in rays(centre, 12):
+            mh, rh = mbt.intersects(mn.Vector(o), mn.Vector(d)), rbt.intersects(rn.Vector(o), rn.Vector(d))
+            same(mh, rh)
+            if rh is not None:
+                same(mbt.intersects(mn.Vector(o), mn.Vector(d), rh.batch_index), rbt.intersects(rn.Vector(o), rn.Vector(d), rh.batch_index))
+        pos = [rnd.uniform(-1, 1) for _ in range(dim)]
+        ori = [tuple((1.0 if i == j else 0.0) + rnd.uniform(-0.4, 0.4) for j in range(dim)) for i in range(dim)]
+        for tr, tm in ((R.CUBE, M.CUBE), (R.SPHERE, M.SPHERE)):
+            rs, ms = rn.Solid(tr, rn.Vector(pos), rn.Matrix(ori), rmat), mn.Solid(tm, mn.Vector(pos), mn.Matrix(ori), mmat)
+            # the solid sits where inv_orientation*x - position is small (the reference's frame, SURVEY 8a-Q5)
+            world = list(arr(rn.Matrix(ori) * rn.Vector(pos)))
+            for o, d in rays(world, 12):
+                same(ms.intersects(mn.Vector(o), mn.Vector(d)), rs.intersects(rn.Vector(o), rn.Vector(d)))
+    assert hits > 40 and misses > 10
