@@ -35,6 +35,7 @@ CONFIGS = {
     'c4': ('ggs120:refl_transp', 3840, 2160, "config 4: great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4, 12 of 120 cells opacity 0.5"),
     'c5': ('soup10:1000000', 3840, 2160, "config 5: 10-D synthetic simplex soup, 1,000,000 TrianglePrototypes (SURVEY 8d C5 generator, seed 1234), run-time-dimension kernels, 3840x2160, camera light only; tree from this repo's native builder (max_depth 17)"),
     'c5s': ('soup10:16000', 3840, 2160, "config 5 reduced: the same 10-D soup generator with 16,000 simplexes (what the reference CPU renderer can be timed on), 3840x2160"),
+    'c4b': ('ssc120:refl_transp', 3840, 2160, "config 4 as BASELINE.json spells its symbol: small stellated 120-cell {5/2,5,3} (7,200 simplexes, leaves <= 48 items), 3840x2160, lights, shadows, reflectivity 0.3 depth 4, 12 transparent cells (opacity 0.5)"),
     'c4o': ('ggs120', 3840, 2160, "config 4 (opaque variant): great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4"),
 }
 METRIC = 'Mrays/s (primary+shadow+reflection)'

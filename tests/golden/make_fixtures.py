@@ -274,9 +274,10 @@ def make_cell120():
     save('cell120', sc, **golden)
 
 
-def make_ggs120():
-    # config 4: great grand stellated 120-cell {5/2,3,3}
-    nt, scene, cam = rb.polytope_scene('5/2 3 3')
+def make_star(fixture='ggs120', schlafli='5/2 3 3'):
+    # config 4: great grand stellated 120-cell {5/2,3,3}; the same recipe serves
+    # {5/2,5,3} (small stellated 120-cell), the symbol BASELINE.json's configs[3] literally names
+    nt, scene, cam = rb.polytope_scene(schlafli)
     add_c2_lights(nt, scene)
     mat = first_material(nt, scene)
     w, h = 128, 72
@@ -315,7 +316,15 @@ def make_ggs120():
         golden['v_refl_transp_' + k] = a
     golden['v_refl_transp_simplex_mat'] = s2['simplex_mat']
     golden['variants'] = np.array([n for n, _ in variants] + ['refl_transp'])
-    save('ggs120', sc, **golden)
+    save(fixture, sc, **golden)
+
+
+def make_ggs120():
+    make_star('ggs120', '5/2 3 3')
+
+
+def make_ssc120():
+    make_star('ssc120', '5/2 5 3')
 
 
 def rot(nt, i, j, theta):
@@ -468,7 +477,7 @@ def make_rotation():
 
 
 ALL = {'box': make_box, 'pack': make_pack, 'kdtree_kat': make_kdtree_kat, 'cell120': make_cell120,
-       'ggs120': make_ggs120, 'solids6': make_solids6, 'mixed3': make_mixed3, 'soup9': make_soup9, 'rotation': make_rotation}
+       'ggs120': make_ggs120, 'ssc120': make_ssc120, 'solids6': make_solids6, 'mixed3': make_mixed3, 'soup9': make_soup9, 'rotation': make_rotation}
 
 if __name__ == '__main__':
     random.seed(1)

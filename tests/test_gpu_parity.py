@@ -74,7 +74,7 @@ def test_pack_formats_and_untouched_padding():
             assert np.array_equal(a[:, :w * bpp], o), n
 
 
-@pytest.mark.parametrize('name', ['cell120', 'ggs120'])
+@pytest.mark.parametrize('name', ['cell120', 'ggs120', 'ssc120'])
 def test_polytope_variants(name):
     sc, g = fx.load(name)
     w, h = [int(v) for v in g['size']]

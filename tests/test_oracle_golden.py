@@ -61,7 +61,7 @@ def test_pack_formats():
             assert np.array_equal(out, ref), n
 
 
-@pytest.mark.parametrize('name', ['cell120', 'ggs120'])
+@pytest.mark.parametrize('name', ['cell120', 'ggs120', 'ssc120'])
 def test_polytope_variants(name):
     sc, g = fx.load(name)
     w, h = [int(v) for v in g['size']]

@@ -16,6 +16,7 @@ NTR_BENCH_SOUP_DEPTH=20 python bench.py --config c5 --steps 2 --warmup 3 --no-cp
 # the two ncu captures that were queued at the end of round 1
 python bench.py --config c4 --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/plain_c4.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_pass -s 5 -c 2 -o gpurun_out/r02_prof_c4 python bench.py --config c4 --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/ncu_c4.log 2>&1
 python bench.py --config c5s --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/plain_c5s.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_pass -s 2 -c 1 -o gpurun_out/r02_prof_c5s python bench.py --config c5s --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/ncu_c5s.log 2>&1
+# config 4 under the symbol BASELINE.json spells ({5/2,5,3}, fixture added after the last GPU call of round 1), and
 # full lines (cpu baselines included) for the configs whose round-1 profiles carry fields from two runs
-for c in c3 c5s; do timeout 600 python bench.py --config $c --steps 5 --warmup 3 > gpurun_out/r02_$c.json 2>gpurun_out/r02_$c.err; done
+for c in c4b c3 c5s; do timeout 600 python bench.py --config $c --steps 5 --warmup 3 > gpurun_out/r02_$c.json 2>gpurun_out/r02_$c.err; done
 cat gpurun_out/r02_tests.txt
