@@ -130,9 +130,13 @@ def test_two_rank_flow_prints_one_line_from_rank_0(tmp_path):
     script = tmp_path / 'stub_bench.py'
     script.write_text(STUB % {'root': ROOT, 'refl': 0, 'hang': 0,
                               'argv': ['--gpus', '2', '--config', 'c1', '--steps', '3', '--warmup', '1']})
+    import socket
+    with socket.socket() as sock:                      # a free rendezvous port
+        sock.bind(('127.0.0.1', 0))
+        port = sock.getsockname()[1]
     env = dict(os.environ, MASTER_ADDR='127.0.0.1')
     out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-                          '--master-addr', '127.0.0.1', '--master-port', '29731', str(script)],
+                          '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
                          capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
     assert out.returncode == 0 and len(lines) == 1, (out.stdout[-1500:], out.stderr[-1500:])
