@@ -110,6 +110,7 @@ struct ntr_scene {
     cudaStream_t slab_stream[kSlabMax] = {};
     cudaEvent_t slab_done[kSlabMax] = {};
     bool slabs = true;                  // NTR_NO_SLABS=1 switches it off
+    bool force_tile_sched = false;      // NTR_TILE_SCHED=1: cost-sorted tile hand-out on whole frames too (heavy-tailed scenes)
     bool zero_copy = false;             // NTR_ZEROCOPY=1: ntr_render stores single-pass frames straight into pinned destinations
     uint32_t queue_init = 0;            // NTR_QUEUE_INIT: initial queue capacity override (tests force the regrow path)
     float pass_ns_per_ray = 0.0f;       // measured cost of the wavefront passes of the previous frame (0 = unknown)
@@ -358,7 +359,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     // measured: the cost-sorted schedule pays when the frame is sharded over GPUs (8 GPUs, config 2: strip render
     // 0.258 -> 0.203 ms) -- each rank then has only ~2 blocks per warp and the tail matters -- but costs ~8 % on a
     // whole frame on one GPU (loss of row-major locality + the cost bookkeeping), so it is used for sharded renders only
-    const bool use_sched = n_tiles >= 64 && composite && tgt.out_mode != NTR_OUT_IDS && f.tile_row_step > 1;
+    const bool use_sched = n_tiles >= 64 && composite && tgt.out_mode != NTR_OUT_IDS && (f.tile_row_step > 1 || sc->force_tile_sched);
     if (use_sched) {
         if (sc->tile_cap < n_tiles) {
             cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order);
@@ -714,6 +715,7 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->sort_rays = getenv("NTR_NO_RAY_SORT") == nullptr;
     if (const char *zc = getenv("NTR_ZEROCOPY")) sc->zero_copy = atoi(zc) != 0;
     sc->slabs = getenv("NTR_NO_SLABS") == nullptr;
+    if (const char *ts = getenv("NTR_TILE_SCHED")) sc->force_tile_sched = atoi(ts) != 0;
     if (const char *qi = getenv("NTR_QUEUE_INIT")) sc->queue_init = (uint32_t)strtoul(qi, nullptr, 10);
     sc->tree_depth = depth;
     sc->dev.dim = desc->dim;

@@ -13,6 +13,11 @@ for v in sm64 sm256; do
   NTR_B200_LIB=$PWD/variants/libntr_$v.so python bench.py --config c5 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_c5_$v.json 2>gpurun_out/r02_c5_$v.err
 done
 NTR_BENCH_SOUP_DEPTH=20 python bench.py --config c5 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02_c5_depth20.json 2>gpurun_out/r02_c5_depth20.err
+# longest-first tile hand-out on one GPU for the heavy-tailed scene (model: up to -29 %)
+for c in c4 c4o; do
+  python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_${c}_base.json 2>gpurun_out/r02_${c}_base.err
+  NTR_TILE_SCHED=1 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_${c}_lpt.json 2>gpurun_out/r02_${c}_lpt.err
+done
 # the two ncu captures that were queued at the end of round 1
 python bench.py --config c4 --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/plain_c4.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_pass -s 5 -c 2 -o gpurun_out/r02_prof_c4 python bench.py --config c4 --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/ncu_c4.log 2>&1
 python bench.py --config c5s --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/plain_c5s.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_pass -s 2 -c 1 -o gpurun_out/r02_prof_c5s python bench.py --config c5s --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/ncu_c5s.log 2>&1
