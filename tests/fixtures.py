@@ -122,3 +122,40 @@ def batched_soup(dim, n_batches, seed=7, batch=4):
         'global_lights': np.concatenate([gdir, [0.4, 0.4, 0.4]]).astype(np.float32)[None],
         'cam_origin': cam_origin, 'cam_axes': np.eye(dim, dtype=np.float32),
     }
+
+
+def fuzz_scene(dim, seed):
+    """Random mixed scene for differential tests: fixtures.batched_soup geometry with four materials (opaque,
+    reflective, transparent, transparent + reflective) dealt at random, 0-3 rotated / scaled hypercubes and hyperspheres
+    at the origin (referenced from every leaf), random shadows / camera light / reflection depth / background axis."""
+    rng = np.random.RandomState(seed)
+    sc = batched_soup(dim, int(rng.randint(3, 25)), seed=seed)
+    n = sc['simplex'].shape[0]
+    sc['materials'] = np.array([[1, 0.5, 0.5, 1, 1, 1, 1, 0, 1, 8], [0.4, 0.7, 1.0, 1, 1, 1, 1, 0.35, 0.8, 12],
+                                [0.9, 0.9, 0.2, 1, 1, 1, 0.5, 0, 1, 8], [0.2, 0.9, 0.4, 1, 1, 1, 0.6, 0.25, 0.5, 4]], np.float32)
+    sc['simplex_mat'] = rng.choice(4, size=n, p=[0.4, 0.25, 0.2, 0.15]).astype(np.int32)
+    ns = int(rng.randint(0, 4))
+    if ns:
+        rows = []
+        for _ in range(ns):
+            typ = float(rng.choice([1, 2]))
+            i, j = rng.choice(dim, 2, replace=False)
+            th = rng.uniform(-1, 1)
+            rot = np.eye(dim, dtype=np.float32)
+            rot[i, i] = rot[j, j] = np.cos(th)
+            rot[i, j], rot[j, i] = -np.sin(th), np.sin(th)
+            ori = (rot * rng.uniform(0.3, 0.8)).astype(np.float32)
+            # position 0 keeps orientation*position == position, where the reference is self-consistent (SURVEY 8a-Q5)
+            rows.append(np.concatenate([[typ], ori.ravel(), np.linalg.inv(ori).astype(np.float32).ravel(), np.zeros(dim, np.float32)]))
+        sc['solids'] = np.array(rows, np.float32)
+        sc['solid_mat'] = rng.choice(4, size=ns).astype(np.int32)
+        nodes, refs = sc['nodes'].copy(), []
+        for k in range(len(nodes)):
+            if nodes[k, 0] & 0x80000000:
+                a, m = int(nodes[k, 1]), int(nodes[k, 2])
+                seg = list(sc['leaf_refs'][a:a + m]) + [(2 << 30) | q for q in range(ns)]
+                nodes[k, 1], nodes[k, 2] = len(refs), len(seg)
+                refs += seg
+        sc['nodes'], sc['leaf_refs'] = nodes, np.array(refs, np.uint32)
+    sc['params'] = np.array([0.8, rng.randint(0, 2), rng.randint(0, 2), rng.randint(0, 4), rng.randint(0, dim)], np.float64)
+    return sc
