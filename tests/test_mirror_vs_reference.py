@@ -185,3 +185,88 @@ def test_single_primitive_ray_tests(dim, device, monkeypatch):
             for o, d in rays(world, 12):
                 same(ms.intersects(mn.Vector(o), mn.Vector(d)), rs.intersects(rn.Vector(o), rn.Vector(d)))
     assert hits > 40 and misses > 10
+
+
+class _EmulatedRenderDevice(_EmulatedDevice):
+    """+ the frame-level calls Scene._prepare() makes (camera / parameter updates, float frames)."""
+    def set_camera(self, origin, axes):
+        self.sc = dict(self.sc, cam_origin=np.asarray(origin, np.float32), cam_axes=np.asarray(axes, np.float32))
+
+    def set_params(self, scene):
+        self.sc = dict(self.sc, **{k: v for k, v in scene.items() if k in
+                                   ('params', 'ambient', 'bg1', 'bg2', 'bg3', 'point_lights', 'global_lights', 'boundary')})
+
+    def render_float(self, w, h):
+        from tests import emul_lib as el
+        return el.render(self.sc, w, h)[0]
+
+
+@pytest.mark.parametrize('dim', [3, 4, 5])
+def test_scenes_built_through_the_mirror_render_like_the_reference(dim, monkeypatch):
+    """End to end on random scenes: prototypes -> build_composite_scene (this repo's builder, a different tree than the
+    reference's) -> flattening -> device code (host-emulated here) against the compiled reference's own
+    build_composite_scene + calculate_color.  Simplexes with opaque and reflective materials, point / global / camera
+    lights, no shadows (with shadows the reference's image depends on its tree)."""
+    rb.load_reference()
+    import ntracer as R
+    from ntracer_b200 import tracern
+    monkeypatch.setattr(tracern, 'DeviceScene', _EmulatedRenderDevice)
+    rnd = random.Random(500 + dim)
+    rn, mn = R.NTracer(dim), M.NTracer(dim)
+    w, h = 40, 24
+    for trial in range(4):
+        rm = [R.Material((1, 0.5, 0.5)), R.Material((0.3, 0.6, 1.0), 1, 0.4, 0.7, 10)]
+        mm = [M.Material((1, 0.5, 0.5)), M.Material((0.3, 0.6, 1.0), 1, 0.4, 0.7, 10)]
+        rp, mp = [], []
+        for k in range(30):
+            c = [rnd.uniform(-1.2, 1.2) for _ in range(3)]
+            pts = [tuple([c[i] + rnd.uniform(-0.6, 0.6) for i in range(3)] + [-rnd.uniform(0.01, 0.05)] * (dim - 3)) for _ in range(3)]
+            for e in range(3, dim):                      # one far vertex per extra axis: the slice with the camera's 3-flat is the triangle
+                far = [sum(p[i] for p in pts[:3]) / 3 for i in range(3)] + [-0.02] * (dim - 3)
+                far[e] = rnd.uniform(0.5, 1.5)
+                pts.append(tuple(far))
+            m = rnd.randrange(2)
+            rp.append(rn.TrianglePrototype(pts, rm[m]))
+            mp.append(mn.TrianglePrototype(pts, mm[m]))
+        # simplexes only: the reference's own builder loses hyperspheres from cells they occupy (its box/sphere overlap
+        # test, src/tracer.hpp:1661-1674, has false negatives -- see test_reference_sphere_box_test_has_false_negatives),
+        # so a sphere renders differently under the reference's tree and under any conservative one
+        rs, ms = rn.build_composite_scene(rp), mn.build_composite_scene(mp)
+        for nt, s in ((rn, rs), (mn, ms)):
+            cam = nt.Camera()
+            cam.translate(nt.Vector.axis(2, -4.5))
+            s.set_camera(cam)
+            s.add_light(nt.PointLight(nt.Vector.axis(1, 3) + nt.Vector.axis(2, -3), (8, 8, 8)))
+            s.add_light(nt.GlobalLight(nt.Vector.axis(1, -1), (0.3, 0.3, 0.3)))
+            s.set_max_reflect_depth(2)
+            s.set_ambient_color((0.05, 0.05, 0.05))
+        mine = ms._prepare().render_float(w, h)
+        ref = np.array([[list(rs.calculate_color(x, y, w, h)) for x in range(w)] for y in range(h)], np.float32)
+        d = np.abs(fx_quant8(mine) - fx_quant8(ref)).max(axis=2)
+        assert np.mean(d > 1) <= 0.004, (dim, trial, float(np.mean(d > 1)))       # a handful of grazing pixels at 40x24
+        assert len(np.unique(fx_quant8(ref).reshape(-1, 3), axis=0)) > 30            # a real picture
+
+
+def fx_quant8(rgb):
+    from tests import fixtures as fx
+    return fx.quant8(rgb)
+
+
+def test_reference_sphere_box_test_has_false_negatives():
+    """A finding about the reference, pinned so that it is noticed if a rebuilt oracle/_ref ever changes it:
+    aabb::intersects(solid_prototype) for hyperspheres (src/tracer.hpp:1661-1674) answers "no overlap" for boxes that
+    do overlap the unit sphere, so build_kdtree drops spheres from cells they occupy and parts of them are missing in
+    the reference's images.  The mirror restates the test as it is (parity of AABB.intersects); this repo's own builder
+    splits on bounding boxes and keeps the sphere (brute force agrees with it)."""
+    rb.load_reference()
+    import ntracer as R
+    rn, mn = R.NTracer(3), M.NTracer(3)
+    lo, hi = (0.4192398953352654, 0.08301381049829626, -0.027168209973850832), (1.5601048677108569, 1.5460047934870986, 1.1727048562874036)
+    nearest = [min(max(0.0, a), b) for a, b in zip(lo, hi)]
+    assert sum(c * c for c in nearest) < 0.2                     # the box reaches well inside the unit sphere
+    rsp = rn.SolidPrototype(R.SPHERE, rn.Vector(0, 0, 0), rn.Matrix.identity(), R.Material((1, 1, 1)))
+    msp = mn.SolidPrototype(M.SPHERE, mn.Vector(0, 0, 0), mn.Matrix.identity(), M.Material((1, 1, 1)))
+    assert rn.AABB(lo, hi).intersects(rsp) is False
+    assert mn.AABB(lo, hi).intersects(msp) is False              # restated as is
+    b = msp.boundary
+    assert all(b.start[i] <= hi[i] and b.end[i] >= lo[i] for i in range(3))     # what this repo's builder goes by
