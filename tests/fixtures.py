@@ -124,12 +124,12 @@ def batched_soup(dim, n_batches, seed=7, batch=4):
     }
 
 
-def fuzz_scene(dim, seed):
+def fuzz_scene(dim, seed, max_batches=24):
     """Random mixed scene for differential tests: fixtures.batched_soup geometry with four materials (opaque,
     reflective, transparent, transparent + reflective) dealt at random, 0-3 rotated / scaled hypercubes and hyperspheres
     at the origin (referenced from every leaf), random shadows / camera light / reflection depth / background axis."""
     rng = np.random.RandomState(seed)
-    sc = batched_soup(dim, int(rng.randint(3, 25)), seed=seed)
+    sc = batched_soup(dim, int(rng.randint(min(3, max_batches), max_batches + 1)), seed=seed)
     n = sc['simplex'].shape[0]
     sc['materials'] = np.array([[1, 0.5, 0.5, 1, 1, 1, 1, 0, 1, 8], [0.4, 0.7, 1.0, 1, 1, 1, 1, 0.35, 0.8, 12],
                                 [0.9, 0.9, 0.2, 1, 1, 1, 0.5, 0, 1, 8], [0.2, 0.9, 0.4, 1, 1, 1, 0.6, 0.25, 0.5, 4]], np.float32)

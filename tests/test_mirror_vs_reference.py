@@ -298,3 +298,47 @@ def test_oracle_matches_the_reference_on_random_scenes():
         total += d.size
         scenes += 1
     assert scenes >= 60 and bad <= 0.001 * total, (scenes, bad, total)
+
+
+def test_oracle_ray_hook_matches_kdnode_intersects_on_random_rays():
+    """oracle_trace_rays against the reference's KDNode.intersects (ids of the opaque hit, distances, number of
+    transparent hits) on random rays through small random scenes -- small enough (<= 20 items, <= 10 transparent
+    primitives) that no ray can leave the reference's defined domain.  (KDNode.occludes is left to the committed
+    fixture: it collects duplicates without bound and overruns the reference's list, which crashes it.)"""
+    from tests import fixtures as fx
+    from tests import oracle_lib as ol
+    rb.load_reference()
+    scenes = rays = 0
+    for seed in range(70):
+        dim = 3 + seed % 4
+        sc = fx.fuzz_scene(dim, seed, max_batches=3)
+        transparent = int((sc['materials'][sc['simplex_mat'], 6] < 1).sum())
+        if len(sc['solid_mat']):
+            transparent += int((sc['materials'][sc['solid_mat'], 6] < 1).sum())
+        if transparent > 10 or len(np.unique(sc['leaf_refs'])) > 20:
+            continue
+        nt, scene, prims = rb.import_scene(sc)
+        ref_of = {id(p): r for r, p in prims.items()}
+        rng = np.random.RandomState(seed + 7)
+        n = 100
+        o = np.zeros((n, dim), np.float32)
+        o[:, :3] = rng.uniform(-3, 3, (n, 3))
+        o[:, 3:] = rng.uniform(-0.05, 0.05, (n, dim - 3))
+        target = np.zeros((n, dim), np.float32)
+        target[:, :3] = rng.uniform(-1, 1, (n, 3))
+        d = (target - o).astype(np.float32)
+        ids, dist, ntrans = ol.trace_rays(sc, o, d)
+        for k in range(n):
+            hits = scene.root.intersects(nt.Vector(*[float(x) for x in o[k]]), nt.Vector(*[float(x) for x in d[k]]))
+            opaque = [hh for hh in hits if (hh.primitive.material.opacity if hh.batch_index < 0
+                                            else hh.primitive[hh.batch_index].material.opacity) >= 1]
+            assert len(hits) - len(opaque) == ntrans[k], (seed, k)
+            if opaque:
+                hh = opaque[-1]
+                assert rb.flat_prim_id(sc, ref_of[id(hh.primitive)], hh.batch_index) == ids[k], (seed, k)
+                assert abs(hh.dist - dist[k]) <= 1e-4 * max(1.0, abs(hh.dist))
+            else:
+                assert ids[k] == -1, (seed, k)
+        scenes += 1
+        rays += n
+    assert scenes >= 50 and rays >= 5000
