@@ -342,3 +342,69 @@ def test_oracle_ray_hook_matches_kdnode_intersects_on_random_rays():
         scenes += 1
         rays += n
     assert scenes >= 50 and rays >= 5000
+
+
+def test_pixel_packer_matches_the_reference_on_random_formats():
+    """process_pixel (src/render.cpp:396-466) on random ImageFormats -- 1..6 channels of 1..31 bits or float, arbitrary
+    weights and offsets, either byte order, padded pitches: a frame packed by the reference's BlockingRenderer against
+    the oracle's packer (and the host-emulated device packer, which must equal the oracle's to the bit).  Channels are
+    decoded again and compared with the precision they can carry: 1 LSB, or 2^-22 of full scale for channels wider
+    than 22 bits (the reference sums r,g,b weights under -ffast-math); padding bytes must stay untouched."""
+    import time
+    from tests import emul_lib as el
+    from tests import fixtures as fx
+    from tests import oracle_lib as ol
+    from ntracer_b200 import _capi
+    ntr = rb.load_reference()
+    sc, g = fx.load('box4')
+    nt, scene, _ = rb.import_scene(sc)
+    renderer = ntr.BlockingRenderer(2)
+    time.sleep(0.5)                      # the reference's worker start-up race (DESIGN.md section 4)
+    rnd = random.Random(3)
+    w, h = 37, 23
+    frame = ol.render_float(sc, w, h)
+    done = 0
+    for trial in range(120):
+        ch, bits = [], 0
+        for c in range(rnd.randint(1, 6)):
+            tfloat = rnd.random() < 0.15
+            b = 32 if tfloat else rnd.randint(1, 31)
+            if bits + b > 128:
+                break
+            bits += b
+            ch.append((b, rnd.choice([0, 1, 0.5, rnd.uniform(-1, 1.5)]), rnd.choice([0, 1, 0.3, rnd.uniform(-1, 1.5)]),
+                       rnd.choice([0, 1, 0.1, rnd.uniform(-1, 1.5)]), rnd.choice([0, 0, 0.5, rnd.uniform(-0.5, 1)]), tfloat))
+        bpp = (bits + 7) // 8
+        pitch, rev = w * bpp + rnd.choice([0, 0, 1, 5, 16]), rnd.random() < 0.4
+        buf = bytearray([0xAB]) * (pitch * h)
+        assert renderer.render(buf, ntr.ImageFormat(w, h, [ntr.Channel(*c) for c in ch], pitch, rev), scene)
+        ref = np.frombuffer(bytes(buf), np.uint8)
+        fmt = _capi.make_image_format(w, h, ch, pitch, rev)
+        mine = ol.pack(fmt, frame)
+        assert np.array_equal(el.pack(fmt, frame), mine)
+        rows = ref.reshape(h, pitch)
+        assert np.all(rows[:, w * bpp:] == 0xAB)                     # the reference leaves the padding alone
+
+        def channels(packed):
+            px = packed.reshape(h, pitch)[:, :w * bpp].reshape(h, w, bpp)
+            if rev:
+                px = px[:, :, ::-1]
+            big = np.zeros((h, w), dtype=object)
+            for j in range(bpp):
+                big = big * 256 + px[:, :, j].astype(object)
+            pos, out = bpp * 8, []
+            for c in ch:
+                pos -= c[0]
+                out.append((big >> pos) & ((1 << c[0]) - 1))
+            return out
+
+        for c, a, b in zip(ch, channels(mine), channels(ref)):
+            if c[5]:
+                fa = np.array(a, dtype=np.uint32).view(np.float32)
+                fb = np.array(b, dtype=np.uint32).view(np.float32)
+                assert np.abs(fa - fb).max() <= 2.0 ** -22, (trial, c)
+            else:
+                worst = max(abs(int(x) - int(y)) for x, y in zip(a.ravel(), b.ravel()))
+                assert worst <= max(1, 2 ** (c[0] - 22)), (trial, c, worst)
+        done += 1
+    assert done == 120
