@@ -408,3 +408,33 @@ def test_pixel_packer_matches_the_reference_on_random_formats():
                 assert worst <= max(1, 2 ** (c[0] - 22)), (trial, c, worst)
         done += 1
     assert done == 120
+
+
+def test_box_scene_random_cameras_and_dimensions():
+    """box_scene::calculate_color (src/tracer.hpp:101-152) and flat_origin_ray_source (:60-76) for random dimensions
+    (3..9), camera poses and fields of view: oracle and host-emulated device code against the reference."""
+    from tests import emul_lib as el
+    from tests import fixtures as fx
+    from tests import oracle_lib as ol
+    rb.load_reference()
+    import ntracer as R
+    rnd = random.Random(1)
+    w, h = 40, 30
+    for trial in range(40):
+        dim = rnd.randint(3, 9)
+        nt = R.NTracer(dim)
+        scene, cam = nt.BoxScene(), nt.Camera()
+        cam.translate(nt.Vector.axis(2, -rnd.uniform(2, 7)))
+        for _ in range(3):
+            i, j = rnd.sample(range(dim), 2)
+            cam.transform(nt.Matrix.rotation(nt.Vector.axis(i), nt.Vector.axis(j), rnd.uniform(-0.6, 0.6)))
+        cam.normalize()
+        if rnd.random() < 0.5:
+            cam.origin = cam.axes[2] * -rnd.uniform(2, 7)
+        scene.set_camera(cam)
+        scene.set_fov(rnd.uniform(0.4, 1.4))
+        sc = rb.strip_private(rb.export_scene(nt, scene))
+        ref = np.array([[list(scene.calculate_color(x, y, w, h)) for x in range(w)] for y in range(h)], np.float32)
+        mine = ol.render_float(sc, w, h)
+        assert np.abs(fx.quant8(mine) - fx.quant8(ref)).max() <= 1, (trial, dim)
+        assert np.abs(el.render(sc, w, h)[0] - mine).max() <= 2e-6
