@@ -890,6 +890,111 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
     return true;
 }
 
+// ---- chunked evaluation of a leaf (general variant) -------------------------------------------------------------
+// Groundwork for splitting ONE ray's scan of a big leaf over the lanes of a warp (a single ray
+// through the 1,606-item leaves of {5/2,3,3} is what bounds a frame once the bulk is spread thin).  The leaf is cut
+// into chunks of NTR_CHUNK items; all tests of a chunk are evaluated against the state at the START of the chunk
+// (that is the part 32 lanes can do at once), then their results are REPLAYED in leaf order with the sequential
+// semantics of kd_leaf::intersects.  Exactness of the replay:
+//   * a test run with the looser cutoff of the chunk start returns, for simplexes, batches and spheres, either the same
+//     hit the tighter cutoff would give or a hit at t >= the tighter cutoff, which the replay demotes to a miss (a batch
+//     reports the lowest lane with the smallest t, which does not depend on the cutoff as long as it passes it);
+//   * hypercubes write partial local-space coordinates into o_hit.normal before they compare with the cutoff (Q12), so
+//     a demoted hypercube hit is simply tested again with the current cutoff (rare);
+//   * the mailbox can only change its answer for an item of the chunk by switching itself off (overflow) in the
+//     middle of it; an item skipped at evaluation time but no longer skipped at replay time is tested on the spot;
+//   * the re-test after the first opaque hit (`goto hit`, Q13) always misses its own cutoff: the replay records a miss.
+// This host/device version evaluates the chunk in a loop; it exists so that the replay logic is proven against the
+// oracle in the CPU tier (host emulation, -DNTR_CHUNKED_LEAVES=1) before the warp-cooperative kernel is built on it.
+#ifndef NTR_CHUNKED_LEAVES
+#define NTR_CHUNKED_LEAVES 0
+#endif
+#if NTR_CHUNKED_LEAVES
+#ifndef NTR_CHUNK
+#define NTR_CHUNK 32
+#endif
+#ifndef NTR_CHUNK_LEAF_MIN
+#define NTR_CHUNK_LEAF_MIN 1
+#endif
+template <int DT> struct ChunkEval {
+    float dist;
+    int lane;
+    uint32_t wmask, meta;
+    bool skipped;
+    float P[DimCap<DT>::value], N[DimCap<DT>::value];
+};
+
+template <int DT, int FLAGS>
+NTR_HD bool leaf_general_chunked(const SceneDev &s, const uint4 node, const float *o, const float *dir, const RaySlab<DT> &rs,
+                                 Skip skip, HitRec &oh, GenState<DT> &g, Counters &cnt) {
+    const int D = NTR_D(DT, s);
+    const uint2 *items = s.leaf_items + node.y;
+    const uint32_t size = node.z;
+    const int h_start = g.th.n;
+    float dist = 0;
+    bool phase1 = false;
+    ChunkEval<DT> ev[NTR_CHUNK];
+    for (uint32_t base = 0; base < size; base += NTR_CHUNK) {
+        const uint32_t n = size - base < NTR_CHUNK ? size - base : NTR_CHUNK;
+        // ---- evaluation: every item of the chunk against the cutoff and the mailbox as they are now ----
+        const float cutoff0 = oh.dist;
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint2 it = lditem(items + base + j);
+            const bool is_batch = (it.x >> 30) == NTR_REF_BATCH;
+            ev[j].skipped = (!is_batch && it.x == skip.ref) || g.mb.has(it.x);
+            ev[j].dist = 0; ev[j].wmask = 0; ev[j].meta = 0; ev[j].lane = -1;
+            if (!ev[j].skipped)
+                ev[j].dist = prim_test_general<DT, FLAGS>(s, it, o, dir, cutoff0, skip, ev[j].lane, ev[j].P, ev[j].N, ev[j].wmask, ev[j].meta, cnt);
+        }
+        // ---- replay in leaf order ----
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint2 it = lditem(items + base + j);
+            const uint32_t item = it.x;
+            const bool is_batch = (item >> 30) == NTR_REF_BATCH;
+            if ((!is_batch && item == skip.ref) || g.mb.has(item)) continue;
+            ChunkEval<DT> &e = ev[j];
+            const bool stale_cutoff = e.dist != 0 && !(e.dist < oh.dist);
+            const bool is_cube = (item >> 30) == NTR_REF_SOLID &&
+                                 (int)ldf(s.solids + (size_t)(item & NTR_IDX_MASK) * s.solstride) == NTR_SOLID_CUBE;
+            if (e.skipped || (stale_cutoff && is_cube)) {
+                e.dist = prim_test_general<DT, FLAGS>(s, it, o, dir, oh.dist, skip, e.lane, e.P, e.N, e.wmask, e.meta, cnt);
+            } else if (stale_cutoff) {
+                e.dist = 0;             // simplexes and spheres leave o_hit.normal alone when they miss
+                e.wmask = 0;
+            }
+            dist = e.dist;
+            if (!phase1) {
+    NTR_UNROLL
+                for (int k = 0; k < D; ++k) if (e.wmask & (1u << k)) g.hitP[k] = e.P[k];
+                if (dist) {
+    NTR_UNROLL
+                    for (int k = 0; k < D; ++k) g.hitN[k] = e.N[k];
+                    if (e.meta & NTR_META_OPAQUE) {
+                        oh.dist = dist; oh.ref = item; oh.lane = e.lane;
+                        phase1 = true;
+                        dist = 0;       // the re-test of `goto hit` misses its own cutoff (and then the item is added)
+                    } else {
+                        g.th.add(dist, item, e.lane);
+                    }
+                }
+            } else if (dist) {
+                if (e.meta & NTR_META_OPAQUE) {
+                    oh.dist = dist; oh.ref = item; oh.lane = e.lane;
+    NTR_UNROLL
+                    for (int k = 0; k < D; ++k) { g.hitP[k] = e.P[k]; g.hitN[k] = e.N[k]; }
+                } else {
+                    g.th.add(dist, item, e.lane);
+                }
+            }
+            g.mb.add(item);
+        }
+    }
+    if (!phase1) return false;
+    g.th.trim(dist, h_start);
+    return true;
+}
+#endif
+
 // Per-ray axis tables of the traversal.  A k-d step needs o[axis], dir[axis] and 1/dir[axis] for a run-time axis; with
 // the vectors in registers that is a select chain per value (ncu, config 2: 7.4 % of all instructions).  With
 // NTR_SMEM_AXIS the fixed-dimension kernels keep the three vectors in a per-thread column of shared memory instead
@@ -957,6 +1062,10 @@ NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, S
         while (node != NTR_NULL_NODE) {
             const uint4 n = ldnode(s.nodes + node);
             if (n.x & NTR_LEAF_FLAG) {
+#if NTR_CHUNKED_LEAVES
+                if ((FLAGS & NTR_F_GENERAL) && n.z >= NTR_CHUNK_LEAF_MIN) result = leaf_general_chunked<DT, FLAGS>(s, n, o, dir, rs, skip, oh, *g, cnt);
+                else
+#endif
                 if (FLAGS & NTR_F_GENERAL) result = leaf_general<DT, FLAGS>(s, n, o, dir, rs, skip, oh, *g, cnt);
                 else result = leaf_opaque<DT, FLAGS>(s, n, o, dir, rs, skip, oh, mm, cnt);
                 break;

@@ -62,3 +62,45 @@ def test_random_rays_with_skip_primitives_match_the_oracle():
         rays += n
         assert (oi >= 0).any()
     assert rays == 8000
+
+
+def test_chunked_leaf_scan_is_bit_identical_to_the_sequential_one(tmp_path):
+    """-DNTR_CHUNKED_LEAVES=1: leaves evaluated chunk by chunk against the state at the start of the chunk and then
+    replayed in leaf order (trace_core.cuh: leaf_general_chunked, the groundwork for splitting one ray's leaf scan over
+    the lanes of a warp) must give exactly what the item-by-item scan gives -- images, counters, ray hooks."""
+    import ctypes as C
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    base = el.lib()
+    variants = []
+    for chunk in (3, 32):
+        so = str(tmp_path / ('libhostemul_chunk%d.so' % chunk))
+        subprocess.run(['/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++', '-std=c++17', '-O2', '-fPIC', '-shared',
+                        '-fvisibility=hidden', '-I/usr/local/cuda/include', '-Wno-unknown-pragmas', '-DNTR_CHUNKED_LEAVES=1',
+                        '-DNTR_CHUNK=%d' % chunk, '-o', so, os.path.join(here, 'host_emul', 'emul.cpp')], check=True)
+        variants.append(C.CDLL(so))
+    scenes = [fx.fuzz_scene(3 + seed % 5, seed) for seed in range(60)]
+    sizes = [(48, 27)] * len(scenes)
+    for name, v in (('cell120', 'refl_transp'), ('ggs120', 'refl_transp'), ('solids6', None), ('mixed3', None)):
+        sc, g = fx.load(name)
+        scenes.append(fx.variant(sc, g, v) if v else sc)
+        sizes.append((64, 36))
+    mixed, gm = fx.load('mixed3')
+    try:
+        for sc, (w, h) in zip(scenes, sizes):
+            el._lib = base
+            a, ca = el.render(sc, w, h)
+            for var in variants:
+                el._lib = var
+                b, cb = el.render(sc, w, h)
+                assert np.array_equal(a, b)
+                for k in ('reflection_rays', 'shadow_rays', 'shaded_hits', 'node_steps'):
+                    assert ca[k] == cb[k], k
+                assert np.array_equal(el.render(sc, w, h, generic=True)[0], a)
+        for var in variants:
+            el._lib = var
+            ids, dist, nt = el.trace_rays(mixed, gm['ray_origins'], gm['ray_dirs'])
+            assert np.array_equal(ids, gm['ray_ids']) and np.array_equal(nt, gm['ray_ntrans'])
+    finally:
+        el._lib = base
