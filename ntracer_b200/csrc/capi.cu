@@ -52,7 +52,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 __global__ void pack_kernel(const __grid_constant__ FrameDev f);
 __global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, int D, const __grid_constant__ SceneDev s,
-                                uint32_t *keys, uint32_t *idx);
+                                uint32_t *keys, uint32_t *idx, int heavy_first);
 
 }  // namespace
 
@@ -110,6 +110,7 @@ struct ntr_scene {
     cudaStream_t slab_stream[kSlabMax] = {};
     cudaEvent_t slab_done[kSlabMax] = {};
     bool slabs = true;                  // NTR_NO_SLABS=1 switches it off
+    bool heavy_first = false;           // NTR_HEAVY_FIRST=1: bounce passes start the rays nearest the scene centre first (ray_keys_kernel)
     bool force_tile_sched = false;      // NTR_TILE_SCHED=1: cost-sorted tile hand-out on whole frames too (heavy-tailed scenes)
     bool zero_copy = false;             // NTR_ZEROCOPY=1: ntr_render stores single-pass frames straight into pinned destinations
     uint32_t queue_init = 0;            // NTR_QUEUE_INIT: initial queue capacity override (tests force the regrow path)
@@ -448,9 +449,11 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
                         sc->sort_tmp_bytes = bytes;
                         sc->sort_cap = cap;
                     }
-                    ray_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(q.in, rec4, n, sc->dev.dim, sc->dev, sc->d_keys[0], sc->d_perm[0]);
+                    ray_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(q.in, rec4, n, sc->dev.dim, sc->dev, sc->d_keys[0], sc->d_perm[0],
+                                                                       sc->heavy_first ? 1 : 0);
                     size_t bytes = sc->sort_tmp_bytes;
-                    cub::DeviceRadixSort::SortPairs(sc->d_sort_tmp, bytes, sc->d_keys[0], sc->d_keys[1], sc->d_perm[0], sc->d_perm[1], (int)n, 0, 30, st);
+                    cub::DeviceRadixSort::SortPairs(sc->d_sort_tmp, bytes, sc->d_keys[0], sc->d_keys[1], sc->d_perm[0], sc->d_perm[1], (int)n, 0,
+                                                    sc->heavy_first ? 32 : 30, st);
                     sc->launches += 2;
                     q.in_perm = sc->d_perm[1];
                 }
@@ -636,8 +639,12 @@ __global__ void pack_kernel(const __grid_constant__ FrameDev f) {
 
 // Sort key of a queued bounce: [direction signs, 1 bit x K][direction magnitude, 2 bits x K][origin cell, 3 bits x K]
 // over the first K = min(D, 5) axes (30 bits).
+// With heavy_first the two top bits (30, 31) hold the ray's closest approach to the centre of the scene box, nearest
+// first: on star polytopes the rays through the middle walk the giant leaves and cost 10-40x the mean
+// (tools/ray_cost_map.py), and a pass that starts them first ends when its bulk ends instead of one heavy ray later
+// (tools/sim_schedule.py).  Any order is a valid order: this only changes when a ray is traced, never what it returns.
 __global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, int D, const __grid_constant__ SceneDev s,
-                                uint32_t *keys, uint32_t *idx) {
+                                uint32_t *keys, uint32_t *idx, int heavy_first) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int K = D < 5 ? D : 5;
@@ -656,7 +663,19 @@ __global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, i
         const float u = ext > 0 ? (o[a] - s.bmin[a]) / ext : 0.0f;
         ko = (ko << 3) | (uint32_t)fminf(fmaxf(u * 8.0f, 0.0f), 7.0f);
     }
-    keys[i] = (ks << (5 * K)) | (kd << (3 * K)) | ko;
+    uint32_t key = (ks << (5 * K)) | (kd << (3 * K)) | ko;
+    if (heavy_first) {
+        float oc = 0, od = 0, r2 = 0;
+        for (int a = 0; a < D; ++a) {
+            const float c = 0.5f * (s.bmin[a] + s.bmax[a]), e = 0.5f * (s.bmax[a] - s.bmin[a]);
+            const float v = o[a] - c;
+            oc += v * v; od += v * d[a] * len; r2 += e * e;
+        }
+        const float miss2 = fmaxf(oc - od * od, 0.0f) / fmaxf(r2, 1e-30f);      // (closest approach / box radius)^2
+        const uint32_t ring = miss2 < 0.01f ? 0u : miss2 < 0.05f ? 1u : miss2 < 0.2f ? 2u : 3u;
+        key = (key & 0x3FFFFFFFu) | (ring << 30);
+    }
+    keys[i] = key;
     idx[i] = i;
 }
 
@@ -716,6 +735,7 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     if (const char *zc = getenv("NTR_ZEROCOPY")) sc->zero_copy = atoi(zc) != 0;
     sc->slabs = getenv("NTR_NO_SLABS") == nullptr;
     if (const char *ts = getenv("NTR_TILE_SCHED")) sc->force_tile_sched = atoi(ts) != 0;
+    if (const char *hf = getenv("NTR_HEAVY_FIRST")) sc->heavy_first = atoi(hf) != 0;
     if (const char *qi = getenv("NTR_QUEUE_INIT")) sc->queue_init = (uint32_t)strtoul(qi, nullptr, 10);
     sc->tree_depth = depth;
     sc->dev.dim = desc->dim;

@@ -17,6 +17,7 @@ NTR_BENCH_SOUP_DEPTH=20 python bench.py --config c5 --steps 2 --warmup 3 --no-cp
 for c in c4 c4o; do
   python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_${c}_base.json 2>gpurun_out/r02_${c}_base.err
   NTR_TILE_SCHED=1 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_${c}_lpt.json 2>gpurun_out/r02_${c}_lpt.err
+  NTR_TILE_SCHED=1 NTR_HEAVY_FIRST=1 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_${c}_lpt_heavy.json 2>gpurun_out/r02_${c}_lpt_heavy.err
 done
 # the two ncu captures that were queued at the end of round 1
 python bench.py --config c4 --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/plain_c4.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_pass -s 5 -c 2 -o gpurun_out/r02_prof_c4 python bench.py --config c4 --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/ncu_c4.log 2>&1
