@@ -909,7 +909,10 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
 #ifndef NTR_CHUNKED_LEAVES
 #define NTR_CHUNKED_LEAVES 0
 #endif
-#if NTR_CHUNKED_LEAVES
+#ifndef NTR_COOP_LEAVES
+#define NTR_COOP_LEAVES 0             // see trace_nearest_coop below
+#endif
+#if NTR_CHUNKED_LEAVES || NTR_COOP_LEAVES
 #ifndef NTR_CHUNK
 #define NTR_CHUNK 32
 #endif
@@ -924,10 +927,54 @@ template <int DT> struct ChunkEval {
     float P[DimCap<DT>::value], N[DimCap<DT>::value];
 };
 
+// One step of the replay: what kd_leaf::intersects does with the test of one item, given the result `e` of that test
+// taken earlier (with a cutoff that may have been looser, and before the mailbox may have switched itself off).
+template <int DT, int FLAGS>
+NTR_HD void replay_item(const SceneDev &s, const uint2 it, const float *o, const float *dir, Skip skip, HitRec &oh,
+                        GenState<DT> &g, Counters &cnt, bool &phase1, float &dist, ChunkEval<DT> &e) {
+    const int D = NTR_D(DT, s);
+    const uint32_t item = it.x;
+    const bool is_batch = (item >> 30) == NTR_REF_BATCH;
+    if ((!is_batch && item == skip.ref) || g.mb.has(item)) return;
+    const bool stale_cutoff = e.dist != 0 && !(e.dist < oh.dist);
+    const bool is_cube = (item >> 30) == NTR_REF_SOLID &&
+                         (int)ldf(s.solids + (size_t)(item & NTR_IDX_MASK) * s.solstride) == NTR_SOLID_CUBE;
+    if (e.skipped || (stale_cutoff && is_cube)) {
+        e.dist = prim_test_general<DT, FLAGS>(s, it, o, dir, oh.dist, skip, e.lane, e.P, e.N, e.wmask, e.meta, cnt);
+    } else if (stale_cutoff) {
+        e.dist = 0;             // simplexes and spheres leave o_hit.normal alone when they miss
+        e.wmask = 0;
+    }
+    dist = e.dist;
+    if (!phase1) {
+    NTR_UNROLL
+        for (int k = 0; k < D; ++k) if (e.wmask & (1u << k)) g.hitP[k] = e.P[k];
+        if (dist) {
+    NTR_UNROLL
+            for (int k = 0; k < D; ++k) g.hitN[k] = e.N[k];
+            if (e.meta & NTR_META_OPAQUE) {
+                oh.dist = dist; oh.ref = item; oh.lane = e.lane;
+                phase1 = true;
+                dist = 0;       // the re-test of `goto hit` misses its own cutoff (and then the item is added)
+            } else {
+                g.th.add(dist, item, e.lane);
+            }
+        }
+    } else if (dist) {
+        if (e.meta & NTR_META_OPAQUE) {
+            oh.dist = dist; oh.ref = item; oh.lane = e.lane;
+    NTR_UNROLL
+            for (int k = 0; k < D; ++k) { g.hitP[k] = e.P[k]; g.hitN[k] = e.N[k]; }
+        } else {
+            g.th.add(dist, item, e.lane);
+        }
+    }
+    g.mb.add(item);
+}
+
 template <int DT, int FLAGS>
 NTR_HD bool leaf_general_chunked(const SceneDev &s, const uint4 node, const float *o, const float *dir, const RaySlab<DT> &rs,
                                  Skip skip, HitRec &oh, GenState<DT> &g, Counters &cnt) {
-    const int D = NTR_D(DT, s);
     const uint2 *items = s.leaf_items + node.y;
     const uint32_t size = node.z;
     const int h_start = g.th.n;
@@ -947,47 +994,8 @@ NTR_HD bool leaf_general_chunked(const SceneDev &s, const uint4 node, const floa
                 ev[j].dist = prim_test_general<DT, FLAGS>(s, it, o, dir, cutoff0, skip, ev[j].lane, ev[j].P, ev[j].N, ev[j].wmask, ev[j].meta, cnt);
         }
         // ---- replay in leaf order ----
-        for (uint32_t j = 0; j < n; ++j) {
-            const uint2 it = lditem(items + base + j);
-            const uint32_t item = it.x;
-            const bool is_batch = (item >> 30) == NTR_REF_BATCH;
-            if ((!is_batch && item == skip.ref) || g.mb.has(item)) continue;
-            ChunkEval<DT> &e = ev[j];
-            const bool stale_cutoff = e.dist != 0 && !(e.dist < oh.dist);
-            const bool is_cube = (item >> 30) == NTR_REF_SOLID &&
-                                 (int)ldf(s.solids + (size_t)(item & NTR_IDX_MASK) * s.solstride) == NTR_SOLID_CUBE;
-            if (e.skipped || (stale_cutoff && is_cube)) {
-                e.dist = prim_test_general<DT, FLAGS>(s, it, o, dir, oh.dist, skip, e.lane, e.P, e.N, e.wmask, e.meta, cnt);
-            } else if (stale_cutoff) {
-                e.dist = 0;             // simplexes and spheres leave o_hit.normal alone when they miss
-                e.wmask = 0;
-            }
-            dist = e.dist;
-            if (!phase1) {
-    NTR_UNROLL
-                for (int k = 0; k < D; ++k) if (e.wmask & (1u << k)) g.hitP[k] = e.P[k];
-                if (dist) {
-    NTR_UNROLL
-                    for (int k = 0; k < D; ++k) g.hitN[k] = e.N[k];
-                    if (e.meta & NTR_META_OPAQUE) {
-                        oh.dist = dist; oh.ref = item; oh.lane = e.lane;
-                        phase1 = true;
-                        dist = 0;       // the re-test of `goto hit` misses its own cutoff (and then the item is added)
-                    } else {
-                        g.th.add(dist, item, e.lane);
-                    }
-                }
-            } else if (dist) {
-                if (e.meta & NTR_META_OPAQUE) {
-                    oh.dist = dist; oh.ref = item; oh.lane = e.lane;
-    NTR_UNROLL
-                    for (int k = 0; k < D; ++k) { g.hitP[k] = e.P[k]; g.hitN[k] = e.N[k]; }
-                } else {
-                    g.th.add(dist, item, e.lane);
-                }
-            }
-            g.mb.add(item);
-        }
+        for (uint32_t j = 0; j < n; ++j)
+            replay_item<DT, FLAGS>(s, lditem(items + base + j), o, dir, skip, oh, g, cnt, phase1, dist, ev[j]);
     }
     if (!phase1) return false;
     g.th.trim(dist, h_start);
@@ -1278,6 +1286,175 @@ __device__ __forceinline__ bool trace_nearest_coop(const SceneDev &s, bool enabl
                 result = best_k != 0xFFFFFFFFu;
                 if (result) { oh.dist = best_t; oh.ref = best_ref; oh.lane = best_lane; }
             }
+        }
+    }
+    return ret;
+}
+#endif
+
+// ---- warp-cooperative traversal, general variant (device only; NOT yet run on a GPU) ------------------------------
+// The state machine of trace_nearest_coop with the general variant's frames, where a big leaf of ONE ray is
+// evaluated by the whole warp: the owner's ray is broadcast, lane j tests item base+j of every 32-item chunk against
+// the owner's cutoff at the start of the chunk, and the owner replays the results in leaf order (replay_item: the
+// logic proven bit-identical to the sequential scan in the host emulation, tests/test_fuzz_emul.py).  Lanes never
+// consult the owner's mailbox: an item the owner would skip is evaluated for nothing and dropped by the replay.
+// Written at the end of round 1 without GPU time left: it compiles (-DNTR_COOP_LEAVES=1) and is otherwise untested.
+#if defined(__CUDA_ARCH__) && NTR_COOP_LEAVES
+template <int DT, int FLAGS>
+__device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, uint32_t first, uint32_t size, const float *o,
+                                                  const float *dir, Skip skip, HitRec &oh, GenState<DT> &g, Counters &cnt) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const int D = NTR_D(DT, s);
+    const int lane = threadIdx.x & 31;
+    float bo[DimCap<DT>::value], bd[DimCap<DT>::value];
+    NTR_UNROLL
+    for (int i = 0; i < D; ++i) { bo[i] = __shfl_sync(FULL, o[i], src); bd[i] = __shfl_sync(FULL, dir[i], src); }
+    Skip bskip;
+    bskip.ref = __shfl_sync(FULL, skip.ref, src);
+    bskip.lane = __shfl_sync(FULL, skip.lane, src);
+    const uint2 *items = s.leaf_items + first;
+    const int h_start = g.th.n;             // meaningful on the owner only
+    float dist = 0;
+    bool phase1 = false;
+    for (uint32_t base = 0; base < size; base += 32) {
+        const uint32_t n = size - base < 32u ? size - base : 32u;
+        const float cutoff0 = __shfl_sync(FULL, oh.dist, src);
+        ChunkEval<DT> e;
+        e.dist = 0; e.wmask = 0; e.meta = 0; e.lane = -1; e.skipped = false;
+    NTR_UNROLL
+        for (int i = 0; i < D; ++i) { e.P[i] = 0; e.N[i] = 0; }
+        if ((uint32_t)lane < n) {
+            const uint2 it = lditem(items + base + lane);
+            // the primitive the ray leaves from is skipped by identity, never evaluated
+            if (!(((it.x >> 30) != NTR_REF_BATCH) && it.x == bskip.ref))
+                e.dist = prim_test_general<DT, FLAGS>(s, it, bo, bd, cutoff0, bskip, e.lane, e.P, e.N, e.wmask, e.meta, cnt);
+        }
+        unsigned m = __ballot_sync(FULL, e.dist != 0 || e.wmask != 0);
+        uint32_t prev = 0;
+        for (;;) {
+            const uint32_t j = m ? (uint32_t)(__ffs(m) - 1) : n;
+            if (lane == src) {              // plain misses up to the next interesting item: the owner replays them alone
+                ChunkEval<DT> miss;
+                miss.dist = 0; miss.wmask = 0; miss.meta = 0; miss.lane = -1; miss.skipped = false;
+                for (uint32_t k = prev; k < j; ++k)
+                    replay_item<DT, FLAGS>(s, lditem(items + base + k), o, dir, skip, oh, g, cnt, phase1, dist, miss);
+            }
+            if (j >= n) break;
+            ChunkEval<DT> r;
+            r.dist = __shfl_sync(FULL, e.dist, j); r.lane = __shfl_sync(FULL, e.lane, j);
+            r.wmask = __shfl_sync(FULL, e.wmask, j); r.meta = __shfl_sync(FULL, e.meta, j);
+            r.skipped = false;
+    NTR_UNROLL
+            for (int i = 0; i < D; ++i) { r.P[i] = __shfl_sync(FULL, e.P[i], j); r.N[i] = __shfl_sync(FULL, e.N[i], j); }
+            if (lane == src) replay_item<DT, FLAGS>(s, lditem(items + base + j), o, dir, skip, oh, g, cnt, phase1, dist, r);
+            prev = j + 1;
+            m &= m - 1;
+        }
+    }
+    if (lane != src || !phase1) return false;
+    g.th.trim(dist, h_start);
+    return true;
+}
+
+template <int DT, int FLAGS>
+__device__ __forceinline__ bool trace_nearest_coop_general(const SceneDev &s, bool enabled, const float *o, const float *dir,
+                                                           Skip skip, float t_near, float t_far, HitRec &oh,
+                                                           GenState<DT> &g, Counters &cnt) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    RaySlab<DT> rs;
+    rs.init(s, dir);
+    const float *invdir = rs.invdir;
+    TravStack st;
+    int sp = 0;
+    uint32_t node = s.root;
+    g.mb.clear();
+    bool done = !enabled, pending = false, have_result = false, result = false, ret = false;
+    uint32_t pend_first = 0, pend_size = 0, pend_batches = 0;
+    for (;;) {
+        if (!done) {
+            if (have_result) {                                      // ---- unwind (see trace_nearest) ----
+                have_result = false;
+                for (;;) {
+                    if (sp == 0) { done = true; ret = result; break; }
+                    --sp;
+                    const uint32_t fnode = st.node[sp];
+                    if (fnode == NTR_FRAME_AFTER_FAR) {
+                        if (result) g.th.trim(oh.dist, st.h_start[sp]);
+                        result = true;
+                        continue;
+                    }
+                    const float t = st.t[sp];
+                    if (result && oh.dist <= t) continue;
+                    node = fnode;
+                    t_near = t;
+                    t_far = st.t_far[sp];
+                    if (result) { st.node[sp] = NTR_FRAME_AFTER_FAR; ++sp; }
+                    break;
+                }
+            }
+            if (!done) {                                            // ---- descend ----
+                result = false;
+                while (node != NTR_NULL_NODE) {
+                    const uint4 n = ldnode(s.nodes + node);
+                    if (n.x & NTR_LEAF_FLAG) {
+                        if (n.z >= NTR_COOP_LEAF_MIN) { pending = true; pend_first = n.y; pend_size = n.z; pend_batches = n.x; }
+                        else result = leaf_general<DT, FLAGS>(s, n, o, dir, rs, skip, oh, g, cnt);
+                        break;
+                    }
+                    if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
+                    const int axis = (int)n.x;
+                    const float split = u2f(n.y);
+                    const float da = vsel<DT>(dir, axis), oa = vsel<DT>(o, axis);
+                    if (da != 0) {
+                        if (oa == split) { node = da > 0 ? n.w : n.z; continue; }
+                        const float t = (split - oa) * vsel<DT>(invdir, axis);
+                        const uint32_t n_near = oa > split ? n.w : n.z;
+                        const uint32_t n_far = oa > split ? n.z : n.w;
+                        if (t < 0 || t > t_far) { node = n_near; continue; }
+                        if (t < t_near) { node = n_far; continue; }
+                        if (n_near != NTR_NULL_NODE) {
+                            if (n_far == NTR_NULL_NODE) { node = n_near; t_far = t; continue; }
+                            if (sp < NTR_STACK_CAP) {
+                                st.node[sp] = n_far; st.t[sp] = t; st.t_far[sp] = t_far;
+                                st.h_start[sp] = (unsigned char)g.th.n;
+                                ++sp;
+                            }
+                            node = n_near;
+                            t_far = t;
+                            continue;
+                        }
+                        node = n_far;
+                        t_near = t;
+                        continue;
+                    }
+                    node = oa >= split ? n.w : n.z;
+                }
+                if (!pending) have_result = true;
+            }
+        }
+        // ---- warp-synchronous part: big leaves, one ray at a time, all lanes on its items ----
+        unsigned pm = __ballot_sync(FULL, pending);
+        if (!pm) {
+            if (__all_sync(FULL, done)) break;
+            continue;
+        }
+        if (__popc(pm) > NTR_COOP_MAX_LANES) {
+            // most of the warp waits at big leaves (coherent rays): every lane scans its own leaf, as without cooperation
+            if (pending) {
+                const uint4 n = make_uint4(pend_batches, pend_first, pend_size, 0u);
+                result = leaf_general<DT, FLAGS>(s, n, o, dir, rs, skip, oh, g, cnt);
+                pending = false;
+                have_result = true;
+            }
+            continue;
+        }
+        while (pm) {
+            const int src = __ffs(pm) - 1;
+            pm &= pm - 1;
+            const uint32_t first = __shfl_sync(FULL, pend_first, src), size = __shfl_sync(FULL, pend_size, src);
+            const bool r = coop_leaf_general<DT, FLAGS>(s, src, first, size, o, dir, skip, oh, g, cnt);
+            if (lane == src) { pending = false; have_result = true; result = r; }
         }
     }
     return ret;
@@ -1607,7 +1784,7 @@ NTR_HD void ray_color(const SceneDev &s, bool enabled, const float *o, const flo
     const float t0 = enabled ? aabb_distance<DT>(s, o, dir) : -1.0f;
 #if defined(__CUDA_ARCH__) && NTR_COOP_LEAVES
     bool hit;
-    if (FLAGS & NTR_F_GENERAL) hit = t0 >= 0 && trace_nearest<DT, FLAGS>(s, o, dir, source, t0, FLT_MAX, oh, &g, cnt);
+    if (FLAGS & NTR_F_GENERAL) hit = trace_nearest_coop_general<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, g, cnt);
     else hit = trace_nearest_coop<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, cnt);
 #else
     const bool hit = t0 >= 0 && trace_nearest<DT, FLAGS>(s, o, dir, source, t0, FLT_MAX, oh, &g, cnt);

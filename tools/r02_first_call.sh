@@ -19,6 +19,12 @@ for c in c4 c4o; do
   NTR_TILE_SCHED=1 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_${c}_lpt.json 2>gpurun_out/r02_${c}_lpt.err
   NTR_TILE_SCHED=1 NTR_HEAVY_FIRST=1 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_${c}_lpt_heavy.json 2>gpurun_out/r02_${c}_lpt_heavy.err
 done
+# warp-cooperative big leaves (general + opaque variants), never run so far: parity first, then the numbers
+#   tools/build_variants.sh coop="-DNTR_COOP_LEAVES=1 -DNTR_MIN_CTAS=6"
+if [ -f variants/libntr_coop.so ]; then
+  NTR_B200_LIB=$PWD/variants/libntr_coop.so timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -5 > gpurun_out/r02_coop_tests.txt
+  for c in c4 c4o c2; do NTR_B200_LIB=$PWD/variants/libntr_coop.so timeout 600 python bench.py --config $c --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_${c}_coop.json 2>gpurun_out/r02_${c}_coop.err; done
+fi
 # the two ncu captures that were queued at the end of round 1
 python bench.py --config c4 --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/plain_c4.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_pass -s 5 -c 2 -o gpurun_out/r02_prof_c4 python bench.py --config c4 --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/ncu_c4.log 2>&1
 python bench.py --config c5s --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/plain_c5s.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_pass -s 2 -c 1 -o gpurun_out/r02_prof_c5s python bench.py --config c5s --steps 1 --warmup 3 --no-cpu-baseline --stream-frames 0 > gpurun_out/ncu_c5s.log 2>&1
