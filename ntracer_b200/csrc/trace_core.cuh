@@ -912,6 +912,13 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
 #ifndef NTR_COOP_LEAVES
 #define NTR_COOP_LEAVES 0             // see trace_nearest_coop below
 #endif
+// warp-synchronous code exists on the device, and on the host when the test harness emulates a warp with 32 threads
+// (tests/host_emul/emul.cpp, -DNTR_EMULATE_WARP)
+#if defined(__CUDA_ARCH__) || defined(NTR_EMULATE_WARP)
+#define NTR_WARP_CODE 1
+#else
+#define NTR_WARP_CODE 0
+#endif
 #if NTR_CHUNKED_LEAVES || NTR_COOP_LEAVES
 #ifndef NTR_CHUNK
 #define NTR_CHUNK 32
@@ -1148,7 +1155,7 @@ NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, S
 #ifndef NTR_COOP_LEAVES
 #define NTR_COOP_LEAVES 0
 #endif
-#if defined(__CUDA_ARCH__) && NTR_COOP_LEAVES
+#if NTR_WARP_CODE && NTR_COOP_LEAVES
 #ifndef NTR_COOP_LEAF_MIN
 #define NTR_COOP_LEAF_MIN 64
 #endif
@@ -1299,7 +1306,7 @@ __device__ __forceinline__ bool trace_nearest_coop(const SceneDev &s, bool enabl
 // logic proven bit-identical to the sequential scan in the host emulation, tests/test_fuzz_emul.py).  Lanes never
 // consult the owner's mailbox: an item the owner would skip is evaluated for nothing and dropped by the replay.
 // Written at the end of round 1 without GPU time left: it compiles (-DNTR_COOP_LEAVES=1) and is otherwise untested.
-#if defined(__CUDA_ARCH__) && NTR_COOP_LEAVES
+#if NTR_WARP_CODE && NTR_COOP_LEAVES
 template <int DT, int FLAGS>
 __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, uint32_t first, uint32_t size, const float *o,
                                                   const float *dir, Skip skip, HitRec &oh, GenState<DT> &g, Counters &cnt) {
@@ -1782,7 +1789,7 @@ NTR_HD void ray_color(const SceneDev &s, bool enabled, const float *o, const flo
     // `enabled` = this lane has a ray.  (With NTR_COOP_LEAVES all 32 lanes of a warp enter so that big leaves can be
     // evaluated cooperatively; everything after the traversal is per lane again.)
     const float t0 = enabled ? aabb_distance<DT>(s, o, dir) : -1.0f;
-#if defined(__CUDA_ARCH__) && NTR_COOP_LEAVES
+#if NTR_WARP_CODE && NTR_COOP_LEAVES
     bool hit;
     if (FLAGS & NTR_F_GENERAL) hit = trace_nearest_coop_general<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, g, cnt);
     else hit = trace_nearest_coop<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, cnt);

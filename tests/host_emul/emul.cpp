@@ -9,7 +9,59 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
+
+// -DNTR_EMULATE_WARP (with -DNTR_COOP_LEAVES=1 -pthread): the warp-synchronous parts of trace_core.cuh (cooperative
+// leaf scans: __shfl_sync / __ballot_sync / __all_sync between the 32 lanes of a warp) run on the host too, each lane
+// as an OS thread and every warp intrinsic as a rendezvous of the 32 threads.  Lanes of a correct kernel execute the
+// same sequence of warp intrinsics, so a barrier per intrinsic reproduces the data exchange exactly; a divergent
+// sequence shows up as a hang or a wrong image.
+#ifdef NTR_EMULATE_WARP
+#include <pthread.h>
+
+#include <thread>
+namespace warp_emu {
+struct Warp {
+    pthread_barrier_t bar;
+    uint32_t slot[32];
+    Warp() { pthread_barrier_init(&bar, nullptr, 32); }
+    ~Warp() { pthread_barrier_destroy(&bar); }
+};
+thread_local int lane = 0;
+thread_local Warp *warp = nullptr;
+struct Idx { int x; };
+inline Idx tidx() { return Idx{lane}; }
+}  // namespace warp_emu
+#define threadIdx (warp_emu::tidx())
+template <typename T> inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    memcpy(&warp_emu::warp->slot[warp_emu::lane], &v, 4);
+    pthread_barrier_wait(&warp_emu::warp->bar);
+    T r;
+    memcpy(&r, &warp_emu::warp->slot[src & 31], 4);
+    pthread_barrier_wait(&warp_emu::warp->bar);
+    return r;
+}
+template <typename T> inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) {
+    return __shfl_sync(m, v, warp_emu::lane ^ lane_mask);
+}
+inline unsigned __ballot_sync(unsigned, bool p) {
+    warp_emu::warp->slot[warp_emu::lane] = p ? 1u : 0u;
+    pthread_barrier_wait(&warp_emu::warp->bar);
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= warp_emu::warp->slot[i] << i;
+    pthread_barrier_wait(&warp_emu::warp->bar);
+    return m;
+}
+inline bool __all_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) == 0xFFFFFFFFu; }
+inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+#define __device__
+#define __forceinline__ inline
+#include <vector_types.h>
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#endif
 
 #include "../../ntracer_b200/csrc/arena_pack.h"
 #include "../../ntracer_b200/csrc/trace_core.cuh"
@@ -109,7 +161,115 @@ void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, un
     }
 }
 
+#ifdef NTR_EMULATE_WARP
+// The same frame, 32 rays at a time: every group of 32 consecutive rays is a warp whose lanes run as threads.
+template <int DT> struct LaneEmit {
+    std::vector<std::pair<size_t, Bounce<DT>>> *out;
+    std::vector<uint32_t> *pix;
+    size_t order;
+    uint32_t pixel;
+    void operator()(const Bounce<DT> &b) { out->push_back({order, b}); pix->push_back(pixel); }
+};
+
+template <int DT, int FLAGS>
+void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, unsigned long long *cnt_out) {
+    constexpr int CAP = DimCap<DT>::value;
+    FrameDev f;
+    memset(&f, 0, sizeof f);
+    f.width = w; f.height = h;
+    f.half_w = (float)w / 2.0f; f.half_h = (float)h / 2.0f;
+    f.fovI = tanf(S.dev.fov / 2) / f.half_w;
+    const float one[3] = {1, 1, 1};
+    std::vector<Bounce<DT>> q;          // rays of the current pass (empty = primary pass)
+    std::vector<uint32_t> qp;
+    Counters total;
+    bool primary = true;
+    while (primary || !q.empty()) {
+        const size_t n = primary ? (size_t)w * h : q.size();
+        warp_emu::Warp W;
+        std::vector<std::pair<size_t, Bounce<DT>>> out[32];
+        std::vector<uint32_t> outpix[32];
+        Counters cnts[32];
+        std::vector<std::thread> lanes;
+        for (int L = 0; L < 32; ++L) {
+            lanes.emplace_back([&, L]() {
+                warp_emu::lane = L;
+                warp_emu::warp = &W;
+                for (size_t base = 0; base < n; base += 32) {
+                    const size_t idx = base + L;
+                    const bool enabled = idx < n;
+                    float o[CAP], dir[CAP], acc[3] = {0, 0, 0}, wgt[3] = {1, 1, 1};
+                    for (int k = 0; k < CAP; ++k) { o[k] = 0; dir[k] = 1; }
+                    Skip skip = {NTR_NONE_REF, 0};
+                    int depth = 0;
+                    uint32_t pix = 0;
+                    HitRec prim;
+                    prim.dist = 0; prim.ref = NTR_NONE_REF; prim.lane = -1;
+                    if (enabled) {
+                        if (primary) {
+                            pix = (uint32_t)idx;
+                            primary_ray<DT>(S.dev, S.cam, f, (int)(idx % w), (int)(idx / w), o, dir);
+                        } else {
+                            pix = qp[idx];
+                            for (int k = 0; k < CAP; ++k) { o[k] = q[idx].o[k]; dir[k] = q[idx].d[k]; }
+                            depth = q[idx].depth; skip = q[idx].skip;
+                            wgt[0] = q[idx].w[0]; wgt[1] = q[idx].w[1]; wgt[2] = q[idx].w[2];
+                        }
+                    }
+                    LaneEmit<DT> emit{&out[L], &outpix[L], idx, pix};
+                    ray_color<DT, FLAGS>(S.dev, enabled, o, dir, depth, skip, primary ? one : wgt, acc, emit, cnts[L], primary ? &prim : nullptr);
+                    if (!enabled) continue;
+                    if (primary) {
+                        if (rgb) { rgb[(size_t)pix * 3] = acc[0]; rgb[(size_t)pix * 3 + 1] = acc[1]; rgb[(size_t)pix * 3 + 2] = acc[2]; }
+                        if (ids) ids[pix] = prim.ref == NTR_NONE_REF ? -1 : flat_prim_id(S.dev, prim.ref, prim.lane);
+                        if (dists) dists[pix] = prim.dist;
+                    }
+                    // (bounce results are added below, in ray order, so that the float sums match the sequential driver)
+                    else { out[L].push_back({idx, Bounce<DT>{}}); outpix[L].push_back(0xFFFFFFFFu); out[L].back().second.w[0] = acc[0]; out[L].back().second.w[1] = acc[1]; out[L].back().second.w[2] = acc[2]; }
+                }
+            });
+        }
+        for (auto &t : lanes) t.join();
+        // merge the lanes' emissions in ray order (= the order the sequential driver produces)
+        struct Item { size_t order; int lane; size_t k; };
+        std::vector<Item> items;
+        for (int L = 0; L < 32; ++L)
+            for (size_t k = 0; k < out[L].size(); ++k) items.push_back({out[L][k].first, L, k});
+        std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.order < b.order; });
+        std::vector<Bounce<DT>> qn;
+        std::vector<uint32_t> qpn;
+        for (const Item &it : items) {
+            const uint32_t px = outpix[it.lane][it.k];
+            const Bounce<DT> &b = out[it.lane][it.k].second;
+            if (px == 0xFFFFFFFFu) {                 // result of bounce ray `order`
+                if (rgb) { const uint32_t p = qp[it.order]; rgb[(size_t)p * 3] += b.w[0]; rgb[(size_t)p * 3 + 1] += b.w[1]; rgb[(size_t)p * 3 + 2] += b.w[2]; }
+            } else { qn.push_back(b); qpn.push_back(px); }
+        }
+        for (int L = 0; L < 32; ++L) {
+            total.reflection_rays += cnts[L].reflection_rays; total.shadow_rays += cnts[L].shadow_rays;
+            total.node_steps += cnts[L].node_steps; total.simplex_tests += cnts[L].simplex_tests;
+            total.solid_tests += cnts[L].solid_tests; total.shaded_hits += cnts[L].shaded_hits;
+        }
+        q.swap(qn); qp.swap(qpn);
+        primary = false;
+        if (!rgb) break;
+    }
+    if (cnt_out) {
+        cnt_out[0] = (unsigned long long)w * h; cnt_out[1] = total.reflection_rays; cnt_out[2] = total.shadow_rays;
+        cnt_out[3] = total.node_steps; cnt_out[4] = total.simplex_tests; cnt_out[5] = total.solid_tests; cnt_out[6] = total.shaded_hits;
+        cnt_out[7] = 0;
+    }
+}
+#endif
+
 template <int DT> void render_d(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, unsigned long long *cnt) {
+#ifdef NTR_EMULATE_WARP
+    if (S.dev.kind != NTR_SCENE_BOX) {
+        if (S.flags & NTR_F_GENERAL) render_warp_t<DT, NTR_F_GENERAL | NTR_F_COUNT>(S, w, h, rgb, ids, dists, cnt);
+        else render_warp_t<DT, NTR_F_COUNT>(S, w, h, rgb, ids, dists, cnt);
+        return;
+    }
+#endif
     if (S.flags & NTR_F_GENERAL) render_t<DT, NTR_F_GENERAL | NTR_F_COUNT>(S, w, h, rgb, ids, dists, cnt);
     else render_t<DT, NTR_F_COUNT>(S, w, h, rgb, ids, dists, cnt);
 }

@@ -104,3 +104,43 @@ def test_chunked_leaf_scan_is_bit_identical_to_the_sequential_one(tmp_path):
             assert np.array_equal(ids, gm['ray_ids']) and np.array_equal(nt, gm['ray_ntrans'])
     finally:
         el._lib = base
+
+
+def test_warp_cooperative_traversal_on_an_emulated_warp(tmp_path):
+    """-DNTR_COOP_LEAVES=1: the warp-cooperative traversals (trace_nearest_coop for the opaque variant,
+    trace_nearest_coop_general + coop_leaf_general for the general one) have never run on a GPU.  Here they run on an
+    emulated warp -- 32 host threads, every __shfl_sync / __ballot_sync / __all_sync a rendezvous of the 32
+    (tests/host_emul/emul.cpp, -DNTR_EMULATE_WARP) -- with cooperation forced onto almost every leaf (leaf minimum 4
+    items, up to 31 waiting lanes), and must reproduce the sequential emulation bit for bit.  A lane sequence that
+    diverged between warp intrinsics would hang here (the test is under a timeout) or change the image."""
+    import ctypes as C
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path / 'libhostemul_warp.so')
+    subprocess.run(['/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++', '-std=c++17', '-O2', '-fPIC', '-shared',
+                    '-fvisibility=hidden', '-I/usr/local/cuda/include', '-Wno-unknown-pragmas', '-pthread',
+                    '-DNTR_EMULATE_WARP', '-DNTR_COOP_LEAVES=1', '-DNTR_COOP_LEAF_MIN=4', '-DNTR_COOP_MAX_LANES=31',
+                    '-o', so, os.path.join(here, 'host_emul', 'emul.cpp')], check=True)
+    base, warp = el.lib(), C.CDLL(so)
+    cases = [(fx.fuzz_scene(3 + seed % 5, seed), 32, 18) for seed in (1, 2, 3, 4, 5, 7, 8, 14)]
+    for name, v, w, h in (('mixed3', None, 32, 18), ('ssc120', 'refl_transp', 24, 14), ('ggs120', 'refl_transp', 16, 9),
+                          ('ggs120', 'refl', 16, 9)):
+        sc, g = fx.load(name)
+        cases.append((fx.variant(sc, g, v) if v else sc, w, h))
+    general = opaque = 0
+    try:
+        for sc, w, h in cases:
+            el._lib = base
+            a, ca = el.render(sc, w, h)
+            el._lib = warp
+            b, cb = el.render(sc, w, h)
+            assert np.array_equal(a, b)
+            for k in ('reflection_rays', 'shadow_rays', 'shaded_hits', 'node_steps'):
+                assert ca[k] == cb[k], k
+            is_general = bool(np.any(sc['materials'][:, 6] < 1)) or len(sc['solids']) > 0
+            general += is_general
+            opaque += not is_general
+    finally:
+        el._lib = base
+    assert general >= 4 and opaque >= 1
