@@ -1776,7 +1776,8 @@ NTR_HD void hit_geometry(const SceneDev &s, uint32_t ref, int lane, float dist, 
 // EMIT(const Bounce<DT>&) receives the deferred reflection rays.
 template <int DT, int FLAGS, typename EMIT>
 NTR_HD void ray_color(const SceneDev &s, bool enabled, const float *o, const float *dir, int depth, Skip source,
-                      const float *weight, float *acc, EMIT &emit, Counters &cnt, HitRec *primary_out) {
+                      const float *weight, float *acc, EMIT &emit, Counters &cnt, HitRec *primary_out,
+                      bool coop = true /* warp-uniform; only read with NTR_COOP_LEAVES */) {
     const int D = NTR_D(DT, s);
     GenState<DT> g;
     HitRec oh;
@@ -1790,8 +1791,11 @@ NTR_HD void ray_color(const SceneDev &s, bool enabled, const float *o, const flo
     // evaluated cooperatively; everything after the traversal is per lane again.)
     const float t0 = enabled ? aabb_distance<DT>(s, o, dir) : -1.0f;
 #if NTR_WARP_CODE && NTR_COOP_LEAVES
+    // `coop` is the same for all 32 lanes: the cooperative traversals (every lane takes part, with or without a ray) or
+    // the plain per-lane one -- kernels.cuh switches to cooperation for the tail of a pass only (NTR_COOP_TAIL_ONLY)
     bool hit;
-    if (FLAGS & NTR_F_GENERAL) hit = trace_nearest_coop_general<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, g, cnt);
+    if (!coop) hit = t0 >= 0 && trace_nearest<DT, FLAGS>(s, o, dir, source, t0, FLT_MAX, oh, &g, cnt);
+    else if (FLAGS & NTR_F_GENERAL) hit = trace_nearest_coop_general<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, g, cnt);
     else hit = trace_nearest_coop<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, cnt);
 #else
     const bool hit = t0 >= 0 && trace_nearest<DT, FLAGS>(s, o, dir, source, t0, FLT_MAX, oh, &g, cnt);

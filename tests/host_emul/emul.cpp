@@ -217,7 +217,11 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
                         }
                     }
                     LaneEmit<DT> emit{&out[L], &outpix[L], idx, pix};
-                    ray_color<DT, FLAGS>(S.dev, enabled, o, dir, depth, skip, primary ? one : wgt, acc, emit, cnts[L], primary ? &prim : nullptr);
+#ifndef NTR_EMUL_COOP_EVERY
+#define NTR_EMUL_COOP_EVERY 1       // groups g with g % NTR_EMUL_COOP_EVERY == 0 use the cooperative traversal (1 = all)
+#endif
+                    const bool coop = (base / 32) % NTR_EMUL_COOP_EVERY == 0;       // the same for the 32 lanes of a group
+                    ray_color<DT, FLAGS>(S.dev, enabled, o, dir, depth, skip, primary ? one : wgt, acc, emit, cnts[L], primary ? &prim : nullptr, coop);
                     if (!enabled) continue;
                     if (primary) {
                         if (rgb) { rgb[(size_t)pix * 3] = acc[0]; rgb[(size_t)pix * 3 + 1] = acc[1]; rgb[(size_t)pix * 3 + 2] = acc[2]; }

@@ -121,6 +121,7 @@ def test_warp_cooperative_traversal_on_an_emulated_warp(tmp_path):
     subprocess.run(['/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++', '-std=c++17', '-O2', '-fPIC', '-shared',
                     '-fvisibility=hidden', '-I/usr/local/cuda/include', '-Wno-unknown-pragmas', '-pthread',
                     '-DNTR_EMULATE_WARP', '-DNTR_COOP_LEAVES=1', '-DNTR_COOP_LEAF_MIN=4', '-DNTR_COOP_MAX_LANES=31',
+                    '-DNTR_EMUL_COOP_EVERY=2',      # every other warp cooperates, the others trace per lane (tail-only switch)
                     '-o', so, os.path.join(here, 'host_emul', 'emul.cpp')], check=True)
     base, warp = el.lib(), C.CDLL(so)
     cases = [(fx.fuzz_scene(3 + seed % 5, seed), 32, 18) for seed in (1, 2, 3, 4, 5, 7, 8, 14)]
