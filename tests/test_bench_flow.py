@@ -91,6 +91,7 @@ def test_bench_line_has_every_contract_key_and_the_optional_legs():
     for k in REQUIRED:
         assert k in line, k
     assert line['warmup'] >= 3 and line['steps'] == 3 and line['n_gpus'] == 1
+    assert line['metric'] == 'Mrays/sec (primary+shadow)' and line['unit'] == 'Mrays/s'      # BASELINE.json's metric
     assert line['e2e']['d2h_bytes_per_step'] == 640 * 480 * 3 and line['e2e']['value'] > 0
     assert line['roofline']['bound'] == 'fp32' and line['roofline']['peak'] == 64.5
     assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
