@@ -276,9 +276,10 @@ def test_oracle_matches_the_reference_on_random_scenes():
     """The oracle pinned beyond the committed fixtures: fixtures.fuzz_scene corpora rebuilt inside the compiled reference
     with the same tree (ref_bridge.import_scene), Scene.calculate_color for every pixel.  Only scenes the oracle flags
     as fully inside the reference's defined domain are sent to the reference (outside it, it can crash).  The few
-    pixels that differ sit behind a transparent + reflective layer and flip sign from pixel to pixel: secondary rays
-    leaving a surface that coincides with a k-d split plane take the `origin == split` branch (tracer.hpp:1192-1195) or
-    not depending on the last bit of the hit point, and the reference is built with -ffast-math."""
+    pixels that differ sit behind a transparent layer and flip sign from pixel to pixel: they are the "Q12 pixels" of
+    DESIGN.md section 5 (an opaque hit whose shading point was overwritten by a transparent hit shoots its secondary
+    rays from ON the transparent surface; whether they re-hit it at t ~ 0 is decided by the last bit, and the reference
+    is built with -ffast-math)."""
     from tests import fixtures as fx
     from tests import oracle_lib as ol
     rb.load_reference()
