@@ -47,7 +47,9 @@ typedef struct {
     const float *cam_o, *right, *up, *fwd;
     float half_w, half_h, fovI;
     ntr_counters cnt;
-    int undefined;      /* bit 0: a transparent-hit list, bit 1: the mailbox outgrew its preallocation during this pixel */
+    int undefined;      /* bit 0: a transparent-hit list, bit 1: the mailbox outgrew its preallocation during this pixel;
+                         * bit 2: ill-conditioned -- an opaque hit was shaded at a point that is not on its own surface
+                         * (see ray_color) */
 } octx;
 
 static void hits_add(octx *c, ohits *l, const ohit *h) {
@@ -640,6 +642,27 @@ static ocolor ray_color(octx *c, const oray *target, int depth, otarget source) 
     float dist = aabb_distance(c, target);
     hit.dist = FLT_MAX;
     if (dist >= 0 && tree_intersects(c, s->root, target, source, &hit, &th, dist, FLT_MAX)) {
+        /* kd_leaf::intersects lets every test made before the first opaque hit of a leaf write straight into
+         * o_hit.normal (tracer.hpp:1001,1020), so a transparent hit -- or a hypercube test that misses after writing
+         * some coordinates (:131-139) -- in a leaf visited later replaces the shading point of an opaque hit found
+         * earlier.  The secondary rays of such a pixel start ON that other surface while `source` names the opaque
+         * primitive, so whether they re-hit the surface they start on at t ~ 0 is decided by the last bit of t: the
+         * reference's own answer depends on its build (-ffast-math, FMA contraction).  Restated as it is, and
+         * flagged so that parity tests can tell these pixels apart. */
+        {
+            oray clean;
+            memset(&clean, 0, sizeof clean);
+            int same = 1;
+            if ((hit.target.ref >> 30) == NTR_REF_SOLID) {
+                ntr_counters keep = c->cnt;
+                solid_intersects(c, hit.target.ref & 0x3FFFFFFFu, target, &clean, FLT_MAX);
+                c->cnt = keep;
+                for (int i = 0; i < c->D; ++i) same = same && clean.o[i] == hit.normal.o[i];
+            } else {
+                for (int i = 0; i < c->D; ++i) same = same && (target->o[i] + hit.dist * target->d[i]) == hit.normal.o[i];
+            }
+            if (!same) c->undefined |= 4;
+        }
         r = base_color(c, target, &hit.normal, hit.target, depth);
     } else {
         float intensity = target->d[s->bg_gradient_axis];

@@ -18,12 +18,13 @@ def test_random_mixed_scenes_match_the_oracle():
         a, mask, cnt_o = ol.render_float(sc, w, h, with_mask=True, with_counters=True)
         b, cnt_e = el.render(sc, w, h)
         g, _ = el.render(sc, w, h, generic=True)
-        ok = mask == 0                       # pixels where the reference's own lists stay inside their preallocation
+        ok = mask == 0                       # pixels where the reference's own lists stay inside their preallocation (and
+                                             # no opaque hit is shaded off its own surface: oracle mask bit 2)
         d = np.abs(a - b).max(axis=2)
         assert (d[ok].max() if ok.any() else 0) <= 2e-5, (seed, dim)
         assert np.mean(d > 1e-3) <= 0.01, (seed, dim)          # and even outside that domain nothing drifts far
         assert np.abs(b - g).max() <= 2e-5, (seed, dim)        # fixed- and run-time-dimension code agree
-        if ok.all():
+        if ((mask & 3) == 0).all():
             for k in ('primary_rays', 'reflection_rays', 'shadow_rays', 'shaded_hits'):
                 assert cnt_o[k] == cnt_e[k], (seed, dim, k)
             defined_scenes += 1

@@ -90,7 +90,7 @@ def test_polytope_variants(name):
             # same algorithm, same inputs: only FMA contraction / libm differences remain.  Pixels where the reference
             # itself is undefined (a quick_list outgrew its preallocation: mask != 0, see test_oracle_golden) are held
             # to a loose bound only; the product's mailbox is bounded (40) where the oracle's is unbounded.
-            undefined = mask != 0
+            undefined = (mask & 3) != 0
             bad_o, _ = fx.lsb_stats(img, oimg, exclude=col | undefined)
             bad_g, _ = fx.lsb_stats(img, g['v_%s_float' % v], exclude=col | undefined)
             assert bad_o <= 0.001, (name, v, bad_o)
@@ -147,8 +147,13 @@ def test_mixed_transparent_scene_and_ray_hooks():
         ok = ids == g['ray_ids']
         assert np.allclose(dist[ok], g['ray_dists'][ok], rtol=1e-5, atol=1e-5)
         img = ds.render_float(w, h)
+        oimg, mask = ol.render_float(sc, w, h, with_mask=True)
+        # the Q12 pixels (oracle mask bit 2, 5 % of this frame: see test_random_mixed_scenes_match_the_oracle) are
+        # rounding noise in the reference itself; every other pixel is held to BASELINE.json's bound
+        assert fx.lsb_stats(img, g['float'], exclude=mask != 0)[0] <= 0.001
+        assert fx.lsb_stats(img, oimg, exclude=mask != 0)[0] <= 0.001
         assert fx.lsb_stats(img, g['float'])[0] <= 0.015
-        assert fx.lsb_stats(img, ol.render_float(sc, w, h))[0] <= 0.015
+        assert fx.lsb_stats(img, oimg)[0] <= 0.015
     sc, g = fx.load('kdtree_kat')
     with DeviceScene(sc) as ds:
         ids, dist, nt = ds.trace_rays(g['origin'][None], g['direction'][None])
@@ -310,22 +315,44 @@ def test_batched_soup_every_fixed_dimension_and_generic(dim, monkeypatch):
 
 def test_random_mixed_scenes_match_the_oracle():
     """The differential fuzz corpus of tests/test_fuzz_emul.py through the CUDA library: batches, single simplexes,
-    solids, transparency, reflections and shadows in 3..7 dimensions.  Float images within 1 LSB of an 8-bit channel
-    on the reference's defined domain: per scene on >= 98 % of the pixels (a 64x36 frame is small: one flipped
-    grazing hit is 0.04 %), over the whole corpus on >= 99.8 %."""
+    solids, transparency, reflections and shadows in 3..7 dimensions.
+
+    Three classes of pixels (oracle mask): bits 0/1 = the reference's own lists outgrew their preallocation (undefined
+    behaviour there, not compared); bit 2 = "Q12 pixels", an opaque hit shaded at a point that lies on ANOTHER
+    (transparent) surface, whose secondary rays re-hit the surface they start on at t ~ 0 or not depending on the last
+    bit of t -- measured against the real reference (tests/test_mirror_vs_reference.py): 0 of 104,720 clean pixels
+    differ, 36 of 256 Q12 pixels do, and the same pixels flip when the host emulation of this very code is compiled
+    with FMA contraction.  So: clean pixels must agree within 1 LSB (>= 99.5 % per 64x36 scene, >= 99.9 % over the
+    corpus -- BASELINE.json's bound); Q12 pixels are held to a loose bound only; and the ray-level hook, which has no
+    secondary rays, must agree on every scene."""
     w, h = 64, 36
-    bad_px = all_px = 0
+    bad_px = all_px = bad_q = all_q = 0
     for seed in range(40):
         dim = 3 + seed % 5
         sc = fx.fuzz_scene(dim, seed)
         o, mask = ol.render_float(sc, w, h, with_mask=True)
+        rng = np.random.RandomState(seed + 999)
+        n = 256
+        ro = np.zeros((n, dim), np.float32)
+        ro[:, :3] = rng.uniform(-3, 3, (n, 3))
+        ro[:, 3:] = rng.uniform(-0.05, 0.05, (n, dim - 3))
+        tgt = np.zeros((n, dim), np.float32)
+        tgt[:, :3] = rng.uniform(-1, 1, (n, 3))
+        rd = (tgt - ro).astype(np.float32)
+        oi, od, ont = ol.trace_rays(sc, ro, rd)
         with DeviceScene(sc) as ds:
             img = ds.render_float(w, h)
-        ok = mask == 0
-        if not ok.any():
-            continue
-        d = np.abs(fx.quant8(img) - fx.quant8(o)).max(axis=2)[ok]
-        assert np.mean(d > 1) <= 0.02, (seed, dim, float(np.mean(d > 1)))
-        bad_px += int((d > 1).sum())
-        all_px += int(ok.sum())
-    assert all_px > 30000 and bad_px <= 0.002 * all_px, (bad_px, all_px)
+            ids, dist, nt = ds.trace_rays(ro, rd)
+        assert np.mean(ids == oi) >= 0.99 and np.mean(nt == ont) >= 0.99, (seed, dim)
+        same = ids == oi
+        assert np.allclose(dist[same], od[same], rtol=1e-5, atol=1e-5), (seed, dim)
+        d = np.abs(fx.quant8(img) - fx.quant8(o)).max(axis=2)
+        clean, q12 = mask == 0, mask == 4
+        if clean.any():
+            assert np.mean(d[clean] > 1) <= 0.005, (seed, dim, float(np.mean(d[clean] > 1)))
+        bad_px += int((d[clean] > 1).sum())
+        all_px += int(clean.sum())
+        bad_q += int((d[q12] > 1).sum())
+        all_q += int(q12.sum())
+    assert all_px > 30000 and bad_px <= 0.001 * all_px, (bad_px, all_px)
+    assert bad_q <= 0.5 * max(all_q, 1), (bad_q, all_q)

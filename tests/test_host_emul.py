@@ -26,7 +26,7 @@ def test_polytope_matches_oracle(name, variants):
         if v == 'refl_transp' and name in ('ggs120', 'ssc120'):
             # giant leaves: far beyond the 20 mailbox entries up to which the reference is defined; the product keeps 40,
             # the oracle an unbounded list -- corner-case pixels (trim + re-add) differ, only where the reference is undefined
-            assert fx.lsb_stats(a, b, exclude=mask != 0)[0] <= 0.001
+            assert fx.lsb_stats(a, b, exclude=(mask & 3) != 0)[0] <= 0.001
             assert fx.lsb_stats(a, b)[0] <= 0.02
             continue
         assert np.abs(a - b).max() <= 2e-6, (name, v)

@@ -74,7 +74,7 @@ def test_polytope_variants(name):
         # reference quick_list outgrew its preallocation are undefined behaviour in the reference itself
         # (tracer.hpp:670-680: uninitialised mailbox slots -> primitives skipped at random, seen as holes in its
         # {5/2,3,3} images); they are only held to a loose bound.
-        undefined = mask != 0
+        undefined = (mask & 3) != 0
         bad_defined, _ = fx.lsb_stats(img, gold, exclude=col | undefined)
         bad_all, _ = fx.lsb_stats(img, gold, exclude=col)
         assert bad_defined <= 0.001, (name, v, bad_defined)
@@ -109,7 +109,10 @@ def test_mixed_transparent_scene():
     assert np.array_equal(ids, g['ray_ids'])
     assert np.array_equal(nt, g['ray_ntrans'])
     assert np.allclose(dist, g['ray_dists'], rtol=1e-5, atol=1e-5)
-    img = ol.render_float(sc, w, h)
+    img, mask = ol.render_float(sc, w, h, with_mask=True)
     # pixels whose opaque hit had its normal overwritten by a later transparent hit (reference quirk, DESIGN.md
-    # Q12) shoot secondary rays from ON a transparent surface: their t ~ 0 self-hits are rounding noise
+    # Q12; oracle mask bit 2) shoot secondary rays from ON a transparent surface: their t ~ 0 self-hits are rounding
+    # noise.  Every other pixel agrees with the reference's frame.
+    assert (mask & 3).max() == 0 and 0.02 <= np.mean(mask == 4) <= 0.1
+    assert fx.lsb_stats(img, g['float'], exclude=mask != 0)[0] == 0
     assert fx.lsb_stats(img, g['float'])[0] <= 0.015
