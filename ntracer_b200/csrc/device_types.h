@@ -16,6 +16,7 @@
 
 #define NTR_THITS_CAP 16            // transparent hits kept per ray (reference is defined up to 10, tracer.hpp:26)
 #define NTR_MAILBOX_CAP 40          // mailbox entries kept per traversal (reference is defined up to 20, tracer.hpp:27)
+#define NTR_MAILBOX_SLOTS 64        // open-addressing table that holds them (trace_core.cuh: Mailbox)
 #define NTR_STACK_CAP (NTR_MAX_TREE_DEPTH + 2)
 
 // meta word stored in the last float slot of every simplex / solid record

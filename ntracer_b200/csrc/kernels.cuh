@@ -11,7 +11,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "trace_core.cuh"
+#include "trace_warp.cuh"
 
 namespace ntr {
 
@@ -115,9 +115,6 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 #ifndef NTR_MIN_CTAS
 #define NTR_MIN_CTAS 8
 #endif
-#ifndef NTR_COOP_TAIL_ONLY
-#define NTR_COOP_TAIL_ONLY 1       // with NTR_COOP_LEAVES: cooperative traversal for the tail of each pass only
-#endif
 // above 8 dimensions the ray alone (origin, direction, hit point) is 30+ registers: fewer CTAs per SM, more registers
 #ifndef NTR_MIN_CTAS_HI
 #define NTR_MIN_CTAS_HI 5          // measured on config 5 (16 k simplexes): 3 -> 31.7 ms, 4 -> 25.5, 5 -> 23.3, 6 -> 24.6, 8 -> 32.6
@@ -220,27 +217,14 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                 active = true;
             }
         }
-        // ---------------- the per-ray path ----------------
-#if NTR_COOP_LEAVES
-        if (s.kind != NTR_SCENE_BOX) {       // warp-uniform: every lane enters (cooperative leaves), `active` says who has a ray
+        // ---------------- the per-ray path: all 32 lanes enter (trace_warp.cuh), `active` says who has a ray ----------------
+        if (s.kind != NTR_SCENE_BOX) {       // warp-uniform
             if (!active) {
 #pragma unroll
                 for (int k = 0; k < CAP; ++k) { o[k] = 0.0f; dir[k] = 1.0f; }
             }
-#else
-        if (active) {
-#endif
             QueueEmit<DT> emit{q, ctl, pix, !primary || f.out_mode == NTR_OUT_ACCUM};
-#if NTR_COOP_LEAVES
-            // cooperation costs ballots per leaf visit while the warp is full of equally busy rays and pays when a few
-            // lanes are left with giant leaves: with NTR_COOP_TAIL_ONLY it is used for (roughly) the last fetch of every
-            // warp in a pass only -- `b` close enough to `total` that no further work will be there to fetch
-            const uint32_t tail_span = gridDim.x * (uint32_t)(kCtaThreads / 32) * (primary ? 1u : 32u);
-            const bool coop_now = !NTR_COOP_TAIL_ONLY || total - b <= tail_span;
-            ray_color<DT, FLAGS>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim, coop_now);
-#else
-            ray_color<DT, FLAGS>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim);
-#endif
+            ray_color_warp<DT, FLAGS>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim);
         }
         if (primary && f.tile_cost && lane == 0) atomicAdd(f.tile_cost + cost_tile, (unsigned long long)(clock64() - t_start));
         // ---------------- epilogue ----------------

@@ -529,21 +529,38 @@ struct HitList {                        // quick_list<ray_intersection>, tracer.
 };
 
 struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,832-834
-    uint32_t v[NTR_MAILBOX_CAP];
-    int n;
-    NTR_HD void clear() { n = 0; }
     // The reference's list is defined up to 20 entries (quick_list growth copies bytes, tracer.hpp:670-680: beyond
     // that has() scans uninitialised slots).  This one is exact up to NTR_MAILBOX_CAP entries and then switches itself
     // off -- in that regime the reference skips primitives at random, so there is nothing left to be faithful to, and
-    // a linear scan per item of a 1,600-item leaf would dominate the frame.
+    // a membership test per item of a 1,600-item leaf would dominate the frame.
+    // Only membership matters (the reference scans its list linearly, :832-834), so the entries live in a small
+    // open-addressing table: one or two probes per query instead of up to 40 compares (ncu, config 4, round 2: the
+    // linear scan was 16 % of all executed instructions and a quarter of the local-memory traffic of the kernel).
+    uint32_t v[NTR_MAILBOX_SLOTS];      // NTR_NONE_REF = empty slot (no item ref has both type bits set)
+    int n;
+    static_assert((NTR_MAILBOX_SLOTS & (NTR_MAILBOX_SLOTS - 1)) == 0 && NTR_MAILBOX_SLOTS > NTR_MAILBOX_CAP, "mailbox table size");
+    NTR_HD static uint32_t slot_of(uint32_t r) { return (r * 2654435761u) >> 16 & (uint32_t)(NTR_MAILBOX_SLOTS - 1); }
+    NTR_HD void clear() {
+        n = 0;
+        for (int i = 0; i < NTR_MAILBOX_SLOTS; ++i) v[i] = NTR_NONE_REF;
+    }
     NTR_HD bool has(uint32_t r) const {
-        if (n > NTR_MAILBOX_CAP) return false;
-        for (int i = 0; i < n; ++i) if (v[i] == r) return true;
-        return false;
+        if (n > NTR_MAILBOX_CAP || n == 0) return false;
+        uint32_t h = slot_of(r);
+        for (;;) {
+            const uint32_t x = v[h];
+            if (x == r) return true;
+            if (x == NTR_NONE_REF) return false;
+            h = (h + 1) & (uint32_t)(NTR_MAILBOX_SLOTS - 1);
+        }
     }
     NTR_HD void add(uint32_t r) {
-        if (n < NTR_MAILBOX_CAP) v[n++] = r;
-        else n = NTR_MAILBOX_CAP + 1;
+        if (n < NTR_MAILBOX_CAP) {
+            uint32_t h = slot_of(r);
+            while (v[h] != NTR_NONE_REF) h = (h + 1) & (uint32_t)(NTR_MAILBOX_SLOTS - 1);
+            v[h] = r;
+            ++n;
+        } else n = NTR_MAILBOX_CAP + 1;
     }
 };
 
@@ -858,8 +875,10 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
         dist = prim_test_general<DT, FLAGS>(s, it, o, dir, oh.dist, skip, lane, P, N, wmask, meta, cnt);
         last_tested = i;
         if (!phase1) {
+            if (wmask) {
     NTR_UNROLL
-            for (int k = 0; k < D; ++k) if (wmask & (1u << k)) g.hitP[k] = P[k];
+                for (int k = 0; k < D; ++k) if (wmask & (1u << k)) g.hitP[k] = P[k];
+            }
             if (dist) {
     NTR_UNROLL
                 for (int k = 0; k < D; ++k) g.hitN[k] = N[k];
@@ -891,11 +910,11 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
 }
 
 // ---- chunked evaluation of a leaf (general variant) -------------------------------------------------------------
-// Groundwork for splitting ONE ray's scan of a big leaf over the lanes of a warp (a single ray
-// through the 1,606-item leaves of {5/2,3,3} is what bounds a frame once the bulk is spread thin).  The leaf is cut
-// into chunks of NTR_CHUNK items; all tests of a chunk are evaluated against the state at the START of the chunk
-// (that is the part 32 lanes can do at once), then their results are REPLAYED in leaf order with the sequential
-// semantics of kd_leaf::intersects.  Exactness of the replay:
+// What lets ONE ray's scan of a big leaf be split over the lanes of a warp (trace_warp.cuh; DESIGN.md section 4: a single
+// ray through the 1,600-item leaves of {5/2,3,3} is what bounds a frame once the bulk is spread thin).  The leaf is cut
+// into chunks; all tests of a chunk are evaluated against the state at the START of the chunk (that is the part 32 lanes
+// can do at once), then their results are REPLAYED in leaf order with the sequential semantics of kd_leaf::intersects.
+// Exactness of the replay:
 //   * a test run with the looser cutoff of the chunk start returns, for simplexes, batches and spheres, either the same
 //     hit the tighter cutoff would give or a hit at t >= the tighter cutoff, which the replay demotes to a miss (a batch
 //     reports the lowest lane with the smallest t, which does not depend on the cutoff as long as it passes it);
@@ -904,22 +923,18 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
 //   * the mailbox can only change its answer for an item of the chunk by switching itself off (overflow) in the
 //     middle of it; an item skipped at evaluation time but no longer skipped at replay time is tested on the spot;
 //   * the re-test after the first opaque hit (`goto hit`, Q13) always misses its own cutoff: the replay records a miss.
-// This host/device version evaluates the chunk in a loop; it exists so that the replay logic is proven against the
-// oracle in the CPU tier (host emulation, -DNTR_CHUNKED_LEAVES=1) before the warp-cooperative kernel is built on it.
+// leaf_general_chunked below evaluates the chunk in a loop on one thread; it exists so that the replay logic is proven
+// against the oracle in the CPU tier (host emulation, -DNTR_CHUNKED_LEAVES=1, tests/test_fuzz_emul.py).
 #ifndef NTR_CHUNKED_LEAVES
 #define NTR_CHUNKED_LEAVES 0
 #endif
-#ifndef NTR_COOP_LEAVES
-#define NTR_COOP_LEAVES 0             // see trace_nearest_coop below
-#endif
 // warp-synchronous code exists on the device, and on the host when the test harness emulates a warp with 32 threads
 // (tests/host_emul/emul.cpp, -DNTR_EMULATE_WARP)
-#if defined(__CUDA_ARCH__) || defined(NTR_EMULATE_WARP)
+#if defined(__CUDACC__) || defined(NTR_EMULATE_WARP)
 #define NTR_WARP_CODE 1
 #else
 #define NTR_WARP_CODE 0
 #endif
-#if NTR_CHUNKED_LEAVES || NTR_COOP_LEAVES
 #ifndef NTR_CHUNK
 #define NTR_CHUNK 32
 #endif
@@ -931,8 +946,32 @@ template <int DT> struct ChunkEval {
     int lane;
     uint32_t wmask, meta;
     bool skipped;
+    bool geom;          // P / N hold what the test wrote (always for solids; simplex hits may leave it to the replay)
     float P[DimCap<DT>::value], N[DimCap<DT>::value];
 };
+
+// One primitive test of the general variant without the hit geometry of simplexes (the replay computes it for the
+// hits that survive): what a lane of a cooperating warp evaluates.
+template <int DT, int FLAGS>
+NTR_HD void prim_eval(const SceneDev &s, uint2 it, const float *o, const float *dir, float cutoff, Skip skip,
+                      ChunkEval<DT> &e, Counters &cnt) {
+    const uint32_t item = it.x, off = it.y;
+    const uint32_t kind = item >> 30;
+    e.wmask = 0; e.meta = 0; e.geom = false; e.skipped = false;
+    if (kind == NTR_REF_BATCH) {
+        e.lane = skip.ref == item ? skip.lane : -1;
+        e.dist = batch_test<DT, FLAGS>(s, off, o, dir, e.lane, cutoff, e.meta, cnt);
+    } else if (kind == NTR_REF_SIMPLEX) {
+        e.lane = -1;
+        if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
+        e.dist = simplex_single<DT>(s, off, o, dir, cutoff, e.meta);
+    } else {
+        e.lane = -1;
+        if (FLAGS & NTR_F_COUNT) cnt.solid_tests++;
+        e.dist = solid_test<DT>(s, item & NTR_IDX_MASK, o, dir, cutoff, e.P, e.N, e.wmask, e.meta);
+        e.geom = true;
+    }
+}
 
 // One step of the replay: what kd_leaf::intersects does with the test of one item, given the result `e` of that test
 // taken earlier (with a cutoff that may have been looser, and before the mailbox may have switched itself off).
@@ -948,11 +987,17 @@ NTR_HD void replay_item(const SceneDev &s, const uint2 it, const float *o, const
                          (int)ldf(s.solids + (size_t)(item & NTR_IDX_MASK) * s.solstride) == NTR_SOLID_CUBE;
     if (e.skipped || (stale_cutoff && is_cube)) {
         e.dist = prim_test_general<DT, FLAGS>(s, it, o, dir, oh.dist, skip, e.lane, e.P, e.N, e.wmask, e.meta, cnt);
+        e.geom = true;
     } else if (stale_cutoff) {
         e.dist = 0;             // simplexes and spheres leave o_hit.normal alone when they miss
         e.wmask = 0;
     }
     dist = e.dist;
+    if (dist && !e.geom) {      // a simplex hit evaluated without its geometry (prim_eval)
+        simplex_normal<DT>(s, (item & NTR_IDX_MASK) + (is_batch ? (uint32_t)e.lane : 0u), o, dir, dist, e.P, e.N);
+        e.wmask = 0xFFFFFFFFu;
+        e.geom = true;
+    }
     if (!phase1) {
     NTR_UNROLL
         for (int k = 0; k < D; ++k) if (e.wmask & (1u << k)) g.hitP[k] = e.P[k];
@@ -995,10 +1040,10 @@ NTR_HD bool leaf_general_chunked(const SceneDev &s, const uint4 node, const floa
         for (uint32_t j = 0; j < n; ++j) {
             const uint2 it = lditem(items + base + j);
             const bool is_batch = (it.x >> 30) == NTR_REF_BATCH;
-            ev[j].skipped = (!is_batch && it.x == skip.ref) || g.mb.has(it.x);
-            ev[j].dist = 0; ev[j].wmask = 0; ev[j].meta = 0; ev[j].lane = -1;
-            if (!ev[j].skipped)
-                ev[j].dist = prim_test_general<DT, FLAGS>(s, it, o, dir, cutoff0, skip, ev[j].lane, ev[j].P, ev[j].N, ev[j].wmask, ev[j].meta, cnt);
+            const bool skipped = (!is_batch && it.x == skip.ref) || g.mb.has(it.x);
+            ev[j].dist = 0; ev[j].wmask = 0; ev[j].meta = 0; ev[j].lane = -1; ev[j].geom = false;
+            if (!skipped) prim_eval<DT, FLAGS>(s, it, o, dir, cutoff0, skip, ev[j], cnt);
+            ev[j].skipped = skipped;
         }
         // ---- replay in leaf order ----
         for (uint32_t j = 0; j < n; ++j)
@@ -1008,7 +1053,6 @@ NTR_HD bool leaf_general_chunked(const SceneDev &s, const uint4 node, const floa
     g.th.trim(dist, h_start);
     return true;
 }
-#endif
 
 // Per-ray axis tables of the traversal.  A k-d step needs o[axis], dir[axis] and 1/dir[axis] for a run-time axis; with
 // the vectors in registers that is a select chain per value (ncu, config 2: 7.4 % of all instructions).  With
@@ -1136,337 +1180,6 @@ NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, S
         }
     }
 }
-
-// ---- warp-cooperative nearest-hit traversal (device only, opaque variant) -----------------------------------------
-// Same state machine as trace_nearest, but leaves with at least NTR_COOP_LEAF_MIN items are evaluated by the WHOLE
-// warp for one ray at a time: the ray is broadcast, lane j tests items j, j+32, ..., and the winner is the
-// lexicographic minimum of (t, item index) -- exactly what the sequential scan with its strict `t < cutoff` rule
-// keeps (nearest hit, first-tested wins ties, tracer.hpp:1041-1082).  Why: rays that cross many of the 1,600-item
-// leaves of a star polytope take milliseconds each; in the wavefront passes a handful of such stragglers held a
-// whole pass hostage (measured: 1/8 of the rays took the same time as all of them).  With cooperation a straggler's
-// leaf costs 1/32 of the time whenever its warp-mates are idle, and nothing when they are busy too.
-// MUST be called by all 32 lanes of the warp (lanes without a ray pass enabled = false).
-// MEASURED (B200, config 4 opaque, 3840x2160): with cooperation enabled the frame went from 47.4 ms to 54.7 ms
-// (to 64.5 ms when every big leaf was served cooperatively): the extra ballots per leaf visit and the loss of the
-// shrinking per-lane cutoff cost more than the idle lanes give back, because the expensive wavefront passes turned
-// out to be throughput bound by INCOHERENT reflection rays (6-16 ns/ray against 1.5 ns/ray for primaries), not by a few
-// stragglers.  It is therefore compiled out by default (-DNTR_COOP_LEAVES=1 to enable); ray re-binning for
-// coherence is the lever that remains.
-#ifndef NTR_COOP_LEAVES
-#define NTR_COOP_LEAVES 0
-#endif
-#if NTR_WARP_CODE && NTR_COOP_LEAVES
-#ifndef NTR_COOP_LEAF_MIN
-#define NTR_COOP_LEAF_MIN 64
-#endif
-#ifndef NTR_COOP_MAX_LANES
-#define NTR_COOP_MAX_LANES 10       // cooperate only while at most this many lanes of the warp wait at big leaves
-#endif
-template <int DT, int FLAGS>
-__device__ __forceinline__ bool trace_nearest_coop(const SceneDev &s, bool enabled, const float *o, const float *dir,
-                                                   Skip skip, float t_near, float t_far, HitRec &oh, Counters &cnt) {
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    const int D = NTR_D(DT, s);
-    const int lane = threadIdx.x & 31;
-    RaySlab<DT> rs;
-    rs.init(s, dir);
-    const float *invdir = rs.invdir;
-    TravStack st;
-    int sp = 0;
-    uint32_t node = s.root;
-    MiniMailbox mm;
-    mm.clear();
-    bool done = !enabled, pending = false, have_result = false, result = false, ret = false;
-    uint32_t pend_first = 0, pend_size = 0;
-    for (;;) {
-        if (!done) {
-            if (have_result) {                                      // ---- unwind (see trace_nearest) ----
-                have_result = false;
-                for (;;) {
-                    if (sp == 0) { done = true; ret = result; break; }
-                    --sp;
-                    const uint32_t fnode = st.node[sp];
-                    if (fnode == NTR_FRAME_AFTER_FAR) { result = true; continue; }
-                    const float t = st.t[sp];
-                    if (result && oh.dist <= t) continue;
-                    node = fnode;
-                    t_near = t;
-                    t_far = st.t_far[sp];
-                    if (result) { st.node[sp] = NTR_FRAME_AFTER_FAR; ++sp; }
-                    break;
-                }
-            }
-            if (!done) {                                            // ---- descend ----
-                result = false;
-                while (node != NTR_NULL_NODE) {
-                    const uint4 n = ldnode(s.nodes + node);
-                    if (n.x & NTR_LEAF_FLAG) {
-                        if (n.z >= NTR_COOP_LEAF_MIN) { pending = true; pend_first = n.y; pend_size = n.z; }
-                        else result = leaf_opaque<DT, FLAGS>(s, n, o, dir, rs, skip, oh, mm, cnt);
-                        break;
-                    }
-                    if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
-                    const int axis = (int)n.x;
-                    const float split = u2f(n.y);
-                    const float da = vsel<DT>(dir, axis), oa = vsel<DT>(o, axis);
-                    if (da != 0) {
-                        if (oa == split) { node = da > 0 ? n.w : n.z; continue; }
-                        const float t = (split - oa) * vsel<DT>(invdir, axis);
-                        const uint32_t n_near = oa > split ? n.w : n.z;
-                        const uint32_t n_far = oa > split ? n.z : n.w;
-                        if (t < 0 || t > t_far) { node = n_near; continue; }
-                        if (t < t_near) { node = n_far; continue; }
-                        if (n_near != NTR_NULL_NODE) {
-                            if (n_far == NTR_NULL_NODE) { node = n_near; t_far = t; continue; }
-                            if (sp < NTR_STACK_CAP) { st.node[sp] = n_far; st.t[sp] = t; st.t_far[sp] = t_far; ++sp; }
-                            node = n_near;
-                            t_far = t;
-                            continue;
-                        }
-                        node = n_far;
-                        t_near = t;
-                        continue;
-                    }
-                    node = oa >= split ? n.w : n.z;
-                }
-                if (!pending) have_result = true;
-            }
-        }
-        // ---- warp-synchronous part: serve the lanes that wait at a big leaf, one ray at a time ----
-        unsigned pm = __ballot_sync(FULL, pending);
-        if (!pm) {
-            if (__all_sync(FULL, done)) break;
-            continue;
-        }
-        if (__popc(pm) > NTR_COOP_MAX_LANES) {
-            // most of the warp sits at big leaves (coherent rays, typically the same leaf): the plain per-lane scan is
-            // the better schedule then -- every lane reads the same items (broadcast loads) and its own cutoff shrinks
-            // as it goes
-            if (pending) {
-                const uint4 n = make_uint4(NTR_LEAF_FLAG, pend_first, pend_size, 0u);
-                result = leaf_opaque<DT, FLAGS>(s, n, o, dir, rs, skip, oh, mm, cnt);
-                pending = false;
-                have_result = true;
-            }
-            continue;
-        }
-        while (pm) {
-            const int src = __ffs(pm) - 1;
-            pm &= pm - 1;
-            float bo[DimCap<DT>::value], bd[DimCap<DT>::value];
-    NTR_UNROLL
-            for (int i = 0; i < D; ++i) { bo[i] = __shfl_sync(FULL, o[i], src); bd[i] = __shfl_sync(FULL, dir[i], src); }
-            const uint32_t first = __shfl_sync(FULL, pend_first, src), size = __shfl_sync(FULL, pend_size, src);
-            const float cutoff = __shfl_sync(FULL, oh.dist, src);
-            const uint32_t sk_ref = __shfl_sync(FULL, skip.ref, src);
-            const int sk_lane = __shfl_sync(FULL, skip.lane, src);
-            const uint2 *items = s.leaf_items + first;
-            float best_t = cutoff;
-            uint32_t best_k = 0xFFFFFFFFu, best_ref = NTR_NONE_REF;
-            int best_lane = -1;
-            for (uint32_t k = lane; k < size; k += 32) {
-                const uint2 it = lditem(items + k);
-                uint32_t meta;
-                if ((it.x >> 30) == NTR_REF_BATCH) {
-                    int index = sk_ref == it.x ? sk_lane : -1;
-                    const float dist = batch_test<DT, FLAGS>(s, it.y, bo, bd, index, best_t, meta, cnt);
-                    if (dist) { best_t = dist; best_k = k; best_ref = it.x; best_lane = index; }
-                } else if (it.x != sk_ref) {
-                    if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
-                    const float dist = simplex_single<DT>(s, it.y, bo, bd, best_t, meta);
-                    if (dist) { best_t = dist; best_k = k; best_ref = it.x; best_lane = -1; }
-                }
-            }
-            // lexicographic minimum of (t, item index) over the warp
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const float ot = __shfl_xor_sync(FULL, best_t, off);
-                const uint32_t ok = __shfl_xor_sync(FULL, best_k, off), orf = __shfl_xor_sync(FULL, best_ref, off);
-                const int ol = __shfl_xor_sync(FULL, best_lane, off);
-                if (ok != 0xFFFFFFFFu && (best_k == 0xFFFFFFFFu || ot < best_t || (ot == best_t && ok < best_k))) {
-                    best_t = ot; best_k = ok; best_ref = orf; best_lane = ol;
-                }
-            }
-            if (lane == src) {
-                pending = false;
-                have_result = true;
-                result = best_k != 0xFFFFFFFFu;
-                if (result) { oh.dist = best_t; oh.ref = best_ref; oh.lane = best_lane; }
-            }
-        }
-    }
-    return ret;
-}
-#endif
-
-// ---- warp-cooperative traversal, general variant (device only; NOT yet run on a GPU) ------------------------------
-// The state machine of trace_nearest_coop with the general variant's frames, where a big leaf of ONE ray is
-// evaluated by the whole warp: the owner's ray is broadcast, lane j tests item base+j of every 32-item chunk against
-// the owner's cutoff at the start of the chunk, and the owner replays the results in leaf order (replay_item: the
-// logic proven bit-identical to the sequential scan in the host emulation, tests/test_fuzz_emul.py).  Lanes never
-// consult the owner's mailbox: an item the owner would skip is evaluated for nothing and dropped by the replay.
-// Written at the end of round 1 without GPU time left: it compiles (-DNTR_COOP_LEAVES=1) and is otherwise untested.
-#if NTR_WARP_CODE && NTR_COOP_LEAVES
-template <int DT, int FLAGS>
-__device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, uint32_t first, uint32_t size, const float *o,
-                                                  const float *dir, Skip skip, HitRec &oh, GenState<DT> &g, Counters &cnt) {
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    const int D = NTR_D(DT, s);
-    const int lane = threadIdx.x & 31;
-    float bo[DimCap<DT>::value], bd[DimCap<DT>::value];
-    NTR_UNROLL
-    for (int i = 0; i < D; ++i) { bo[i] = __shfl_sync(FULL, o[i], src); bd[i] = __shfl_sync(FULL, dir[i], src); }
-    Skip bskip;
-    bskip.ref = __shfl_sync(FULL, skip.ref, src);
-    bskip.lane = __shfl_sync(FULL, skip.lane, src);
-    const uint2 *items = s.leaf_items + first;
-    const int h_start = g.th.n;             // meaningful on the owner only
-    float dist = 0;
-    bool phase1 = false;
-    for (uint32_t base = 0; base < size; base += 32) {
-        const uint32_t n = size - base < 32u ? size - base : 32u;
-        const float cutoff0 = __shfl_sync(FULL, oh.dist, src);
-        ChunkEval<DT> e;
-        e.dist = 0; e.wmask = 0; e.meta = 0; e.lane = -1; e.skipped = false;
-    NTR_UNROLL
-        for (int i = 0; i < D; ++i) { e.P[i] = 0; e.N[i] = 0; }
-        if ((uint32_t)lane < n) {
-            const uint2 it = lditem(items + base + lane);
-            // the primitive the ray leaves from is skipped by identity, never evaluated
-            if (!(((it.x >> 30) != NTR_REF_BATCH) && it.x == bskip.ref))
-                e.dist = prim_test_general<DT, FLAGS>(s, it, bo, bd, cutoff0, bskip, e.lane, e.P, e.N, e.wmask, e.meta, cnt);
-        }
-        unsigned m = __ballot_sync(FULL, e.dist != 0 || e.wmask != 0);
-        uint32_t prev = 0;
-        for (;;) {
-            const uint32_t j = m ? (uint32_t)(__ffs(m) - 1) : n;
-            if (lane == src) {              // plain misses up to the next interesting item: the owner replays them alone
-                ChunkEval<DT> miss;
-                miss.dist = 0; miss.wmask = 0; miss.meta = 0; miss.lane = -1; miss.skipped = false;
-                for (uint32_t k = prev; k < j; ++k)
-                    replay_item<DT, FLAGS>(s, lditem(items + base + k), o, dir, skip, oh, g, cnt, phase1, dist, miss);
-            }
-            if (j >= n) break;
-            ChunkEval<DT> r;
-            r.dist = __shfl_sync(FULL, e.dist, j); r.lane = __shfl_sync(FULL, e.lane, j);
-            r.wmask = __shfl_sync(FULL, e.wmask, j); r.meta = __shfl_sync(FULL, e.meta, j);
-            r.skipped = false;
-    NTR_UNROLL
-            for (int i = 0; i < D; ++i) { r.P[i] = __shfl_sync(FULL, e.P[i], j); r.N[i] = __shfl_sync(FULL, e.N[i], j); }
-            if (lane == src) replay_item<DT, FLAGS>(s, lditem(items + base + j), o, dir, skip, oh, g, cnt, phase1, dist, r);
-            prev = j + 1;
-            m &= m - 1;
-        }
-    }
-    if (lane != src || !phase1) return false;
-    g.th.trim(dist, h_start);
-    return true;
-}
-
-template <int DT, int FLAGS>
-__device__ __forceinline__ bool trace_nearest_coop_general(const SceneDev &s, bool enabled, const float *o, const float *dir,
-                                                           Skip skip, float t_near, float t_far, HitRec &oh,
-                                                           GenState<DT> &g, Counters &cnt) {
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    const int lane = threadIdx.x & 31;
-    RaySlab<DT> rs;
-    rs.init(s, dir);
-    const float *invdir = rs.invdir;
-    TravStack st;
-    int sp = 0;
-    uint32_t node = s.root;
-    g.mb.clear();
-    bool done = !enabled, pending = false, have_result = false, result = false, ret = false;
-    uint32_t pend_first = 0, pend_size = 0, pend_batches = 0;
-    for (;;) {
-        if (!done) {
-            if (have_result) {                                      // ---- unwind (see trace_nearest) ----
-                have_result = false;
-                for (;;) {
-                    if (sp == 0) { done = true; ret = result; break; }
-                    --sp;
-                    const uint32_t fnode = st.node[sp];
-                    if (fnode == NTR_FRAME_AFTER_FAR) {
-                        if (result) g.th.trim(oh.dist, st.h_start[sp]);
-                        result = true;
-                        continue;
-                    }
-                    const float t = st.t[sp];
-                    if (result && oh.dist <= t) continue;
-                    node = fnode;
-                    t_near = t;
-                    t_far = st.t_far[sp];
-                    if (result) { st.node[sp] = NTR_FRAME_AFTER_FAR; ++sp; }
-                    break;
-                }
-            }
-            if (!done) {                                            // ---- descend ----
-                result = false;
-                while (node != NTR_NULL_NODE) {
-                    const uint4 n = ldnode(s.nodes + node);
-                    if (n.x & NTR_LEAF_FLAG) {
-                        if (n.z >= NTR_COOP_LEAF_MIN) { pending = true; pend_first = n.y; pend_size = n.z; pend_batches = n.x; }
-                        else result = leaf_general<DT, FLAGS>(s, n, o, dir, rs, skip, oh, g, cnt);
-                        break;
-                    }
-                    if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
-                    const int axis = (int)n.x;
-                    const float split = u2f(n.y);
-                    const float da = vsel<DT>(dir, axis), oa = vsel<DT>(o, axis);
-                    if (da != 0) {
-                        if (oa == split) { node = da > 0 ? n.w : n.z; continue; }
-                        const float t = (split - oa) * vsel<DT>(invdir, axis);
-                        const uint32_t n_near = oa > split ? n.w : n.z;
-                        const uint32_t n_far = oa > split ? n.z : n.w;
-                        if (t < 0 || t > t_far) { node = n_near; continue; }
-                        if (t < t_near) { node = n_far; continue; }
-                        if (n_near != NTR_NULL_NODE) {
-                            if (n_far == NTR_NULL_NODE) { node = n_near; t_far = t; continue; }
-                            if (sp < NTR_STACK_CAP) {
-                                st.node[sp] = n_far; st.t[sp] = t; st.t_far[sp] = t_far;
-                                st.h_start[sp] = (unsigned char)g.th.n;
-                                ++sp;
-                            }
-                            node = n_near;
-                            t_far = t;
-                            continue;
-                        }
-                        node = n_far;
-                        t_near = t;
-                        continue;
-                    }
-                    node = oa >= split ? n.w : n.z;
-                }
-                if (!pending) have_result = true;
-            }
-        }
-        // ---- warp-synchronous part: big leaves, one ray at a time, all lanes on its items ----
-        unsigned pm = __ballot_sync(FULL, pending);
-        if (!pm) {
-            if (__all_sync(FULL, done)) break;
-            continue;
-        }
-        if (__popc(pm) > NTR_COOP_MAX_LANES) {
-            // most of the warp waits at big leaves (coherent rays): every lane scans its own leaf, as without cooperation
-            if (pending) {
-                const uint4 n = make_uint4(pend_batches, pend_first, pend_size, 0u);
-                result = leaf_general<DT, FLAGS>(s, n, o, dir, rs, skip, oh, g, cnt);
-                pending = false;
-                have_result = true;
-            }
-            continue;
-        }
-        while (pm) {
-            const int src = __ffs(pm) - 1;
-            pm &= pm - 1;
-            const uint32_t first = __shfl_sync(FULL, pend_first, src), size = __shfl_sync(FULL, pend_size, src);
-            const bool r = coop_leaf_general<DT, FLAGS>(s, src, first, size, o, dir, skip, oh, g, cnt);
-            if (lane == src) { pending = false; have_result = true; result = r; }
-        }
-    }
-    return ret;
-}
-#endif
 
 // ---- occlusion (shadow) traversal ------------------------------------------------------------------------
 // kd_leaf::occludes (tracer.hpp:1088-1124): any opaque hit nearer than the light blocks; transparent
@@ -1641,85 +1354,97 @@ template <int DT> struct Bounce {
     int depth;
 };
 
-// composite_scene::base_color (tracer.hpp:1768-1854) for one hit (P, N) of primitive (ref, lane), with the
-// result multiplied by `w` and added to `acc`.  Returns true and fills `b` when a reflection ray follows.
-template <int DT, int FLAGS>
-NTR_HD bool shade_hit(const SceneDev &s, const float *view, const float *P, const float *N, uint32_t ref, int lane,
-                      int depth, const float *w, float *acc, Bounce<DT> &b, Counters &cnt) {
+// composite_scene::base_color (tracer.hpp:1768-1854) in three pieces, so that the per-lane version below (shade_hit) and
+// the warp-synchronous one (trace_warp.cuh: shadow rays of a whole warp traced together) share every line of arithmetic:
+//   light_prepare   geometry of one light at the hit: direction, distance, sine, strength; says whether the light
+//                   contributes at all and whether a shadow ray decides it
+//   light_apply     adds the light (after light_reaches filtered its colour) and its Blinn-Phong term, in light order
+//   shade_finish    camera light, ambient + diffuse, the deferred reflection ray, accumulation into `acc`
+template <int DT> struct LightSample {
+    float lv[DimCap<DT>::value];
+    float dist, sine, strength;
+    float lc[3];
+    bool is_point;
+};
+struct ShadeAcc { float light[3], spec[3], spec_a; };
+enum : int { NTR_LIGHT_NONE = 0, NTR_LIGHT_DIRECT = 1, NTR_LIGHT_SHADOWED = 2 };
+
+template <int DT>
+NTR_HD int light_prepare(const SceneDev &s, int li, const float *P, const float *N, LightSample<DT> &ls) {
     const int D = NTR_D(DT, s);
-    const Mat m = load_mat(s, target_meta<DT>(s, ref, lane));
-    const Skip source = {ref, lane};
-    float light[3] = {0, 0, 0}, spec[3] = {0, 0, 0};
-    float spec_a = 0;
-    cnt.shaded_hits++;
-
-    // point lights first, then global lights (tracer.hpp:1776-1827), as ONE loop so that the shadow traversal
-    // (light_reaches) is instantiated once
-    const int n_lights = s.n_point + s.n_global;
-    for (int li = 0; li < n_lights; ++li) {
-        const bool is_point = li < s.n_point;
-        const float *L = is_point ? s.point_lights + (size_t)li * (D + 3) : s.global_lights + (size_t)(li - s.n_point) * (D + 3);
-        const float lc[3] = {ldf(L + D), ldf(L + D + 1), ldf(L + D + 2)};
-        float lv[DimCap<DT>::value];
-        float dist = FLT_MAX, sine = 0, strength = 1.0f;
-        if (is_point) {
-            float sq = 0;
+    ls.is_point = li < s.n_point;
+    const float *L = ls.is_point ? s.point_lights + (size_t)li * (D + 3) : s.global_lights + (size_t)(li - s.n_point) * (D + 3);
+    ls.lc[0] = ldf(L + D); ls.lc[1] = ldf(L + D + 1); ls.lc[2] = ldf(L + D + 2);
+    ls.dist = FLT_MAX; ls.sine = 0; ls.strength = 1.0f;
+    if (ls.is_point) {
+        float sq = 0;
     NTR_UNROLL
-            for (int i = 0; i < D; ++i) { lv[i] = P[i] - ldf(L + i); sq += lv[i] * lv[i]; }
-            dist = sqrtf(sq);
+        for (int i = 0; i < D; ++i) { ls.lv[i] = P[i] - ldf(L + i); sq += ls.lv[i] * ls.lv[i]; }
+        ls.dist = sqrtf(sq);
     NTR_UNROLL
-            for (int i = 0; i < D; ++i) { lv[i] /= dist; sine += N[i] * lv[i]; }
-        } else {
+        for (int i = 0; i < D; ++i) { ls.lv[i] /= ls.dist; ls.sine += N[i] * ls.lv[i]; }
+    } else {
     NTR_UNROLL
-            for (int i = 0; i < D; ++i) { lv[i] = -ldf(L + i); sine += N[i] * lv[i]; }
-        }
-        if (!(sine > 0)) continue;
-        if (is_point) strength = light_strength(dist, D);
-        if (s.shadows) {
-            // LIGHT_THRESHOLD applies to point lights only, and drops the light entirely (tracer.hpp:1784-1803)
-            if (is_point && !(fmaxf(lc[0], fmaxf(lc[1], lc[2])) * strength * sine > NTR_LIGHT_THRESHOLD)) continue;
-            float filtered[3] = {lc[0], lc[1], lc[2]};
-            if (!light_reaches<DT, FLAGS>(s, P, lv, dist, source, filtered, cnt)) continue;
-            if (is_point) { filtered[0] *= strength; filtered[1] *= strength; filtered[2] *= strength; }
-    NTR_UNROLL
-            for (int c = 0; c < 3; ++c) light[c] += filtered[c] * sine;
-            if (m.spec_int != 0) append_specular<DT>(s, spec, spec_a, m, filtered, view, N, lv);
-        } else if (is_point) {
-    NTR_UNROLL
-            for (int c = 0; c < 3; ++c) light[c] += lc[c] * strength * sine;
-        } else {
-    NTR_UNROLL
-            for (int c = 0; c < 3; ++c) light[c] += lc[c] * sine;
-        }
+        for (int i = 0; i < D; ++i) { ls.lv[i] = -ldf(L + i); ls.sine += N[i] * ls.lv[i]; }
     }
+    if (!(ls.sine > 0)) return NTR_LIGHT_NONE;
+    if (ls.is_point) ls.strength = light_strength(ls.dist, D);
+    if (!s.shadows) return NTR_LIGHT_DIRECT;
+    // LIGHT_THRESHOLD applies to point lights only, and drops the light entirely (tracer.hpp:1784-1803)
+    if (ls.is_point && !(fmaxf(ls.lc[0], fmaxf(ls.lc[1], ls.lc[2])) * ls.strength * ls.sine > NTR_LIGHT_THRESHOLD)) return NTR_LIGHT_NONE;
+    return NTR_LIGHT_SHADOWED;
+}
 
+// `filtered` = the light's colour as light_reaches left it (NTR_LIGHT_SHADOWED only)
+template <int DT>
+NTR_HD void light_apply(const SceneDev &s, int kind, const LightSample<DT> &ls, float *filtered, const Mat &m,
+                        const float *view, const float *N, ShadeAcc &a) {
+    if (kind == NTR_LIGHT_SHADOWED) {
+        if (ls.is_point) { filtered[0] *= ls.strength; filtered[1] *= ls.strength; filtered[2] *= ls.strength; }
+    NTR_UNROLL
+        for (int c = 0; c < 3; ++c) a.light[c] += filtered[c] * ls.sine;
+        if (m.spec_int != 0) append_specular<DT>(s, a.spec, a.spec_a, m, filtered, view, N, ls.lv);
+    } else if (ls.is_point) {
+    NTR_UNROLL
+        for (int c = 0; c < 3; ++c) a.light[c] += ls.lc[c] * ls.strength * ls.sine;
+    } else {
+    NTR_UNROLL
+        for (int c = 0; c < 3; ++c) a.light[c] += ls.lc[c] * ls.sine;
+    }
+}
+
+// Returns true and fills `b` when a reflection ray follows.
+template <int DT>
+NTR_HD bool shade_finish(const SceneDev &s, const Mat &m, const float *view, const float *P, const float *N, Skip source,
+                         int depth, const float *w, float *acc, ShadeAcc &a, Bounce<DT> &b, Counters &cnt) {
+    const int D = NTR_D(DT, s);
     float sine = 0;
     NTR_UNROLL
     for (int i = 0; i < D; ++i) sine += view[i] * N[i];
     sine = -sine;
     if (s.camera_light && sine > 0) {
     NTR_UNROLL
-        for (int c = 0; c < 3; ++c) light[c] += sine;
+        for (int c = 0; c < 3; ++c) a.light[c] += sine;
         if (m.spec_int != 0) {
             const float base = powf(sine, m.spec_exp) * m.spec_int;
-            const float k = base * (1 - spec_a);
+            const float k = base * (1 - a.spec_a);
     NTR_UNROLL
-            for (int c = 0; c < 3; ++c) spec[c] += m.spec[c] * k;
-            spec_a += k;
+            for (int c = 0; c < 3; ++c) a.spec[c] += m.spec[c] * k;
+            a.spec_a += k;
     NTR_UNROLL
-            for (int c = 0; c < 3; ++c) spec[c] *= spec_a;
+            for (int c = 0; c < 3; ++c) a.spec[c] *= a.spec_a;
         }
     }
 
     const bool reflect = m.reflectivity != 0 && depth < s.max_depth;
-    const float keep = (reflect ? (1 - m.reflectivity) : 1.0f) * (1 - spec_a);
+    const float keep = (reflect ? (1 - m.reflectivity) : 1.0f) * (1 - a.spec_a);
     NTR_UNROLL
     for (int c = 0; c < 3; ++c) {
-        const float local = s.ambient[c] + m.c[c] * light[c];
-        acc[c] += w[c] * (spec[c] + local * keep);
+        const float local = s.ambient[c] + m.c[c] * a.light[c];
+        acc[c] += w[c] * (a.spec[c] + local * keep);
     }
     if (reflect) {
-        const float k = m.reflectivity * (1 - spec_a);
+        const float k = m.reflectivity * (1 - a.spec_a);
     NTR_UNROLL
         for (int i = 0; i < D; ++i) { b.o[i] = P[i]; b.d[i] = view[i] - N[i] * (-2 * sine); }
     NTR_UNROLL
@@ -1729,6 +1454,28 @@ NTR_HD bool shade_hit(const SceneDev &s, const float *view, const float *P, cons
         cnt.reflection_rays++;
     }
     return reflect;
+}
+
+// base_color for one hit (P, N) of primitive (ref, lane), with the result multiplied by `w` and added to `acc`.
+template <int DT, int FLAGS>
+NTR_HD bool shade_hit(const SceneDev &s, const float *view, const float *P, const float *N, uint32_t ref, int lane,
+                      int depth, const float *w, float *acc, Bounce<DT> &b, Counters &cnt) {
+    const Mat m = load_mat(s, target_meta<DT>(s, ref, lane));
+    const Skip source = {ref, lane};
+    ShadeAcc a = {{0, 0, 0}, {0, 0, 0}, 0};
+    cnt.shaded_hits++;
+    // point lights first, then global lights (tracer.hpp:1776-1827), as ONE loop so that the shadow traversal
+    // (light_reaches) is instantiated once
+    const int n_lights = s.n_point + s.n_global;
+    for (int li = 0; li < n_lights; ++li) {
+        LightSample<DT> ls;
+        const int kind = light_prepare<DT>(s, li, P, N, ls);
+        if (kind == NTR_LIGHT_NONE) continue;
+        float filtered[3] = {ls.lc[0], ls.lc[1], ls.lc[2]};
+        if (kind == NTR_LIGHT_SHADOWED && !light_reaches<DT, FLAGS>(s, P, ls.lv, ls.dist, source, filtered, cnt)) continue;
+        light_apply<DT>(s, kind, ls, filtered, m, view, N, a);
+    }
+    return shade_finish<DT>(s, m, view, P, N, source, depth, w, acc, a, b, cnt);
 }
 
 // composite_scene::aabb_distance (tracer.hpp:1892-1918)
@@ -1776,8 +1523,7 @@ NTR_HD void hit_geometry(const SceneDev &s, uint32_t ref, int lane, float dist, 
 // EMIT(const Bounce<DT>&) receives the deferred reflection rays.
 template <int DT, int FLAGS, typename EMIT>
 NTR_HD void ray_color(const SceneDev &s, bool enabled, const float *o, const float *dir, int depth, Skip source,
-                      const float *weight, float *acc, EMIT &emit, Counters &cnt, HitRec *primary_out,
-                      bool coop = true /* warp-uniform; only read with NTR_COOP_LEAVES */) {
+                      const float *weight, float *acc, EMIT &emit, Counters &cnt, HitRec *primary_out) {
     const int D = NTR_D(DT, s);
     GenState<DT> g;
     HitRec oh;
@@ -1787,19 +1533,8 @@ NTR_HD void ray_color(const SceneDev &s, bool enabled, const float *o, const flo
     NTR_UNROLL
         for (int i = 0; i < D; ++i) { g.hitP[i] = 0; g.hitN[i] = 0; }
     }
-    // `enabled` = this lane has a ray.  (With NTR_COOP_LEAVES all 32 lanes of a warp enter so that big leaves can be
-    // evaluated cooperatively; everything after the traversal is per lane again.)
     const float t0 = enabled ? aabb_distance<DT>(s, o, dir) : -1.0f;
-#if NTR_WARP_CODE && NTR_COOP_LEAVES
-    // `coop` is the same for all 32 lanes: the cooperative traversals (every lane takes part, with or without a ray) or
-    // the plain per-lane one -- kernels.cuh switches to cooperation for the tail of a pass only (NTR_COOP_TAIL_ONLY)
-    bool hit;
-    if (!coop) hit = t0 >= 0 && trace_nearest<DT, FLAGS>(s, o, dir, source, t0, FLT_MAX, oh, &g, cnt);
-    else if (FLAGS & NTR_F_GENERAL) hit = trace_nearest_coop_general<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, g, cnt);
-    else hit = trace_nearest_coop<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, cnt);
-#else
     const bool hit = t0 >= 0 && trace_nearest<DT, FLAGS>(s, o, dir, source, t0, FLT_MAX, oh, &g, cnt);
-#endif
     if (!enabled) return;
     if (primary_out) { *primary_out = oh; if (!hit) { primary_out->ref = NTR_NONE_REF; primary_out->dist = 0; } }
 

@@ -12,9 +12,10 @@
 #include <algorithm>
 #include <vector>
 
-// -DNTR_EMULATE_WARP (with -DNTR_COOP_LEAVES=1 -pthread): the warp-synchronous parts of trace_core.cuh (cooperative
-// leaf scans: __shfl_sync / __ballot_sync / __all_sync between the 32 lanes of a warp) run on the host too, each lane
-// as an OS thread and every warp intrinsic as a rendezvous of the 32 threads.  Lanes of a correct kernel execute the
+// -DNTR_EMULATE_WARP (with -pthread): the warp-synchronous form of the per-ray path (trace_warp.cuh: cooperative leaf
+// scans, shadow rays of a warp traced together; __shfl_sync / __ballot_sync / __any_sync / __reduce_*_sync between the
+// 32 lanes of a warp) runs on the host too, each lane as an OS thread and every warp intrinsic as a rendezvous of the
+// 32 threads.  Lanes of a correct kernel execute the
 // same sequence of warp intrinsics, so a barrier per intrinsic reproduces the data exchange exactly; a divergent
 // sequence shows up as a hang or a wrong image.
 #ifdef NTR_EMULATE_WARP
@@ -55,6 +56,18 @@ inline unsigned __ballot_sync(unsigned, bool p) {
     return m;
 }
 inline bool __all_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) == 0xFFFFFFFFu; }
+inline bool __any_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) != 0u; }
+template <typename F> inline unsigned warp_reduce_u32(unsigned v, F f) {
+    warp_emu::warp->slot[warp_emu::lane] = v;
+    pthread_barrier_wait(&warp_emu::warp->bar);
+    unsigned r = warp_emu::warp->slot[0];
+    for (int i = 1; i < 32; ++i) r = f(r, warp_emu::warp->slot[i]);
+    pthread_barrier_wait(&warp_emu::warp->bar);
+    return r;
+}
+inline unsigned __reduce_min_sync(unsigned, unsigned v) { return warp_reduce_u32(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
+inline unsigned __reduce_max_sync(unsigned, unsigned v) { return warp_reduce_u32(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
+inline unsigned __reduce_add_sync(unsigned, unsigned v) { return warp_reduce_u32(v, [](unsigned a, unsigned b) { return a + b; }); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 #define __device__
@@ -65,6 +78,9 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 
 #include "../../ntracer_b200/csrc/arena_pack.h"
 #include "../../ntracer_b200/csrc/trace_core.cuh"
+#ifdef NTR_EMULATE_WARP
+#include "../../ntracer_b200/csrc/trace_warp.cuh"
+#endif
 
 using namespace ntr;
 
@@ -217,11 +233,7 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
                         }
                     }
                     LaneEmit<DT> emit{&out[L], &outpix[L], idx, pix};
-#ifndef NTR_EMUL_COOP_EVERY
-#define NTR_EMUL_COOP_EVERY 1       // groups g with g % NTR_EMUL_COOP_EVERY == 0 use the cooperative traversal (1 = all)
-#endif
-                    const bool coop = (base / 32) % NTR_EMUL_COOP_EVERY == 0;       // the same for the 32 lanes of a group
-                    ray_color<DT, FLAGS>(S.dev, enabled, o, dir, depth, skip, primary ? one : wgt, acc, emit, cnts[L], primary ? &prim : nullptr, coop);
+                    ray_color_warp<DT, FLAGS>(S.dev, enabled, o, dir, depth, skip, primary ? one : wgt, acc, emit, cnts[L], primary ? &prim : nullptr);
                     if (!enabled) continue;
                     if (primary) {
                         if (rgb) { rgb[(size_t)pix * 3] = acc[0]; rgb[(size_t)pix * 3 + 1] = acc[1]; rgb[(size_t)pix * 3 + 2] = acc[2]; }

@@ -107,28 +107,33 @@ def test_chunked_leaf_scan_is_bit_identical_to_the_sequential_one(tmp_path):
         el._lib = base
 
 
-def test_warp_cooperative_traversal_on_an_emulated_warp(tmp_path):
-    """-DNTR_COOP_LEAVES=1: the warp-cooperative traversals (trace_nearest_coop for the opaque variant,
-    trace_nearest_coop_general + coop_leaf_general for the general one) have never run on a GPU.  Here they run on an
-    emulated warp -- 32 host threads, every __shfl_sync / __ballot_sync / __all_sync a rendezvous of the 32
-    (tests/host_emul/emul.cpp, -DNTR_EMULATE_WARP) -- with cooperation forced onto almost every leaf (leaf minimum 4
-    items, up to 31 waiting lanes), and must reproduce the sequential emulation bit for bit.  A lane sequence that
-    diverged between warp intrinsics would hang here (the test is under a timeout) or change the image."""
+def test_warp_synchronous_path_on_an_emulated_warp(tmp_path):
+    """trace_warp.cuh is what the render kernels run: the 32 rays of a warp traced together, big leaves split over the
+    lanes (coop_leaf_opaque / coop_leaf_general / coop_leaf_occludes), shadow rays of a warp in one occlusion traversal.
+    Here it runs on an emulated warp -- 32 host threads, every __shfl_sync / __ballot_sync / __any_sync /
+    __reduce_*_sync a rendezvous of the 32 (tests/host_emul/emul.cpp, -DNTR_EMULATE_WARP) -- once with cooperation
+    forced onto almost every leaf (leaf minimum 4 items, no overhead term in the cost model) and once with the shipped
+    thresholds, and must reproduce the per-ray form (trace_core.cuh, itself checked against the oracle) bit for bit:
+    images and ray counters.  A lane sequence that diverged between warp intrinsics would hang here (the test is under
+    a timeout) or change the image.  (The wider sweep -- 200 random scenes at 24x14, the 1,600-item leaves of
+    {5/2,3,3} at 48x27 -- was run once with the same result)"""
     import ctypes as C
     import os
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
-    so = str(tmp_path / 'libhostemul_warp.so')
-    subprocess.run(['/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++', '-std=c++17', '-O0', '-fPIC', '-shared',
-                    '-fvisibility=hidden', '-I/usr/local/cuda/include', '-Wno-unknown-pragmas', '-pthread',
-                    '-DNTR_EMULATE_WARP', '-DNTR_COOP_LEAVES=1', '-DNTR_COOP_LEAF_MIN=4', '-DNTR_COOP_MAX_LANES=31',
-                    '-DNTR_EMUL_COOP_EVERY=2',      # every other warp cooperates, the others trace per lane (tail-only switch)
-                    '-o', so, os.path.join(here, 'host_emul', 'emul.cpp')], check=True)
-    base, warp = el.lib(), C.CDLL(so)
-    # small frames: 32 threads meeting at a barrier for every warp intrinsic are slow on a few cores (the wider sweep --
-    # 200 random scenes, bigger frames, the 1,606-item leaves of {5/2,3,3} -- was run once, DESIGN.md section 8)
-    cases = [(fx.fuzz_scene(3 + seed % 5, seed), 16, 10) for seed in (1, 2, 3, 7)]
-    for name, v, w, h in (('mixed3', None, 16, 10), ('ssc120', 'refl_transp', 8, 6), ('ssc120', 'refl', 8, 6)):
+    gxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+    libs = []
+    for name, flags in (('forced', ['-DNTR_COOP_LEAF_MIN=4', '-DNTR_COOP_OVERHEAD=0']), ('shipped', [])):
+        so = str(tmp_path / ('libhostemul_warp_%s.so' % name))
+        subprocess.run([gxx, '-std=c++17', '-O1', '-fPIC', '-shared', '-fvisibility=hidden', '-I/usr/local/cuda/include',
+                        '-Wno-unknown-pragmas', '-pthread', '-DNTR_EMULATE_WARP'] + flags +
+                       ['-o', so, os.path.join(here, 'host_emul', 'emul.cpp')], check=True)
+        libs.append(C.CDLL(so))
+    base = el.lib()
+    cases = [(fx.fuzz_scene(3 + seed % 5, seed), 16, 10) for seed in range(16)]
+    cases += [(fx.batched_soup(5, 60), 16, 10), (fx.batched_soup(10, 40), 12, 8)]      # opaque: batches + singles, reflective
+    for name, v, w, h in (('mixed3', None, 24, 18), ('ssc120', 'refl_transp', 16, 9), ('ggs120', 'refl_transp', 24, 14),
+                          ('ggs120', 'refl', 16, 9), ('cell120', 'shadows', 16, 9), ('solids6', None, 16, 9)):
         sc, g = fx.load(name)
         cases.append((fx.variant(sc, g, v) if v else sc, w, h))
     general = opaque = 0
@@ -136,14 +141,15 @@ def test_warp_cooperative_traversal_on_an_emulated_warp(tmp_path):
         for sc, w, h in cases:
             el._lib = base
             a, ca = el.render(sc, w, h)
-            el._lib = warp
-            b, cb = el.render(sc, w, h)
-            assert np.array_equal(a, b)
-            for k in ('reflection_rays', 'shadow_rays', 'shaded_hits', 'node_steps'):
-                assert ca[k] == cb[k], k
+            for lib in libs:
+                el._lib = lib
+                b, cb = el.render(sc, w, h)
+                assert np.array_equal(a, b)
+                for k in ('reflection_rays', 'shadow_rays', 'shaded_hits', 'node_steps'):
+                    assert ca[k] == cb[k], k
             is_general = bool(np.any(sc['materials'][:, 6] < 1)) or len(sc['solids']) > 0
             general += is_general
             opaque += not is_general
     finally:
         el._lib = base
-    assert general >= 3 and opaque >= 1
+    assert general >= 10 and opaque >= 3
