@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
 #include <string>
 #include <vector>
@@ -51,8 +52,8 @@ enum { CTL_TILE_CURSOR = 0, CTL_OVERFLOW = 1, CTL_COUNT0 = 2, CTL_CURSOR0 = CTL_
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 __global__ void pack_kernel(const __grid_constant__ FrameDev f);
-__global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, int D, const __grid_constant__ SceneDev s,
-                                uint32_t *keys, uint32_t *idx, int heavy_first);
+__global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, const uint32_t *count, uint32_t capacity, int D,
+                                const __grid_constant__ SceneDev s, uint32_t *keys, uint32_t *idx, int heavy_first);
 
 }  // namespace
 
@@ -86,8 +87,12 @@ struct ntr_scene {
     int tree_depth = 0;
     uint32_t *d_ctl = nullptr;
     unsigned long long *d_counters = nullptr;
-    int *h_abort = nullptr;             // mapped pinned
+    // abort words (mapped pinned): [0] = the synchronous entry points and asynchronous ntr_render_device frames,
+    // [1 + k] = frame slot k of ntr_render_begin / ntr_render_end.  One word per open frame: an abort hits exactly
+    // the frames that were open when it came, and a frame begun afterwards starts clean.
+    int *h_abort = nullptr;
     int *d_abort = nullptr;
+    int abort_idx = 0;                  // word the frame being enqueued polls
     float *d_accum = nullptr; size_t accum_cap = 0;
     unsigned char *d_packed = nullptr; size_t packed_cap = 0;
     int32_t *d_ids = nullptr; float *d_dists = nullptr; size_t ids_cap = 0;
@@ -107,6 +112,10 @@ struct ntr_scene {
     // ntr_render of single-pass frames into pinned memory: the frame is cut into slabs of tile rows, one persistent
     // kernel + copy per slab on its own stream, so that all but the last slab cross PCIe underneath the tracing
     int ctl_slot = 0;
+    // the last frame enqueued with each control block: a frame on ANOTHER stream waits for it before it resets the block
+    // (asynchronous ntr_render_device frames return while their persistent kernel still runs)
+    cudaEvent_t frame_done[kSlabMax] = {};
+    cudaStream_t frame_stream[kSlabMax] = {};
     cudaStream_t slab_stream[kSlabMax] = {};
     cudaEvent_t slab_done[kSlabMax] = {};
     bool slabs = true;                  // NTR_NO_SLABS=1 switches it off
@@ -115,6 +124,7 @@ struct ntr_scene {
     bool zero_copy = false;             // NTR_ZEROCOPY=1: ntr_render stores single-pass frames straight into pinned destinations
     uint32_t queue_init = 0;            // NTR_QUEUE_INIT: initial queue capacity override (tests force the regrow path)
     float pass_ns_per_ray = 0.0f;       // measured cost of the wavefront passes of the previous frame (0 = unknown)
+    uint32_t prev_pass_count[kMaxPasses + 2] = {};      // rays per pass of the previous frame: the sort sizes of this one
     // diagnostic per-pass timing (NTR_PASS_TIMING=1): events between the passes of one frame
     cudaEvent_t pass_ev[kMaxPasses + 4] = {};
     int n_pass_ev = 0;
@@ -123,7 +133,7 @@ struct ntr_scene {
     uint64_t launches = 0;
     int grid_blocks[4] = {0, 0, 0, 0};
     const KernelSet *(*kset)(int) = nullptr;
-    volatile bool busy = false;
+    std::atomic<bool> busy{false};
     // begin/end frames (ntr_render_begin / ntr_render_end)
     FrameSlot slots[NTR_FRAMES_IN_FLIGHT];
     cudaStream_t copy_stream = nullptr;
@@ -313,6 +323,8 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
                   int compact, bool *used_passes) {
     uint32_t *const d_ctl = sc->d_ctl + (size_t)sc->ctl_slot * CTL_WORDS;                 // one control block per slab
     unsigned long long *const d_counters = sc->d_counters + (size_t)sc->ctl_slot * 8;
+    if (sc->frame_done[sc->ctl_slot] && sc->frame_stream[sc->ctl_slot] != st)
+        CUDA_TRY(cudaStreamWaitEvent(st, sc->frame_done[sc->ctl_slot], 0));
     FrameDev f;
     memset(&f, 0, sizeof f);
     f.width = width; f.height = height;
@@ -382,7 +394,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     ControlDev ctl;
     ctl.tile_cursor = d_ctl + CTL_TILE_CURSOR;
     ctl.overflow = d_ctl + CTL_OVERFLOW;
-    ctl.abort_flag = sc->d_abort;
+    ctl.abort_flag = sc->d_abort + sc->abort_idx;
     ctl.counters = d_counters;
     CUDA_TRY(cudaMemsetAsync(d_ctl, 0, CTL_WORDS * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), st));
@@ -423,40 +435,37 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
             q.out_count = d_ctl + CTL_COUNT0 + depth + 1;
             q.in_cursor = d_ctl + CTL_CURSOR0 + depth;
             q.in_perm = nullptr;
+            q.n_sorted = 0;
             // adaptive: the sort (one read-back + key kernel + radix sort per pass) only pays for expensive rays; cheap scenes
             // (config 3: 0.45 ns/ray) lose 20 % to it, star polytopes (6-16 ns/ray unsorted) gain 26-29 %
-            if (sc->sort_rays && sc->pass_ns_per_ray > 1.5f) {
+            if (sc->sort_rays && sc->pass_ns_per_ray > 1.5f && sc->prev_pass_count[depth] >= (1u << 15)) {
                 // Re-bin the bounces for coherence: reflection rays get more divergent with every depth (measured on
                 // config 4: 1.5 ns/ray for primaries, 6 -> 16 ns/ray for depths 1 -> 4).  Sorting them by a key made of
                 // direction signs + quantised direction + quantised origin hands every warp 32 rays that walk the same
-                // part of the tree.  Needs the exact count on the host (CUB): one 4-byte read-back per pass.
-                uint32_t n = 0;
-                CUDA_TRY(cudaMemcpyAsync(&n, d_ctl + CTL_COUNT0 + depth, 4, cudaMemcpyDeviceToHost, st));
-                CUDA_TRY(cudaStreamSynchronize(st));
-                n = std::min(n, sc->queue_capacity);
-                if (n >= (1u << 15)) {
-                    if (sc->sort_cap < n) {
-                        for (int k = 0; k < 2; ++k) { cudaFree(sc->d_keys[k]); cudaFree(sc->d_perm[k]); sc->d_keys[k] = sc->d_perm[k] = nullptr; }
-                        cudaFree(sc->d_sort_tmp); sc->d_sort_tmp = nullptr; sc->sort_cap = 0;
-                        const uint32_t cap = n + n / 4;
-                        for (int k = 0; k < 2; ++k) {
-                            CUDA_TRY(cudaMalloc(&sc->d_keys[k], (size_t)cap * 4));
-                            CUDA_TRY(cudaMalloc(&sc->d_perm[k], (size_t)cap * 4));
-                        }
-                        size_t bytes = 0;
-                        cub::DeviceRadixSort::SortPairs(nullptr, bytes, sc->d_keys[0], sc->d_keys[1], sc->d_perm[0], sc->d_perm[1], (int)cap);
-                        CUDA_TRY(cudaMalloc(&sc->d_sort_tmp, bytes));
-                        sc->sort_tmp_bytes = bytes;
-                        sc->sort_cap = cap;
+                // part of the tree.  The sort size is the count this pass had in the previous frame plus a margin (no
+                // read-back between the passes; see ray_keys_kernel).
+                const uint32_t n = (uint32_t)std::min<uint64_t>((uint64_t)sc->prev_pass_count[depth] + sc->prev_pass_count[depth] / 8 + 4096, sc->queue_capacity);
+                if (sc->sort_cap < n) {
+                    for (int k = 0; k < 2; ++k) { cudaFree(sc->d_keys[k]); cudaFree(sc->d_perm[k]); sc->d_keys[k] = sc->d_perm[k] = nullptr; }
+                    cudaFree(sc->d_sort_tmp); sc->d_sort_tmp = nullptr; sc->sort_cap = 0;
+                    const uint32_t cap = n + n / 4;
+                    for (int k = 0; k < 2; ++k) {
+                        CUDA_TRY(cudaMalloc(&sc->d_keys[k], (size_t)cap * 4));
+                        CUDA_TRY(cudaMalloc(&sc->d_perm[k], (size_t)cap * 4));
                     }
-                    ray_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(q.in, rec4, n, sc->dev.dim, sc->dev, sc->d_keys[0], sc->d_perm[0],
-                                                                       sc->heavy_first ? 1 : 0);
-                    size_t bytes = sc->sort_tmp_bytes;
-                    cub::DeviceRadixSort::SortPairs(sc->d_sort_tmp, bytes, sc->d_keys[0], sc->d_keys[1], sc->d_perm[0], sc->d_perm[1], (int)n, 0,
-                                                    sc->heavy_first ? 32 : 30, st);
-                    sc->launches += 2;
-                    q.in_perm = sc->d_perm[1];
+                    size_t bytes = 0;
+                    cub::DeviceRadixSort::SortPairs(nullptr, bytes, sc->d_keys[0], sc->d_keys[1], sc->d_perm[0], sc->d_perm[1], (int)cap);
+                    CUDA_TRY(cudaMalloc(&sc->d_sort_tmp, bytes));
+                    sc->sort_tmp_bytes = bytes;
+                    sc->sort_cap = cap;
                 }
+                ray_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(q.in, rec4, n, q.in_count, sc->queue_capacity, sc->dev.dim, sc->dev,
+                                                                   sc->d_keys[0], sc->d_perm[0], sc->heavy_first ? 1 : 0);
+                size_t bytes = sc->sort_tmp_bytes;
+                cub::DeviceRadixSort::SortPairs(sc->d_sort_tmp, bytes, sc->d_keys[0], sc->d_keys[1], sc->d_perm[0], sc->d_perm[1], (int)n, 0, 32, st);
+                sc->launches += 2;
+                q.in_perm = sc->d_perm[1];
+                q.n_sorted = n;
             }
             ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
             ++sc->launches;
@@ -471,6 +480,9 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
         }
     }
     CUDA_TRY(cudaGetLastError());
+    if (!sc->frame_done[sc->ctl_slot]) CUDA_TRY(cudaEventCreateWithFlags(&sc->frame_done[sc->ctl_slot], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(sc->frame_done[sc->ctl_slot], st));
+    sc->frame_stream[sc->ctl_slot] = st;
     return NTR_OK;
 }
 
@@ -509,6 +521,7 @@ int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win
             for (int d = 1; d <= sc->dev.max_depth && d <= kMaxPasses; ++d) rays += std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
             if (rays > 0) sc->pass_ns_per_ray = ms * 1e6f / (float)rays;
         }
+        if (passes) for (int d = 1; d <= kMaxPasses; ++d) sc->prev_pass_count[d] = std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
         if (sc->pass_timing && sc->n_pass_ev > 1) {
             fprintf(stderr, "ntr pass ms:");
             for (int i = 0; i + 1 < sc->n_pass_ev; ++i) {
@@ -520,7 +533,7 @@ int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win
             for (int d = 1; d <= sc->dev.max_depth + 1 && d <= kMaxPasses; ++d) fprintf(stderr, " %u", h_ctl[CTL_COUNT0 + d]);
             fprintf(stderr, "\n");
         }
-        if (*sc->h_abort) return fail(NTR_ERR_ABORTED, "render aborted");
+        if (sc->h_abort[sc->abort_idx]) return fail(NTR_ERR_ABORTED, "render aborted");
         const uint64_t overflows = sc->counters.queue_overflows;
         sc->counters.primary_rays = (uint64_t)win_w * win_h;
         if (trs > 1) {
@@ -582,7 +595,7 @@ int run_frame_slabs(ntr_scene *sc, const ntr_image_format *fmt, unsigned char *d
     unsigned long long h_cnt[kSlabMax * 8];
     CUDA_TRY(cudaMemcpyAsync(h_cnt, sc->d_counters, sizeof(unsigned long long) * 8 * S, cudaMemcpyDeviceToHost, sc->stream));
     CUDA_TRY(cudaStreamSynchronize(sc->stream));
-    if (*sc->h_abort) return fail(NTR_ERR_ABORTED, "render aborted");
+    if (sc->h_abort[0]) return fail(NTR_ERR_ABORTED, "render aborted");
     const uint64_t overflows = sc->counters.queue_overflows;
     sc->counters = ntr_counters{};
     sc->counters.queue_overflows = overflows;
@@ -597,8 +610,8 @@ int run_frame_slabs(ntr_scene *sc, const ntr_image_format *fmt, unsigned char *d
 struct BusyGuard {
     ntr_scene *sc;
     bool ok;
-    explicit BusyGuard(ntr_scene *s) : sc(s), ok(!s->busy) { if (ok) { s->busy = true; *s->h_abort = 0; } }
-    ~BusyGuard() { if (ok) sc->busy = false; }
+    explicit BusyGuard(ntr_scene *s) : sc(s), ok(!s->busy.exchange(true)) { if (ok) { s->h_abort[0] = 0; s->abort_idx = 0; } }
+    ~BusyGuard() { if (ok) sc->busy.store(false); }
 };
 
 #define ENTER(sc)                                                                               \
@@ -614,6 +627,11 @@ __global__ void pack_kernel(const __grid_constant__ FrameDev f) {
     const long long total = (long long)groups_x * f.out_rows;
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
         const int y = (int)(g / groups_x), x0 = (int)(g % groups_x) * 4;
+        if (!f.compact && f.tile_row_step > 1) {
+            // interleaved render at frame positions: the rows of the other ranks' tile rows are not this rank's to write
+            const int ty = y / NTR_TILE;
+            if (ty < f.tile_row_first || (ty - f.tile_row_first) % f.tile_row_step != 0) continue;
+        }
         const int n = min(4, f.win_w - x0);
         const int bpp = f.fmt.bytes_per_pixel;
         __align__(16) unsigned char buf[64];
@@ -643,10 +661,14 @@ __global__ void pack_kernel(const __grid_constant__ FrameDev f) {
 // first: on star polytopes the rays through the middle walk the giant leaves and cost 10-40x the mean
 // (tools/ray_cost_map.py), and a pass that starts them first ends when its bulk ends instead of one heavy ray later
 // (tools/sim_schedule.py).  Any order is a valid order: this only changes when a ray is traced, never what it returns.
-__global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, int D, const __grid_constant__ SceneDev s,
-                                uint32_t *keys, uint32_t *idx, int heavy_first) {
+// `n` is the host's ESTIMATE of the pass size (the count of the same pass in the previous frame plus a margin), so that
+// no read-back sits between the passes of a frame; the real count is *count.  Slots beyond it get the largest key and,
+// the sort being stable, end up behind every real record; records beyond the estimate are read unsorted (kernels.cuh).
+__global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, const uint32_t *count, uint32_t capacity, int D,
+                                const __grid_constant__ SceneDev s, uint32_t *keys, uint32_t *idx, int heavy_first) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (i >= min(*count, capacity)) { keys[i] = 0xFFFFFFFFu; idx[i] = i; return; }
     const int K = D < 5 ? D : 5;
     const int D4 = (int)(rec4 - 2) / 2;
     const float *o = reinterpret_cast<const float *>(recs + (size_t)i * rec4 + 2);
@@ -763,8 +785,8 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     if ((rc = cu(cudaEventCreate(&sc->ev1), "cudaEventCreate"))) return bail(rc);
     if ((rc = cu(cudaMalloc(&sc->d_ctl, kSlabMax * CTL_WORDS * sizeof(uint32_t)), "cudaMalloc"))) return bail(rc);
     if ((rc = cu(cudaMalloc(&sc->d_counters, kSlabMax * 8 * sizeof(unsigned long long)), "cudaMalloc"))) return bail(rc);
-    if ((rc = cu(cudaHostAlloc(&sc->h_abort, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc"))) return bail(rc);
-    *sc->h_abort = 0;
+    if ((rc = cu(cudaHostAlloc(&sc->h_abort, sizeof(int) * (1 + NTR_FRAMES_IN_FLIGHT), cudaHostAllocMapped), "cudaHostAlloc"))) return bail(rc);
+    for (int i = 0; i <= NTR_FRAMES_IN_FLIGHT; ++i) sc->h_abort[i] = 0;
     if ((rc = cu(cudaHostGetDevicePointer(&sc->d_abort, sc->h_abort, 0), "cudaHostGetDevicePointer"))) return bail(rc);
     *out = sc;
     return NTR_OK;
@@ -783,6 +805,7 @@ NTR_API void ntr_scene_destroy(ntr_scene *sc) {
     for (int i = 0; i < kSlabMax; ++i) {
         if (sc->slab_stream[i]) { cudaStreamSynchronize(sc->slab_stream[i]); cudaStreamDestroy(sc->slab_stream[i]); }
         if (sc->slab_done[i]) cudaEventDestroy(sc->slab_done[i]);
+        if (sc->frame_done[i]) cudaEventDestroy(sc->frame_done[i]);
     }
     for (FrameSlot &fs : sc->slots) {
         cudaFree(fs.d_buf);
@@ -906,17 +929,18 @@ NTR_API int ntr_render(ntr_scene *sc, const ntr_image_format *fmt, void *dst, si
 NTR_API int ntr_render_begin(ntr_scene *sc, const ntr_image_format *fmt, void *dst, size_t dst_len, uint64_t *ticket_out) {
     if (!sc) return fail(NTR_ERR_VALUE, "scene is NULL");
     CUDA_TRY(cudaSetDevice(sc->device));
-    if (sc->busy) return fail(NTR_ERR_RUNTIME, "the renderer is already running");
     int rc = check_format(fmt);
     if (rc) return rc;
     if (!dst || !ticket_out) return fail(NTR_ERR_VALUE, "NULL argument");
     const size_t bytes = (size_t)fmt->pitch * fmt->height;
     if (dst_len < bytes) return fail(NTR_ERR_VALUE, "the buffer is too small for an image with the given dimensions");
-    FrameSlot &fs = sc->slots[sc->next_ticket % NTR_FRAMES_IN_FLIGHT];
+    const int slot = (int)(sc->next_ticket % NTR_FRAMES_IN_FLIGHT);
+    FrameSlot &fs = sc->slots[slot];
     if (fs.open) return fail(NTR_ERR_RUNTIME, "the renderer is already running: %d frames are in flight, end one first", NTR_FRAMES_IN_FLIGHT);
-    bool any_open = false;
-    for (const FrameSlot &o : sc->slots) any_open |= o.open;
-    if (!any_open) *sc->h_abort = 0;           // a pending abort keeps hitting every frame that was open when it came
+    if (sc->busy.exchange(true)) return fail(NTR_ERR_RUNTIME, "the renderer is already running");
+    struct Unbusy { ntr_scene *s; ~Unbusy() { s->busy.store(false); } } unbusy{sc};
+    sc->h_abort[1 + slot] = 0;                  // this frame's own word: an earlier abort belongs to the frames it hit
+    sc->abort_idx = 1 + slot;
     if (!sc->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking));
     if (!fs.rendered) CUDA_TRY(cudaEventCreateWithFlags(&fs.rendered, cudaEventDisableTiming));
     if (!fs.copied) CUDA_TRY(cudaEventCreateWithFlags(&fs.copied, cudaEventDisableTiming));
@@ -940,7 +964,6 @@ NTR_API int ntr_render_begin(ntr_scene *sc, const ntr_image_format *fmt, void *d
     tgt.packed = fs.d_buf;
     const bool composite = sc->dev.kind == NTR_SCENE_COMPOSITE;
     const bool passes = composite && sc->any_reflective && sc->dev.max_depth > 0;
-    sc->busy = true;
     if (!passes) {
         // one persistent kernel: fully asynchronous
         bool p = false;
@@ -955,7 +978,6 @@ NTR_API int ntr_render_begin(ntr_scene *sc, const ntr_image_format *fmt, void *d
         rc = run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, sc->stream);
         if (rc == NTR_ERR_ABORTED) rc = NTR_OK;     // reported by ntr_render_end
     }
-    sc->busy = false;
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(fs.rendered, sc->stream));
     CUDA_TRY(cudaStreamWaitEvent(sc->copy_stream, fs.rendered, 0));
@@ -980,7 +1002,7 @@ NTR_API int ntr_render_end(ntr_scene *sc, uint64_t ticket) {
     const cudaError_t e = cudaEventSynchronize(fs->copied);
     fs->open = false;
     if (e != cudaSuccess) return fail(NTR_ERR_RUNTIME, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
-    if (*sc->h_abort) return fail(NTR_ERR_ABORTED, "render aborted");
+    if (sc->h_abort[1 + (int)(fs - sc->slots)]) return fail(NTR_ERR_ABORTED, "render aborted");
     if (fs->staged) {
         // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
         if (fs->row_bytes == fs->pitch) memcpy(fs->dst, fs->h_stage, fs->pitch * (size_t)fs->height);
@@ -1116,9 +1138,16 @@ NTR_API int ntr_occludes_rays(ntr_scene *sc, uint32_t n, const float *origins, c
 
 NTR_API int ntr_abort(ntr_scene *sc) {
     if (!sc) return fail(NTR_ERR_VALUE, "scene is NULL");
-    bool open = sc->busy;
-    for (const FrameSlot &fs : sc->slots) open |= fs.open;     // frames between ntr_render_begin and ntr_render_end
-    if (open) *sc->h_abort = 1;             // polled by every warp before it takes the next block of work
+    // polled by every warp before it takes the next block of work.  Word 0: a synchronous call in progress, or an
+    // asynchronous ntr_render_device frame whose kernels have not finished; words 1..: the open begin/end frames.
+    bool async_running = false;
+    if (sc->frame_done[0] && !sc->busy.load()) {
+        cudaSetDevice(sc->device);
+        async_running = cudaEventQuery(sc->frame_done[0]) == cudaErrorNotReady;
+        cudaGetLastError();
+    }
+    if (sc->busy.load() || async_running) sc->h_abort[0] = 1;
+    for (int k = 0; k < NTR_FRAMES_IN_FLIGHT; ++k) if (sc->slots[k].open) sc->h_abort[1 + k] = 1;
     return NTR_OK;
 }
 

@@ -96,7 +96,8 @@ struct QueueDev {
     uint32_t *in_count;             // device counter written by the previous pass
     uint32_t *out_count;
     uint32_t *in_cursor;            // work-fetch cursor of this pass
-    const uint32_t *in_perm;        // optional: coherence-sorted order of the input records (nullptr = as emitted)
+    const uint32_t *in_perm;        // optional: coherence-sorted order of the first n_sorted input records (nullptr = as emitted)
+    uint32_t n_sorted;              // records beyond it (the pass grew past the host's estimate) are read in emission order
     uint32_t capacity;              // in records
     uint32_t rec4;                  // record size in float4 units
 };

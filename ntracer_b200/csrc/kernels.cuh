@@ -196,7 +196,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
         } else {
             const uint32_t idx = b + lane;
             if (idx < total) {
-                const float4 *rec = q.in + (size_t)(q.in_perm ? __ldg(q.in_perm + idx) : idx) * q.rec4;
+                const float4 *rec = q.in + (size_t)((q.in_perm && idx < q.n_sorted) ? __ldg(q.in_perm + idx) : idx) * q.rec4;
                 const float4 h = rec[0], wv = rec[1];
                 pix = __float_as_uint(h.x);
                 skip.ref = __float_as_uint(h.y);
