@@ -54,6 +54,7 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __global__ void pack_kernel(const __grid_constant__ FrameDev f);
 __global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, const uint32_t *count, uint32_t capacity, int D,
                                 const __grid_constant__ SceneDev s, uint32_t *keys, uint32_t *idx, int heavy_first);
+__global__ void ring_bounds_kernel(const uint32_t *sorted_keys, uint32_t n, const uint32_t *count, uint32_t capacity, uint32_t *ring_start);
 
 }  // namespace
 
@@ -119,7 +120,11 @@ struct ntr_scene {
     cudaStream_t slab_stream[kSlabMax] = {};
     cudaEvent_t slab_done[kSlabMax] = {};
     bool slabs = true;                  // NTR_NO_SLABS=1 switches it off
-    bool heavy_first = false;           // NTR_HEAVY_FIRST=1: bounce passes start the rays nearest the scene centre first (ray_keys_kernel)
+    // bounce passes of scenes with big leaves start the rays nearest the scene centre first (ray_keys_kernel) and hand
+    // them out a few per warp (kernels.cuh: NTR_FETCH_RING*); NTR_HEAVY_FIRST / NTR_ADAPTIVE_FETCH = 0|1 override
+    bool heavy_first = false, adaptive_fetch = false;
+    uint32_t max_leaf = 0;              // items in the largest leaf of the tree
+    uint32_t *d_ring = nullptr;
     bool force_tile_sched = false;      // NTR_TILE_SCHED=1: cost-sorted tile hand-out on whole frames too (heavy-tailed scenes)
     bool zero_copy = false;             // NTR_ZEROCOPY=1: ntr_render stores single-pass frames straight into pinned destinations
     uint32_t queue_init = 0;            // NTR_QUEUE_INIT: initial queue capacity override (tests force the regrow path)
@@ -130,6 +135,8 @@ struct ntr_scene {
     int n_pass_ev = 0;
     bool pass_timing = false;
     ntr_counters counters{};
+    uint32_t *h_ctl = nullptr;              // pinned read-back of the control block and the counters (frame_readback)
+    unsigned long long *h_cnt = nullptr;
     uint64_t launches = 0;
     int grid_blocks[4] = {0, 0, 0, 0};
     const KernelSet *(*kset)(int) = nullptr;
@@ -436,6 +443,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
             q.in_cursor = d_ctl + CTL_CURSOR0 + depth;
             q.in_perm = nullptr;
             q.n_sorted = 0;
+            q.ring_start = nullptr;
             // adaptive: the sort (one read-back + key kernel + radix sort per pass) only pays for expensive rays; cheap scenes
             // (config 3: 0.45 ns/ray) lose 20 % to it, star polytopes (6-16 ns/ray unsorted) gain 26-29 %
             if (sc->sort_rays && sc->pass_ns_per_ray > 1.5f && sc->prev_pass_count[depth] >= (1u << 15)) {
@@ -466,6 +474,14 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
                 sc->launches += 2;
                 q.in_perm = sc->d_perm[1];
                 q.n_sorted = n;
+                if (sc->heavy_first && sc->adaptive_fetch) {
+                    if (!sc->d_ring) CUDA_TRY(cudaMalloc(&sc->d_ring, (kMaxPasses + 2) * 4 * sizeof(uint32_t)));
+                    uint32_t *ring = sc->d_ring + (size_t)depth * 4;
+                    CUDA_TRY(cudaMemsetAsync(ring, 0xFF, 4 * sizeof(uint32_t), st));
+                    ring_bounds_kernel<<<(n + 255) / 256, 256, 0, st>>>(sc->d_keys[1], n, q.in_count, sc->queue_capacity, ring);
+                    ++sc->launches;
+                    q.ring_start = ring;
+                }
             }
             ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
             ++sc->launches;
@@ -493,65 +509,98 @@ struct HostCopy {
     bool done;
 };
 
-// Runs a frame on the scene's own stream, waits for it, handles queue overflow (regrow + retry) and abort.
+// One frame in two halves, so that a caller with several devices can have all of them tracing before it waits for any:
+// frame_submit enqueues the kernels and the read-back of the control block (into pinned memory: never blocks),
+// frame_collect waits, does the bookkeeping and says whether the frame has to be traced again (a wavefront queue
+// overflowed and was regrown).
+struct FrameJob {
+    int width, height, x0, y0, win_w, win_h;
+    const ntr_image_format *fmt;
+    RenderTarget tgt;
+    int trf, trs, compact;
+    cudaStream_t st;
+    bool passes = false;
+};
+
+int frame_submit(ntr_scene *sc, FrameJob &j) {
+    CUDA_TRY(cudaEventRecord(sc->ev0, j.st));
+    int rc = enqueue_frame(sc, j.st, j.width, j.height, j.x0, j.y0, j.win_w, j.win_h, j.fmt, j.tgt, j.trf, j.trs, j.compact, &j.passes);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(sc->ev1, j.st));
+    sc->timing_valid = true;
+    return NTR_OK;
+}
+
+int frame_readback(ntr_scene *sc, FrameJob &j) {
+    CUDA_TRY(cudaMemcpyAsync(sc->h_ctl, sc->d_ctl, CTL_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, j.st));
+    CUDA_TRY(cudaMemcpyAsync(sc->h_cnt, sc->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, j.st));
+    return NTR_OK;
+}
+
+int frame_collect(ntr_scene *sc, FrameJob &j, bool *again) {
+    *again = false;
+    CUDA_TRY(cudaStreamSynchronize(j.st));
+    const uint32_t *h_ctl = sc->h_ctl;
+    const unsigned long long *h_cnt = sc->h_cnt;
+    if (j.passes && sc->n_pass_ev > 2) {
+        // cost of the wavefront passes per ray: feeds the decision to re-bin rays in the next frame
+        float ms = 0;
+        cudaEventElapsedTime(&ms, sc->pass_ev[1], sc->pass_ev[sc->n_pass_ev - 1]);
+        uint64_t rays = 0;
+        for (int d = 1; d <= sc->dev.max_depth && d <= kMaxPasses; ++d) rays += std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
+        if (rays > 0) sc->pass_ns_per_ray = ms * 1e6f / (float)rays;
+    }
+    if (j.passes) for (int d = 1; d <= kMaxPasses; ++d) sc->prev_pass_count[d] = std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
+    if (sc->pass_timing && sc->n_pass_ev > 1) {
+        fprintf(stderr, "ntr pass ms:");
+        for (int i = 0; i + 1 < sc->n_pass_ev; ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, sc->pass_ev[i], sc->pass_ev[i + 1]);
+            fprintf(stderr, " %.3f", ms);
+        }
+        fprintf(stderr, "  rays:");
+        for (int d = 1; d <= sc->dev.max_depth + 1 && d <= kMaxPasses; ++d) fprintf(stderr, " %u", h_ctl[CTL_COUNT0 + d]);
+        fprintf(stderr, "\n");
+    }
+    if (sc->h_abort[sc->abort_idx]) return fail(NTR_ERR_ABORTED, "render aborted");
+    const uint64_t overflows = sc->counters.queue_overflows;
+    sc->counters.primary_rays = (uint64_t)j.win_w * j.win_h;
+    if (j.trs > 1) {
+        const int tiles_y = (j.win_h + NTR_TILE - 1) / NTR_TILE;
+        uint64_t rows = 0;
+        for (int ty = j.trf; ty < tiles_y; ty += j.trs) rows += std::min(NTR_TILE, j.win_h - ty * NTR_TILE);
+        sc->counters.primary_rays = rows * (uint64_t)j.win_w;
+    }
+    sc->counters.reflection_rays = h_cnt[1]; sc->counters.shadow_rays = h_cnt[2]; sc->counters.node_steps = h_cnt[3];
+    sc->counters.simplex_tests = h_cnt[4]; sc->counters.solid_tests = h_cnt[5]; sc->counters.shaded_hits = h_cnt[6];
+    sc->counters.queue_overflows = overflows;
+    if (!j.passes || !h_ctl[CTL_OVERFLOW]) return NTR_OK;
+    // a wavefront queue was too small: the counters say how many records were wanted
+    uint32_t need = 0;
+    for (int d = 1; d <= kMaxPasses; ++d) need = std::max(need, h_ctl[CTL_COUNT0 + d]);
+    sc->counters.queue_overflows = overflows + 1;
+    int rc = ensure_queues(sc, (uint32_t)std::min<uint64_t>((uint64_t)need * 2 + 1024, 0x7FFFFFFFu));
+    if (rc) return rc;
+    *again = true;
+    return NTR_OK;
+}
+
+// Runs a frame on `st`, waits for it, handles queue overflow (regrow + retry) and abort.
 int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win_w, int win_h,
                    const ntr_image_format *fmt, const RenderTarget &tgt, int trf, int trs, int compact,
                    cudaStream_t st, HostCopy *hc = nullptr) {
+    FrameJob j{width, height, x0, y0, win_w, win_h, fmt, tgt, trf, trs, compact, st};
     for (int attempt = 0; attempt < 8; ++attempt) {
-        bool passes = false;
-        CUDA_TRY(cudaEventRecord(sc->ev0, st));
-        int rc = enqueue_frame(sc, st, width, height, x0, y0, win_w, win_h, fmt, tgt, trf, trs, compact, &passes);
+        int rc = frame_submit(sc, j);
         if (rc) return rc;
-        CUDA_TRY(cudaEventRecord(sc->ev1, st));
-        sc->timing_valid = true;
-        if (hc && !passes) {            // no overflow / retry possible: the frame in d_packed is final
+        if (hc && !j.passes) {            // no overflow / retry possible: the frame in d_packed is final
             CUDA_TRY(cudaMemcpy2DAsync(hc->dst, hc->dpitch, hc->src, hc->spitch, hc->row_bytes, hc->rows, cudaMemcpyDeviceToHost, st));
             hc->done = true;
         }
-        uint32_t h_ctl[CTL_WORDS];
-        unsigned long long h_cnt[8];
-        CUDA_TRY(cudaMemcpyAsync(h_ctl, sc->d_ctl, sizeof h_ctl, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(h_cnt, sc->d_counters, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if (passes && sc->n_pass_ev > 2) {
-            // cost of the wavefront passes per ray: feeds the decision to re-bin rays in the next frame
-            float ms = 0;
-            cudaEventElapsedTime(&ms, sc->pass_ev[1], sc->pass_ev[sc->n_pass_ev - 1]);
-            uint64_t rays = 0;
-            for (int d = 1; d <= sc->dev.max_depth && d <= kMaxPasses; ++d) rays += std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
-            if (rays > 0) sc->pass_ns_per_ray = ms * 1e6f / (float)rays;
-        }
-        if (passes) for (int d = 1; d <= kMaxPasses; ++d) sc->prev_pass_count[d] = std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
-        if (sc->pass_timing && sc->n_pass_ev > 1) {
-            fprintf(stderr, "ntr pass ms:");
-            for (int i = 0; i + 1 < sc->n_pass_ev; ++i) {
-                float ms = 0;
-                cudaEventElapsedTime(&ms, sc->pass_ev[i], sc->pass_ev[i + 1]);
-                fprintf(stderr, " %.3f", ms);
-            }
-            fprintf(stderr, "  rays:");
-            for (int d = 1; d <= sc->dev.max_depth + 1 && d <= kMaxPasses; ++d) fprintf(stderr, " %u", h_ctl[CTL_COUNT0 + d]);
-            fprintf(stderr, "\n");
-        }
-        if (sc->h_abort[sc->abort_idx]) return fail(NTR_ERR_ABORTED, "render aborted");
-        const uint64_t overflows = sc->counters.queue_overflows;
-        sc->counters.primary_rays = (uint64_t)win_w * win_h;
-        if (trs > 1) {
-            const int tiles_y = (win_h + NTR_TILE - 1) / NTR_TILE;
-            uint64_t rows = 0;
-            for (int ty = trf; ty < tiles_y; ty += trs) rows += std::min(NTR_TILE, win_h - ty * NTR_TILE);
-            sc->counters.primary_rays = rows * (uint64_t)win_w;
-        }
-        sc->counters.reflection_rays = h_cnt[1]; sc->counters.shadow_rays = h_cnt[2]; sc->counters.node_steps = h_cnt[3];
-        sc->counters.simplex_tests = h_cnt[4]; sc->counters.solid_tests = h_cnt[5]; sc->counters.shaded_hits = h_cnt[6];
-        sc->counters.queue_overflows = overflows;
-        if (!passes || !h_ctl[CTL_OVERFLOW]) return NTR_OK;
-        // a wavefront queue was too small: the counters say how many records were wanted
-        uint32_t need = 0;
-        for (int d = 1; d <= kMaxPasses; ++d) need = std::max(need, h_ctl[CTL_COUNT0 + d]);
-        sc->counters.queue_overflows = overflows + 1;
-        rc = ensure_queues(sc, (uint32_t)std::min<uint64_t>((uint64_t)need * 2 + 1024, 0x7FFFFFFFu));
-        if (rc) return rc;
+        if ((rc = frame_readback(sc, j))) return rc;
+        bool again = false;
+        if ((rc = frame_collect(sc, j, &again))) return rc;
+        if (!again) return NTR_OK;
     }
     return fail(NTR_ERR_RUNTIME, "wavefront queue kept overflowing");
 }
@@ -701,6 +750,15 @@ __global__ void ray_keys_kernel(const float4 *recs, uint32_t rec4, uint32_t n, c
     idx[i] = i;
 }
 
+// First sorted index of cost rings 1..3 (the two top key bits, heavy-first sort): ring_start[1..3], preset to 0xFFFFFFFF.
+__global__ void ring_bounds_kernel(const uint32_t *sorted_keys, uint32_t n, const uint32_t *count, uint32_t capacity, uint32_t *ring_start) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t valid = min(min(*count, capacity), n);
+    if (i >= valid) return;
+    const uint32_t r = sorted_keys[i] >> 30, rp = i ? sorted_keys[i - 1] >> 30 : 0u;
+    for (uint32_t k = rp + 1; k <= r; ++k) atomicMin(ring_start + k, i);
+}
+
 __global__ void fma_peak_kernel(float *out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const float b = 1.0000001f, c = 1e-7f;
@@ -757,7 +815,11 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     if (const char *zc = getenv("NTR_ZEROCOPY")) sc->zero_copy = atoi(zc) != 0;
     sc->slabs = getenv("NTR_NO_SLABS") == nullptr;
     if (const char *ts = getenv("NTR_TILE_SCHED")) sc->force_tile_sched = atoi(ts) != 0;
+    for (uint32_t i = 0; desc->kind == NTR_SCENE_COMPOSITE && i < desc->n_nodes; ++i)
+        if (desc->nodes[i].meta & NTR_LEAF_FLAG) sc->max_leaf = std::max(sc->max_leaf, desc->nodes[i].w2);
+    sc->heavy_first = sc->adaptive_fetch = sc->max_leaf >= 256;
     if (const char *hf = getenv("NTR_HEAVY_FIRST")) sc->heavy_first = atoi(hf) != 0;
+    if (const char *af = getenv("NTR_ADAPTIVE_FETCH")) sc->adaptive_fetch = atoi(af) != 0;
     if (const char *qi = getenv("NTR_QUEUE_INIT")) sc->queue_init = (uint32_t)strtoul(qi, nullptr, 10);
     sc->tree_depth = depth;
     sc->dev.dim = desc->dim;
@@ -787,6 +849,8 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     if ((rc = cu(cudaMalloc(&sc->d_counters, kSlabMax * 8 * sizeof(unsigned long long)), "cudaMalloc"))) return bail(rc);
     if ((rc = cu(cudaHostAlloc(&sc->h_abort, sizeof(int) * (1 + NTR_FRAMES_IN_FLIGHT), cudaHostAllocMapped), "cudaHostAlloc"))) return bail(rc);
     for (int i = 0; i <= NTR_FRAMES_IN_FLIGHT; ++i) sc->h_abort[i] = 0;
+    if ((rc = cu(cudaHostAlloc(&sc->h_ctl, CTL_WORDS * sizeof(uint32_t), cudaHostAllocDefault), "cudaHostAlloc"))) return bail(rc);
+    if ((rc = cu(cudaHostAlloc(&sc->h_cnt, 8 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc"))) return bail(rc);
     if ((rc = cu(cudaHostGetDevicePointer(&sc->d_abort, sc->h_abort, 0), "cudaHostGetDevicePointer"))) return bail(rc);
     *out = sc;
     return NTR_OK;
@@ -799,7 +863,7 @@ NTR_API void ntr_scene_destroy(ntr_scene *sc) {
     cudaFree(sc->arena); cudaFree(sc->d_lights); cudaFree(sc->d_ctl); cudaFree(sc->d_counters);
     cudaFree(sc->d_accum); cudaFree(sc->d_packed); cudaFree(sc->d_ids); cudaFree(sc->d_dists);
     cudaFree(sc->d_queue[0]); cudaFree(sc->d_queue[1]); cudaFree(sc->d_scratch);
-    cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order);
+    cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order); cudaFree(sc->d_ring);
     cudaFree(sc->d_keys[0]); cudaFree(sc->d_keys[1]); cudaFree(sc->d_perm[0]); cudaFree(sc->d_perm[1]); cudaFree(sc->d_sort_tmp);
     if (sc->copy_stream) { cudaStreamSynchronize(sc->copy_stream); cudaStreamDestroy(sc->copy_stream); }
     for (int i = 0; i < kSlabMax; ++i) {
@@ -814,6 +878,8 @@ NTR_API void ntr_scene_destroy(ntr_scene *sc) {
         if (fs.copied) cudaEventDestroy(fs.copied);
     }
     if (sc->h_abort) cudaFreeHost(sc->h_abort);
+    if (sc->h_ctl) cudaFreeHost(sc->h_ctl);
+    if (sc->h_cnt) cudaFreeHost(sc->h_cnt);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
     if (sc->ev1) cudaEventDestroy(sc->ev1);
     if (sc->stream) cudaStreamDestroy(sc->stream);

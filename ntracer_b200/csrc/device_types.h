@@ -98,6 +98,8 @@ struct QueueDev {
     uint32_t *in_cursor;            // work-fetch cursor of this pass
     const uint32_t *in_perm;        // optional: coherence-sorted order of the first n_sorted input records (nullptr = as emitted)
     uint32_t n_sorted;              // records beyond it (the pass grew past the host's estimate) are read in emission order
+    const uint32_t *ring_start;     // optional (sorted, heavy-first passes): first sorted index of cost ring 1, 2, 3 at [1..3];
+                                    // warps take fewer rays per fetch from the expensive rings (kernels.cuh)
     uint32_t capacity;              // in records
     uint32_t rec4;                  // record size in float4 units
 };

@@ -115,6 +115,22 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 #ifndef NTR_MIN_CTAS
 #define NTR_MIN_CTAS 8
 #endif
+#ifndef NTR_WARP_PATH
+#define NTR_WARP_PATH 1            // 1: the warp-synchronous per-ray path (trace_warp.cuh); 0: every lane for itself (trace_core.cuh)
+#endif
+// Rays a warp takes per fetch from cost rings 0 (rays through the centre of the scene box: on star polytopes they walk
+// the giant leaves and cost 10-90x the mean), 1 and 2; ring 3 and unsorted passes: 32.  A warp with a few expensive rays
+// and otherwise idle lanes splits their big leaves over all 32 lanes (trace_warp.cuh) -- the expensive rays of a pass
+// then run side by side in many warps instead of 32 to a warp, one lane each.
+#ifndef NTR_FETCH_RING0
+#define NTR_FETCH_RING0 4
+#endif
+#ifndef NTR_FETCH_RING1
+#define NTR_FETCH_RING1 8
+#endif
+#ifndef NTR_FETCH_RING2
+#define NTR_FETCH_RING2 16
+#endif
 // above 8 dimensions the ray alone (origin, direction, hit point) is 30+ registers: fewer CTAs per SM, more registers
 #ifndef NTR_MIN_CTAS_HI
 #define NTR_MIN_CTAS_HI 5          // measured on config 5 (16 k simplexes): 3 -> 31.7 ms, 4 -> 25.5, 5 -> 23.3, 6 -> 24.6, 8 -> 32.6
@@ -130,7 +146,9 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                    const __grid_constant__ ControlDev ctl) {
     constexpr int CAP = DimCap<DT>::value;
     __shared__ __align__(16) unsigned char stage_all[(kCtaThreads / 32) * 512];
+    __shared__ int done_all[kCtaThreads / 32];
     unsigned char *stage = stage_all + (threadIdx.x >> 5) * 512;
+    int *done_ctr = done_all + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     Counters cnt;
 
@@ -145,15 +163,29 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
         total = *q.in_count;
         if (total > q.capacity) total = q.capacity;
     }
+    uint32_t fetches = 0;
     for (;;) {
-        // ---------------- fetch: an 8x4 pixel block of a tile (primary) or 32 queued bounces ----------------
-        uint32_t b = 0;
-        if (lane == 0) b = primary ? atomicAdd(ctl.tile_cursor, 1u) : atomicAdd(q.in_cursor, 32u);
+        // ---------------- fetch: an 8x4 pixel block of a tile (primary) or up to 32 queued bounces ----------------
+        uint32_t b = 0, take = 32;
+        if (lane == 0) {
+            if (primary) b = atomicAdd(ctl.tile_cursor, 1u);
+            else {
+                if (q.ring_start) {
+                    const uint32_t pos = *(volatile uint32_t *)q.in_cursor;         // a peek: good enough to pick the size
+                    take = pos < __ldg(q.ring_start + 1) ? NTR_FETCH_RING0 : pos < __ldg(q.ring_start + 2) ? NTR_FETCH_RING1
+                           : pos < __ldg(q.ring_start + 3) ? NTR_FETCH_RING2 : 32;
+                }
+                b = atomicAdd(q.in_cursor, take);
+            }
+        }
         b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        take = __shfl_sync(0xFFFFFFFFu, take, 0);
         if (b >= total) break;
         // renderer::state poll (reference render.cpp:412).  The flag lives in mapped host memory, so only every
-        // 512th fetch looks at it (ncu: at every 64th the PCIe read was 2.9 % of all stall samples); whoever sees it pushes the cursor past the end for everybody.
-        if ((b & (primary ? 511u : 8191u)) == 0 && *ctl.abort_flag) {
+        // 512th block / every 64th fetch of a warp looks at it (ncu: at every 64th block the PCIe read was 2.9 % of all
+        // stall samples); whoever sees it pushes the cursor past the end for everybody.
+        ++fetches;
+        if ((primary ? (b & 511u) == 0 : (fetches & 63u) == 1) && *ctl.abort_flag) {
             if (lane == 0) atomicAdd(primary ? ctl.tile_cursor : q.in_cursor, 0x40000000u);
             break;
         }
@@ -195,7 +227,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
             }
         } else {
             const uint32_t idx = b + lane;
-            if (idx < total) {
+            if ((uint32_t)lane < take && idx < total) {
                 const float4 *rec = q.in + (size_t)((q.in_perm && idx < q.n_sorted) ? __ldg(q.in_perm + idx) : idx) * q.rec4;
                 const float4 h = rec[0], wv = rec[1];
                 pix = __float_as_uint(h.x);
@@ -217,6 +249,12 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                 active = true;
             }
         }
+#if !NTR_WARP_PATH
+        if (active) {
+            QueueEmit<DT> emit{q, ctl, pix, !primary || f.out_mode == NTR_OUT_ACCUM};
+            ray_color<DT, FLAGS>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim);
+        }
+#else
         // ---------------- the per-ray path: all 32 lanes enter (trace_warp.cuh), `active` says who has a ray ----------------
         if (s.kind != NTR_SCENE_BOX) {       // warp-uniform
             if (!active) {
@@ -224,8 +262,9 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                 for (int k = 0; k < CAP; ++k) { o[k] = 0.0f; dir[k] = 1.0f; }
             }
             QueueEmit<DT> emit{q, ctl, pix, !primary || f.out_mode == NTR_OUT_ACCUM};
-            ray_color_warp<DT, FLAGS>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim);
+            ray_color_warp<DT, FLAGS>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim, done_ctr);
         }
+#endif
         if (primary && f.tile_cost && lane == 0) atomicAdd(f.tile_cost + cost_tile, (unsigned long long)(clock64() - t_start));
         // ---------------- epilogue ----------------
         if (!primary) {

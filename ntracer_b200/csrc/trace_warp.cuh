@@ -35,6 +35,17 @@ namespace ntr {
 #ifndef NTR_COOP_OVERHEAD
 #define NTR_COOP_OVERHEAD 3         // cost of serving one parked ray (broadcast + fold), in units of one item test
 #endif
+#ifndef NTR_COOP_CHUNK_COST
+#define NTR_COOP_CHUNK_COST 2       // cost of one cooperative 32-item chunk (test + votes + fold), in units of one item test
+#endif
+#ifndef NTR_COOP_MIN_DONE
+#define NTR_COOP_MIN_DONE 16        // a ray parks at a big leaf only while at least this many lanes of its warp have nothing
+                                    // left to do (idle lanes are what cooperation feeds on; parking in a busy warp
+                                    // stalls the parked lane until every other lane has finished or parked too)
+#endif
+#ifndef NTR_WARP_SHADE
+#define NTR_WARP_SHADE 1            // 0: shade per lane after the warp's nearest-hit traversal (shadow rays per lane)
+#endif
 
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
 
@@ -50,9 +61,19 @@ __device__ __forceinline__ void broadcast_ray(const SceneDev &s, int src, const 
     bskip.lane = __shfl_sync(kFullMask, skip.lane, src);
 }
 
+// Per-warp count of lanes that have finished the traversal in progress (shared memory, one int per warp).
+__device__ __forceinline__ void done_reset(int *done_ctr, bool enabled) {
+    const unsigned idle = __ballot_sync(kFullMask, !enabled);
+    if (warp_lane() == 0) *done_ctr = __popc(idle);
+    __syncwarp();
+}
+__device__ __forceinline__ bool idle_lanes_wait(const int *done_ctr) {
+    return *(const volatile int *)done_ctr >= NTR_COOP_MIN_DONE;
+}
+
 // true when serving the parked leaves cooperatively costs less than every parked lane scanning its own
 __device__ __forceinline__ bool coop_pays(bool parked, uint32_t size) {
-    const unsigned chunks = __reduce_add_sync(kFullMask, parked ? (size + 31u) / 32u + (unsigned)NTR_COOP_OVERHEAD : 0u);
+    const unsigned chunks = __reduce_add_sync(kFullMask, parked ? (size + 31u) / 32u * (unsigned)NTR_COOP_CHUNK_COST + (unsigned)NTR_COOP_OVERHEAD : 0u);
     const unsigned longest = __reduce_max_sync(kFullMask, parked ? size : 0u);
     return chunks < longest;
 }
@@ -185,8 +206,9 @@ enum : int { NTR_S_DESCEND = 0, NTR_S_LEAF = 1, NTR_S_PARKED = 2, NTR_S_UNWIND =
 template <int DT, int FLAGS>
 __device__ __forceinline__ bool trace_nearest_warp(const SceneDev &s, bool enabled, const float *o, const float *dir,
                                                    Skip skip, float t_near, float t_far, HitRec &oh, GenState<DT> &g,
-                                                   Counters &cnt) {
+                                                   Counters &cnt, int *done_ctr) {
     const int lane = warp_lane();
+    done_reset(done_ctr, enabled);
     RaySlab<DT> rs;
     rs.init(s, dir);
     const float *invdir = rs.invdir;
@@ -208,7 +230,7 @@ __device__ __forceinline__ bool trace_nearest_warp(const SceneDev &s, bool enabl
                     const uint4 n = ldnode(s.nodes + node);
                     if (n.x & NTR_LEAF_FLAG) {
                         leaf = n;
-                        state = n.z >= (uint32_t)NTR_COOP_LEAF_MIN ? NTR_S_PARKED : NTR_S_LEAF;
+                        state = (n.z >= (uint32_t)NTR_COOP_LEAF_MIN && idle_lanes_wait(done_ctr)) ? NTR_S_PARKED : NTR_S_LEAF;
                         break;
                     }
                     if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
@@ -245,7 +267,7 @@ __device__ __forceinline__ bool trace_nearest_warp(const SceneDev &s, bool enabl
                 state = NTR_S_UNWIND;
             } else {                                        // NTR_S_UNWIND (see trace_nearest)
                 for (;;) {
-                    if (sp == 0) { ret = result; state = NTR_S_DONE; break; }
+                    if (sp == 0) { ret = result; state = NTR_S_DONE; atomicAdd(done_ctr, 1); break; }
                     --sp;
                     const uint32_t fnode = st.node[sp];
                     if (fnode == NTR_FRAME_AFTER_FAR) {
@@ -345,8 +367,9 @@ __device__ __forceinline__ bool coop_leaf_occludes(const SceneDev &s, int src, u
 template <int DT, int FLAGS>
 __device__ __forceinline__ bool trace_occludes_warp(const SceneDev &s, bool enabled, const float *o, const float *dir,
                                                     float ldistance, Skip skip, float t_near, float t_far, HitList *hits,
-                                                    Counters &cnt) {
+                                                    Counters &cnt, int *done_ctr) {
     const int lane = warp_lane();
+    done_reset(done_ctr, enabled);
     RaySlab<DT> rs;
     rs.init(s, dir);
     const float *invdir = rs.invdir;
@@ -365,7 +388,7 @@ __device__ __forceinline__ bool trace_occludes_warp(const SceneDev &s, bool enab
                     const uint4 n = ldnode(s.nodes + node);
                     if (n.x & NTR_LEAF_FLAG) {
                         leaf = n;
-                        state = n.z >= (uint32_t)NTR_COOP_LEAF_MIN ? NTR_S_PARKED : NTR_S_LEAF;
+                        state = (n.z >= (uint32_t)NTR_COOP_LEAF_MIN && idle_lanes_wait(done_ctr)) ? NTR_S_PARKED : NTR_S_LEAF;
                         break;
                     }
                     if (FLAGS & NTR_F_COUNT) cnt.node_steps++;
@@ -394,12 +417,12 @@ __device__ __forceinline__ bool trace_occludes_warp(const SceneDev &s, bool enab
                     node = oa >= split ? n.w : n.z;
                 }
             } else if (state == NTR_S_LEAF) {
-                if (leaf_occludes<DT, FLAGS>(s, leaf, o, dir, rs, ldistance, skip, hits, cnt)) { ret = true; state = NTR_S_DONE; }
+                if (leaf_occludes<DT, FLAGS>(s, leaf, o, dir, rs, ldistance, skip, hits, cnt)) { ret = true; state = NTR_S_DONE; atomicAdd(done_ctr, 1); }
                 else state = NTR_S_UNWIND;
             } else {
                 // the (sub)call returned false: resume the innermost pending far child
                 for (;;) {
-                    if (sp == 0) { ret = false; state = NTR_S_DONE; break; }
+                    if (sp == 0) { ret = false; state = NTR_S_DONE; atomicAdd(done_ctr, 1); break; }
                     --sp;
                     if (st_t[sp] < ldistance) continue;     // `return false` of that frame
                     node = st_node[sp];
@@ -422,7 +445,7 @@ __device__ __forceinline__ bool trace_occludes_warp(const SceneDev &s, bool enab
             const uint32_t first = __shfl_sync(kFullMask, leaf.y, src), size = __shfl_sync(kFullMask, leaf.z, src);
             const bool r = coop_leaf_occludes<DT, FLAGS>(s, src, first, size, o, dir, ldistance, skip, hits, cnt);
             if (lane == src) {
-                if (r) { ret = true; state = NTR_S_DONE; }
+                if (r) { ret = true; state = NTR_S_DONE; atomicAdd(done_ctr, 1); }
                 else state = NTR_S_UNWIND;
             }
         }
@@ -433,11 +456,11 @@ __device__ __forceinline__ bool trace_occludes_warp(const SceneDev &s, bool enab
 // composite_scene::light_reaches (tracer.hpp:1750-1766) for the lanes with need = true
 template <int DT, int FLAGS>
 __device__ __forceinline__ bool light_reaches_warp(const SceneDev &s, bool need, const float *o, const float *dir,
-                                                   float ldistance, Skip skip, float *filtered, Counters &cnt) {
+                                                   float ldistance, Skip skip, float *filtered, Counters &cnt, int *done_ctr) {
     HitList hits;
     if (FLAGS & NTR_F_GENERAL) hits.clear();
     if (need) cnt.shadow_rays++;
-    const bool occluded = trace_occludes_warp<DT, FLAGS>(s, need, o, dir, ldistance, skip, 0.0f, FLT_MAX, &hits, cnt);
+    const bool occluded = trace_occludes_warp<DT, FLAGS>(s, need, o, dir, ldistance, skip, 0.0f, FLT_MAX, &hits, cnt, done_ctr);
     if (!need || occluded) return false;
     if (FLAGS & NTR_F_GENERAL) {
         if (hits.n) {
@@ -456,7 +479,7 @@ __device__ __forceinline__ bool light_reaches_warp(const SceneDev &s, bool need,
 template <int DT, int FLAGS, typename EMIT>
 __device__ __forceinline__ void ray_color_warp(const SceneDev &s, bool enabled, const float *o, const float *dir, int depth,
                                                Skip source, const float *weight, float *acc, EMIT &emit, Counters &cnt,
-                                               HitRec *primary_out) {
+                                               HitRec *primary_out, int *done_ctr) {
     const int D = NTR_D(DT, s);
     GenState<DT> g;
     HitRec oh;
@@ -467,7 +490,7 @@ __device__ __forceinline__ void ray_color_warp(const SceneDev &s, bool enabled, 
         for (int i = 0; i < D; ++i) { g.hitP[i] = 0; g.hitN[i] = 0; }
     }
     const float t0 = enabled ? aabb_distance<DT>(s, o, dir) : -1.0f;
-    const bool hit = trace_nearest_warp<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, g, cnt);
+    const bool hit = trace_nearest_warp<DT, FLAGS>(s, t0 >= 0, o, dir, source, t0, FLT_MAX, oh, g, cnt, done_ctr);
     if (enabled && primary_out) { *primary_out = oh; if (!hit) { primary_out->ref = NTR_NONE_REF; primary_out->dist = 0; } }
 
     float w[3] = {weight[0], weight[1], weight[2]};
@@ -477,6 +500,35 @@ __device__ __forceinline__ void ray_color_warp(const SceneDev &s, bool enabled, 
         n_layers = enabled ? g.th.n : 0;
     }
     const int n_total = enabled ? n_layers + (hit ? 1 : 0) : 0;
+#if !NTR_WARP_SHADE
+    // per-lane shading (shadow rays traced by the lane that needs them), as in ray_color
+    for (int i = 0; i < n_total; ++i) {
+        uint32_t ref;
+        int hl;
+        float wl[3];
+        float P[DimCap<DT>::value], N[DimCap<DT>::value];
+        if (i < n_layers) {
+            ref = g.th.ref[i];
+            hl = g.th.lane[i];
+            const float op = load_mat(s, target_meta<DT>(s, ref, hl)).opacity;
+            hit_geometry<DT, FLAGS>(s, ref, hl, g.th.dist[i], o, dir, P, N);
+            wl[0] = w[0] * op; wl[1] = w[1] * op; wl[2] = w[2] * op;
+            w[0] *= 1 - op; w[1] *= 1 - op; w[2] *= 1 - op;
+        } else {
+            ref = oh.ref;
+            hl = oh.lane;
+            wl[0] = w[0]; wl[1] = w[1]; wl[2] = w[2];
+            if (FLAGS & NTR_F_GENERAL) {
+    NTR_UNROLL
+                for (int k = 0; k < D; ++k) { P[k] = g.hitP[k]; N[k] = g.hitN[k]; }
+            } else {
+                hit_geometry<DT, FLAGS>(s, ref, hl, oh.dist, o, dir, P, N);
+            }
+        }
+        Bounce<DT> b;
+        if (shade_hit<DT, FLAGS>(s, dir, P, N, ref, hl, depth, wl, acc, b, cnt)) emit(b);
+    }
+#else
     const int n_lights = s.n_point + s.n_global;
     // layers near -> far (the surviving transparent hits, then the opaque hit), lights in order: warp-uniform loops
     for (int i = 0; __any_sync(kFullMask, i < n_total); ++i) {
@@ -521,7 +573,7 @@ __device__ __forceinline__ void ray_color_warp(const SceneDev &s, bool enabled, 
             if (s.shadows) {            // scene constant: uniform
                 const bool need = kind == NTR_LIGHT_SHADOWED;
                 if (__any_sync(kFullMask, need)) {
-                    const bool reaches = light_reaches_warp<DT, FLAGS>(s, need, P, ls.lv, ls.dist, src, filtered, cnt);
+                    const bool reaches = light_reaches_warp<DT, FLAGS>(s, need, P, ls.lv, ls.dist, src, filtered, cnt, done_ctr);
                     if (need && !reaches) kind = NTR_LIGHT_NONE;
                 }
             }
@@ -532,6 +584,7 @@ __device__ __forceinline__ void ray_color_warp(const SceneDev &s, bool enabled, 
             if (shade_finish<DT>(s, m, dir, P, N, src, depth, wl, acc, a, b, cnt)) emit(b);
         }
     }
+#endif
     if (enabled && !hit) {
         const float I = vsel<DT>(dir, s.bg_axis);       // tracer.hpp:1866-1867
     NTR_UNROLL

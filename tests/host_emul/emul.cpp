@@ -67,6 +67,8 @@ template <typename F> inline unsigned warp_reduce_u32(unsigned v, F f) {
 }
 inline unsigned __reduce_min_sync(unsigned, unsigned v) { return warp_reduce_u32(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
 inline unsigned __reduce_max_sync(unsigned, unsigned v) { return warp_reduce_u32(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
+inline void __syncwarp() { pthread_barrier_wait(&warp_emu::warp->bar); }
+inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); }
 inline unsigned __reduce_add_sync(unsigned, unsigned v) { return warp_reduce_u32(v, [](unsigned a, unsigned b) { return a + b; }); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
@@ -203,6 +205,7 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
     while (primary || !q.empty()) {
         const size_t n = primary ? (size_t)w * h : q.size();
         warp_emu::Warp W;
+        int done_ctr = 0;               // the per-warp counter the kernels keep in shared memory
         std::vector<std::pair<size_t, Bounce<DT>>> out[32];
         std::vector<uint32_t> outpix[32];
         Counters cnts[32];
@@ -233,7 +236,7 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
                         }
                     }
                     LaneEmit<DT> emit{&out[L], &outpix[L], idx, pix};
-                    ray_color_warp<DT, FLAGS>(S.dev, enabled, o, dir, depth, skip, primary ? one : wgt, acc, emit, cnts[L], primary ? &prim : nullptr);
+                    ray_color_warp<DT, FLAGS>(S.dev, enabled, o, dir, depth, skip, primary ? one : wgt, acc, emit, cnts[L], primary ? &prim : nullptr, &done_ctr);
                     if (!enabled) continue;
                     if (primary) {
                         if (rgb) { rgb[(size_t)pix * 3] = acc[0]; rgb[(size_t)pix * 3 + 1] = acc[1]; rgb[(size_t)pix * 3 + 2] = acc[2]; }
