@@ -1,12 +1,15 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the render path (BASELINE.json: Mrays/s and frame time).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c4|c1] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c4|c4b|c2|...] [--impl ours|reference]
 
-A step = one frame of the workload.  At N=1 the workload is BASELINE.json configs[1]: the 4-D 120-cell
-{5,3,3} CompositeScene (the reference's own k-d tree, tests/golden/cell120.npz), 1920x1080, one PointLight
-+ one GlobalLight, shadows on, RGB8 output.  N>1 (launched with torchrun, one rank per GPU): the same
-frame partitioned by interleaved 32-pixel tile rows, scene replicated, strips gathered with NCCL.
+A step = one frame of the workload.  The workload is the frame BASELINE.json's metric and north star are quoted on
+(configs[3]): the great grand stellated 120-cell {5/2,3,3} as a CompositeScene over the reference's own k-d tree
+(tests/golden/ggs120.npz), 3840x2160, PointLight + GlobalLight, shadows, reflections depth 4, 12 transparent cells,
+RGB8 output.  The line also carries `secondary`: the same measurement for {5/2,5,3} (the symbol BASELINE.json spells,
+c4b) and for configs[1] (c2, 1920x1080 {5,3,3}).  N>1 (launched with torchrun, one rank per GPU): the same frame
+partitioned by interleaved 32-pixel tile rows, scene replicated, every rank storing its rows into one frame on rank
+0's GPU over NVLink.
 
 One JSON line is printed by rank 0; see the prompt contract for the keys.  `value` = device-resident
 throughput (kernels only, CUDA events), `e2e` = the same metric through ntr_render with a HOST destination
@@ -38,10 +41,10 @@ CONFIGS = {
     'c4b': ('ssc120:refl_transp', 3840, 2160, "config 4 as BASELINE.json spells its symbol: small stellated 120-cell {5/2,5,3} (7,200 simplexes, leaves <= 48 items), 3840x2160, lights, shadows, reflectivity 0.3 depth 4, 12 transparent cells (opacity 0.5)"),
     'c4o': ('ggs120', 3840, 2160, "config 4 (opaque variant): great grand stellated 120-cell {5/2,3,3} 3840x2160, lights, shadows, reflectivity 0.3 depth 4"),
 }
-def metric_name(reflection_rays):
-    """BASELINE.json's metric is 'Mrays/sec (primary+shadow)'; frames with bounce passes also count their reflection /
-    transparency rays, and say so."""
-    return 'Mrays/sec (primary+shadow)' if not reflection_rays else 'Mrays/sec (primary+shadow+reflection)'
+# BASELINE.json's metric, verbatim.  `value` is the Mrays/s half (rays of a frame / frame time; frames with bounce passes
+# count their reflection / transparency rays too, SURVEY.md 8d, see config.rays_counted); the "4K frame time" half is
+# ms_per_step / config.frame_ms of the same line, and the 1/2/4/8 curve is this line at --gpus 1, 2, 4, 8.
+METRIC = 'Mrays/sec (primary+shadow) and 4K frame time at 1/2/4/8 B200 vs CPU cores'
 
 
 def load_fixture(name):
@@ -227,14 +230,120 @@ def reference_arm_subprocess(args):
     return {'value': None, 'unit': 'Mrays/s', 'cores': os.cpu_count() or 1, 'kind': 'reference', 'sample': 'reference arm failed: ' + why}
 
 
+def kernel_name(sc, dim):
+    """The kernel that dominates a frame of this scene (one render_pass_kernel instantiation per dimension and variant)."""
+    fixed = 3 <= dim <= 10 and not int(os.environ.get('NTR_FORCE_GENERIC', '0') or 0)
+    general = int(sc['kind']) == 1 and (bool(np.any(np.asarray(sc['materials'])[:, 6] < 1)) or len(sc['solids']) > 0)
+    return 'render_pass_kernel<%d,%d>' % (dim if fixed else 0, 1 if general else 0)
+
+
+def measured_traffic(config, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture of this workload (profiles/r02_traffic.json, written by tools/ncu_traffic.py); None when there is none."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))[config]
+        if t['kernel'] == kernel:
+            return t
+    except Exception:
+        pass
+    return None
+
+
+class Workload:
+    """One bench config on this rank's GPU: scene upload, the frame in the memory of rank 0's GPU, timed steps."""
+    def __init__(self, name, rank, local_rank, world):
+        import torch
+        from ntracer_b200 import _capi
+        from ntracer_b200 import dist as ntd
+        from ntracer_b200.backend import DeviceScene
+        self.name, self.rank, self.world = name, rank, world
+        fixture, self.w, self.h, self.desc = CONFIGS[name]
+        self.sc, self.g = load_fixture(fixture)
+        self.dim = int(self.sc['dim'])
+        self.ds = DeviceScene(self.sc, local_rank)
+        self.fmt = _capi.make_image_format(self.w, self.h, _capi.RGB8)
+        self.frame_bytes = self.w * self.h * 3
+        self.gather = os.environ.get('NTR_BENCH_GATHER', 'peer')
+        if world > 1 and self.gather == 'nccl':
+            self.dr = ntd.DistributedRenderer(self.ds, self.fmt)
+        else:
+            self.dr = ntd.PeerFrameRenderer(self.ds, self.fmt)
+        self.host_frame = torch.zeros(self.fmt.pitch * self.h, dtype=torch.uint8).pin_memory()
+        self.cam_o = np.ascontiguousarray(self.sc['cam_origin'], np.float32)
+        self.cam_a = np.ascontiguousarray(self.sc['cam_axes'], np.float32)
+        self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # ray counts of the frame (device counters of a synchronous render of the whole frame)
+        self.ds.render_float(self.w, self.h)
+        self.cnt = self.ds.counters()
+        self.rays = self.cnt['primary_rays'] + self.cnt['shadow_rays'] + self.cnt['reflection_rays']
+
+    def step_device(self):
+        """one frame, inputs resident, output stays on the device (the whole frame ends up in rank 0's GPU memory);
+        returns device ms between CUDA events on the launching stream"""
+        dr = self.dr
+        self.ev0.record(dr.stream)
+        if self.gather == 'nccl' and self.world > 1:
+            dr.render_strip(); dr.gather(); dr.frame_on_device()
+        else:
+            dr.render(); dr.fence()
+        self.ev1.record(dr.stream)
+        self.ev1.synchronize()
+        return self.ev0.elapsed_time(self.ev1)
+
+    def step_e2e(self):
+        """the same frame through the host-buffer path: camera upload + render (+ completion fence) + D2H"""
+        self.ds.set_camera(self.cam_o, self.cam_a)
+        if self.world == 1:
+            self.ds.render(self.fmt, self.host_frame.numpy())       # ntr_render: what BlockingRenderer.render calls
+        else:
+            self.dr.render_to_host()
+
+    def close(self):
+        if hasattr(self.dr, 'close'):
+            self.dr.close()
+        self.ds.close()
+
+
+def timed(wl, steps, warmup, flush, barrier):
+    """-> (device ms per step, e2e ms per step, launches), each the MAX over ranks of the per-rank totals"""
+    import torch
+    import torch.distributed as dist
+    for _ in range(warmup):
+        wl.step_device()
+        wl.step_e2e()
+    barrier()
+    launches0 = wl.ds.launch_count()
+    dev_ms = []
+    for _ in range(steps):
+        flush.zero_()                   # L2 flush between timed iterations
+        barrier()
+        dev_ms.append(wl.step_device())
+    barrier()
+    e2e_s = []
+    for _ in range(steps):
+        flush.zero_()
+        barrier()
+        t = time.perf_counter()
+        wl.step_e2e()
+        e2e_s.append(time.perf_counter() - t)
+    barrier()
+    launches = wl.ds.launch_count() - launches0
+    tot = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3, float(launches)], dtype=torch.float64, device='cuda')
+    if wl.world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    d, e, l = [float(v) for v in tot.tolist()]
+    return d / steps, e / steps, int(l), dev_ms
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--config', default='c2', choices=sorted(CONFIGS))
+    ap.add_argument('--config', default='c4', choices=sorted(CONFIGS))
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the secondary workloads (c4b, c2) reported beside the headline one')
     ap.add_argument('--stream-frames', type=int, default=160,
                     help='frames of the rotating-camera loop (polytope.py --benchmark); 0 = skip that leg')
     args = ap.parse_args()
@@ -244,14 +353,11 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     fixture, w, h, desc = CONFIGS[args.config]
-    sc, g = load_fixture(fixture)
-    dim = int(sc['dim'])
-    frame_bytes = w * h * 3
-    n_lights = (len(sc.get('point_lights', [])) + len(sc.get('global_lights', []))) if int(sc['kind']) == 1 else 0
 
     if args.impl == 'reference':
         if rank != 0:
             return 0
+        sc, g = load_fixture(fixture)
 
         def ref_watchdog():
             print(json.dumps({'impl': 'reference', 'unavailable': 'the reference renderer did not finish within %d s '
@@ -260,15 +366,19 @@ def main():
         rwd = threading.Timer(2 * REFERENCE_TIMEOUT_S, ref_watchdog)
         rwd.daemon = True
         rwd.start()
-        # ray counts of the frame from the counting CPU restatement (the reference does not count rays)
+        # ray counts of the frame from the counting CPU restatement (the reference does not count rays); counted on a
+        # frame of 1/4 the linear size and scaled when the full frame would take the restatement minutes (the counts per
+        # pixel of the same view agree to 0.1 % between the two sizes)
         from tests import oracle_lib as ol
-        _, cnt = ol.render_float(sc, w, h, with_counters=True)
-        rays = cnt['primary_rays'] + cnt['shadow_rays'] + cnt['reflection_rays']
+        div = 4 if w * h > 4000000 else 1
+        _, cnt = ol.render_float(sc, w // div, h // div, with_counters=True)
+        rays = (cnt['primary_rays'] + cnt['shadow_rays'] + cnt['reflection_rays']) * div * div
         base = reference_arm(args, sc, g, w, h, rays)
-        line = {'impl': 'reference', 'metric': metric_name(cnt['reflection_rays']), 'value': base['value'], 'unit': 'Mrays/s', 'n_gpus': args.gpus,
+        line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'Mrays/s', 'n_gpus': args.gpus,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': base['sec_per_frame'] * 1e3,
                 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': desc, 'rays_per_frame': rays},
+                'config': {'workload': desc, 'width': w, 'height': h, 'rays_per_frame': rays,
+                           'frame_ms': base['sec_per_frame'] * 1e3, 'frames_per_s': 1.0 / base['sec_per_frame']},
                 'cpu_baseline': base,
                 'e2e': {'value': base['value'], 'unit': 'Mrays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
         rwd.cancel()
@@ -277,149 +387,90 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from ntracer_b200 import _capi
-    from ntracer_b200.backend import DeviceScene, measure_fp32_peak
+    from ntracer_b200.backend import measure_fp32_peak
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     dev = torch.device('cuda', local_rank)
-    ds = DeviceScene(sc, local_rank)
-    fmt = _capi.make_image_format(w, h, _capi.RGB8)
-    from ntracer_b200 import dist as ntd
-    dr = ntd.DistributedRenderer(ds, fmt)           # world == 1: the strip is the whole frame
-    host_frame = torch.zeros(fmt.pitch * h, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    cam_o = np.ascontiguousarray(sc['cam_origin'], np.float32)
-    cam_a = np.ascontiguousarray(sc['cam_axes'], np.float32)
-
-    # ray counts of this frame (device counters of a synchronous render)
-    ds.render_float(w, h)
-    cnt_gpu = ds.counters()
-    rays = cnt_gpu['primary_rays'] + cnt_gpu['shadow_rays'] + cnt_gpu['reflection_rays']
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def step_device():
-        """one frame, inputs resident, output stays on the device (rank 0 ends up with the composed frame);
-        returns device ms between CUDA events on the launching stream"""
-        ev0.record(dr.stream)
-        dr.render_strip()
-        if world > 1:
-            dr.gather()
-            dr.frame_on_device()
-        ev1.record(dr.stream)
-        ev1.synchronize()
-        return ev0.elapsed_time(ev1)
-
-    def breakdown():
-        """per-phase device times of one step (diagnostic, NTR_BENCH_BREAKDOWN=1): render, gather, compose"""
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        e[0].record(dr.stream)
-        dr.render_strip()
-        e[1].record(dr.stream)
-        if world > 1:
-            dr.gather()
-        e[2].record(dr.stream)
-        if world > 1:
-            dr.frame_on_device()
-        e[3].record(dr.stream)
-        e[3].synchronize()
-        return [e[i].elapsed_time(e[i + 1]) for i in range(3)]
-
-    def step_e2e():
-        """the same frame through the host-buffer path: camera upload + render (+ gather) + D2H"""
-        ds.set_camera(cam_o, cam_a)
-        if world == 1:
-            ds.render(fmt, host_frame.numpy())
-        else:
-            dr.render_to_host()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-        step_e2e()
+    wl = Workload(args.config, rank, local_rank, world)
+    sc, g, dim, frame_bytes = wl.sc, wl.g, wl.dim, wl.frame_bytes
+    n_lights = (len(sc.get('point_lights', [])) + len(sc.get('global_lights', []))) if int(sc['kind']) == 1 else 0
+    cnt_gpu, rays = wl.cnt, wl.rays
 
     if os.environ.get('NTR_BENCH_BREAKDOWN'):
-        rows = []
-        for _ in range(10):
-            flush.zero_()
-            barrier()
-            rows.append(breakdown())
-        if rank == 0:
-            med = [statistics.median(r[i] for r in rows) for i in range(3)]
-            print('breakdown ms (median of 10): render %.4f gather %.4f compose %.4f' % tuple(med), file=sys.stderr)
+        os.environ['NTR_PASS_TIMING'] = '1'
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    # ---- timed region 1: device-resident ----
-    barrier()
-    launches0 = ds.launch_count()
-    dev_ms = []
-    for _ in range(args.steps):
-        flush.zero_()                   # L2 flush between timed iterations
-        torch.cuda.synchronize()
-        dev_ms.append(step_device())
-    barrier()
-    # ---- timed region 2: end to end through host buffers ----
-    e2e_s = []
-    for _ in range(args.steps):
-        flush.zero_()
-        barrier()
-        t = time.perf_counter()
-        step_e2e()
-        e2e_s.append(time.perf_counter() - t)
-    barrier()
+    ms_per_step, e2e_ms, launches, dev_ms = timed(wl, args.steps, args.warmup, flush, barrier)
     clocks = sampler.stop() if sampler else None
-    launches = ds.launch_count() - launches0      # kernels of this library launched inside the two timed regions
+
+    # the secondary workloads, measured the same way with fewer steps: BASELINE.json spells config 4's symbol {5/2,5,3}
+    # (c4b) while naming the {5/2,3,3} polytope (c4, the headline); c2 is the round-1 headline
+    secondary = {}
+    if not args.no_secondary and args.config == 'c4':
+        for name in ('c4b', 'c2'):
+            w2 = Workload(name, rank, local_rank, world)
+            k = max(3, min(args.steps, 10))
+            d2, e2, l2, _ = timed(w2, k, 3, flush, barrier)
+            secondary[name] = {'workload': w2.desc, 'width': w2.w, 'height': w2.h, 'rays_per_frame': w2.rays, 'steps': k,
+                               'ms_per_step': d2, 'value': w2.rays / (d2 * 1e-3) / 1e6, 'unit': 'Mrays/s',
+                               'e2e_ms_per_step': e2, 'e2e_value': w2.rays / (e2 * 1e-3) / 1e6, 'frames_per_s': 1e3 / d2,
+                               'gpu_launches': l2}
+            w2.close()
+
+    ds = wl.ds
 
     def stream_leg():
         """the interactive loop: rotating camera, one frame per camera, two frames in flight, every frame
         copied into a pinned host buffer (ntr_render_begin / ntr_render_end); wall clock around the whole loop"""
         from ntracer_b200 import stream as nts
         n_frames = int(max(8, min(args.stream_frames, 4000.0 / max(statistics.median(dev_ms), 1e-3))))
-        cams = nts.rotation_cameras(cam_o, cam_a, args.stream_frames)[:n_frames]
-        bufs = [host_frame.numpy(), torch.zeros(fmt.pitch * h, dtype=torch.uint8).pin_memory().numpy()]
-        nts.render_sequence(ds, fmt, cams[:4], bufs)                    # warm-up
+        cams = nts.rotation_cameras(wl.cam_o, wl.cam_a, args.stream_frames)[:n_frames]
+        bufs = [wl.host_frame.numpy(), torch.zeros(wl.fmt.pitch * h, dtype=torch.uint8).pin_memory().numpy()]
+        nts.render_sequence(ds, wl.fmt, cams[:4], bufs)                    # warm-up
         torch.cuda.synchronize()
         launches_s0 = ds.launch_count()
         t = time.perf_counter()
-        nts.render_sequence(ds, fmt, cams, bufs)
+        nts.render_sequence(ds, wl.fmt, cams, bufs)
         torch.cuda.synchronize()
         el = time.perf_counter() - t
-        ds.set_camera(cam_o, cam_a)
+        ds.set_camera(wl.cam_o, wl.cam_a)
         return {'frames': n_frames, 'camera_path': 'polytope.py RotatingCamera, %d steps per turn' % args.stream_frames,
                 'in_flight': 2, 'ms_per_frame': 1e3 * el / n_frames, 'frames_per_s': n_frames / el,
                 'Mpix_per_s': w * h * n_frames / el / 1e6, 'd2h_bytes_per_frame': int(frame_bytes),
                 'gpu_launches': int(ds.launch_count() - launches_s0)}
 
-    tot_dev = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot_dev, op=dist.ReduceOp.MAX)
-    dev_total_ms, e2e_total_ms = [float(v) for v in tot_dev.tolist()]
-
     if rank == 0:
-        ms_per_step = dev_total_ms / args.steps
         value = rays / (ms_per_step * 1e-3) / 1e6
-        e2e_ms = e2e_total_ms / args.steps
         line = {
-            'metric': metric_name(cnt_gpu['reflection_rays']), 'value': value, 'unit': 'Mrays/s', 'n_gpus': world, 'steps': args.steps,
+            'metric': METRIC, 'value': value, 'unit': 'Mrays/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': desc, 'width': w, 'height': h, 'dim': dim, 'rays_per_frame': rays,
                        'ray_counts': {k: cnt_gpu[k] for k in ('primary_rays', 'shadow_rays', 'reflection_rays')},
+                       'rays_counted': 'primary + shadow + reflection/transparency rays of the frame (device counters)',
+                       'frame_ms': ms_per_step, 'frame_ms_e2e': e2e_ms,
                        'l2_flush_between_iterations': True, 'tree': 'reference k-d tree (exported, tests/golden)',
-                       'partition': 'interleaved 32-px tile rows over %d GPU(s)' % world,
+                       'partition': 'interleaved 32-px tile rows over %d GPU(s); every GPU stores its rows into one frame on GPU 0 over NVLink (peer stores, no gather)' % world
+                                    if wl.gather != 'nccl' else 'interleaved 32-px tile rows over %d GPU(s), NCCL all-gather' % world,
                        'frames_per_s': 1e3 / ms_per_step, 'Mpix_per_s': w * h / (ms_per_step * 1e-3) / 1e6},
             'e2e': {'value': rays / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mrays/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': int(4 * (dim + dim * dim)), 'd2h_bytes_per_step': int(frame_bytes)},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
+        if secondary:
+            line['secondary'] = secondary
         # The headline numbers are complete here.  The legs below (roofline counts, CPU baseline, interactive loop) run
         # under a watchdog: if one of them hangs -- the reference's renderer has a refcount race that can corrupt its
         # heap (oracle/ref_bridge.make_immortal) -- the line is printed without it instead of never.
@@ -440,9 +491,9 @@ def main():
         wd.daemon = True
         wd.start()
         if world == 1:
-            # ---- roofline of the dominant kernel (render_pass_kernel: the only kernel of this frame) ----
+            # ---- roofline of the dominant kernel (render_pass_kernel: >= 99 % of the step, profiles/*_launches*) ----
             from tests import oracle_lib as ol
-            counts_from = 'counting CPU restatement of the reference algorithm (oracle) on the same tree'
+            counts_from = 'counting CPU restatement of the reference algorithm (oracle) on the same tree, same frame'
             if int(sc['kind']) == 1 and int(sc['simplex'].shape[0]) > 20000:
                 # far too slow for the scalar restatement at this size: the instrumented GPU build traverses the same
                 # tree with the same control flow (it only lacks the reference's mailbox for single simplexes)
@@ -452,7 +503,10 @@ def main():
                 ds.set_instrumented(False)
                 counts_from = 'device counters of the instrumented kernels (NTR_F_COUNT) on the same tree'
             else:
-                _, cnt_ref = ol.render_float(sc, w, h, with_counters=True)     # reference-algorithm counts
+                _, mask, cnt_ref = ol.render_float(sc, w, h, with_mask=True, with_counters=True)     # reference-algorithm counts
+                # share of the pixels on which the reference itself is defined (its mailbox / hit lists stay inside
+                # their preallocation, tracer.hpp:670-680) and not decided by rounding noise (Q12): where parity is claimed
+                line['config']['defined_pixel_fraction'] = float(np.mean(mask == 0))
             flops = flops_per_frame(dim, cnt_ref, n_lights)
             fp32_peak = measure_fp32_peak(local_rank)
             achieved = flops / (ms_per_step * 1e-3) / 1e12
@@ -463,19 +517,21 @@ def main():
                 pass
             hbm_peak = peaks.get('hbm_gbs', 6650.0)
             abytes = bytes_per_frame(dim, cnt_ref, frame_bytes)
+            kern = kernel_name(sc, dim)
+            traffic = measured_traffic(args.config, kern)
             line['roofline'] = {
                 'bound': 'fp32', 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': achieved / fp32_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
-                # (profiles/r01_c2_render_pass_ncu_full_summary.txt); only measured for the default workload
-                'traffic': 10.28e6 if args.config == 'c2' else None,
+                'traffic': traffic['bytes_per_launch'] if traffic else None,
+                'traffic_source': traffic['source'] if traffic else None,
                 'peak_source': 'FP32 FMA micro-benchmark measured live in this run (ntr_measure_fp32_peak); MEASURED_PEAKS.json has HBM/BF16 only',
-                'algorithmic_flops_per_launch': flops, 'kernel': 'render_pass_kernel<%s,%d>' % (dim if (3 <= dim <= 10 and not int(os.environ.get('NTR_FORCE_GENERIC', '0') or 0)) else 0, 0), 'kernel_ms': ms_per_step,
+                'algorithmic_flops_per_launch': flops, 'kernel': kern, 'kernel_ms': ms_per_step,
+                'launches_per_step': launches / (2.0 * args.steps),
                 'reference_algorithm_counts': cnt_ref, 'counts_from': counts_from,
                 'hbm': {'achieved': abytes / (ms_per_step * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                         'frac': abytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                         'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback',
                         'algorithmic_bytes_per_launch': abytes,
-                        'note': 'working set (nodes+refs+simplexes, ~1.3 MB) is L2/L1-resident; DRAM traffic is the frame write'},
+                        'note': 'working set (nodes+refs+simplexes, a few MB) is L2/L1-resident; DRAM traffic is the frame, the accumulators and the ray queues'},
             }
             if not args.no_cpu_baseline:
                 line['cpu_baseline'] = reference_arm_subprocess(args)
@@ -485,9 +541,9 @@ def main():
                 line['stream'] = stream_leg()
         wd.cancel()
         emit()
+    wl.close()
     if world > 1:
         dist.destroy_process_group()
-    ds.close()
     return 0
 
 

@@ -199,6 +199,47 @@ NTR_API int ntr_occludes_rays(ntr_scene *scene, uint32_t n, const float *origins
                               const float *distance, const uint32_t *skip_ref, const int32_t *skip_lane,
                               int32_t *occluded_out, int32_t *n_transparent_out);
 
+/* ---- several GPUs of one box (no counterpart in the reference, whose parallelism is worker
+ * threads pulling 32x32 tiles, src/render.cpp:468-493,829-838) ---------------------------------------------------
+ * A group replicates the scene on n devices.  A frame is split by interleaved 32-pixel tile rows (tile row ty belongs
+ * to device ty % n, which balances the centre-heavy cost of polytope scenes); every device traces its rows and its
+ * packing epilogue stores the pixels straight into ONE frame buffer in the memory of the first device, over NVLink
+ * (peer access) -- there is no gather step and no second copy; one device->host transfer follows.  This is what
+ * BlockingRenderer(threads=N) maps to ("threads" = how many workers trace the frame).
+ * devices = NULL: the first n usable devices.  n = 0: all of them.  Every device must be able to reach devices[0]. */
+typedef struct ntr_group ntr_group;
+NTR_API int ntr_group_create(const ntr_scene_desc *desc, int n, const int *devices, ntr_group **out);
+NTR_API void ntr_group_destroy(ntr_group *group);
+NTR_API int ntr_group_size(ntr_group *group);
+NTR_API int ntr_group_set_camera(ntr_group *group, const float *origin, const float *axes);
+NTR_API int ntr_group_set_params(ntr_group *group, const ntr_scene_desc *desc);
+/* ntr_render over the group: host destination, same contract (NTR_ERR_ABORTED after ntr_group_abort). */
+NTR_API int ntr_group_render(ntr_group *group, const ntr_image_format *fmt, void *dst, size_t dst_len);
+/* The same frame left in device memory: *dev_frame_out receives the frame buffer on the first device (pitch*height
+ * bytes, owned by the group, valid until the next render of the group). */
+NTR_API int ntr_group_render_device(ntr_group *group, const ntr_image_format *fmt, void **dev_frame_out);
+NTR_API int ntr_group_abort(ntr_group *group);
+/* Counters of the last frame summed over the devices; device time of the last frame from the first kernel to the last
+ * one of the slowest device (CUDA events on the first device's stream, which waits for the others). */
+NTR_API int ntr_group_get_counters(ntr_group *group, ntr_counters *out);
+NTR_API int ntr_group_last_kernel_ms(ntr_group *group, float *ms_out);
+NTR_API uint64_t ntr_group_launch_count(ntr_group *group);
+
+/* One process per GPU (torchrun): the frame buffer lives in the process of rank 0 and the other ranks store into it
+ * through a CUDA IPC mapping -- ntr_frame_alloc + ntr_frame_export on rank 0, ntr_frame_import on the others, then
+ * ntr_render_device(scene, fmt, frame, len, stream, rank, world, 0) on every rank (compact = 0: rows at their frame
+ * position) and a stream-ordered barrier of the caller's choice (bench.py: a 4-byte NCCL all-reduce). */
+#define NTR_IPC_HANDLE_BYTES 64
+NTR_API int ntr_frame_alloc(int device, size_t bytes, void **dev_ptr_out);
+NTR_API int ntr_frame_free(int device, void *dev_ptr);
+NTR_API int ntr_frame_export(void *dev_ptr, unsigned char handle_out[NTR_IPC_HANDLE_BYTES]);
+NTR_API int ntr_frame_import(int device, const unsigned char handle[NTR_IPC_HANDLE_BYTES], void **dev_ptr_out);
+NTR_API int ntr_frame_release(int device, void *imported_ptr);
+/* Fills a frame with one byte value (cudaMemsetAsync; e.g. a background the renderers leave alone outside their rows). */
+NTR_API int ntr_frame_fill(int device, void *dev_ptr, int value, size_t bytes, void *stream);
+/* device frame -> host buffer (pixel bytes of every row; the pitch padding of dst is left alone), stream-ordered. */
+NTR_API int ntr_frame_download(int device, const void *dev_ptr, const ntr_image_format *fmt, void *dst, size_t dst_len, void *stream);
+
 /* ---- control --------------------------------------------------------------------------------- */
 /* renderer::state = CANCEL (src/render.cpp:333,412,702-722,911-923): polled per tile on the device. */
 NTR_API int ntr_abort(ntr_scene *scene);

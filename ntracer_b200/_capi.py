@@ -139,6 +139,15 @@ def make_desc(sc):
         pl = arr('point_lights', np.float32)
         gl = arr('global_lights', np.float32)
         stride = (dim + 1) * dim + 1
+        sol_stride = 1 + 2 * dim * dim + dim
+        if simplex.size % stride or solids.size % sol_stride or mats.size % 10 or nodes.size % 4:
+            raise ValueError('scene arrays do not match the record sizes of a %d-dimensional scene' % dim)
+        if smat.size != simplex.size // stride or solmat.size != solids.size // sol_stride:
+            raise ValueError('one material index per simplex / solid is required')
+        if bnd.size != 2 * dim:
+            raise ValueError('boundary must hold 2 x %d floats' % dim)
+        if pl.size % (dim + 3) or gl.size % (dim + 3):
+            raise ValueError('lights are rows of %d floats' % (dim + 3))
         d.root = int(sc['root']) & 0xFFFFFFFF
         d.n_nodes, d.nodes = nodes.shape[0], _ptr(nodes)
         d.n_leaf_refs, d.leaf_refs = refs.size, _ptr(refs)
@@ -208,6 +217,24 @@ def load():
         'ntr_build_kdtree': (C.c_int, [i32, u32, vp, vp, i32, i32, C.c_float, C.c_float, C.POINTER(vp), C.POINTER(u32),
                                        C.POINTER(vp), C.POINTER(u32), C.POINTER(u32), vp]),
         'ntr_free': (None, [vp]),
+        'ntr_group_create': (C.c_int, [C.POINTER(SceneDesc), i32, vp, C.POINTER(vp)]),
+        'ntr_group_destroy': (None, [vp]),
+        'ntr_group_size': (C.c_int, [vp]),
+        'ntr_group_set_camera': (C.c_int, [vp, vp, vp]),
+        'ntr_group_set_params': (C.c_int, [vp, C.POINTER(SceneDesc)]),
+        'ntr_group_render': (C.c_int, [vp, C.POINTER(ImageFormat), vp, C.c_size_t]),
+        'ntr_group_render_device': (C.c_int, [vp, C.POINTER(ImageFormat), C.POINTER(vp)]),
+        'ntr_group_abort': (C.c_int, [vp]),
+        'ntr_group_get_counters': (C.c_int, [vp, C.POINTER(Counters)]),
+        'ntr_group_last_kernel_ms': (C.c_int, [vp, f32p]),
+        'ntr_group_launch_count': (C.c_uint64, [vp]),
+        'ntr_frame_alloc': (C.c_int, [i32, C.c_size_t, C.POINTER(vp)]),
+        'ntr_frame_free': (C.c_int, [i32, vp]),
+        'ntr_frame_export': (C.c_int, [vp, vp]),
+        'ntr_frame_import': (C.c_int, [i32, vp, C.POINTER(vp)]),
+        'ntr_frame_release': (C.c_int, [i32, vp]),
+        'ntr_frame_fill': (C.c_int, [i32, vp, i32, C.c_size_t, vp]),
+        'ntr_frame_download': (C.c_int, [i32, vp, C.POINTER(ImageFormat), vp, C.c_size_t, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)       # AttributeError if the library does not export what the header declares
@@ -222,7 +249,12 @@ EXPORTED_SYMBOLS = (
     'ntr_render_end', 'ntr_render_float',
     'ntr_calculate_color', 'ntr_primary_hit_ids', 'ntr_trace_rays', 'ntr_occludes_rays', 'ntr_abort',
     'ntr_get_counters', 'ntr_set_instrumented', 'ntr_last_kernel_ms', 'ntr_launch_count',
-    'ntr_measure_fp32_peak', 'ntr_simplex_from_points', 'ntr_build_kdtree', 'ntr_free')
+    'ntr_measure_fp32_peak', 'ntr_simplex_from_points', 'ntr_build_kdtree', 'ntr_free',
+    'ntr_group_create', 'ntr_group_destroy', 'ntr_group_size', 'ntr_group_set_camera', 'ntr_group_set_params',
+    'ntr_group_render', 'ntr_group_render_device', 'ntr_group_abort', 'ntr_group_get_counters',
+    'ntr_group_last_kernel_ms', 'ntr_group_launch_count',
+    'ntr_frame_alloc', 'ntr_frame_free', 'ntr_frame_export', 'ntr_frame_import', 'ntr_frame_release',
+    'ntr_frame_fill', 'ntr_frame_download')
 
 
 class AbortedError(RuntimeError):

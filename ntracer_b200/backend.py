@@ -161,6 +161,106 @@ class DeviceScene:
         return int(self._lib.ntr_launch_count(self._h))
 
 
+class DeviceGroup:
+    """One scene replicated on several B200s of one box (ntr_group_*): a frame is split by interleaved 32-pixel tile rows
+    and every device stores its rows straight into one frame buffer on the first device over NVLink."""
+    def __init__(self, scene, n=0, devices=None):
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        self.dim = int(scene['dim'])
+        desc, keep = _capi.make_desc(scene)
+        devs = None if devices is None else (C.c_int * len(devices))(*[int(d) for d in devices])
+        _capi.check(self._lib.ntr_group_create(C.byref(desc), len(devices) if devices is not None else int(n), devs, C.byref(self._h)))
+        self.size = int(self._lib.ntr_group_size(self._h))
+        if 'cam_origin' in scene and 'cam_axes' in scene:
+            self.set_camera(scene['cam_origin'], scene['cam_axes'])
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            self._lib.ntr_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_camera(self, origin, axes):
+        o = np.ascontiguousarray(origin, dtype=np.float32).reshape(self.dim)
+        a = np.ascontiguousarray(axes, dtype=np.float32).reshape(self.dim, self.dim)
+        _capi.check(self._lib.ntr_group_set_camera(self._h, _p(o), _p(a)))
+
+    def set_params(self, scene):
+        desc, keep = _capi.make_desc(scene)
+        _capi.check(self._lib.ntr_group_set_params(self._h, C.byref(desc)))
+
+    def render(self, fmt, dest=None):
+        need = fmt.pitch * fmt.height
+        out = np.zeros(need, dtype=np.uint8) if dest is None else dest
+        buf = out if dest is None else np.frombuffer(dest, dtype=np.uint8)
+        if buf.size < need:
+            raise ValueError('the buffer is too small for an image with the given dimensions')
+        _capi.check(self._lib.ntr_group_render(self._h, C.byref(fmt), _p(buf), buf.size))
+        return out
+
+    def render_device(self, fmt):
+        """-> address of the frame on the first device (valid until the next render)"""
+        ptr = C.c_void_p()
+        _capi.check(self._lib.ntr_group_render_device(self._h, C.byref(fmt), C.byref(ptr)))
+        return ptr.value
+
+    def abort(self):
+        _capi.check(self._lib.ntr_group_abort(self._h))
+
+    def counters(self):
+        c = _capi.Counters()
+        _capi.check(self._lib.ntr_group_get_counters(self._h, C.byref(c)))
+        return c.as_dict()
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _capi.check(self._lib.ntr_group_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self._lib.ntr_group_launch_count(self._h))
+
+
+class SharedFrame:
+    """A frame buffer in the memory of one GPU that kernels of OTHER processes store into (one process per GPU):
+    rank 0 allocates and exports it, the others import the handle (CUDA IPC)."""
+    def __init__(self, device, nbytes=0, handle=None):
+        self._lib = _capi.load()
+        self.device, self.owner = int(device), handle is None
+        ptr = C.c_void_p()
+        if self.owner:
+            _capi.check(self._lib.ntr_frame_alloc(self.device, int(nbytes), C.byref(ptr)))
+        else:
+            h = (C.c_ubyte * 64).from_buffer_copy(bytes(handle))
+            _capi.check(self._lib.ntr_frame_import(self.device, h, C.byref(ptr)))
+        self.ptr = ptr.value
+
+    def export(self):
+        h = (C.c_ubyte * 64)()
+        _capi.check(self._lib.ntr_frame_export(C.c_void_p(self.ptr), h))
+        return bytes(h)
+
+    def fill(self, value, nbytes, stream=0):
+        _capi.check(self._lib.ntr_frame_fill(self.device, C.c_void_p(self.ptr), int(value), int(nbytes), C.c_void_p(stream)))
+
+    def download(self, fmt, dest, stream=0):
+        buf = np.frombuffer(dest, dtype=np.uint8)
+        _capi.check(self._lib.ntr_frame_download(self.device, C.c_void_p(self.ptr), C.byref(fmt), _p(buf), buf.size, C.c_void_p(stream)))
+
+    def close(self):
+        if self.ptr:
+            (self._lib.ntr_frame_free if self.owner else self._lib.ntr_frame_release)(self.device, C.c_void_p(self.ptr))
+            self.ptr = None
+
+
 def device_count():
     return int(_capi.load().ntr_device_count())
 

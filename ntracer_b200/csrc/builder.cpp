@@ -17,10 +17,12 @@
 #include <future>
 #include <memory>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <vector>
 
 #include "../../include/ntracer_b200.h"
+#include "errors.h"
 
 namespace {
 
@@ -168,7 +170,8 @@ NTR_API void ntr_free(void *p) { free(p); }
 
 // points: n x D x D (n simplexes of D vertices); records: n x ((D+1)*D+1) = face_normal[D], d, p1[D], edge_normals[D-1][D]
 NTR_API int ntr_simplex_from_points(int dim, uint32_t n, const float *points, float *records) {
-    if (dim < 3 || dim > NTR_MAX_DIM || (!points && n) || (!records && n)) return NTR_ERR_VALUE;
+    if (dim < 3 || dim > NTR_MAX_DIM) return ntr_fail(NTR_ERR_VALUE, "dimension must be between 3 and %d", NTR_MAX_DIM);
+    if ((!points && n) || (!records && n)) return ntr_fail(NTR_ERR_VALUE, "points / records is NULL");
     const int D = dim, S = (D + 1) * D + 1;
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const unsigned nthreads = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, n / 256));
@@ -194,12 +197,18 @@ NTR_API int ntr_simplex_from_points(int dim, uint32_t n, const float *points, fl
         }
     };
     std::vector<std::thread> th;
-    for (unsigned t = 0; t < nthreads; ++t) {
-        const uint32_t a = (uint32_t)((uint64_t)n * t / nthreads), b = (uint32_t)((uint64_t)n * (t + 1) / nthreads);
-        th.emplace_back(work, a, b);
-    }
+    uint32_t started = 0;                   // simplexes handed to threads so far
+    try {
+        for (unsigned t = 0; t + 1 < nthreads; ++t) {
+            const uint32_t a = (uint32_t)((uint64_t)n * t / nthreads), b = (uint32_t)((uint64_t)n * (t + 1) / nthreads);
+            th.emplace_back(work, a, b);
+            started = b;
+        }
+    } catch (const std::system_error &) {}  // no more threads to be had: the caller's thread does the rest
+    int rc = NTR_OK;
+    try { work(started, n); } catch (const std::bad_alloc &) { rc = ntr_fail(NTR_ERR_MEMORY, "out of memory"); }
     for (auto &t : th) t.join();
-    return NTR_OK;
+    return rc;
 }
 
 // lo/hi: n x D item bounds.  Outputs are malloc'ed (release with ntr_free): nodes (16-byte ntr_node, root = node 0 or
@@ -207,12 +216,13 @@ NTR_API int ntr_simplex_from_points(int dim, uint32_t n, const float *points, fl
 NTR_API int ntr_build_kdtree(int dim, uint32_t n, const float *lo, const float *hi, int max_depth, int split_threshold,
                              float traversal_cost, float intersection_cost, ntr_node **nodes_out, uint32_t *n_nodes_out,
                              uint32_t **refs_out, uint32_t *n_refs_out, uint32_t *root_out, float *boundary_out) {
-    if (dim < 3 || dim > NTR_MAX_DIM || !nodes_out || !refs_out || !n_nodes_out || !n_refs_out || !root_out || !boundary_out)
-        return NTR_ERR_VALUE;
-    if (n && (!lo || !hi)) return NTR_ERR_VALUE;
+    if (dim < 3 || dim > NTR_MAX_DIM) return ntr_fail(NTR_ERR_VALUE, "dimension must be between 3 and %d", NTR_MAX_DIM);
+    if (!nodes_out || !refs_out || !n_nodes_out || !n_refs_out || !root_out || !boundary_out) return ntr_fail(NTR_ERR_VALUE, "NULL output argument");
+    if (n && (!lo || !hi)) return ntr_fail(NTR_ERR_VALUE, "item bounds are NULL");
     const int D = dim;
     for (size_t k = 0; k < (size_t)n * D; ++k)             // NaN, infinite or inverted bounds would poison the SAH sweep
-        if (!(lo[k] <= hi[k]) || !(lo[k] > -3e38f) || !(hi[k] < 3e38f)) return NTR_ERR_VALUE;
+        if (!(lo[k] <= hi[k]) || !(lo[k] > -3e38f) || !(hi[k] < 3e38f))
+            return ntr_fail(NTR_ERR_VALUE, "item %zu: bounds are NaN, infinite or inverted", k / D);
     Builder b;
     b.D = D; b.lo = lo; b.hi = hi;
     b.max_depth = max_depth > 0 ? std::min(max_depth, NTR_MAX_TREE_DEPTH - 2) : 25;
@@ -294,14 +304,16 @@ NTR_API int ntr_build_kdtree(int dim, uint32_t n, const float *lo, const float *
         } par{b, 4};
         root = par.run(tree, idx, blo, bhi, 0);
     } catch (const std::bad_alloc &) {
-        return NTR_ERR_MEMORY;
+        return ntr_fail(NTR_ERR_MEMORY, "out of memory building the k-d tree");
+    } catch (const std::system_error &e) {
+        return ntr_fail(NTR_ERR_RUNTIME, "k-d tree builder: %s", e.what());
     }
     *n_nodes_out = (uint32_t)tree.nodes.size();
     *n_refs_out = (uint32_t)tree.refs.size();
     *root_out = root;
     *nodes_out = (ntr_node *)malloc(std::max<size_t>(1, tree.nodes.size()) * sizeof(ntr_node));
     *refs_out = (uint32_t *)malloc(std::max<size_t>(1, tree.refs.size()) * sizeof(uint32_t));
-    if (!*nodes_out || !*refs_out) { free(*nodes_out); free(*refs_out); return NTR_ERR_MEMORY; }
+    if (!*nodes_out || !*refs_out) { free(*nodes_out); free(*refs_out); return ntr_fail(NTR_ERR_MEMORY, "out of memory"); }
     if (!tree.nodes.empty()) memcpy(*nodes_out, tree.nodes.data(), tree.nodes.size() * sizeof(ntr_node));
     if (!tree.refs.empty()) memcpy(*refs_out, tree.refs.data(), tree.refs.size() * sizeof(uint32_t));
     return NTR_OK;

@@ -16,6 +16,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "arena_pack.h"
+#include "errors.h"
 #include "kernels.cuh"
 
 using namespace ntr;
@@ -24,13 +25,17 @@ namespace {
 
 thread_local std::string g_err;
 
-int fail(int code, const char *fmt, ...) {
+void set_error(const char *fmt, va_list ap) {
     char buf[512];
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    g_err = buf;
+}
+
+int fail(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
+    set_error(fmt, ap);
     va_end(ap);
-    g_err = buf;
     return code;
 }
 
@@ -70,6 +75,14 @@ struct FrameSlot {
     bool open = false, staged = false;
     uint64_t ticket = 0;
 };
+
+int ntr_fail(int code, const char *fmt, ...) {        // errors.h: for builder.cpp
+    va_list ap;
+    va_start(ap, fmt);
+    set_error(fmt, ap);
+    va_end(ap);
+    return code;
+}
 
 struct ntr_scene {
     int device = 0;
@@ -121,10 +134,11 @@ struct ntr_scene {
     cudaEvent_t slab_done[kSlabMax] = {};
     bool slabs = true;                  // NTR_NO_SLABS=1 switches it off
     // bounce passes of scenes with big leaves start the rays nearest the scene centre first (ray_keys_kernel) and hand
-    // them out a few per warp (kernels.cuh: NTR_FETCH_RING*); NTR_HEAVY_FIRST / NTR_ADAPTIVE_FETCH = 0|1 override
+    // them out a few per warp (fetch_sizes below); NTR_HEAVY_FIRST / NTR_ADAPTIVE_FETCH = 0|1 override
     bool heavy_first = false, adaptive_fetch = false;
     uint32_t max_leaf = 0;              // items in the largest leaf of the tree
     uint32_t *d_ring = nullptr;
+    uint32_t fetch_sizes = 4u | (8u << 8) | (16u << 16);      // NTR_FETCH_SIZES=a,b,c: rays per fetch from cost rings 0, 1, 2
     bool force_tile_sched = false;      // NTR_TILE_SCHED=1: cost-sorted tile hand-out on whole frames too (heavy-tailed scenes)
     bool zero_copy = false;             // NTR_ZEROCOPY=1: ntr_render stores single-pass frames straight into pinned destinations
     uint32_t queue_init = 0;            // NTR_QUEUE_INIT: initial queue capacity override (tests force the regrow path)
@@ -173,6 +187,11 @@ int validate_desc(const ntr_scene_desc *d, int *tree_depth_out) {
     if (!d->boundary) return fail(NTR_ERR_VALUE, "composite scene needs a boundary");
     if (d->bg_gradient_axis < 0 || d->bg_gradient_axis >= d->dim) return fail(NTR_ERR_VALUE, "bg_gradient_axis out of range");
     if (d->n_nodes && !d->nodes) return fail(NTR_ERR_VALUE, "nodes is NULL");
+    if (d->n_leaf_refs && !d->leaf_refs) return fail(NTR_ERR_VALUE, "leaf_refs is NULL");
+    if (d->n_simplex && (!d->simplex || !d->simplex_mat)) return fail(NTR_ERR_VALUE, "simplex / simplex_mat is NULL");
+    if (d->n_solids && (!d->solids || !d->solid_mat)) return fail(NTR_ERR_VALUE, "solids / solid_mat is NULL");
+    if (d->n_materials && !d->materials) return fail(NTR_ERR_VALUE, "materials is NULL");
+    if ((d->n_point_lights && !d->point_lights) || (d->n_global_lights && !d->global_lights)) return fail(NTR_ERR_VALUE, "lights array is NULL");
     if (d->root != NTR_NULL_NODE && d->root >= d->n_nodes) return fail(NTR_ERR_VALUE, "root node out of range");
     if (d->n_materials == 0 && (d->n_simplex || d->n_solids)) return fail(NTR_ERR_VALUE, "primitives without materials");
     for (uint32_t i = 0; i < d->n_simplex; ++i)
@@ -403,6 +422,24 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     ctl.overflow = d_ctl + CTL_OVERFLOW;
     ctl.abort_flag = sc->d_abort + sc->abort_idx;
     ctl.counters = d_counters;
+    ctl.fetch_stats = nullptr;
+#if NTR_FETCH_STATS
+    static unsigned long long *d_stats = nullptr;
+    if (!d_stats) cudaMalloc(&d_stats, 80 * sizeof(unsigned long long));
+    ctl.fetch_stats = d_stats;
+    auto dump_stats = [&](const char *what, int depth) {
+        unsigned long long h[80];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_stats, sizeof h, cudaMemcpyDeviceToHost);
+        cudaMemset(d_stats, 0, sizeof h);
+        if (!h[2]) return;
+        fprintf(stderr, "ntr fetch stats %s %d: fetches %llu, mean %.0f kcyc, longest %.0f kcyc; log2(cycles) histogram:", what, depth, h[2],
+                (double)h[1] / h[2] / 1e3, (double)h[0] / 1e3);
+        for (int k = 8; k < 40; ++k) if (h[8 + k]) fprintf(stderr, " %d:%llu", k, h[8 + k]);
+        fprintf(stderr, "\n");
+    };
+    cudaMemsetAsync(d_stats, 0, 80 * sizeof(unsigned long long), st);
+#endif
     CUDA_TRY(cudaMemsetAsync(d_ctl, 0, CTL_WORDS * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), st));
 
@@ -426,6 +463,9 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
     ++sc->launches;
     mark();
+#if NTR_FETCH_STATS
+    dump_stats("primary", 0);
+#endif
     if (use_sched) {
         // schedule for the next frame of this view, computed on the device right behind the primary pass
         const int tb = (int)((n_tiles + 127) / 128);
@@ -481,11 +521,15 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
                     ring_bounds_kernel<<<(n + 255) / 256, 256, 0, st>>>(sc->d_keys[1], n, q.in_count, sc->queue_capacity, ring);
                     ++sc->launches;
                     q.ring_start = ring;
+                    q.fetch_sizes = sc->fetch_sizes;
                 }
             }
             ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
             ++sc->launches;
             mark();
+#if NTR_FETCH_STATS
+            dump_stats("bounce", depth);
+#endif
         }
         if (tgt.out_mode == NTR_OUT_PACKED) {
             f.out_mode = NTR_OUT_PACKED;
@@ -820,6 +864,13 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->heavy_first = sc->adaptive_fetch = sc->max_leaf >= 256;
     if (const char *hf = getenv("NTR_HEAVY_FIRST")) sc->heavy_first = atoi(hf) != 0;
     if (const char *af = getenv("NTR_ADAPTIVE_FETCH")) sc->adaptive_fetch = atoi(af) != 0;
+    if (const char *fs = getenv("NTR_FETCH_SIZES")) {
+        unsigned a = 4, b = 8, c = 16;
+        if (sscanf(fs, "%u,%u,%u", &a, &b, &c) >= 1) {
+            auto cl = [](unsigned v) { return v < 1 ? 1u : v > 32 ? 32u : v; };
+            sc->fetch_sizes = cl(a) | (cl(b) << 8) | (cl(c) << 16);
+        }
+    }
     if (const char *qi = getenv("NTR_QUEUE_INIT")) sc->queue_init = (uint32_t)strtoul(qi, nullptr, 10);
     sc->tree_depth = depth;
     sc->dev.dim = desc->dim;
@@ -1268,6 +1319,280 @@ NTR_API int ntr_measure_fp32_peak(int device, float *tflops_out) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *tflops_out = best;
+    return NTR_OK;
+}
+
+// ---- several GPUs of one box ------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct ntr_group {
+    std::vector<ntr_scene *> sc;
+    std::vector<int> dev;
+    unsigned char *d_frame = nullptr;       // on dev[0]; every device stores its tile rows into it (peer access)
+    size_t frame_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;           // on dev[0]
+    std::vector<cudaEvent_t> done;                      // per device: its part of the frame is complete
+    ntr_counters counters{};
+    float last_ms = 0;
+    bool timing_valid = false;
+    std::atomic<bool> busy{false};
+};
+
+namespace {
+
+// Traces one frame with every device of the group into g->d_frame.  On return the frame is complete in the memory of
+// dev[0] and the stream of sc[0] is ordered behind every device's work (the caller may enqueue a copy on it).
+int group_trace(ntr_group *g, const ntr_image_format *fmt) {
+    const int n = (int)g->sc.size();
+    const size_t bytes = (size_t)fmt->pitch * fmt->height;
+    CUDA_TRY(cudaSetDevice(g->dev[0]));
+    if (g->frame_cap < bytes) {
+        if (g->d_frame) { cudaFree(g->d_frame); g->d_frame = nullptr; g->frame_cap = 0; }
+        CUDA_TRY(cudaMalloc(&g->d_frame, bytes + bytes / 8));
+        g->frame_cap = bytes + bytes / 8;
+    }
+    std::vector<FrameJob> jobs(n);
+    std::vector<char> pending(n, 1);
+    for (int i = 0; i < n; ++i) {
+        ntr_scene *sc = g->sc[i];
+        if (sc->busy.exchange(true)) {
+            for (int k = 0; k < i; ++k) g->sc[k]->busy.store(false);
+            return fail(NTR_ERR_RUNTIME, "the renderer is already running");
+        }
+        sc->h_abort[0] = 0;
+        sc->abort_idx = 0;
+        RenderTarget tgt;
+        tgt.out_mode = NTR_OUT_PACKED;
+        tgt.packed = g->d_frame;
+        jobs[i] = FrameJob{fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, i, n, 0, sc->stream};
+    }
+    struct Release { ntr_group *g; ~Release() { for (ntr_scene *s : g->sc) s->busy.store(false); } } release{g};
+    CUDA_TRY(cudaEventRecord(g->ev0, g->sc[0]->stream));
+    int rc = NTR_OK;
+    for (int attempt = 0; attempt < 8 && rc == NTR_OK; ++attempt) {
+        bool any = false;
+        for (int i = 0; i < n && rc == NTR_OK; ++i) {
+            if (!pending[i]) continue;
+            any = true;
+            CUDA_TRY(cudaSetDevice(g->dev[i]));
+            if (i && attempt == 0) CUDA_TRY(cudaStreamWaitEvent(g->sc[i]->stream, g->ev0, 0));   // the frame's clock starts on dev[0]
+            if ((rc = frame_submit(g->sc[i], jobs[i])) == NTR_OK) rc = frame_readback(g->sc[i], jobs[i]);
+        }
+        if (!any) break;
+        for (int i = 0; i < n; ++i) {
+            if (!pending[i]) continue;
+            cudaSetDevice(g->dev[i]);
+            bool again = false;
+            const int r = rc == NTR_OK ? frame_collect(g->sc[i], jobs[i], &again) : (cudaStreamSynchronize(g->sc[i]->stream), NTR_OK);
+            if (r != NTR_OK && rc == NTR_OK) rc = r;
+            pending[i] = again;
+        }
+    }
+    if (rc == NTR_OK) for (int i = 0; i < n; ++i) if (pending[i]) rc = fail(NTR_ERR_RUNTIME, "wavefront queue kept overflowing");
+    // order dev[0]'s stream behind the others and stop the frame's clock there
+    for (int i = 1; i < n; ++i) {
+        cudaSetDevice(g->dev[i]);
+        cudaEventRecord(g->done[i], g->sc[i]->stream);
+    }
+    CUDA_TRY(cudaSetDevice(g->dev[0]));
+    for (int i = 1; i < n; ++i) CUDA_TRY(cudaStreamWaitEvent(g->sc[0]->stream, g->done[i], 0));
+    CUDA_TRY(cudaEventRecord(g->ev1, g->sc[0]->stream));
+    g->timing_valid = rc == NTR_OK;
+    if (rc) return rc;
+    g->counters = ntr_counters{};
+    for (ntr_scene *sc : g->sc) {
+        g->counters.primary_rays += sc->counters.primary_rays; g->counters.reflection_rays += sc->counters.reflection_rays;
+        g->counters.shadow_rays += sc->counters.shadow_rays; g->counters.node_steps += sc->counters.node_steps;
+        g->counters.simplex_tests += sc->counters.simplex_tests; g->counters.solid_tests += sc->counters.solid_tests;
+        g->counters.shaded_hits += sc->counters.shaded_hits; g->counters.queue_overflows += sc->counters.queue_overflows;
+    }
+    return NTR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+NTR_API int ntr_group_create(const ntr_scene_desc *desc, int n, const int *devices, ntr_group **out) {
+    if (!out) return fail(NTR_ERR_VALUE, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(NTR_ERR_NO_DEVICE, "no CUDA device available: ntracer_b200 renders on sm_100a only and has no CPU fallback");
+    }
+    if (n < 0 || n > ndev) return fail(NTR_ERR_VALUE, "the box has %d device(s), %d asked for", ndev, n);
+    if (n == 0) n = ndev;
+    ntr_group *g = new (std::nothrow) ntr_group();
+    if (!g) return fail(NTR_ERR_MEMORY, "out of memory");
+    auto bail = [&](int code) { ntr_group_destroy(g); return code; };
+    for (int i = 0; i < n; ++i) {
+        const int d = devices ? devices[i] : i;
+        if (d < 0 || d >= ndev) return bail(fail(NTR_ERR_VALUE, "device %d out of range", d));
+        for (int k : g->dev) if (k == d) return bail(fail(NTR_ERR_VALUE, "device %d listed twice", d));
+        ntr_scene *sc = nullptr;
+        const int rc = ntr_scene_create(desc, d, &sc);
+        if (rc) return bail(rc);
+        g->sc.push_back(sc);
+        g->dev.push_back(d);
+    }
+    // every device stores into the frame buffer of dev[0]
+    for (int i = 1; i < n; ++i) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, g->dev[i], g->dev[0]) != cudaSuccess || !can)
+            return bail(fail(NTR_ERR_RUNTIME, "device %d cannot access the memory of device %d (no peer access)", g->dev[i], g->dev[0]));
+        cudaSetDevice(g->dev[i]);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(g->dev[0], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return bail(fail(NTR_ERR_RUNTIME, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e)));
+        cudaGetLastError();
+    }
+    g->done.assign(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        cudaSetDevice(g->dev[i]);
+        if (cudaEventCreateWithFlags(&g->done[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(NTR_ERR_RUNTIME, "cudaEventCreate failed"));
+    }
+    cudaSetDevice(g->dev[0]);
+    if (cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess) return bail(fail(NTR_ERR_RUNTIME, "cudaEventCreate failed"));
+    *out = g;
+    return NTR_OK;
+}
+
+NTR_API void ntr_group_destroy(ntr_group *g) {
+    if (!g) return;
+    for (size_t i = 0; i < g->done.size(); ++i) if (g->done[i]) { cudaSetDevice(g->dev[i]); cudaEventDestroy(g->done[i]); }
+    if (!g->dev.empty()) {
+        cudaSetDevice(g->dev[0]);
+        if (!g->sc.empty() && g->sc[0]->stream) cudaStreamSynchronize(g->sc[0]->stream);
+        cudaFree(g->d_frame);
+        if (g->ev0) cudaEventDestroy(g->ev0);
+        if (g->ev1) cudaEventDestroy(g->ev1);
+    }
+    for (ntr_scene *sc : g->sc) ntr_scene_destroy(sc);
+    cudaGetLastError();
+    delete g;
+}
+
+NTR_API int ntr_group_size(ntr_group *g) { return g ? (int)g->sc.size() : 0; }
+
+NTR_API int ntr_group_set_camera(ntr_group *g, const float *origin, const float *axes) {
+    if (!g) return fail(NTR_ERR_VALUE, "group is NULL");
+    for (ntr_scene *sc : g->sc) { const int rc = ntr_scene_set_camera(sc, origin, axes); if (rc) return rc; }
+    return NTR_OK;
+}
+
+NTR_API int ntr_group_set_params(ntr_group *g, const ntr_scene_desc *desc) {
+    if (!g) return fail(NTR_ERR_VALUE, "group is NULL");
+    for (ntr_scene *sc : g->sc) { const int rc = ntr_scene_set_params(sc, desc); if (rc) return rc; }
+    return NTR_OK;
+}
+
+NTR_API int ntr_group_render_device(ntr_group *g, const ntr_image_format *fmt, void **dev_frame_out) {
+    if (!g || !dev_frame_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    int rc = check_format(fmt);
+    if (rc) return rc;
+    if (g->busy.exchange(true)) return fail(NTR_ERR_RUNTIME, "the renderer is already running");
+    rc = group_trace(g, fmt);
+    if (rc == NTR_OK && cudaStreamSynchronize(g->sc[0]->stream) != cudaSuccess) rc = fail(NTR_ERR_RUNTIME, "cudaStreamSynchronize failed");
+    g->busy.store(false);
+    *dev_frame_out = g->d_frame;
+    return rc;
+}
+
+NTR_API int ntr_group_render(ntr_group *g, const ntr_image_format *fmt, void *dst, size_t dst_len) {
+    if (!g) return fail(NTR_ERR_VALUE, "group is NULL");
+    int rc = check_format(fmt);
+    if (rc) return rc;
+    if (!dst) return fail(NTR_ERR_VALUE, "destination is NULL");
+    if (dst_len < (size_t)fmt->pitch * fmt->height) return fail(NTR_ERR_VALUE, "the buffer is too small for an image with the given dimensions");
+    if (g->busy.exchange(true)) return fail(NTR_ERR_RUNTIME, "the renderer is already running");
+    rc = group_trace(g, fmt);
+    if (rc == NTR_OK) {
+        // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
+        cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)fmt->pitch, g->d_frame, (size_t)fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel,
+                                          fmt->height, cudaMemcpyDeviceToHost, g->sc[0]->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g->sc[0]->stream);
+        if (e != cudaSuccess) rc = fail(NTR_ERR_RUNTIME, "device -> host copy failed: %s", cudaGetErrorString(e));
+    }
+    g->busy.store(false);
+    return rc;
+}
+
+NTR_API int ntr_group_abort(ntr_group *g) {
+    if (!g) return fail(NTR_ERR_VALUE, "group is NULL");
+    for (ntr_scene *sc : g->sc) ntr_abort(sc);
+    return NTR_OK;
+}
+
+NTR_API int ntr_group_get_counters(ntr_group *g, ntr_counters *out) {
+    if (!g || !out) return fail(NTR_ERR_VALUE, "NULL argument");
+    *out = g->counters;
+    return NTR_OK;
+}
+
+NTR_API int ntr_group_last_kernel_ms(ntr_group *g, float *ms_out) {
+    if (!g || !ms_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    if (!g->timing_valid) return fail(NTR_ERR_RUNTIME, "nothing has been rendered yet");
+    CUDA_TRY(cudaSetDevice(g->dev[0]));
+    CUDA_TRY(cudaEventSynchronize(g->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms_out, g->ev0, g->ev1));
+    return NTR_OK;
+}
+
+NTR_API uint64_t ntr_group_launch_count(ntr_group *g) {
+    uint64_t n = 0;
+    if (g) for (ntr_scene *sc : g->sc) n += sc->launches;
+    return n;
+}
+
+// ---- frame buffers shared between processes (one process per GPU) ----------------------------------------------
+NTR_API int ntr_frame_alloc(int device, size_t bytes, void **dev_ptr_out) {
+    if (!dev_ptr_out || !bytes) return fail(NTR_ERR_VALUE, "bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(dev_ptr_out, bytes));       // a dedicated allocation: its base address is what cudaIpcGetMemHandle exports
+    return NTR_OK;
+}
+NTR_API int ntr_frame_free(int device, void *dev_ptr) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaFree(dev_ptr));
+    return NTR_OK;
+}
+NTR_API int ntr_frame_export(void *dev_ptr, unsigned char handle_out[NTR_IPC_HANDLE_BYTES]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) <= NTR_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!dev_ptr || !handle_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, dev_ptr));
+    memset(handle_out, 0, NTR_IPC_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof h);
+    return NTR_OK;
+}
+NTR_API int ntr_frame_import(int device, const unsigned char handle[NTR_IPC_HANDLE_BYTES], void **dev_ptr_out) {
+    if (!handle || !dev_ptr_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return NTR_OK;
+}
+NTR_API int ntr_frame_release(int device, void *imported_ptr) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaIpcCloseMemHandle(imported_ptr));
+    return NTR_OK;
+}
+NTR_API int ntr_frame_fill(int device, void *dev_ptr, int value, size_t bytes, void *stream) {
+    if (!dev_ptr) return fail(NTR_ERR_VALUE, "NULL argument");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemsetAsync(dev_ptr, value, bytes, (cudaStream_t)stream));
+    return NTR_OK;
+}
+NTR_API int ntr_frame_download(int device, const void *dev_ptr, const ntr_image_format *fmt, void *dst, size_t dst_len, void *stream) {
+    int rc = check_format(fmt);
+    if (rc) return rc;
+    if (!dev_ptr || !dst) return fail(NTR_ERR_VALUE, "NULL argument");
+    if (dst_len < (size_t)fmt->pitch * fmt->height) return fail(NTR_ERR_VALUE, "the buffer is too small for an image with the given dimensions");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)fmt->pitch, dev_ptr, (size_t)fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel, fmt->height,
+                               cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return NTR_OK;
 }
 

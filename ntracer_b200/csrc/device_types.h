@@ -100,6 +100,7 @@ struct QueueDev {
     uint32_t n_sorted;              // records beyond it (the pass grew past the host's estimate) are read in emission order
     const uint32_t *ring_start;     // optional (sorted, heavy-first passes): first sorted index of cost ring 1, 2, 3 at [1..3];
                                     // warps take fewer rays per fetch from the expensive rings (kernels.cuh)
+    uint32_t fetch_sizes;           // rays per fetch from rings 0, 1, 2 (one byte each; ring 3 and unsorted passes: 32)
     uint32_t capacity;              // in records
     uint32_t rec4;                  // record size in float4 units
 };
@@ -109,4 +110,5 @@ struct ControlDev {
     volatile int *abort_flag;       // host-mapped; renderer::state == CANCEL (reference src/render.cpp:333,412)
     unsigned long long *counters;   // ntr_counters layout (8 x u64)
     uint32_t *overflow;             // set when a wavefront queue was too small
+    unsigned long long *fetch_stats;  // diagnostic builds (-DNTR_FETCH_STATS=1): [0] longest fetch, [1] sum, [2] fetches, [8+k] fetches of 2^k..2^(k+1) cycles
 };

@@ -115,21 +115,11 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 #ifndef NTR_MIN_CTAS
 #define NTR_MIN_CTAS 8
 #endif
+#ifndef NTR_FETCH_STATS
+#define NTR_FETCH_STATS 0          // diagnostic: per-fetch durations (see ControlDev::fetch_stats); never in the shipped build
+#endif
 #ifndef NTR_WARP_PATH
 #define NTR_WARP_PATH 1            // 1: the warp-synchronous per-ray path (trace_warp.cuh); 0: every lane for itself (trace_core.cuh)
-#endif
-// Rays a warp takes per fetch from cost rings 0 (rays through the centre of the scene box: on star polytopes they walk
-// the giant leaves and cost 10-90x the mean), 1 and 2; ring 3 and unsorted passes: 32.  A warp with a few expensive rays
-// and otherwise idle lanes splits their big leaves over all 32 lanes (trace_warp.cuh) -- the expensive rays of a pass
-// then run side by side in many warps instead of 32 to a warp, one lane each.
-#ifndef NTR_FETCH_RING0
-#define NTR_FETCH_RING0 4
-#endif
-#ifndef NTR_FETCH_RING1
-#define NTR_FETCH_RING1 8
-#endif
-#ifndef NTR_FETCH_RING2
-#define NTR_FETCH_RING2 16
 #endif
 // above 8 dimensions the ray alone (origin, direction, hit point) is 30+ registers: fewer CTAs per SM, more registers
 #ifndef NTR_MIN_CTAS_HI
@@ -172,8 +162,12 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
             else {
                 if (q.ring_start) {
                     const uint32_t pos = *(volatile uint32_t *)q.in_cursor;         // a peek: good enough to pick the size
-                    take = pos < __ldg(q.ring_start + 1) ? NTR_FETCH_RING0 : pos < __ldg(q.ring_start + 2) ? NTR_FETCH_RING1
-                           : pos < __ldg(q.ring_start + 3) ? NTR_FETCH_RING2 : 32;
+                    // Rays through the centre of the scene box walk the giant leaves of star polytopes and cost 10-90x the
+                    // mean (tools/ray_cost_map.py); the heavy-first sort puts them in rings 0..2 at the front of the pass.
+                    // Warps take fewer of them per fetch, so that the expensive rays of a pass run side by side in many
+                    // warps instead of 32 to a warp in lockstep.
+                    take = pos < __ldg(q.ring_start + 1) ? (q.fetch_sizes & 0xFFu) : pos < __ldg(q.ring_start + 2) ? ((q.fetch_sizes >> 8) & 0xFFu)
+                           : pos < __ldg(q.ring_start + 3) ? ((q.fetch_sizes >> 16) & 0xFFu) : 32u;
                 }
                 b = atomicAdd(q.in_cursor, take);
             }
@@ -185,7 +179,11 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
         // 512th block / every 64th fetch of a warp looks at it (ncu: at every 64th block the PCIe read was 2.9 % of all
         // stall samples); whoever sees it pushes the cursor past the end for everybody.
         ++fetches;
-        if ((primary ? (b & 511u) == 0 : (fetches & 63u) == 1) && *ctl.abort_flag) {
+#if NTR_FETCH_STATS
+        const long long fetch_t0 = clock64();
+#endif
+        // (bounce passes: the fetch whose range crosses a multiple of 8192 rays looks, whatever its size)
+        if ((primary ? (b & 511u) == 0 : (b & 8191u) < take) && *ctl.abort_flag) {
             if (lane == 0) atomicAdd(primary ? ctl.tile_cursor : q.in_cursor, 0x40000000u);
             break;
         }
@@ -266,6 +264,15 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
         }
 #endif
         if (primary && f.tile_cost && lane == 0) atomicAdd(f.tile_cost + cost_tile, (unsigned long long)(clock64() - t_start));
+#if NTR_FETCH_STATS
+        if (lane == 0 && ctl.fetch_stats) {
+            const unsigned long long dt = (unsigned long long)(clock64() - fetch_t0);
+            atomicMax(ctl.fetch_stats, dt);
+            atomicAdd(ctl.fetch_stats + 1, dt);
+            atomicAdd(ctl.fetch_stats + 2, 1ull);
+            atomicAdd(ctl.fetch_stats + 8 + (63 - __clzll((long long)(dt | 1ull))), 1ull);
+        }
+#endif
         // ---------------- epilogue ----------------
         if (!primary) {
             if (active) {

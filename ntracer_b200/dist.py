@@ -1,8 +1,15 @@
 """Multi-GPU frame partitioning (no counterpart in the reference): one process per GPU,
 scene replicated, the frame split by interleaved 32-pixel tile rows (tile row ty belongs to rank ty % world, which
-balances the centre-heavy cost of polytope scenes), every rank renders its rows into a compact strip
-(ntr_render_device(..., compact=1)), the strips are gathered with one NCCL all-gather and un-interleaved with one
-index_select.  torch / torch.distributed are plumbing only (device buffers, NCCL)."""
+balances the centre-heavy cost of polytope scenes).  Two ways to put the frame together:
+
+  PeerFrameRenderer     the frame buffer lives on rank 0's GPU and every rank's packing epilogue stores its rows straight
+                        into it over NVLink (CUDA IPC mapping, ntr_frame_*); the only collective is a 4-byte NCCL
+                        all-reduce that orders rank 0's stream behind everybody's kernels.  What bench.py times.
+  DistributedRenderer   every rank renders a compact strip (ntr_render_device(..., compact=1)), the strips are gathered
+                        with one NCCL all-gather and un-interleaved with one index_select (round 1; NTR_BENCH_GATHER=nccl).
+
+A single process that owns several GPUs uses ntr_group_* instead (backend.DeviceGroup): same partition, same peer stores.
+torch / torch.distributed are plumbing only (device buffers, NCCL)."""
 import torch
 import torch.distributed as dist
 
@@ -89,3 +96,58 @@ class DistributedRenderer:
                 self.host.copy_(self.frame_on_device(), non_blocking=True)
         self.stream.synchronize()
         return self.host
+
+
+class PeerFrameRenderer:
+    """One frame buffer on rank 0's GPU, written by every rank's kernels over NVLink (no gather, no compose)."""
+    def __init__(self, scene, fmt, group=None):
+        from .backend import SharedFrame
+        self.ds, self.fmt, self.group = scene, fmt, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.cuda.current_device()
+        dev = torch.device('cuda', self.device)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.nbytes = fmt.pitch * fmt.height
+        box = [None]
+        if self.rank == 0:
+            self.frame = SharedFrame(self.device, self.nbytes)
+            box[0] = self.frame.export()
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        if self.rank != 0:
+            self.frame = SharedFrame(self.device, handle=box[0])
+        self.token = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.host = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory() if self.rank == 0 else None
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def render(self):
+        """Enqueue this rank's tile rows on self.stream; the pixels land in rank 0's frame at their frame position."""
+        self.ds.render_device(self.fmt, self.frame.ptr, self.nbytes, self.stream.cuda_stream, self.rank, self.world, False)
+
+    def fence(self):
+        """Order self.stream behind the kernels of every rank (a 4-byte all-reduce: the frame's only collective)."""
+        if self.world > 1:
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(self.token, group=self.group)
+
+    def render_to_host(self):
+        """Whole frame into pinned host memory on rank 0 (returns the pinned tensor there, None elsewhere)."""
+        self.render()
+        self.fence()
+        if self.rank == 0:
+            self.frame.download(self.fmt, self.host.numpy(), self.stream.cuda_stream)
+        self.stream.synchronize()
+        return self.host
+
+    def close(self):
+        self.stream.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)      # nobody unmaps the frame while a peer may still store into it
+        if self.rank != 0:
+            self.frame.close()
+        if self.world > 1:
+            dist.barrier(group=self.group)      # ... and the owner frees it only after every mapping is gone
+        if self.rank == 0:
+            self.frame.close()

@@ -146,11 +146,26 @@ def _writable_buffer(dest):
     return np.frombuffer(mv, dtype=np.uint8)
 
 
+def _gpus_for(threads):
+    """How many GPUs trace a frame.  The reference's `threads` is its worker count (0 / -1: one per core,
+    src/render.cpp:829-838); here a value above 1 asks for that many B200s of the box (interleaved tile rows, every GPU
+    storing its rows into one frame on the first over NVLink: ntr_group_*), anything else for one.  NTR_GPUS overrides."""
+    import os
+    from .backend import device_count
+    want = int(os.environ.get('NTR_GPUS', '0') or 0) or int(threads)
+    return max(1, min(want, device_count())) if want > 1 else 1
+
+
+def _render_call(dev):
+    return dev._lib.ntr_group_render if hasattr(dev, 'size') else dev._lib.ntr_render
+
+
 class BlockingRenderer:
-    """BlockingRenderer([threads=-1]) (src/render.cpp:829-929).  `threads` has no meaning for the GPU backend."""
+    """BlockingRenderer([threads=-1]) (src/render.cpp:829-929).  threads > 1: that many GPUs trace the frame."""
     def __init__(self, threads=-1):
         self._lock = threading.Lock()
         self._dev = None
+        self._gpus = _gpus_for(threads)
 
     def render(self, dest, format, scene):
         """-> True, or False if signal_abort() was called while rendering."""
@@ -167,9 +182,9 @@ class BlockingRenderer:
         try:
             scene.locked += 1
             try:
-                dev = scene._prepare()
+                dev = scene._prepare(self._gpus) if self._gpus > 1 else scene._prepare()
                 self._dev = dev
-                rc = dev._lib.ntr_render(dev._h, C.byref(fmt), buf.ctypes.data_as(C.c_void_p), buf.size)
+                rc = _render_call(dev)(dev._h, C.byref(fmt), buf.ctypes.data_as(C.c_void_p), buf.size)
                 if rc == _capi.NTR_ERR_ABORTED:
                     return False
                 _capi.check(rc)
@@ -193,6 +208,7 @@ class CallbackRenderer:
         self._thread = None
         self._dev = None
         self._lock = threading.Lock()
+        self._gpus = _gpus_for(threads)
 
     def begin_render(self, dest, format, scene, callback):
         if not isinstance(format, ImageFormat):
@@ -208,7 +224,7 @@ class CallbackRenderer:
                 raise RuntimeError('the renderer is already running')
             scene.locked += 1
             try:
-                dev = scene._prepare()
+                dev = scene._prepare(self._gpus) if self._gpus > 1 else scene._prepare()
             except Exception:
                 scene.locked -= 1
                 raise
@@ -216,7 +232,7 @@ class CallbackRenderer:
 
             def work():
                 try:
-                    rc = dev._lib.ntr_render(dev._h, C.byref(fmt), buf.ctypes.data_as(C.c_void_p), buf.size)
+                    rc = _render_call(dev)(dev._h, C.byref(fmt), buf.ctypes.data_as(C.c_void_p), buf.size)
                 finally:
                     scene.locked -= 1
                     self._dev = None

@@ -13,7 +13,7 @@ import math
 import numpy as np
 
 from . import _capi
-from .backend import DeviceScene, FLT_MAX
+from .backend import DeviceGroup, DeviceScene, FLT_MAX
 from .render import Color, LockedError, Material, Scene, _color_tuple
 
 BATCH_SIZE = 4      # lanes of a TriangleBatch; the reference's SSE build has v_real::size == 4
@@ -949,7 +949,7 @@ class _SceneBase(Scene):
 
     def __getstate__(self):
         # device copy and lock count belong to this process (pickle codecs of the reference: src/render.cpp:1391-1657)
-        st = {k: v for k, v in self.__dict__.items() if k not in ('_dev', '_flat', '_mat_snapshot')}
+        st = {k: v for k, v in self.__dict__.items() if k not in ('_dev', '_flat', '_mat_snapshot', '_group', '_group_of', '_sc')}
         st['_dev'] = None
         st['locked'] = 0
         return st
@@ -974,8 +974,20 @@ class _SceneBase(Scene):
     def _device_scene(self):
         raise NotImplementedError
 
-    def _prepare(self):
+    def _prepare(self, gpus=1):
+        """-> the device copy of the scene, camera set: a DeviceScene, or a DeviceGroup over `gpus` devices (the frame split
+        by interleaved tile rows, BlockingRenderer(threads=N))."""
         dev = self._device_scene()
+        if gpus > 1:
+            grp = getattr(self, '_group', None)
+            if grp is None or grp.size != gpus or self._group_of is not dev:
+                if grp is not None:
+                    grp.close()
+                grp = self._group = DeviceGroup(self._scene_dict(), gpus)
+                self._group_of = dev            # rebuilt whenever the single-device copy is (materials changed)
+            else:
+                grp.set_params(self._scene_dict())
+            dev = grp
         dev.set_camera(self._cam._origin, self._cam._axes)
         return dev
 
@@ -997,6 +1009,9 @@ class BoxScene(_SceneBase):
     def _flat(self):
         return {'dim': np.int64(self.dimension), 'kind': np.int64(0), 'batch_size': np.int64(1),
                 'params': np.array([self.fov, 0, 0, 0, 0], np.float64)}
+
+    def _scene_dict(self):
+        return self._flat()
 
     def _device_scene(self):
         if self._dev is None:
@@ -1067,13 +1082,18 @@ class CompositeScene(_SceneBase):
             root = flat.walk(self.root)
             self._flat = flat
             self._mat_snapshot = flat.material_snapshot()
-            self._dev = DeviceScene(flat.scene_dict(root, self.boundary, self))
+            self._sc = flat.scene_dict(root, self.boundary, self)
+            self._dev = DeviceScene(self._sc)
         else:
             sc = {'dim': np.int64(self.dimension), 'kind': np.int64(1), 'batch_size': np.int64(BATCH_SIZE), 'root': np.int64(0),
                   'boundary': np.stack([self.boundary.start._v, self.boundary.end._v])}
             sc.update(_scene_params(self, self.dimension))
             self._dev.set_params(sc)
+            self._sc.update(_scene_params(self, self.dimension))
         return self._dev
+
+    def _scene_dict(self):
+        return self._sc
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -35,6 +35,7 @@ torch.cuda.set_device = lambda d: None
 torch.cuda.synchronize = lambda *a: None
 torch.cuda.Event = _Ev
 torch.cuda.Stream = _Stream
+torch.cuda.current_device = lambda: 0
 _real_empty, _real_tensor = torch.empty, torch.tensor
 torch.empty = lambda *a, **k: _real_empty(*a, **{kk: vv for kk, vv in k.items() if kk != 'device'})
 torch.tensor = lambda *a, **k: _real_tensor(*a, **{kk: vv for kk, vv in k.items() if kk != 'device'})
@@ -63,10 +64,14 @@ backend.measure_fp32_peak = lambda dev=0: 64.5
 class FakeDR:
     def __init__(self, ds, fmt, group=None): self.ds, self.stream = ds, _Stream()
     def render_strip(self): self.ds.render_device()
+    def render(self): self.ds.render_device()
     def gather(self): pass
+    def fence(self): pass
     def frame_on_device(self): pass
     def render_to_host(self): self.ds.render_device()
+    def close(self): pass
 ntd.DistributedRenderer = FakeDR
+ntd.PeerFrameRenderer = FakeDR
 import torch.distributed as _dist
 _real_init = _dist.init_process_group
 _dist.init_process_group = lambda backend=None, **k: _real_init('gloo')      # NCCL needs GPUs; the flow is the same
@@ -91,7 +96,10 @@ def test_bench_line_has_every_contract_key_and_the_optional_legs():
     for k in REQUIRED:
         assert k in line, k
     assert line['warmup'] >= 3 and line['steps'] == 3 and line['n_gpus'] == 1
-    assert line['metric'] == 'Mrays/sec (primary+shadow)' and line['unit'] == 'Mrays/s'      # BASELINE.json's metric
+    baseline = json.load(open(os.path.join(ROOT, 'BASELINE.json')))
+    assert line['metric'] == baseline['metric'] and line['unit'] == 'Mrays/s'                # BASELINE.json's metric, verbatim
+    assert line['config']['frame_ms'] == line['ms_per_step'] and line['config']['frame_ms_e2e'] > 0
+    assert line['roofline']['traffic'] is None or line['roofline']['traffic_source']       # measured (ncu) or null, never a literal
     assert line['e2e']['d2h_bytes_per_step'] == 640 * 480 * 3 and line['e2e']['value'] > 0
     assert line['roofline']['bound'] == 'fp32' and line['roofline']['peak'] == 64.5
     assert line['cpu_baseline']['kind'] in ('reference', 'port') and line['cpu_baseline']['cores'] >= 1
@@ -100,6 +108,18 @@ def test_bench_line_has_every_contract_key_and_the_optional_legs():
     assert line['stream']['frames'] == 12 and line['stream']['in_flight'] == 2
     assert 'incomplete' not in line
     assert line['gpu_launches'] == 2 * 3
+
+
+def test_default_workload_is_the_4k_frame_with_the_secondary_workloads_beside_it():
+    """No --config: the frame BASELINE.json's metric is quoted on (configs[3], 3840x2160), {5/2,5,3} and config 2 beside it."""
+    line, out = run_stubbed(['--steps', '2', '--warmup', '1', '--no-cpu-baseline', '--stream-frames', '0'], refl=500, timeout=900)
+    assert line['config']['width'] == 3840 and line['config']['height'] == 2160 and '{5/2,3,3}' in line['config']['workload']
+    assert set(line['secondary']) == {'c4b', 'c2'}
+    assert '{5/2,5,3}' in line['secondary']['c4b']['workload'] and line['secondary']['c2']['width'] == 1920
+    for v in line['secondary'].values():
+        assert v['value'] > 0 and v['e2e_value'] > 0 and v['ms_per_step'] > 0
+    assert 0.3 < line['config']['defined_pixel_fraction'] < 0.7          # {5/2,3,3}: about half the frame (DESIGN.md section 5)
+    assert line['roofline']['kernel'] == 'render_pass_kernel<4,1>'
 
 
 def test_stream_leg_is_skipped_for_scenes_with_wavefront_passes():

@@ -66,8 +66,25 @@ def test_scene_validation_errors_without_touching_a_device():
     assert b'out of range' in lib.ntr_last_error()
     bad = dict(sc)
     bad['dim'] = np.int64(2)
-    desc, keep = _capi.make_desc(bad)
+    with pytest.raises(ValueError):         # the arrays no longer fit the record sizes: caught before the library sees them
+        _capi.make_desc(bad)
+    desc, keep = _capi.make_desc(sc)
+    desc.dim = 2
     assert lib.ntr_scene_create(C.byref(desc), -1, C.byref(h)) == _capi.NTR_ERR_VALUE
+    # counts without arrays: the C ABI answers NTR_ERR_VALUE, it never dereferences NULL
+    for field in ('simplex', 'simplex_mat', 'leaf_refs', 'materials', 'nodes'):
+        desc, keep = _capi.make_desc(sc)
+        setattr(desc, field, None)
+        assert lib.ntr_scene_create(C.byref(desc), -1, C.byref(h)) == _capi.NTR_ERR_VALUE, field
+        assert b'NULL' in lib.ntr_last_error(), field
+    for missing in ('simplex_mat', 'boundary'):
+        bad = {k: v for k, v in sc.items() if k != missing}
+        with pytest.raises(ValueError):
+            _capi.make_desc(bad)
+    # the host-side builders report their own errors
+    out = np.zeros(4 * 13, np.float32)
+    assert lib.ntr_simplex_from_points(2, 4, None, out.ctypes.data_as(C.c_void_p)) == _capi.NTR_ERR_VALUE
+    assert lib.ntr_last_error()
 
 
 @pytest.mark.skipif(_capi.load().ntr_device_count() > 0, reason='a B200 is present')
