@@ -195,6 +195,14 @@ NTR_API int ntr_primary_hit_ids(ntr_scene *scene, int width, int height, int32_t
 NTR_API int ntr_trace_rays(ntr_scene *scene, uint32_t n, const float *origins, const float *dirs,
                            float t_near, float t_far, const uint32_t *skip_ref, const int32_t *skip_lane,
                            int32_t *ids_out, float *dist_out, int32_t *n_transparent_out);
+/* The same with the transparent hits themselves: KDNode.intersects returns every surviving transparent hit as a
+ * RayIntersection ahead of the opaque one (src/ntracer_body.hpp:1438-1456, 1759-1766).  hit_ids_out / hit_dist_out are
+ * n x max_hits: flat primitive id (-1 = unused slot) and distance of the first max_hits entries of the ray's list, in
+ * the list's order (unsorted, as the reference's quick_list leaves them after trimming; the kernels keep up to 16). */
+NTR_API int ntr_trace_rays_hits(ntr_scene *scene, uint32_t n, const float *origins, const float *dirs,
+                                float t_near, float t_far, const uint32_t *skip_ref, const int32_t *skip_lane,
+                                int32_t *ids_out, float *dist_out, int32_t *n_transparent_out, int max_hits,
+                                int32_t *hit_ids_out, float *hit_dist_out);
 NTR_API int ntr_occludes_rays(ntr_scene *scene, uint32_t n, const float *origins, const float *dirs,
                               const float *distance, const uint32_t *skip_ref, const int32_t *skip_lane,
                               int32_t *occluded_out, int32_t *n_transparent_out);
@@ -266,6 +274,11 @@ NTR_API int ntr_build_kdtree(int dim, uint32_t n, const float *lo, const float *
                              float traversal_cost, float intersection_cost, ntr_node **nodes_out, uint32_t *n_nodes_out,
                              uint32_t **refs_out, uint32_t *n_refs_out, uint32_t *root_out, float *boundary_out);
 NTR_API void ntr_free(void *p);
+/* Batch grouping ahead of the tree build (group_primitives, src/tracer.hpp:2395-2427: triangles are packed into
+ * triangle_batch items of v_real::size lanes).  order_out receives a permutation of the n items (bounds lo/hi: n x D)
+ * in which every consecutive run of `group` entries is one batch of spatially close items; the last n % group entries
+ * stay single primitives.  Own algorithm: recursive median split of the item centres, O(n log n). */
+NTR_API int ntr_group_items(int dim, uint32_t n, const float *lo, const float *hi, int group, uint32_t *order_out);
 
 /* FP32 FMA peak micro-benchmark (TFLOP/s) on the scene's device: the roofline denominator the
  * north star asks for (MEASURED_PEAKS.json has HBM and BF16 only). */

@@ -206,6 +206,7 @@ def load():
         'ntr_calculate_color': (C.c_int, [vp, i32, i32, i32, i32, f32p]),
         'ntr_primary_hit_ids': (C.c_int, [vp, i32, i32, vp, vp]),
         'ntr_trace_rays': (C.c_int, [vp, u32, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp]),
+        'ntr_trace_rays_hits': (C.c_int, [vp, u32, vp, vp, C.c_float, C.c_float, vp, vp, vp, vp, vp, i32, vp, vp]),
         'ntr_occludes_rays': (C.c_int, [vp, u32, vp, vp, vp, vp, vp, vp, vp]),
         'ntr_abort': (C.c_int, [vp]),
         'ntr_get_counters': (C.c_int, [vp, C.POINTER(Counters)]),
@@ -247,7 +248,7 @@ EXPORTED_SYMBOLS = (
     'ntr_abi_version', 'ntr_last_error', 'ntr_device_count', 'ntr_scene_create', 'ntr_scene_destroy',
     'ntr_scene_set_camera', 'ntr_scene_set_params', 'ntr_render', 'ntr_render_device', 'ntr_render_begin',
     'ntr_render_end', 'ntr_render_float',
-    'ntr_calculate_color', 'ntr_primary_hit_ids', 'ntr_trace_rays', 'ntr_occludes_rays', 'ntr_abort',
+    'ntr_calculate_color', 'ntr_primary_hit_ids', 'ntr_trace_rays', 'ntr_trace_rays_hits', 'ntr_occludes_rays', 'ntr_abort',
     'ntr_get_counters', 'ntr_set_instrumented', 'ntr_last_kernel_ms', 'ntr_launch_count',
     'ntr_measure_fp32_peak', 'ntr_simplex_from_points', 'ntr_build_kdtree', 'ntr_free',
     'ntr_group_create', 'ntr_group_destroy', 'ntr_group_size', 'ntr_group_set_camera', 'ntr_group_set_params',

@@ -130,6 +130,23 @@ class DeviceScene:
                                              _p(ids), _p(dist), _p(nt)))
         return ids, dist, nt
 
+    def trace_rays_hits(self, origins, dirs, t_near=-FLT_MAX, t_far=FLT_MAX, skip_ref=None, skip_lane=None, max_hits=16):
+        """trace_rays plus the surviving transparent hits of every ray: (ids, dist, n_transparent, hit_ids [n, max_hits]
+        (-1 = unused), hit_dists [n, max_hits]) -- what KDNode.intersects returns ahead of the opaque hit."""
+        origins = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, self.dim)
+        dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, self.dim)
+        n = origins.shape[0]
+        ids = np.zeros(n, dtype=np.int32)
+        dist = np.zeros(n, dtype=np.float32)
+        nt = np.zeros(n, dtype=np.int32)
+        hid = np.full((n, max_hits), -1, dtype=np.int32)
+        hdist = np.zeros((n, max_hits), dtype=np.float32)
+        sr = None if skip_ref is None else np.ascontiguousarray(skip_ref, dtype=np.uint32)
+        sl = None if skip_lane is None else np.ascontiguousarray(skip_lane, dtype=np.int32)
+        _capi.check(self._lib.ntr_trace_rays_hits(self._h, n, _p(origins), _p(dirs), t_near, t_far, _p(sr), _p(sl),
+                                                  _p(ids), _p(dist), _p(nt), int(max_hits), _p(hid), _p(hdist)))
+        return ids, dist, nt, hid, hdist
+
     def occludes_rays(self, origins, dirs, distance=None, skip_ref=None, skip_lane=None):
         origins = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, self.dim)
         dirs = np.ascontiguousarray(dirs, dtype=np.float32).reshape(-1, self.dim)

@@ -211,6 +211,53 @@ NTR_API int ntr_simplex_from_points(int dim, uint32_t n, const float *points, fl
     return rc;
 }
 
+// Groups n items (simplexes, by their bounds lo/hi: n x D) into runs of `group` spatially close items: order_out receives a
+// permutation of 0..n-1 in which every consecutive run of `group` entries is one group (what becomes a triangle_batch);
+// the last n % group entries are the left-overs that stay single primitives.  The reference groups greedily in O(n^2)
+// (group_primitives, src/tracer.hpp:2395-2427: each unassigned triangle takes the v_real::size - 1 nearest unassigned
+// ones by grouping_metric); this is an O(n log n) recursive median split of the item centres along their widest axis,
+// with every split placed on a multiple of `group`.
+NTR_API int ntr_group_items(int dim, uint32_t n, const float *lo, const float *hi, int group, uint32_t *order_out) {
+    if (dim < 3 || dim > NTR_MAX_DIM) return ntr_fail(NTR_ERR_VALUE, "dimension must be between 3 and %d", NTR_MAX_DIM);
+    if (group < 1 || group > 64) return ntr_fail(NTR_ERR_VALUE, "group size must be in 1..64");
+    if (n && (!lo || !hi || !order_out)) return ntr_fail(NTR_ERR_VALUE, "NULL argument");
+    const int D = dim;
+    try {
+        std::vector<float> c((size_t)n * D);
+        for (size_t k = 0; k < (size_t)n * D; ++k) c[k] = 0.5f * (lo[k] + hi[k]);
+        for (uint32_t i = 0; i < n; ++i) order_out[i] = i;
+        std::vector<std::pair<uint32_t, uint32_t>> stack;
+        stack.push_back({0u, n});
+        while (!stack.empty()) {
+            const auto [a, b] = stack.back();
+            stack.pop_back();
+            if (b - a <= (uint32_t)group) continue;
+            int axis = 0;
+            float best = -1.0f;
+            for (int k = 0; k < D; ++k) {
+                float mn = c[(size_t)order_out[a] * D + k], mx = mn;
+                for (uint32_t i = a + 1; i < b; ++i) {
+                    const float v = c[(size_t)order_out[i] * D + k];
+                    mn = std::min(mn, v); mx = std::max(mx, v);
+                }
+                if (mx - mn > best) { best = mx - mn; axis = k; }
+            }
+            const uint32_t groups = (b - a) / (uint32_t)group;              // whole groups in this range (>= 1)
+            const uint32_t mid = a + std::max(1u, (groups + 1) / 2) * (uint32_t)group;
+            if (mid >= b) continue;
+            std::nth_element(order_out + a, order_out + mid, order_out + b, [&](uint32_t x, uint32_t y) {
+                const float cx = c[(size_t)x * D + axis], cy = c[(size_t)y * D + axis];
+                return cx < cy || (cx == cy && x < y);
+            });
+            stack.push_back({a, mid});
+            stack.push_back({mid, b});
+        }
+    } catch (const std::bad_alloc &) {
+        return ntr_fail(NTR_ERR_MEMORY, "out of memory grouping the items");
+    }
+    return NTR_OK;
+}
+
 // lo/hi: n x D item bounds.  Outputs are malloc'ed (release with ntr_free): nodes (16-byte ntr_node, root = node 0 or
 // NTR_NULL_NODE when n == 0), refs = item indices per leaf (the caller turns them into leaf refs), boundary = 2 x D.
 NTR_API int ntr_build_kdtree(int dim, uint32_t n, const float *lo, const float *hi, int max_depth, int split_threshold,

@@ -1186,17 +1186,18 @@ static int ray_batch_scratch(ntr_scene *sc, uint32_t n, size_t *offs, const size
     return ensure(&sc->d_scratch, &sc->scratch_cap, std::max<size_t>(total, 256));
 }
 
-NTR_API int ntr_trace_rays(ntr_scene *sc, uint32_t n, const float *origins, const float *dirs, float t_near, float t_far,
-                           const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids_out, float *dist_out,
-                           int32_t *n_transparent_out) {
+NTR_API int ntr_trace_rays_hits(ntr_scene *sc, uint32_t n, const float *origins, const float *dirs, float t_near, float t_far,
+                                const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids_out, float *dist_out,
+                                int32_t *n_transparent_out, int max_hits, int32_t *hit_ids_out, float *hit_dist_out) {
     ENTER(sc);
     if (sc->dev.kind != NTR_SCENE_COMPOSITE) return fail(NTR_ERR_VALUE, "only composite scenes have a k-d tree");
     if (!origins || !dirs || !ids_out) return fail(NTR_ERR_VALUE, "NULL argument");
+    if (max_hits < 0 || (max_hits > 0 && !hit_ids_out)) return fail(NTR_ERR_VALUE, "bad transparent-hit output arguments");
     if (n == 0) return NTR_OK;
-    const size_t vb = (size_t)n * sc->dev.dim * sizeof(float), ib = (size_t)n * 4;
-    size_t offs[7];
-    const size_t sizes[7] = {vb, vb, ib, ib, ib, ib, ib};
-    int rc = ray_batch_scratch(sc, n, offs, sizes, 7);
+    const size_t vb = (size_t)n * sc->dev.dim * sizeof(float), ib = (size_t)n * 4, hb = (size_t)n * 4 * (size_t)max_hits;
+    size_t offs[9];
+    const size_t sizes[9] = {vb, vb, ib, ib, ib, ib, ib, hb, hb};
+    int rc = ray_batch_scratch(sc, n, offs, sizes, 9);
     if (rc) return rc;
     unsigned char *b = static_cast<unsigned char *>(sc->d_scratch);
     cudaStream_t st = sc->stream;
@@ -1204,19 +1205,32 @@ NTR_API int ntr_trace_rays(ntr_scene *sc, uint32_t n, const float *origins, cons
     CUDA_TRY(cudaMemcpyAsync(b + offs[1], dirs, vb, cudaMemcpyHostToDevice, st));
     if (skip_ref) CUDA_TRY(cudaMemcpyAsync(b + offs[2], skip_ref, ib, cudaMemcpyHostToDevice, st));
     if (skip_lane) CUDA_TRY(cudaMemcpyAsync(b + offs[3], skip_lane, ib, cudaMemcpyHostToDevice, st));
+    if (max_hits) CUDA_TRY(cudaMemsetAsync(b + offs[7], 0xFF, hb, st));          // -1: no hit in this slot
     const int flags = sc->base_flags;
     sc->kset(flags)->trace_rays(dim3((n + kCtaThreads - 1) / kCtaThreads), dim3(kCtaThreads), st, sc->dev, n,
                                 (const float *)(b + offs[0]), (const float *)(b + offs[1]), t_near, t_far,
                                 skip_ref ? (const uint32_t *)(b + offs[2]) : nullptr,
                                 skip_lane ? (const int32_t *)(b + offs[3]) : nullptr, (int32_t *)(b + offs[4]),
-                                (float *)(b + offs[5]), (int32_t *)(b + offs[6]));
+                                (float *)(b + offs[5]), (int32_t *)(b + offs[6]),
+                                max_hits ? (int32_t *)(b + offs[7]) : nullptr, max_hits ? (float *)(b + offs[8]) : nullptr, max_hits);
     ++sc->launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(ids_out, b + offs[4], ib, cudaMemcpyDeviceToHost, st));
     if (dist_out) CUDA_TRY(cudaMemcpyAsync(dist_out, b + offs[5], ib, cudaMemcpyDeviceToHost, st));
     if (n_transparent_out) CUDA_TRY(cudaMemcpyAsync(n_transparent_out, b + offs[6], ib, cudaMemcpyDeviceToHost, st));
+    if (max_hits) {
+        CUDA_TRY(cudaMemcpyAsync(hit_ids_out, b + offs[7], hb, cudaMemcpyDeviceToHost, st));
+        if (hit_dist_out) CUDA_TRY(cudaMemcpyAsync(hit_dist_out, b + offs[8], hb, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     return NTR_OK;
+}
+
+NTR_API int ntr_trace_rays(ntr_scene *sc, uint32_t n, const float *origins, const float *dirs, float t_near, float t_far,
+                           const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids_out, float *dist_out,
+                           int32_t *n_transparent_out) {
+    return ntr_trace_rays_hits(sc, n, origins, dirs, t_near, t_far, skip_ref, skip_lane, ids_out, dist_out, n_transparent_out,
+                               0, nullptr, nullptr);
 }
 
 NTR_API int ntr_occludes_rays(ntr_scene *sc, uint32_t n, const float *origins, const float *dirs, const float *distance,

@@ -323,7 +323,7 @@ template <int DT, int FLAGS>
 __global__ void __launch_bounds__(kCtaThreads)
 trace_rays_kernel(const __grid_constant__ SceneDev s, uint32_t n, const float *origins, const float *dirs,
                   float t_near, float t_far, const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids,
-                  float *dist, int32_t *ntrans) {
+                  float *dist, int32_t *ntrans, int32_t *hit_ids, float *hit_dists, int max_hits) {
     constexpr int CAP = DimCap<DT>::value;
     const int D = NTR_D(DT, s);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -341,6 +341,14 @@ trace_rays_kernel(const __grid_constant__ SceneDev s, uint32_t n, const float *o
     ids[i] = hit ? flat_prim_id(s, oh.ref, oh.lane) : -1;
     if (dist) dist[i] = hit ? oh.dist : 0.0f;
     if (ntrans) ntrans[i] = (FLAGS & NTR_F_GENERAL) ? g.th.n : 0;
+    // the surviving transparent hits in the order the reference's list holds them (kdnode_intersects returns them
+    // before the opaque hit, src/ntracer_body.hpp:1438-1456)
+    if ((FLAGS & NTR_F_GENERAL) && hit_ids) {
+        for (int k = 0; k < g.th.n && k < max_hits; ++k) {
+            hit_ids[(size_t)i * max_hits + k] = flat_prim_id(s, g.th.ref[k], g.th.lane[k]);
+            if (hit_dists) hit_dists[(size_t)i * max_hits + k] = g.th.dist[k];
+        }
+    }
 }
 
 // KDNode.occludes (reference src/ntracer_body.hpp:1460-1496)
@@ -371,7 +379,7 @@ struct KernelSet {
     void (*render_pass)(dim3, dim3, cudaStream_t, const SceneDev &, const CameraDev &, const FrameDev &,
                         const QueueDev &, const ControlDev &);
     void (*trace_rays)(dim3, dim3, cudaStream_t, const SceneDev &, uint32_t, const float *, const float *, float,
-                       float, const uint32_t *, const int32_t *, int32_t *, float *, int32_t *);
+                       float, const uint32_t *, const int32_t *, int32_t *, float *, int32_t *, int32_t *, float *, int);
     void (*occludes_rays)(dim3, dim3, cudaStream_t, const SceneDev &, uint32_t, const float *, const float *,
                           const float *, const uint32_t *, const int32_t *, int32_t *, int32_t *);
     int (*max_blocks_per_sm)();
@@ -384,8 +392,8 @@ template <int DT, int FLAGS> struct Launch {
     }
     static void trace_rays(dim3 g, dim3 b, cudaStream_t st, const SceneDev &s, uint32_t n, const float *o,
                            const float *d, float tn, float tf, const uint32_t *sr, const int32_t *sl, int32_t *ids,
-                           float *dist, int32_t *nt) {
-        trace_rays_kernel<DT, FLAGS><<<g, b, 0, st>>>(s, n, o, d, tn, tf, sr, sl, ids, dist, nt);
+                           float *dist, int32_t *nt, int32_t *hit_ids, float *hit_dists, int max_hits) {
+        trace_rays_kernel<DT, FLAGS><<<g, b, 0, st>>>(s, n, o, d, tn, tf, sr, sl, ids, dist, nt, hit_ids, hit_dists, max_hits);
     }
     static void occludes_rays(dim3 g, dim3 b, cudaStream_t st, const SceneDev &s, uint32_t n, const float *o,
                               const float *d, const float *ld, const uint32_t *sr, const int32_t *sl, int32_t *occ,

@@ -712,28 +712,32 @@ class KDNode:
         return np.array([ref], np.uint32), np.array([batch_index if isinstance(source, PrimitiveBatch) else -1], np.int32)
 
     def intersects(self, origin, direction, t_near=-FLT_MAX, t_far=FLT_MAX, source=None, batch_index=-1):
-        """-> list of RayIntersection; the opaque hit (if any) is last (src/ntracer_body.hpp:1412-1458).
-        Transparent hits are counted by the backend but only the opaque hit is materialised here."""
+        """-> list of RayIntersection: the surviving transparent hits in the order the traversal's list holds them, then
+        the opaque hit (if any) last (src/ntracer_body.hpp:1412-1458)."""
         o, d = _as_vector(origin, self.dimension), _as_vector(direction, self.dimension)
         dev, flat = self._device()
         sr, sl = self._skip(flat, source, batch_index)
-        ids, dist, nt = dev.trace_rays(o._v[None], d._v[None], t_near, t_far, sr, sl)
-        if ids[0] < 0:
-            return []
-        prim, lane = flat.prim_of_flat_id(int(ids[0]))
-        t = float(dist[0])
-        tri = prim[lane] if lane >= 0 else prim
-        P = o + d * t
-        if isinstance(tri, Triangle):
-            n = tri.face_normal.unit()
-            if dot(tri.face_normal, d) > 0:
-                n = -n
-        else:
-            frame = tri._hit_frame(o._v, d._v)
-            n = None
-            if frame is not None:
-                P, n = Vector._wrap(frame[0]), Vector._wrap(frame[1])
-        return [RayIntersection(t, P, n, prim, lane)]
+        ids, dist, nt, hid, hdist = dev.trace_rays_hits(o._v[None], d._v[None], t_near, t_far, sr, sl)
+
+        def materialise(flat_id, t):
+            prim, lane = flat.prim_of_flat_id(int(flat_id))
+            tri = prim[lane] if lane >= 0 else prim
+            P = o + d * t
+            if isinstance(tri, Triangle):
+                n = tri.face_normal.unit()
+                if dot(tri.face_normal, d) > 0:
+                    n = -n
+            else:
+                frame = tri._hit_frame(o._v, d._v)
+                n = None
+                if frame is not None:
+                    P, n = Vector._wrap(frame[0]), Vector._wrap(frame[1])
+            return RayIntersection(t, P, n, prim, lane)
+
+        out = [materialise(hid[0, k], float(hdist[0, k])) for k in range(min(int(nt[0]), hid.shape[1])) if hid[0, k] >= 0]
+        if ids[0] >= 0:
+            out.append(materialise(ids[0], float(dist[0])))
+        return out
 
     def occludes(self, origin, direction, distance=FLT_MAX, t_near=-FLT_MAX, t_far=FLT_MAX, source=None, batch_index=-1):
         o, d = _as_vector(origin, self.dimension), _as_vector(direction, self.dimension)

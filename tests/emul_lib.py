@@ -71,6 +71,24 @@ def trace_rays(sc, origins, dirs, t_near=-3.4028234663852886e38, t_far=3.4028234
     return ids, dist, nt
 
 
+def trace_rays_hits(sc, origins, dirs, t_near=-3.4028234663852886e38, t_far=3.4028234663852886e38, skip_ref=None,
+                    skip_lane=None, max_hits=16, generic=False):
+    d, keep = _capi.make_desc(sc)
+    origins = np.ascontiguousarray(origins, dtype=np.float32)
+    dirs = np.ascontiguousarray(dirs, dtype=np.float32)
+    n = origins.shape[0]
+    ids = np.zeros(n, dtype=np.int32)
+    dist = np.zeros(n, dtype=np.float32)
+    nt = np.zeros(n, dtype=np.int32)
+    hid = np.full((n, max_hits), -1, dtype=np.int32)
+    hdist = np.zeros((n, max_hits), dtype=np.float32)
+    sr = None if skip_ref is None else np.ascontiguousarray(skip_ref, dtype=np.uint32)
+    sl = None if skip_lane is None else np.ascontiguousarray(skip_lane, dtype=np.int32)
+    lib().emul_trace_rays_hits(C.byref(d), C.c_uint32(n), _p(origins), _p(dirs), C.c_float(t_near), C.c_float(t_far),
+                               _p(sr), _p(sl), int(generic), _p(ids), _p(dist), _p(nt), int(max_hits), _p(hid), _p(hdist))
+    return ids, dist, nt, hid, hdist
+
+
 def occludes_rays(sc, origins, dirs, distance=None, skip_ref=None, skip_lane=None, generic=False):
     d, keep = _capi.make_desc(sc)
     origins = np.ascontiguousarray(origins, dtype=np.float32)

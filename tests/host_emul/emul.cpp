@@ -295,7 +295,8 @@ template <int DT> void render_d(Scene &S, int w, int h, float *rgb, int32_t *ids
 
 template <int DT, int FLAGS>
 void trace_t(Scene &S, uint32_t n, const float *origins, const float *dirs, float t_near, float t_far,
-             const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids, float *dist, int32_t *ntrans) {
+             const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids, float *dist, int32_t *ntrans,
+             int max_hits = 0, int32_t *hit_ids = nullptr, float *hit_dists = nullptr) {
     const int D = S.dev.dim;
     for (uint32_t i = 0; i < n; ++i) {
         Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
@@ -308,6 +309,12 @@ void trace_t(Scene &S, uint32_t n, const float *origins, const float *dirs, floa
         ids[i] = hit ? flat_prim_id(S.dev, oh.ref, oh.lane) : -1;
         if (dist) dist[i] = hit ? oh.dist : 0;
         if (ntrans) ntrans[i] = (FLAGS & NTR_F_GENERAL) ? g.th.n : 0;
+        if ((FLAGS & NTR_F_GENERAL) && hit_ids) {
+            for (int k = 0; k < g.th.n && k < max_hits; ++k) {
+                hit_ids[(size_t)i * max_hits + k] = flat_prim_id(S.dev, g.th.ref[k], g.th.lane[k]);
+                if (hit_dists) hit_dists[(size_t)i * max_hits + k] = g.th.dist[k];
+            }
+        }
     }
 }
 
@@ -365,6 +372,22 @@ __attribute__((visibility("default"))) int emul_trace_rays(const ntr_scene_desc 
     setup(S, d, nullptr, nullptr);
 #define CALL(DT)                                                                                                  \
     if (S.flags & NTR_F_GENERAL) trace_t<DT, NTR_F_GENERAL>(S, n, origins, dirs, t_near, t_far, skip_ref, skip_lane, ids, dist, ntrans); \
+    else trace_t<DT, 0>(S, n, origins, dirs, t_near, t_far, skip_ref, skip_lane, ids, dist, ntrans)
+    DISPATCH_DIM(force_generic ? 0 : d->dim, CALL)
+#undef CALL
+    return 0;
+}
+
+__attribute__((visibility("default"))) int emul_trace_rays_hits(const ntr_scene_desc *d, uint32_t n, const float *origins,
+                                                                 const float *dirs, float t_near, float t_far,
+                                                                 const uint32_t *skip_ref, const int32_t *skip_lane,
+                                                                 int force_generic, int32_t *ids, float *dist, int32_t *ntrans,
+                                                                 int max_hits, int32_t *hit_ids, float *hit_dists) {
+    Scene S;
+    setup(S, d, nullptr, nullptr);
+    for (size_t k = 0; k < (size_t)n * max_hits; ++k) hit_ids[k] = -1;
+#define CALL(DT)                                                                                                  \
+    if (S.flags & NTR_F_GENERAL) trace_t<DT, NTR_F_GENERAL>(S, n, origins, dirs, t_near, t_far, skip_ref, skip_lane, ids, dist, ntrans, max_hits, hit_ids, hit_dists); \
     else trace_t<DT, 0>(S, n, origins, dirs, t_near, t_far, skip_ref, skip_lane, ids, dist, ntrans)
     DISPATCH_DIM(force_generic ? 0 : d->dim, CALL)
 #undef CALL

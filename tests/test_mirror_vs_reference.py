@@ -118,6 +118,10 @@ class _EmulatedDevice:
     def __init__(self, sc, device=-1):
         self.sc = sc
 
+    def trace_rays_hits(self, origins, dirs, t_near, t_far, skip_ref=None, skip_lane=None, max_hits=16):
+        from tests import emul_lib as el
+        return el.trace_rays_hits(self.sc, origins, dirs, t_near, t_far, skip_ref, skip_lane, max_hits)
+
     def trace_rays(self, origins, dirs, t_near, t_far, skip_ref=None, skip_lane=None):
         from tests import emul_lib as el
         return el.trace_rays(self.sc, origins, dirs, t_near, t_far, skip_ref, skip_lane)
@@ -443,3 +447,43 @@ def test_box_scene_random_cameras_and_dimensions():
         mine = ol.render_float(sc, w, h)
         assert np.abs(fx.quant8(mine) - fx.quant8(ref)).max() <= 1, (trial, dim)
         assert np.abs(el.render(sc, w, h)[0] - mine).max() <= 2e-6
+
+
+def test_transparent_hit_lists_match_kdnode_intersects():
+    """ntr_trace_rays_hits (here: the same per-ray code, host-emulated) against the reference's KDNode.intersects: every
+    surviving transparent hit ahead of the opaque one, same primitives, same distances, in the same list order
+    (src/ntracer_body.hpp:1438-1456; the list is the traversal's quick_list after its swap-with-last trims)."""
+    from tests import emul_lib as el
+    from tests import fixtures as fx
+    rb.load_reference()
+    rays = with_transparent = 0
+    for seed in range(60):
+        dim = 3 + seed % 4
+        sc = fx.fuzz_scene(dim, seed, max_batches=3)
+        transparent = int((sc['materials'][sc['simplex_mat'], 6] < 1).sum())
+        if len(sc['solid_mat']):
+            transparent += int((sc['materials'][sc['solid_mat'], 6] < 1).sum())
+        if transparent > 10 or len(np.unique(sc['leaf_refs'])) > 20:
+            continue                                    # stay inside the reference's defined domain (it can crash outside)
+        nt, scene, prims = rb.import_scene(sc)
+        ref_of = {id(p): r for r, p in prims.items()}
+        rng = np.random.RandomState(seed + 11)
+        n = 80
+        o = np.zeros((n, dim), np.float32)
+        o[:, :3] = rng.uniform(-3, 3, (n, 3))
+        o[:, 3:] = rng.uniform(-0.05, 0.05, (n, dim - 3))
+        target = np.zeros((n, dim), np.float32)
+        target[:, :3] = rng.uniform(-1, 1, (n, 3))
+        d = (target - o).astype(np.float32)
+        ids, dist, ntrans, hid, hdist = el.trace_rays_hits(sc, o, d)
+        for k in range(n):
+            hits = scene.root.intersects(nt.Vector(*[float(x) for x in o[k]]), nt.Vector(*[float(x) for x in d[k]]))
+            ref_list = [(rb.flat_prim_id(sc, ref_of[id(hh.primitive)], hh.batch_index), hh.dist) for hh in hits]
+            mine = [(int(hid[k, j]), float(hdist[k, j])) for j in range(int(ntrans[k]))]
+            if ids[k] >= 0:
+                mine.append((int(ids[k]), float(dist[k])))
+            assert [a for a, _ in mine] == [a for a, _ in ref_list], (seed, k, mine, ref_list)
+            assert np.allclose([b for _, b in mine], [b for _, b in ref_list], rtol=1e-4, atol=1e-5)
+            with_transparent += int(ntrans[k]) > 0
+        rays += n
+    assert rays >= 2000 and with_transparent >= 150
