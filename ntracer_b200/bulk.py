@@ -48,22 +48,67 @@ def build_kdtree(lo, hi, max_depth=0, split_threshold=0, traversal_cost=-1.0, in
     return nodes, refs, int(root.value), boundary
 
 
-def simplex_scene(points, material_ids=None, materials=None, **tree_kw):
-    """Flat CompositeScene dict for n simplexes given by their vertices (float32 [n, D, D])."""
+def group_items(lo, hi, group=4):
+    """Permutation of the n items (bounds lo/hi: [n, D]) in which every consecutive run of `group` entries is one batch of
+    spatially close items (ntr_group_items: what the reference's group_primitives does before its tree build)."""
+    lo = np.ascontiguousarray(lo, dtype=np.float32)
+    hi = np.ascontiguousarray(hi, dtype=np.float32)
+    n, d = lo.shape
+    order = np.zeros(n, dtype=np.uint32)
+    _capi.check(_capi.load().ntr_group_items(d, n, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), int(group),
+                                             order.ctypes.data_as(C.c_void_p)))
+    return order
+
+
+def batched_tree(lo, hi, batch=4, **tree_kw):
+    """Groups n simplexes into batches of `batch` and builds the tree over the ITEMS (batches + left-over singles), the
+    way build_kdtree does in the reference's SIMD builds (src/tracer.hpp:2431-2455).
+    -> (order [n]: new position -> old simplex index, nodes, leaf refs ((1<<30)|first record for batches), root, boundary)"""
+    n = lo.shape[0]
+    order = group_items(lo, hi, batch) if batch > 1 else np.arange(n, dtype=np.uint32)
+    lo, hi = lo[order], hi[order]
+    nb = n // batch if batch > 1 else 0
+    ilo = np.concatenate([lo[:nb * batch].reshape(nb, batch, -1).min(axis=1), lo[nb * batch:]]) if nb else lo
+    ihi = np.concatenate([hi[:nb * batch].reshape(nb, batch, -1).max(axis=1), hi[nb * batch:]]) if nb else hi
+    item_ref = np.concatenate([(1 << 30) | (np.arange(nb, dtype=np.uint32) * batch),
+                               np.arange(nb * batch, n, dtype=np.uint32)]).astype(np.uint32)
+    nodes, items, root, boundary = build_kdtree(ilo, ihi, **tree_kw)
+    nodes = nodes.copy()
+    refs = item_ref[items]
+    # the reference keeps the batches of a leaf in front of its single primitives (tracer.hpp:1142-1150) and stores
+    # their number in the leaf
+    for k in np.nonzero(nodes[:, 0] & 0x80000000)[0]:
+        a, m = int(nodes[k, 1]), int(nodes[k, 2])
+        seg = refs[a:a + m]
+        isb = (seg >> 30) == 1
+        if isb.any() and not isb.all():
+            refs[a:a + m] = np.concatenate([seg[isb], seg[~isb]])
+        nodes[k, 0] = 0x80000000 | int(isb.sum())
+    return order, nodes, refs, root, boundary
+
+
+def simplex_scene(points, material_ids=None, materials=None, batch=1, **tree_kw):
+    """Flat CompositeScene dict for n simplexes given by their vertices (float32 [n, D, D]).  batch = 4 packs them into
+    4-lane batch items first (the layout the tuned batch test of the kernels works on)."""
     pts = np.ascontiguousarray(points, dtype=np.float32)
     n, d, _ = pts.shape
     rec = simplex_records(pts)
     lo, hi = pts.min(axis=1), pts.max(axis=1)
-    nodes, refs, root, boundary = build_kdtree(lo, hi, **tree_kw)
-    if materials is None:
-        materials = np.array([[1, 0.5, 0.5, 1, 1, 1, 1, 0, 1, 8]], dtype=np.float32)      # Material((1,0.5,0.5))
     if material_ids is None:
         material_ids = np.zeros(n, dtype=np.int32)
+    material_ids = np.ascontiguousarray(material_ids, dtype=np.int32)
+    if batch > 1:
+        order, nodes, refs, root, boundary = batched_tree(lo, hi, batch, **tree_kw)
+        rec, material_ids = rec[order], material_ids[order]
+    else:
+        nodes, refs, root, boundary = build_kdtree(lo, hi, **tree_kw)
+    if materials is None:
+        materials = np.array([[1, 0.5, 0.5, 1, 1, 1, 1, 0, 1, 8]], dtype=np.float32)      # Material((1,0.5,0.5))
     cam_axes = np.eye(d, dtype=np.float32)
     return {
-        'dim': np.int64(d), 'kind': np.int64(1), 'batch_size': np.int64(1), 'root': np.int64(root),
-        'nodes': nodes, 'leaf_refs': refs.astype(np.uint32),           # item index == simplex index, type 0 (single simplex)
-        'simplex': rec, 'simplex_mat': np.ascontiguousarray(material_ids, dtype=np.int32),
+        'dim': np.int64(d), 'kind': np.int64(1), 'batch_size': np.int64(batch), 'root': np.int64(root),
+        'nodes': nodes, 'leaf_refs': refs.astype(np.uint32),           # single simplex: item index == record index (type 0)
+        'simplex': np.ascontiguousarray(rec), 'simplex_mat': material_ids,
         'solids': np.zeros((0, 1 + 2 * d * d + d), np.float32), 'solid_mat': np.zeros(0, np.int32),
         'materials': np.ascontiguousarray(materials, dtype=np.float32).reshape(-1, 10), 'boundary': boundary,
         'params': np.array([0.8, 0, 1, 4, 1], dtype=np.float64),

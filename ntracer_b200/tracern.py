@@ -1112,9 +1112,9 @@ def screen_coord_to_ray(cam, x, y, w, h, fov):
 def build_kdtree(primitives, extra_threads=-1, *, max_depth=None, split_threshold=None, traversal_cost=None,
                  intersection_cost=None, update_primitives=False):
     """-> (AABB, KDNode).  The tree comes from this backend's native host-side builder (csrc/builder.cpp,
-    ntr_build_kdtree: binned SAH over the prototypes' bounding boxes).  It is NOT the reference's builder
-    (src/tracer.hpp:1930-2455): colours and hit ids do not depend on the tree, except with shadows on
-    (DESIGN.md section 2)."""
+    ntr_group_items + ntr_build_kdtree: triangles grouped into TriangleBatch items, then a binned SAH over the items'
+    bounding boxes).  It is NOT the reference's builder (src/tracer.hpp:1930-2455): colours and hit ids do not depend on
+    the tree, except with shadows on."""
     from . import bulk
     protos = list(primitives)
     if not protos:
@@ -1127,16 +1127,38 @@ def build_kdtree(primitives, extra_threads=-1, *, max_depth=None, split_threshol
         raise TypeError('the primitive prototypes must all have the same dimension')
     lo = np.stack([p.boundary.start._v for p in protos])
     hi = np.stack([p.boundary.end._v for p in protos])
-    nodes, refs, root, boundary = bulk.build_kdtree(lo, hi, max_depth or 0, split_threshold or 0,
+    # group_primitives (src/tracer.hpp:2395-2427): triangles are packed into TriangleBatch items of BATCH_SIZE lanes before
+    # the tree is built over the ITEMS; solids and the left-over triangles stay single primitives.  The grouping is this
+    # backend's own (ntr_group_items: recursive median split of the centres, O(n log n) against the reference's O(n^2)).
+    prims = [p.primitive for p in protos]
+    tri = [i for i, q in enumerate(prims) if isinstance(q, Triangle)]
+    items, ilo, ihi = [], [], []
+    if BATCH_SIZE > 1 and len(tri) >= BATCH_SIZE:
+        order = bulk.group_items(lo[tri], hi[tri], BATCH_SIZE)
+        nb = len(tri) // BATCH_SIZE
+        for k in range(nb):
+            members = [tri[int(j)] for j in order[k * BATCH_SIZE:(k + 1) * BATCH_SIZE]]
+            items.append(TriangleBatch([prims[j] for j in members]))
+            ilo.append(lo[members].min(axis=0))
+            ihi.append(hi[members].max(axis=0))
+        single = [tri[int(j)] for j in order[nb * BATCH_SIZE:]] + [i for i, q in enumerate(prims) if not isinstance(q, Triangle)]
+    else:
+        single = list(range(len(prims)))
+    for j in single:
+        items.append(prims[j])
+        ilo.append(lo[j])
+        ihi.append(hi[j])
+    nodes, refs, root, boundary = bulk.build_kdtree(np.stack(ilo), np.stack(ihi), max_depth or 0, split_threshold or 0,
                                                     -1.0 if traversal_cost is None else traversal_cost,
                                                     -1.0 if intersection_cost is None else intersection_cost)
-    prims = [p.primitive for p in protos]
     # children always follow their parent in the node array, so a reverse sweep builds the objects bottom-up
     objs = [None] * len(nodes)
     for i in range(len(nodes) - 1, -1, -1):
         meta, a, b, c = (int(x) for x in nodes[i])
         if meta & _capi.LEAF_FLAG:
-            objs[i] = KDLeaf([prims[j] for j in refs[a:a + b]])
+            members = [items[j] for j in refs[a:a + b]]
+            # batches first, like the reference's leaves (tracer.hpp:1142-1150)
+            objs[i] = KDLeaf([m for m in members if isinstance(m, TriangleBatch)] + [m for m in members if not isinstance(m, TriangleBatch)])
         else:
             split = float(np.array([a], np.uint32).view(np.float32)[0])
             objs[i] = KDBranch(meta, split, None if b == _capi.NULL_NODE else objs[b], None if c == _capi.NULL_NODE else objs[c])

@@ -127,3 +127,45 @@ def test_builder_edge_cases_and_input_validation():
     rc = lib.ntr_build_kdtree(3, 1, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), 0, 0, -1.0, -1.0,
                               C.byref(p1), C.byref(a), C.byref(p2), C.byref(b), C.byref(c), bnd.ctypes.data_as(C.c_void_p))
     assert rc == _capi.NTR_ERR_VALUE
+
+
+def test_group_items_is_a_permutation_of_compact_groups():
+    """ntr_group_items (batch grouping ahead of the tree build, the reference's group_primitives): a permutation in which
+    consecutive runs of 4 are spatially close -- far tighter than the same items grouped in input order."""
+    from ntracer_b200 import bulk
+    rng = np.random.RandomState(5)
+    for dim, n in ((3, 1003), (4, 4096), (7, 50), (10, 3)):
+        c = rng.uniform(-1, 1, (n, dim)).astype(np.float32)
+        lo, hi = c - 0.01, c + 0.01
+        order = bulk.group_items(lo, hi, 4)
+        assert sorted(order.tolist()) == list(range(n))
+        if n >= 50:
+            nb = n // 4
+
+            def spread(idx):
+                g = c[idx[:nb * 4]].reshape(nb, 4, dim)
+                return float((g.max(axis=1) - g.min(axis=1)).sum(axis=1).mean())
+            assert spread(order) < 0.5 * spread(np.arange(n))
+    with pytest.raises(ValueError):
+        bulk.group_items(np.zeros((4, 2), np.float32), np.ones((4, 2), np.float32), 4)
+
+
+def test_batched_scene_renders_like_the_single_simplex_scene():
+    """bulk.simplex_scene(batch=4): records reordered into 4-lane batch items, tree over the items, batches first in every
+    leaf -- the oracle must draw the same picture as for the single-simplex scene of the same soup."""
+    from ntracer_b200 import bulk
+    from tests import oracle_lib as ol
+    pts = bulk.soup(4, 2003, thin=0.3, spread=0.2)
+    a = bulk.simplex_scene(pts, max_depth=14)
+    b = bulk.simplex_scene(pts, batch=4, max_depth=14)
+    for sc in (a, b):
+        sc['cam_origin'] = np.array([0, 0, -3, 0], np.float32)
+    assert int(b['batch_size']) == 4 and int((b['leaf_refs'] >> 30 == 1).sum()) > 0
+    n_batches = (b['nodes'][:, 0] & 0x7FFFFFFF)[(b['nodes'][:, 0] >> 31) == 1]
+    for k in np.nonzero((b['nodes'][:, 0] >> 31) == 1)[0][:200]:         # batches come first in a leaf
+        first, m, nb = int(b['nodes'][k, 1]), int(b['nodes'][k, 2]), int(b['nodes'][k, 0] & 0x7FFFFFFF)
+        kinds = b['leaf_refs'][first:first + m] >> 30
+        assert np.all(kinds[:nb] == 1) and np.all(kinds[nb:] == 0)
+    assert np.array_equal(ol.render_float(a, 96, 54), ol.render_float(b, 96, 54))
+    ids_a, _ = ol.primary_hit_ids(a, 96, 54)
+    assert (ids_a >= 0).mean() > 0.2

@@ -160,11 +160,25 @@ def test_builder_tree_gives_reference_hit_ids():
         sc = flat.scene_dict(root, s.boundary, s)
         sc['cam_origin'], sc['cam_axes'] = s._cam._origin, s._cam._axes
         ids, dist = ol.primary_hit_ids(sc, 64, 48)
-        owners = np.array([-1 if i < 0 else [p.primitive for p in protos].index(flat.prim_of_flat_id(int(i))[0]) for i in ids.ravel()])
+        plist = [p.primitive for p in protos]
+
+        def owner(i):                   # the Triangle that was hit: a single primitive, or the lane of a TriangleBatch
+            prim, lane = flat.prim_of_flat_id(int(i))
+            return plist.index(prim[lane] if lane >= 0 else prim)
+        owners = np.array([-1 if i < 0 else owner(i) for i in ids.ravel()])
         out.append((owners, dist.ravel(), ol.render_float(sc, 64, 48)))
     assert np.mean(out[0][0] == out[1][0]) >= 0.999
     assert np.abs(out[0][2] - out[1][2]).max() < 1e-4
     assert (out[0][0] >= 0).mean() > 0.1
+    # the built tree holds the triangles as TriangleBatch items (group_primitives, src/tracer.hpp:2395-2427)
+    def leaves(n):
+        return [n] if isinstance(n, tracern.KDLeaf) else [l for c in (n.left, n.right) if c is not None for l in leaves(c)]
+    items = {id(it): it for l in leaves(scene.root) for it in l}
+    batches = [it for it in items.values() if isinstance(it, tracern.TriangleBatch)]
+    singles = [it for it in items.values() if isinstance(it, tracern.Triangle)]
+    assert len(batches) == 150 // 4 and len(singles) == 150 % 4
+    assert sorted(plist.index(t) for b in batches for t in b) + sorted(plist.index(t) for t in singles) == sorted(range(150)) or \
+        sorted([plist.index(t) for b in batches for t in b] + [plist.index(t) for t in singles]) == list(range(150))
 
 
 # ---- the builder-side geometry tests of the reference's own test-suite (lib/ntracer/tests/test.py), same vectors -------
