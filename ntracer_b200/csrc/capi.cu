@@ -152,7 +152,8 @@ struct ntr_scene {
     uint32_t *h_ctl = nullptr;              // pinned read-back of the control block and the counters (frame_readback)
     unsigned long long *h_cnt = nullptr;
     uint64_t launches = 0;
-    int grid_blocks[4] = {0, 0, 0, 0};
+    int grid_blocks[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool warp_path = false;             // render with the warp-synchronous kernels (scenes with big leaves; NTR_WARP=0|1 overrides)
     const KernelSet *(*kset)(int) = nullptr;
     std::atomic<bool> busy{false};
     // begin/end frames (ntr_render_begin / ntr_render_end)
@@ -364,7 +365,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     f.tile_row_first = tile_row_first; f.tile_row_step = tile_row_step < 1 ? 1 : tile_row_step; f.compact = compact;
     if (fmt) fill_format(f.fmt, fmt);
 
-    int flags = sc->base_flags | (sc->instrumented ? NTR_F_COUNT : 0);
+    int flags = sc->base_flags | (sc->instrumented ? NTR_F_COUNT : 0) | (sc->warp_path ? NTR_F_WARP : 0);
     const bool composite = sc->dev.kind == NTR_SCENE_COMPOSITE;
     const bool passes = composite && tgt.out_mode != NTR_OUT_IDS && sc->any_reflective && sc->dev.max_depth > 0;
     *used_passes = passes;
@@ -656,7 +657,8 @@ int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win
 int run_frame_slabs(ntr_scene *sc, const ntr_image_format *fmt, unsigned char *dst) {
     const int tiles_y = (fmt->height + NTR_TILE - 1) / NTR_TILE;
     const int S = std::min(kSlabMax, tiles_y / 4);
-    if (S < 2 || sc->instrumented) return 1;
+    // (the slabs' kernels run side by side: they would share the columns of the exact mailbox table)
+    if (S < 2 || sc->instrumented || sc->dev.mb_table) return 1;
     for (int i = 1; i < S; ++i) {
         if (!sc->slab_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&sc->slab_stream[i], cudaStreamNonBlocking));
         if (!sc->slab_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&sc->slab_done[i], cudaEventDisableTiming));
@@ -861,7 +863,9 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     if (const char *ts = getenv("NTR_TILE_SCHED")) sc->force_tile_sched = atoi(ts) != 0;
     for (uint32_t i = 0; desc->kind == NTR_SCENE_COMPOSITE && i < desc->n_nodes; ++i)
         if (desc->nodes[i].meta & NTR_LEAF_FLAG) sc->max_leaf = std::max(sc->max_leaf, desc->nodes[i].w2);
-    sc->heavy_first = sc->adaptive_fetch = sc->max_leaf >= 256;
+    sc->heavy_first = sc->warp_path = sc->max_leaf >= 256;
+    sc->adaptive_fetch = false;         // measured (round 2 call 4): fewer rays per warp from the expensive rings loses everywhere
+    if (const char *wp = getenv("NTR_WARP")) sc->warp_path = atoi(wp) != 0;
     if (const char *hf = getenv("NTR_HEAVY_FIRST")) sc->heavy_first = atoi(hf) != 0;
     if (const char *af = getenv("NTR_ADAPTIVE_FETCH")) sc->adaptive_fetch = atoi(af) != 0;
     if (const char *fs = getenv("NTR_FETCH_SIZES")) {
@@ -889,6 +893,25 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
         if ((rc = build_arena(sc, desc))) return bail(rc);
         if ((rc = upload_lights(sc, desc))) return bail(rc);
     }
+    // the exact mailbox of scenes whose leaves overrun the bounded table (trace_core.cuh: MailboxStore): one column per
+    // thread of the persistent grid, zero-initialised (generation 0 is never current)
+    {
+        const uint64_t keys = (uint64_t)desc->n_simplex + desc->n_solids;
+        const char *mbx = getenv("NTR_EXACT_MAILBOX");
+        const bool want = mbx ? atoi(mbx) != 0 : sc->max_leaf > NTR_MAILBOX_CAP;
+        if (desc->kind == NTR_SCENE_COMPOSITE && (sc->base_flags & NTR_F_GENERAL) && want && keys <= NTR_MAILBOX_MAX_KEYS) {
+            int blocks = 0;
+            for (int f = 0; f < 8; ++f) if ((f & NTR_F_GENERAL) == (sc->base_flags & NTR_F_GENERAL)) blocks = std::max(blocks, grid_for(sc, f));
+            sc->dev.mb_threads = (uint32_t)blocks * kCtaThreads;
+            sc->dev.mb_words = (uint32_t)((keys + NTR_MAILBOX_BITS_PER_WORD - 1) / NTR_MAILBOX_BITS_PER_WORD);
+            const size_t bytes = (size_t)(sc->dev.mb_words + 1) * sc->dev.mb_threads * sizeof(uint32_t);
+            if (cudaMalloc(&sc->dev.mb_table, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return bail(fail(NTR_ERR_MEMORY, "out of device memory for the mailbox table (%zu bytes)", bytes));
+            }
+            cudaMemset(sc->dev.mb_table, 0, bytes);
+        }
+    }
     auto cu = [&](cudaError_t e, const char *what) {
         if (e == cudaSuccess) return 0;
         return fail(e == cudaErrorMemoryAllocation ? NTR_ERR_MEMORY : NTR_ERR_RUNTIME, "%s failed: %s", what, cudaGetErrorString(e));
@@ -911,7 +934,7 @@ NTR_API void ntr_scene_destroy(ntr_scene *sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
     if (sc->stream) cudaStreamSynchronize(sc->stream);
-    cudaFree(sc->arena); cudaFree(sc->d_lights); cudaFree(sc->d_ctl); cudaFree(sc->d_counters);
+    cudaFree(sc->arena); cudaFree(sc->d_lights); cudaFree(sc->d_ctl); cudaFree(sc->d_counters); cudaFree(sc->dev.mb_table);
     cudaFree(sc->d_accum); cudaFree(sc->d_packed); cudaFree(sc->d_ids); cudaFree(sc->d_dists);
     cudaFree(sc->d_queue[0]); cudaFree(sc->d_queue[1]); cudaFree(sc->d_scratch);
     cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order); cudaFree(sc->d_ring);
@@ -1207,7 +1230,9 @@ NTR_API int ntr_trace_rays_hits(ntr_scene *sc, uint32_t n, const float *origins,
     if (skip_lane) CUDA_TRY(cudaMemcpyAsync(b + offs[3], skip_lane, ib, cudaMemcpyHostToDevice, st));
     if (max_hits) CUDA_TRY(cudaMemsetAsync(b + offs[7], 0xFF, hb, st));          // -1: no hit in this slot
     const int flags = sc->base_flags;
-    sc->kset(flags)->trace_rays(dim3((n + kCtaThreads - 1) / kCtaThreads), dim3(kCtaThreads), st, sc->dev, n,
+    uint32_t ray_blocks = (n + kCtaThreads - 1) / kCtaThreads;
+    if (sc->dev.mb_table) ray_blocks = std::min(ray_blocks, sc->dev.mb_threads / kCtaThreads);      // one mailbox column per thread
+    sc->kset(flags)->trace_rays(dim3(ray_blocks), dim3(kCtaThreads), st, sc->dev, n,
                                 (const float *)(b + offs[0]), (const float *)(b + offs[1]), t_near, t_far,
                                 skip_ref ? (const uint32_t *)(b + offs[2]) : nullptr,
                                 skip_lane ? (const int32_t *)(b + offs[3]) : nullptr, (int32_t *)(b + offs[4]),

@@ -17,6 +17,11 @@
 #define NTR_THITS_CAP 16            // transparent hits kept per ray (reference is defined up to 10, tracer.hpp:26)
 #define NTR_MAILBOX_CAP 40          // mailbox entries kept per traversal (reference is defined up to 20, tracer.hpp:27)
 #define NTR_MAILBOX_SLOTS 64        // open-addressing table that holds them (trace_core.cuh: Mailbox)
+// Scenes whose leaves are bigger than that table get an EXACT mailbox instead: one bit per leaf item and traversing
+// thread, in a scene-wide table in device memory (trace_core.cuh: MailboxStore).  Up to this many items (simplexes +
+// solids); bigger scenes keep the bounded table.
+#define NTR_MAILBOX_MAX_KEYS 65536
+#define NTR_MAILBOX_BITS_PER_WORD 24   // a word = generation tag (8 bits) | 24 item bits
 #define NTR_STACK_CAP (NTR_MAX_TREE_DEPTH + 2)
 
 // meta word stored in the last float slot of every simplex / solid record
@@ -26,7 +31,9 @@
 enum : int {
     NTR_F_GENERAL = 1,      // scene has transparent materials and/or solids: mailbox, transparent-hit list,
                             // explicit normal mirroring (reference quirks)
-    NTR_F_COUNT = 2         // instrumented: node/primitive counters (never used for timing)
+    NTR_F_COUNT = 2,        // instrumented: node/primitive counters (never used for timing)
+    NTR_F_WARP = 4          // render_pass_kernel only: the warp-synchronous per-ray path (trace_warp.cuh), chosen for scenes
+                            // with big leaves; otherwise every lane traces for itself (trace_core.cuh)
 };
 
 struct SceneDev {
@@ -39,6 +46,8 @@ struct SceneDev {
     const float *leaf_index;        // in-order bounding-box indices of big leaves (arena_pack.h); leaf node w3 = offset/4 + 1
     const float *point_lights;      // stride D+3
     const float *global_lights;     // stride D+3
+    uint32_t *mb_table;             // exact mailbox: mb_words words per thread, word w of thread t at [w * mb_threads + t] (nullptr: none)
+    uint32_t mb_words, mb_threads;
     uint32_t root;
     uint32_t n_simplex;
     int dim, batch, sstride, solstride;

@@ -118,9 +118,6 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 #ifndef NTR_FETCH_STATS
 #define NTR_FETCH_STATS 0          // diagnostic: per-fetch durations (see ControlDev::fetch_stats); never in the shipped build
 #endif
-#ifndef NTR_WARP_PATH
-#define NTR_WARP_PATH 1            // 1: the warp-synchronous per-ray path (trace_warp.cuh); 0: every lane for itself (trace_core.cuh)
-#endif
 // above 8 dimensions the ray alone (origin, direction, hit point) is 30+ registers: fewer CTAs per SM, more registers
 #ifndef NTR_MIN_CTAS_HI
 #define NTR_MIN_CTAS_HI 5          // measured on config 5 (16 k simplexes): 3 -> 31.7 ms, 4 -> 25.5, 5 -> 23.3, 6 -> 24.6, 8 -> 32.6
@@ -154,6 +151,8 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
         if (total > q.capacity) total = q.capacity;
     }
     uint32_t fetches = 0;
+    MailboxStore ms;                    // this thread's column of the exact mailbox (scenes with big leaves), if any
+    ms.attach((FLAGS & NTR_F_GENERAL) ? s.mb_table : nullptr, s.mb_words, s.mb_threads, blockIdx.x * blockDim.x + threadIdx.x, s.n_simplex);
     for (;;) {
         // ---------------- fetch: an 8x4 pixel block of a tile (primary) or up to 32 queued bounces ----------------
         uint32_t b = 0, take = 32;
@@ -247,22 +246,27 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                 active = true;
             }
         }
-#if !NTR_WARP_PATH
-        if (active) {
-            QueueEmit<DT> emit{q, ctl, pix, !primary || f.out_mode == NTR_OUT_ACCUM};
-            ray_color<DT, FLAGS>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim);
-        }
-#else
-        // ---------------- the per-ray path: all 32 lanes enter (trace_warp.cuh), `active` says who has a ray ----------------
-        if (s.kind != NTR_SCENE_BOX) {       // warp-uniform
-            if (!active) {
+        // ---------------- the per-ray path ----------------
+        // Two forms of the same algorithm (FLAGS & NTR_F_WARP, chosen by the host per scene).  Every lane for itself
+        // (trace_core.cuh) is the faster one on ordinary trees: ncu, config 2: the warp form spends 17x the local-memory
+        // traffic and twice the instruction-fetch stalls (profiles/r02_c2_warp_vs_lane_ncu_summary.txt).  The
+        // warp-synchronous form (trace_warp.cuh: all 32 lanes enter, `active` says who has a ray; rays park at big leaves
+        // and the warp splits them over its lanes when enough lanes are idle) wins where single rays walk leaves of
+        // hundreds of items (config 4: 58.4 -> 49.9 ms, its 1/8-frame share 26.3 -> 19.9 ms).
+        constexpr int RF = FLAGS & ~NTR_F_WARP;     // the per-ray code knows nothing of the switch
+        if constexpr ((FLAGS & NTR_F_WARP) != 0) {
+            if (s.kind != NTR_SCENE_BOX) {          // warp-uniform
+                if (!active) {
 #pragma unroll
-                for (int k = 0; k < CAP; ++k) { o[k] = 0.0f; dir[k] = 1.0f; }
+                    for (int k = 0; k < CAP; ++k) { o[k] = 0.0f; dir[k] = 1.0f; }
+                }
+                QueueEmit<DT> emit{q, ctl, pix, !primary || f.out_mode == NTR_OUT_ACCUM};
+                ray_color_warp<DT, RF>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim, done_ctr, &ms);
             }
+        } else if (active) {
             QueueEmit<DT> emit{q, ctl, pix, !primary || f.out_mode == NTR_OUT_ACCUM};
-            ray_color_warp<DT, FLAGS>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim, done_ctr);
+            ray_color<DT, RF>(s, active, o, dir, depth, skip, w, acc, emit, cnt, &prim, &ms);
         }
-#endif
         if (primary && f.tile_cost && lane == 0) atomicAdd(f.tile_cost + cost_tile, (unsigned long long)(clock64() - t_start));
 #if NTR_FETCH_STATS
         if (lane == 0 && ctl.fetch_stats) {
@@ -298,6 +302,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
         }
     }
     __syncwarp();
+    ms.detach();
     flush_counters(ctl, cnt);
 }
 
@@ -326,29 +331,34 @@ trace_rays_kernel(const __grid_constant__ SceneDev s, uint32_t n, const float *o
                   float *dist, int32_t *ntrans, int32_t *hit_ids, float *hit_dists, int max_hits) {
     constexpr int CAP = DimCap<DT>::value;
     const int D = NTR_D(DT, s);
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float o[CAP], dir[CAP];
+    MailboxStore ms;
+    ms.attach((FLAGS & NTR_F_GENERAL) ? s.mb_table : nullptr, s.mb_words, s.mb_threads, blockIdx.x * blockDim.x + threadIdx.x, s.n_simplex);
+    // grid-stride: the host never launches more threads than the mailbox table has columns
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float o[CAP], dir[CAP];
 #pragma unroll
-    for (int k = 0; k < D; ++k) { o[k] = origins[(size_t)i * D + k]; dir[k] = dirs[(size_t)i * D + k]; }
-    Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
-    GenState<DT> g;
-    g.th.clear();
-    HitRec oh;
-    oh.dist = FLT_MAX; oh.ref = NTR_NONE_REF; oh.lane = -1;
-    Counters cnt;
-    const bool hit = trace_nearest<DT, FLAGS>(s, o, dir, skip, t_near, t_far, oh, &g, cnt);
-    ids[i] = hit ? flat_prim_id(s, oh.ref, oh.lane) : -1;
-    if (dist) dist[i] = hit ? oh.dist : 0.0f;
-    if (ntrans) ntrans[i] = (FLAGS & NTR_F_GENERAL) ? g.th.n : 0;
-    // the surviving transparent hits in the order the reference's list holds them (kdnode_intersects returns them
-    // before the opaque hit, src/ntracer_body.hpp:1438-1456)
-    if ((FLAGS & NTR_F_GENERAL) && hit_ids) {
-        for (int k = 0; k < g.th.n && k < max_hits; ++k) {
-            hit_ids[(size_t)i * max_hits + k] = flat_prim_id(s, g.th.ref[k], g.th.lane[k]);
-            if (hit_dists) hit_dists[(size_t)i * max_hits + k] = g.th.dist[k];
+        for (int k = 0; k < D; ++k) { o[k] = origins[(size_t)i * D + k]; dir[k] = dirs[(size_t)i * D + k]; }
+        Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
+        GenState<DT> g;
+        g.mb.big = ms.col ? &ms : nullptr;
+        g.th.clear();
+        HitRec oh;
+        oh.dist = FLT_MAX; oh.ref = NTR_NONE_REF; oh.lane = -1;
+        Counters cnt;
+        const bool hit = trace_nearest<DT, FLAGS>(s, o, dir, skip, t_near, t_far, oh, &g, cnt);
+        ids[i] = hit ? flat_prim_id(s, oh.ref, oh.lane) : -1;
+        if (dist) dist[i] = hit ? oh.dist : 0.0f;
+        if (ntrans) ntrans[i] = (FLAGS & NTR_F_GENERAL) ? g.th.n : 0;
+        // the surviving transparent hits in the order the reference's list holds them (kdnode_intersects returns them
+        // before the opaque hit, src/ntracer_body.hpp:1438-1456)
+        if ((FLAGS & NTR_F_GENERAL) && hit_ids) {
+            for (int k = 0; k < g.th.n && k < max_hits; ++k) {
+                hit_ids[(size_t)i * max_hits + k] = flat_prim_id(s, g.th.ref[k], g.th.lane[k]);
+                if (hit_dists) hit_dists[(size_t)i * max_hits + k] = g.th.dist[k];
+            }
         }
     }
+    ms.detach();
 }
 
 // KDNode.occludes (reference src/ntracer_body.hpp:1460-1496)
@@ -405,10 +415,14 @@ template <int DT, int FLAGS> struct Launch {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, render_pass_kernel<DT, FLAGS>, kCtaThreads, 0);
         return n;
     }
-    static KernelSet get() { return KernelSet{&render_pass, &trace_rays, &occludes_rays, &max_blocks_per_sm}; }
+    // the ray hooks have no warp form: both render variants share them
+    static KernelSet get() {
+        return KernelSet{&render_pass, &Launch<DT, FLAGS & ~NTR_F_WARP>::trace_rays, &Launch<DT, FLAGS & ~NTR_F_WARP>::occludes_rays,
+                         &max_blocks_per_sm};
+    }
 };
 
-// defined in kern_d*.cu: variant index = FLAGS (0..3)
+// defined in kern_d*.cu: variant index = FLAGS (0..7)
 const KernelSet *kernel_set_d3(int flags);
 const KernelSet *kernel_set_d4(int flags);
 const KernelSet *kernel_set_d5(int flags);
@@ -421,9 +435,10 @@ const KernelSet *kernel_set_dn(int flags);
 
 #define NTR_INSTANTIATE_DIM(NAME, DT)                                                                   \
     const KernelSet *NAME(int flags) {                                                                  \
-        static const KernelSet sets[4] = {Launch<DT, 0>::get(), Launch<DT, 1>::get(), Launch<DT, 2>::get(), \
-                                          Launch<DT, 3>::get()};                                        \
-        return &sets[flags & 3];                                                                        \
+        static const KernelSet sets[8] = {Launch<DT, 0>::get(), Launch<DT, 1>::get(), Launch<DT, 2>::get(), \
+                                          Launch<DT, 3>::get(), Launch<DT, 4>::get(), Launch<DT, 5>::get(), \
+                                          Launch<DT, 6>::get(), Launch<DT, 7>::get()};                  \
+        return &sets[flags & 7];                                                                        \
     }
 
 }  // namespace ntr

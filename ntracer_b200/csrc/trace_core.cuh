@@ -528,6 +528,49 @@ struct HitList {                        // quick_list<ray_intersection>, tracer.
     }
 };
 
+// The exact mailbox of scenes with big leaves.  The reference's `checked` list (tracer.hpp:782,832-834) answers "was this
+// item tested during this traversal" for every item; its implementation breaks beyond 20 entries (quick_list growth
+// copies bytes, :670-680), the oracle restates it with a correct unbounded list.  On the star polytopes a leaf alone
+// holds up to 1,600 items and every batch sits in ~80 leaves, so a bounded table is overrun at once and the same
+// batches are tested again in leaf after leaf (host emulation, {5/2,3,3}: 1,318 simplex tests per pixel against the
+// oracle's 764).  Here every traversing thread owns one bit per leaf item in a scene-wide table in device memory
+// (column-interleaved: word w of thread t at [w * threads + t], so that the lanes of a warp of coherent rays, which
+// test the same item at the same time, touch one 128-byte line).  Words carry an 8-bit generation tag, so starting a
+// new traversal costs one increment instead of clearing the column; a word written by an older traversal reads as
+// empty.  This is the oracle's semantics exactly -- pixels beyond the reference's own limit included.
+struct MailboxStore {
+    uint32_t *col;          // this thread's column (nullptr: the scene has none -> bounded table)
+    uint32_t stride;        // threads in the table
+    uint32_t words;         // words per thread
+    uint32_t gen;           // generation of the current traversal, 1..255
+    uint32_t solid_base;    // key of solid 0 (= number of simplex records)
+    // bind to thread `tid` of the scene's table; the generation counter of the column survives between launches in the
+    // word behind its bit words (a column starts all zero: generation 0 is never current)
+    NTR_HD void attach(uint32_t *table, uint32_t n_words, uint32_t n_threads, uint32_t tid, uint32_t n_simplex) {
+        col = (table && tid < n_threads) ? table + tid : nullptr;
+        stride = n_threads; words = n_words; solid_base = n_simplex;
+        gen = col ? col[(size_t)words * stride] : 0u;
+    }
+    NTR_HD void detach() { if (col) col[(size_t)words * stride] = gen; }
+    NTR_HD void begin_traversal() {
+        if (++gen > 255u) {
+            for (uint32_t w = 0; w < words; ++w) col[(size_t)w * stride] = 0u;
+            gen = 1u;
+        }
+    }
+    NTR_HD uint32_t key_of(uint32_t r) const { return (r >> 30) == NTR_REF_SOLID ? solid_base + (r & NTR_IDX_MASK) : (r & NTR_IDX_MASK); }
+    NTR_HD bool has(uint32_t r) const {
+        const uint32_t k = key_of(r), w = col[(size_t)(k / NTR_MAILBOX_BITS_PER_WORD) * stride];
+        return (w >> 24) == gen && ((w >> (k % NTR_MAILBOX_BITS_PER_WORD)) & 1u);
+    }
+    NTR_HD void add(uint32_t r) {
+        const uint32_t k = key_of(r);
+        uint32_t *p = col + (size_t)(k / NTR_MAILBOX_BITS_PER_WORD) * stride;
+        const uint32_t w = *p;
+        *p = ((w >> 24) == gen ? w : gen << 24) | (1u << (k % NTR_MAILBOX_BITS_PER_WORD));
+    }
+};
+
 struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,832-834
     // The reference's list is defined up to 20 entries (quick_list growth copies bytes, tracer.hpp:670-680: beyond
     // that has() scans uninitialised slots).  This one is exact up to NTR_MAILBOX_CAP entries and then switches itself
@@ -538,13 +581,17 @@ struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,8
     // linear scan was 16 % of all executed instructions and a quarter of the local-memory traffic of the kernel).
     uint32_t v[NTR_MAILBOX_SLOTS];      // NTR_NONE_REF = empty slot (no item ref has both type bits set)
     int n;
+    MailboxStore *big;                  // set: the exact per-thread bitset replaces the table (scenes with big leaves)
     static_assert((NTR_MAILBOX_SLOTS & (NTR_MAILBOX_SLOTS - 1)) == 0 && NTR_MAILBOX_SLOTS > NTR_MAILBOX_CAP, "mailbox table size");
     NTR_HD static uint32_t slot_of(uint32_t r) { return (r * 2654435761u) >> 16 & (uint32_t)(NTR_MAILBOX_SLOTS - 1); }
+    NTR_HD bool exact() const { return big != nullptr; }
     NTR_HD void clear() {
         n = 0;
+        if (big) { big->begin_traversal(); return; }
         for (int i = 0; i < NTR_MAILBOX_SLOTS; ++i) v[i] = NTR_NONE_REF;
     }
     NTR_HD bool has(uint32_t r) const {
+        if (big) return big->has(r);
         if (n > NTR_MAILBOX_CAP || n == 0) return false;
         uint32_t h = slot_of(r);
         for (;;) {
@@ -555,6 +602,7 @@ struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,8
         }
     }
     NTR_HD void add(uint32_t r) {
+        if (big) { big->add(r); return; }
         if (n < NTR_MAILBOX_CAP) {
             uint32_t h = slot_of(r);
             while (v[h] != NTR_NONE_REF) h = (h + 1) & (uint32_t)(NTR_MAILBOX_SLOTS - 1);
@@ -977,11 +1025,12 @@ NTR_HD void prim_eval(const SceneDev &s, uint2 it, const float *o, const float *
 // taken earlier (with a cutoff that may have been looser, and before the mailbox may have switched itself off).
 template <int DT, int FLAGS>
 NTR_HD void replay_item(const SceneDev &s, const uint2 it, const float *o, const float *dir, Skip skip, HitRec &oh,
-                        GenState<DT> &g, Counters &cnt, bool &phase1, float &dist, ChunkEval<DT> &e) {
+                        GenState<DT> &g, Counters &cnt, bool &phase1, float &dist, ChunkEval<DT> &e,
+                        bool mailbox_done = false /* the caller consulted and updated the mailbox for this item */) {
     const int D = NTR_D(DT, s);
     const uint32_t item = it.x;
     const bool is_batch = (item >> 30) == NTR_REF_BATCH;
-    if ((!is_batch && item == skip.ref) || g.mb.has(item)) return;
+    if ((!is_batch && item == skip.ref) || (!mailbox_done && g.mb.has(item))) return;
     const bool stale_cutoff = e.dist != 0 && !(e.dist < oh.dist);
     const bool is_cube = (item >> 30) == NTR_REF_SOLID &&
                          (int)ldf(s.solids + (size_t)(item & NTR_IDX_MASK) * s.solstride) == NTR_SOLID_CUBE;
@@ -1021,7 +1070,7 @@ NTR_HD void replay_item(const SceneDev &s, const uint2 it, const float *o, const
             g.th.add(dist, item, e.lane);
         }
     }
-    g.mb.add(item);
+    if (!mailbox_done) g.mb.add(item);
 }
 
 template <int DT, int FLAGS>
@@ -1523,9 +1572,11 @@ NTR_HD void hit_geometry(const SceneDev &s, uint32_t ref, int lane, float dist, 
 // EMIT(const Bounce<DT>&) receives the deferred reflection rays.
 template <int DT, int FLAGS, typename EMIT>
 NTR_HD void ray_color(const SceneDev &s, bool enabled, const float *o, const float *dir, int depth, Skip source,
-                      const float *weight, float *acc, EMIT &emit, Counters &cnt, HitRec *primary_out) {
+                      const float *weight, float *acc, EMIT &emit, Counters &cnt, HitRec *primary_out,
+                      MailboxStore *ms = nullptr) {
     const int D = NTR_D(DT, s);
     GenState<DT> g;
+    g.mb.big = (ms && ms->col) ? ms : nullptr;
     HitRec oh;
     oh.dist = FLT_MAX; oh.ref = NTR_NONE_REF; oh.lane = -1;
     if (FLAGS & NTR_F_GENERAL) {

@@ -44,7 +44,11 @@ namespace ntr {
                                     // stalls the parked lane until every other lane has finished or parked too)
 #endif
 #ifndef NTR_WARP_SHADE
-#define NTR_WARP_SHADE 1            // 0: shade per lane after the warp's nearest-hit traversal (shadow rays per lane)
+#define NTR_WARP_SHADE 0            // 1: the layers and lights of the warp's rays are walked in warp-uniform loops and their
+                                    // shadow rays traced together (cooperative big leaves included); 0: every lane shades its
+                                    // own hits after the warp's nearest-hit traversal.  Measured (B200, round 2 call 4): 1 is
+                                    // slower everywhere -- config 4 121 vs 109 ms, its 1/8 share 24.4 vs 22.9 ms, config 5
+                                    // reduced 36.1 vs 30.3 ms -- so it is off; the emulated-warp test covers both.
 #endif
 
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
@@ -142,25 +146,59 @@ __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, ui
     const int h_start = g.th.n;             // meaningful on the owner only
     float dist = 0;
     bool phase1 = false;
+    // Exact mailbox (scenes with big leaves): every lane looks its item up in the OWNER's column of the scene-wide table
+    // and, after the tests, the lanes enter their items there -- lanes whose items share a word are found with a
+    // match-any vote and the lowest of them writes the word once.  The owner's replay then skips the mailbox.
+    const bool exact = g.mb.exact();                // the same on every lane (a property of the scene)
+    MailboxStore owner_mb = {};
+    if (exact) {
+        const unsigned long long colp = (unsigned long long)(size_t)g.mb.big->col;
+        const uint32_t lo32 = __shfl_sync(kFullMask, (uint32_t)colp, src), hi32 = __shfl_sync(kFullMask, (uint32_t)(colp >> 32), src);
+        owner_mb = *g.mb.big;
+        owner_mb.col = (uint32_t *)(size_t)(((unsigned long long)hi32 << 32) | lo32);
+        owner_mb.gen = __shfl_sync(kFullMask, g.mb.big->gen, src);
+    }
     for (uint32_t base = 0; base < size; base += 32) {
         const uint32_t n = size - base < 32u ? size - base : 32u;
         const float cutoff0 = __shfl_sync(kFullMask, oh.dist, src);
-        const bool mailbox_on = __shfl_sync(kFullMask, (int)(g.mb.n <= NTR_MAILBOX_CAP), src) != 0;
+        const bool mailbox_on = !exact && __shfl_sync(kFullMask, (int)(g.mb.n <= NTR_MAILBOX_CAP), src) != 0;
         ChunkEval<DT> e;
         e.dist = 0; e.wmask = 0; e.meta = 0; e.lane = -1; e.skipped = false; e.geom = false;
     NTR_UNROLL
         for (int i = 0; i < D; ++i) { e.P[i] = 0; e.N[i] = 0; }
         bool tested = false;
+        uint32_t my_item = NTR_NONE_REF;
         if ((uint32_t)lane < n) {
             const uint2 it = lditem(items + base + lane);
             // the primitive the ray leaves from is skipped by identity, never evaluated
-            if (!(((it.x >> 30) != NTR_REF_BATCH) && it.x == bskip.ref)) {
+            if (!(((it.x >> 30) != NTR_REF_BATCH) && it.x == bskip.ref) && !(exact && owner_mb.has(it.x))) {
                 prim_eval<DT, FLAGS>(s, it, bo, bd, cutoff0, bskip, e, cnt);
                 tested = true;
+                my_item = it.x;
             }
         }
         unsigned m = __ballot_sync(kFullMask, e.dist != 0 || e.wmask != 0);        // hits and partial writes
         const unsigned tm = __ballot_sync(kFullMask, tested);
+        if (exact && tm) {
+            const uint32_t key = tested ? owner_mb.key_of(my_item) : 0u;
+            const uint32_t word = tested ? key / NTR_MAILBOX_BITS_PER_WORD : 0x80000000u | (uint32_t)lane;    // idle lanes: a group of one
+            const uint32_t bit = tested ? 1u << (key % NTR_MAILBOX_BITS_PER_WORD) : 0u;
+            const unsigned peers = __match_any_sync(kFullMask, word);
+            const int rounds = (int)__reduce_max_sync(kFullMask, (unsigned)__popc(peers));
+            unsigned rem = peers;
+            uint32_t bits = 0;
+            for (int r = 0; r < rounds; ++r) {                  // OR of the bits of the lanes that share this lane's word
+                const int j = rem ? __ffs(rem) - 1 : lane;
+                rem &= rem - 1;
+                bits |= __shfl_sync(kFullMask, bit, j);
+            }
+            if (tested && lane == __ffs(peers) - 1) {
+                uint32_t *p = owner_mb.col + (size_t)word * owner_mb.stride;
+                const uint32_t w = *p;
+                *p = ((w >> 24) == owner_mb.gen ? w : owner_mb.gen << 24) | bits;
+            }
+            __syncwarp();
+        }
         uint32_t prev = 0;
         for (;;) {
             const uint32_t j = m ? (uint32_t)(__ffs(m) - 1) : n;
@@ -189,7 +227,7 @@ __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, ui
                     for (int i = 0; i < D; ++i) { r.P[i] = __shfl_sync(kFullMask, e.P[i], j); r.N[i] = __shfl_sync(kFullMask, e.N[i], j); }
                 }
             }
-            if (lane == src) replay_item<DT, FLAGS>(s, lditem(items + base + j), o, dir, skip, oh, g, cnt, phase1, dist, r);
+            if (lane == src) replay_item<DT, FLAGS>(s, lditem(items + base + j), o, dir, skip, oh, g, cnt, phase1, dist, r, exact);
             prev = j + 1;
             m &= m - 1;
         }
@@ -479,9 +517,10 @@ __device__ __forceinline__ bool light_reaches_warp(const SceneDev &s, bool need,
 template <int DT, int FLAGS, typename EMIT>
 __device__ __forceinline__ void ray_color_warp(const SceneDev &s, bool enabled, const float *o, const float *dir, int depth,
                                                Skip source, const float *weight, float *acc, EMIT &emit, Counters &cnt,
-                                               HitRec *primary_out, int *done_ctr) {
+                                               HitRec *primary_out, int *done_ctr, MailboxStore *ms) {
     const int D = NTR_D(DT, s);
     GenState<DT> g;
+    g.mb.big = (ms && ms->col) ? ms : nullptr;
     HitRec oh;
     oh.dist = FLT_MAX; oh.ref = NTR_NONE_REF; oh.lane = -1;
     if (FLAGS & NTR_F_GENERAL) {

@@ -68,6 +68,14 @@ template <typename F> inline unsigned warp_reduce_u32(unsigned v, F f) {
 inline unsigned __reduce_min_sync(unsigned, unsigned v) { return warp_reduce_u32(v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
 inline unsigned __reduce_max_sync(unsigned, unsigned v) { return warp_reduce_u32(v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
 inline void __syncwarp() { pthread_barrier_wait(&warp_emu::warp->bar); }
+inline unsigned __match_any_sync(unsigned, unsigned v) {
+    warp_emu::warp->slot[warp_emu::lane] = v;
+    pthread_barrier_wait(&warp_emu::warp->bar);
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i) m |= (warp_emu::warp->slot[i] == v ? 1u : 0u) << i;
+    pthread_barrier_wait(&warp_emu::warp->bar);
+    return m;
+}
 inline int atomicAdd(int *p, int v) { return __sync_fetch_and_add(p, v); }
 inline unsigned __reduce_add_sync(unsigned, unsigned v) { return warp_reduce_u32(v, [](unsigned a, unsigned b) { return a + b; }); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
@@ -98,6 +106,7 @@ template <int DT> struct VecEmit {
 struct Scene {
     std::vector<unsigned char> arena;
     std::vector<float> lights;
+    std::vector<uint32_t> mailbox;      // the exact mailbox table (capi.cu allocates it under the same conditions)
     SceneDev dev;
     CameraDev cam;
     int flags;
@@ -123,6 +132,18 @@ void setup(Scene &S, const ntr_scene_desc *d, const float *cam_origin, const flo
         S.dev.global_lights = S.lights.data() + d->n_point_lights * stride;
         S.dev.n_point = (int)d->n_point_lights;
         S.dev.n_global = (int)d->n_global_lights;
+        uint32_t max_leaf = 0;
+        for (uint32_t i = 0; i < d->n_nodes; ++i) if (d->nodes[i].meta & NTR_LEAF_FLAG) max_leaf = std::max(max_leaf, d->nodes[i].w2);
+        const uint64_t keys = (uint64_t)d->n_simplex + d->n_solids;
+#ifndef NTR_EMUL_EXACT_MAILBOX_ALWAYS
+#define NTR_EMUL_EXACT_MAILBOX_ALWAYS 0
+#endif
+        if ((S.flags & NTR_F_GENERAL) && (max_leaf > NTR_MAILBOX_CAP || NTR_EMUL_EXACT_MAILBOX_ALWAYS) && keys <= NTR_MAILBOX_MAX_KEYS) {
+            S.dev.mb_threads = 32;
+            S.dev.mb_words = (uint32_t)((keys + NTR_MAILBOX_BITS_PER_WORD - 1) / NTR_MAILBOX_BITS_PER_WORD);
+            S.mailbox.assign((size_t)(S.dev.mb_words + 1) * S.dev.mb_threads, 0u);
+            S.dev.mb_table = S.mailbox.data();
+        }
     }
     if (cam_origin && cam_axes) {
         for (int i = 0; i < d->dim; ++i) {
@@ -144,6 +165,8 @@ void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, un
     std::vector<Bounce<DT>> q, qn;
     std::vector<uint32_t> qp, qpn;
     const float one[3] = {1, 1, 1};
+    MailboxStore ms;
+    ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex);
     for (int y = 0; y < h; ++y) {
         for (int x = 0; x < w; ++x) {
             const uint32_t pix = (uint32_t)y * w + x;
@@ -155,7 +178,7 @@ void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, un
             else {
                 VecEmit<DT> emit{&q, &qp, pix};
                 const Skip none = {NTR_NONE_REF, 0};
-                ray_color<DT, FLAGS>(S.dev, true, o, dir, 0, none, one, acc, emit, cnt, &prim);
+                ray_color<DT, FLAGS>(S.dev, true, o, dir, 0, none, one, acc, emit, cnt, &prim, &ms);
             }
             if (rgb) { rgb[pix * 3] = acc[0]; rgb[pix * 3 + 1] = acc[1]; rgb[pix * 3 + 2] = acc[2]; }
             if (ids) ids[pix] = prim.ref == NTR_NONE_REF ? -1 : (S.dev.kind == NTR_SCENE_BOX ? 0 : flat_prim_id(S.dev, prim.ref, prim.lane));
@@ -167,11 +190,12 @@ void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, un
         for (size_t i = 0; i < q.size(); ++i) {
             float acc[3] = {0, 0, 0};
             VecEmit<DT> emit{&qn, &qpn, qp[i]};
-            ray_color<DT, FLAGS>(S.dev, true, q[i].o, q[i].d, q[i].depth, q[i].skip, q[i].w, acc, emit, cnt, nullptr);
+            ray_color<DT, FLAGS>(S.dev, true, q[i].o, q[i].d, q[i].depth, q[i].skip, q[i].w, acc, emit, cnt, nullptr, &ms);
             rgb[(size_t)qp[i] * 3] += acc[0]; rgb[(size_t)qp[i] * 3 + 1] += acc[1]; rgb[(size_t)qp[i] * 3 + 2] += acc[2];
         }
         q.swap(qn); qp.swap(qpn);
     }
+    ms.detach();
     if (cnt_out) {
         cnt_out[0] = (unsigned long long)w * h; cnt_out[1] = cnt.reflection_rays; cnt_out[2] = cnt.shadow_rays;
         cnt_out[3] = cnt.node_steps; cnt_out[4] = cnt.simplex_tests; cnt_out[5] = cnt.solid_tests; cnt_out[6] = cnt.shaded_hits;
@@ -214,6 +238,8 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
             lanes.emplace_back([&, L]() {
                 warp_emu::lane = L;
                 warp_emu::warp = &W;
+                MailboxStore ms;
+                ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, (uint32_t)L, S.dev.n_simplex);
                 for (size_t base = 0; base < n; base += 32) {
                     const size_t idx = base + L;
                     const bool enabled = idx < n;
@@ -236,7 +262,7 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
                         }
                     }
                     LaneEmit<DT> emit{&out[L], &outpix[L], idx, pix};
-                    ray_color_warp<DT, FLAGS>(S.dev, enabled, o, dir, depth, skip, primary ? one : wgt, acc, emit, cnts[L], primary ? &prim : nullptr, &done_ctr);
+                    ray_color_warp<DT, FLAGS>(S.dev, enabled, o, dir, depth, skip, primary ? one : wgt, acc, emit, cnts[L], primary ? &prim : nullptr, &done_ctr, &ms);
                     if (!enabled) continue;
                     if (primary) {
                         if (rgb) { rgb[(size_t)pix * 3] = acc[0]; rgb[(size_t)pix * 3 + 1] = acc[1]; rgb[(size_t)pix * 3 + 2] = acc[2]; }
@@ -246,6 +272,7 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
                     // (bounce results are added below, in ray order, so that the float sums match the sequential driver)
                     else { out[L].push_back({idx, Bounce<DT>{}}); outpix[L].push_back(0xFFFFFFFFu); out[L].back().second.w[0] = acc[0]; out[L].back().second.w[1] = acc[1]; out[L].back().second.w[2] = acc[2]; }
                 }
+                ms.detach();
             });
         }
         for (auto &t : lanes) t.join();
@@ -298,9 +325,12 @@ void trace_t(Scene &S, uint32_t n, const float *origins, const float *dirs, floa
              const uint32_t *skip_ref, const int32_t *skip_lane, int32_t *ids, float *dist, int32_t *ntrans,
              int max_hits = 0, int32_t *hit_ids = nullptr, float *hit_dists = nullptr) {
     const int D = S.dev.dim;
+    MailboxStore ms;
+    ms.attach((FLAGS & NTR_F_GENERAL) ? S.dev.mb_table : nullptr, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex);
     for (uint32_t i = 0; i < n; ++i) {
         Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
         GenState<DT> g;
+        g.mb.big = ms.col ? &ms : nullptr;
         g.th.clear();
         HitRec oh;
         oh.dist = FLT_MAX; oh.ref = NTR_NONE_REF; oh.lane = -1;

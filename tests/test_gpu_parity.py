@@ -87,20 +87,24 @@ def test_polytope_variants(name):
                 img = dv.render_float(w, h)
                 cnt = dv.counters()
             oimg, mask, ocnt = ol.render_float(s2, w, h, with_mask=True, with_counters=True)
-            # same algorithm, same inputs: only FMA contraction / libm differences remain.  Pixels where the reference
-            # itself is undefined (a quick_list outgrew its preallocation: mask != 0, see test_oracle_golden) are held
-            # to a loose bound only; the product's mailbox is bounded (40) where the oracle's is unbounded.
+            # same algorithm, same inputs: only FMA contraction / libm differences remain.  Oracle mask bits 0/1 = the
+            # reference's own lists outgrew their preallocation there (undefined behaviour in the reference: its frames
+            # have holes, see test_oracle_golden), so the reference's golden frame is only held to a loose bound on those
+            # pixels.  The ORACLE is well defined there (a correct unbounded mailbox), and since the kernels keep an exact
+            # mailbox for scenes with big leaves (trace_core.cuh: MailboxStore) they must follow it on those pixels too:
+            # the whole frame but the rounding-noise pixels (bit 2, Q12) is held to the strict bound against the oracle.
             undefined = (mask & 3) != 0
-            bad_o, _ = fx.lsb_stats(img, oimg, exclude=col | undefined)
-            bad_g, _ = fx.lsb_stats(img, g['v_%s_float' % v], exclude=col | undefined)
-            assert bad_o <= 0.001, (name, v, bad_o)
+            noise = (mask & 4) != 0
+            bad_o, _ = fx.lsb_stats(img, oimg, exclude=col | noise)
+            bad_g, _ = fx.lsb_stats(img, g['v_%s_float' % v], exclude=col | undefined | noise)
+            assert bad_o <= 0.002, (name, v, bad_o)
+            assert fx.lsb_stats(img, oimg, exclude=col | undefined | noise)[0] <= 0.001, (name, v)
             assert bad_g <= 0.001, (name, v, bad_g)
             assert fx.lsb_stats(img, oimg, exclude=col)[0] <= 0.03, (name, v)
             assert fx.lsb_stats(img, g['v_%s_float' % v], exclude=col)[0] <= 0.03, (name, v)
             assert cnt['primary_rays'] == w * h
-            tol = 0.15 if undefined.mean() > 0.2 and 'transp' in v else 0.01     # bounded vs unbounded mailbox (see above)
             for k in ('reflection_rays', 'shadow_rays', 'shaded_hits'):
-                assert abs(cnt[k] - ocnt[k]) <= tol * max(ocnt[k], 100), (name, v, k, cnt[k], ocnt[k])
+                assert abs(cnt[k] - ocnt[k]) <= 0.01 * max(ocnt[k], 100), (name, v, k, cnt[k], ocnt[k])
         ids, dist = ds.primary_hit_ids(w, h)
         agree, ties = fx.id_agreement(ids, g['ids'], dist, g['dist'])
         assert agree >= 0.9999

@@ -23,15 +23,14 @@ def test_polytope_matches_oracle(name, variants):
         s2 = fx.variant(sc, g, v)
         a, mask, cnt_o = ol.render_float(s2, w, h, with_mask=True, with_counters=True)
         b, cnt_e = el.render(s2, w, h)
-        if v == 'refl_transp' and name in ('ggs120', 'ssc120'):
-            # giant leaves: far beyond the 20 mailbox entries up to which the reference is defined; the product keeps 40,
-            # the oracle an unbounded list -- corner-case pixels (trim + re-add) differ, only where the reference is undefined
-            assert fx.lsb_stats(a, b, exclude=(mask & 3) != 0)[0] <= 0.001
-            assert fx.lsb_stats(a, b)[0] <= 0.02
-            continue
+        # (giant leaves included: scenes whose leaves overrun the bounded mailbox table get the exact per-thread bitset,
+        # trace_core.cuh: MailboxStore, which is the oracle's unbounded list -- same tests, same counters, same picture,
+        # also on the half of a {5/2,3,3} frame where the reference itself is undefined)
         assert np.abs(a - b).max() <= 2e-6, (name, v)
         for k in ('primary_rays', 'reflection_rays', 'shadow_rays', 'node_steps', 'shaded_hits'):
             assert cnt_o[k] == cnt_e[k], (name, v, k)
+        if name != 'cell120' and 'transp' in v:
+            assert cnt_o['simplex_tests'] == cnt_e['simplex_tests'], (name, v)     # the exact mailbox tests what the oracle tests
 
 
 @pytest.mark.parametrize('name', ['solids6', 'mixed3', 'soup9', 'box4', 'box9'])
