@@ -298,6 +298,13 @@ class Workload:
         else:
             self.dr.render_to_host()
 
+    def step_e2e_pageable(self):
+        """the same call with the destination the API's real caller passes: a plain (pageable) bytearray"""
+        if not hasattr(self, 'pageable'):
+            self.pageable = bytearray(self.fmt.pitch * self.h)
+        self.ds.set_camera(self.cam_o, self.cam_a)
+        self.ds.render(self.fmt, self.pageable)
+
     def close(self):
         if hasattr(self.dr, 'close'):
             self.dr.close()
@@ -328,6 +335,17 @@ def timed(wl, steps, warmup, flush, barrier):
         e2e_s.append(time.perf_counter() - t)
     barrier()
     launches = wl.ds.launch_count() - launches0
+    wl.pageable_ms = None
+    if wl.world == 1:                   # BlockingRenderer.render is handed a bytearray: the same frames into pageable memory
+        wl.step_e2e_pageable()
+        pg = []
+        for _ in range(steps):
+            flush.zero_()
+            barrier()
+            t = time.perf_counter()
+            wl.step_e2e_pageable()
+            pg.append(time.perf_counter() - t)
+        wl.pageable_ms = 1e3 * sum(pg) / steps
     tot = torch.tensor([sum(dev_ms), sum(e2e_s) * 1e3, float(launches)], dtype=torch.float64, device='cuda')
     if wl.world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
@@ -465,7 +483,11 @@ def main():
                                     if wl.gather != 'nccl' else 'interleaved 32-px tile rows over %d GPU(s), NCCL all-gather' % world,
                        'frames_per_s': 1e3 / ms_per_step, 'Mpix_per_s': w * h / (ms_per_step * 1e-3) / 1e6},
             'e2e': {'value': rays / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mrays/s', 'ms_per_step': e2e_ms,
-                    'h2d_bytes_per_step': int(4 * (dim + dim * dim)), 'd2h_bytes_per_step': int(frame_bytes)},
+                    'h2d_bytes_per_step': int(4 * (dim + dim * dim)), 'd2h_bytes_per_step': int(frame_bytes),
+                    'destination': 'pinned host buffer',
+                    # the same call into a plain bytearray (pageable): pinned staging ring inside ntr_render
+                    'pageable_ms_per_step': wl.pageable_ms,
+                    'pageable_value': rays / (wl.pageable_ms * 1e-3) / 1e6 if wl.pageable_ms else None},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }

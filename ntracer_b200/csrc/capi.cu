@@ -149,6 +149,10 @@ struct ntr_scene {
     int n_pass_ev = 0;
     bool pass_timing = false;
     ntr_counters counters{};
+    // pageable destinations (what BlockingRenderer.render is handed: a bytearray): frames cross PCIe into this pinned
+    // staging buffer in row chunks, and the host copies chunk k into the caller's buffer while chunk k+1 is in flight
+    unsigned char *h_stage = nullptr; size_t h_stage_cap = 0;
+    cudaEvent_t stage_ev[8] = {};
     uint32_t *h_ctl = nullptr;              // pinned read-back of the control block and the counters (frame_readback)
     unsigned long long *h_cnt = nullptr;
     uint64_t launches = 0;
@@ -650,20 +654,60 @@ int run_frame_sync(ntr_scene *sc, int width, int height, int x0, int y0, int win
     return fail(NTR_ERR_RUNTIME, "wavefront queue kept overflowing");
 }
 
+int ensure_stage(ntr_scene *sc, size_t bytes) {
+    if (sc->h_stage_cap >= bytes && sc->h_stage) return NTR_OK;
+    if (sc->h_stage) { cudaFreeHost(sc->h_stage); sc->h_stage = nullptr; sc->h_stage_cap = 0; }
+    CUDA_TRY(cudaHostAlloc((void **)&sc->h_stage, bytes + bytes / 8, cudaHostAllocDefault));
+    sc->h_stage_cap = bytes + bytes / 8;
+    return NTR_OK;
+}
+
+// rows [y0, y1) of the staging buffer -> the caller's buffer; only the pixel bytes are written, like process_pixel: the
+// pitch padding of `dst` is left alone
+void unstage_rows(const ntr_scene *sc, unsigned char *dst, size_t pitch, size_t row_bytes, int y0, int y1) {
+    if (row_bytes == pitch) memcpy(dst + (size_t)y0 * pitch, sc->h_stage + (size_t)y0 * pitch, (size_t)(y1 - y0) * pitch);
+    else for (int y = y0; y < y1; ++y) memcpy(dst + (size_t)y * pitch, sc->h_stage + (size_t)y * pitch, row_bytes);
+}
+
+// A finished device frame into a PAGEABLE destination: row chunks go device -> pinned staging back to back on `st`, the
+// host copies chunk k out of the staging buffer as soon as its event fires -- while chunk k+1 crosses PCIe.
+int download_staged(ntr_scene *sc, unsigned char *dst, size_t pitch, size_t row_bytes, int rows, const unsigned char *src, cudaStream_t st) {
+    int rc = ensure_stage(sc, pitch * (size_t)rows);
+    if (rc) return rc;
+    const int chunks = (int)std::min<size_t>(8, std::max<size_t>(1, pitch * (size_t)rows / (1u << 20)));
+    for (int c = 0; c < chunks; ++c) {
+        if (!sc->stage_ev[c]) CUDA_TRY(cudaEventCreateWithFlags(&sc->stage_ev[c], cudaEventDisableTiming));
+        const int y0 = (int)((long long)rows * c / chunks), y1 = (int)((long long)rows * (c + 1) / chunks);
+        CUDA_TRY(cudaMemcpy2DAsync(sc->h_stage + (size_t)y0 * pitch, pitch, src + (size_t)y0 * pitch, pitch, row_bytes, y1 - y0, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(sc->stage_ev[c], st));
+    }
+    for (int c = 0; c < chunks; ++c) {
+        const int y0 = (int)((long long)rows * c / chunks), y1 = (int)((long long)rows * (c + 1) / chunks);
+        CUDA_TRY(cudaEventSynchronize(sc->stage_ev[c]));
+        unstage_rows(sc, dst, pitch, row_bytes, y0, y1);
+    }
+    return NTR_OK;
+}
+
 // ntr_render for frames that need a single pass, into a pinned destination: slabs of tile rows, each with its own
 // persistent kernel and device->host copy on its own stream.  The kernels queue up behind each other on the device
 // (each fills the machine; the next one's CTAs move in as the previous one's retire, so no tail is added) and the copy
 // of slab k runs while slab k+1 is traced.  Returns 1 when it does not apply (the caller uses the plain path).
-int run_frame_slabs(ntr_scene *sc, const ntr_image_format *fmt, unsigned char *dst) {
+// `staged`: the destination is pageable -- the slabs land in the pinned staging buffer and the host copies slab k out
+// while slab k+1 is traced and transferred.
+int run_frame_slabs(ntr_scene *sc, const ntr_image_format *fmt, unsigned char *dst, bool staged) {
     const int tiles_y = (fmt->height + NTR_TILE - 1) / NTR_TILE;
     const int S = std::min(kSlabMax, tiles_y / 4);
     // (the slabs' kernels run side by side: they would share the columns of the exact mailbox table)
     if (S < 2 || sc->instrumented || sc->dev.mb_table) return 1;
-    for (int i = 1; i < S; ++i) {
-        if (!sc->slab_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&sc->slab_stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < S; ++i) {
+        if (i && !sc->slab_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&sc->slab_stream[i], cudaStreamNonBlocking));
         if (!sc->slab_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&sc->slab_done[i], cudaEventDisableTiming));
     }
     const size_t pitch = (size_t)fmt->pitch, row_bytes = (size_t)fmt->width * fmt->bytes_per_pixel;
+    if (staged) { const int rcs = ensure_stage(sc, pitch * (size_t)fmt->height); if (rcs) return rcs; }
+    unsigned char *const host = staged ? sc->h_stage : dst;
+    int slab_y0[kSlabMax], slab_y1[kSlabMax];
     RenderTarget tgt;
     tgt.out_mode = NTR_OUT_PACKED;
     CUDA_TRY(cudaEventRecord(sc->ev0, sc->stream));
@@ -674,19 +718,26 @@ int run_frame_slabs(ntr_scene *sc, const ntr_image_format *fmt, unsigned char *d
         const int y0 = (int)((long long)tiles_y * i / S) * NTR_TILE;
         const int y1 = std::min(fmt->height, (int)((long long)tiles_y * (i + 1) / S) * NTR_TILE);
         tgt.packed = sc->d_packed + (size_t)y0 * pitch;
+        slab_y0[i] = y0; slab_y1[i] = y1;
         bool p = false;
         sc->ctl_slot = i;
         rc = enqueue_frame(sc, st, fmt->width, fmt->height, 0, y0, fmt->width, y1 - y0, fmt, tgt, 0, 1, 0, &p);
         sc->ctl_slot = 0;
         if (rc) break;
         // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
-        CUDA_TRY(cudaMemcpy2DAsync(dst + (size_t)y0 * pitch, pitch, tgt.packed, pitch, row_bytes, y1 - y0, cudaMemcpyDeviceToHost, st));
-        if (i) CUDA_TRY(cudaEventRecord(sc->slab_done[i], st));
+        CUDA_TRY(cudaMemcpy2DAsync(host + (size_t)y0 * pitch, pitch, tgt.packed, pitch, row_bytes, y1 - y0, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(sc->slab_done[i], st));
     }
     for (int i = 1; i < S; ++i) cudaStreamWaitEvent(sc->stream, sc->slab_done[i], 0);
     if (rc) { cudaStreamSynchronize(sc->stream); return rc; }
     CUDA_TRY(cudaEventRecord(sc->ev1, sc->stream));
     sc->timing_valid = true;
+    if (staged) {
+        for (int i = 0; i < S; ++i) {           // slab i leaves the staging buffer while the later ones are traced / in flight
+            CUDA_TRY(cudaEventSynchronize(sc->slab_done[i]));
+            unstage_rows(sc, dst, pitch, row_bytes, slab_y0[i], slab_y1[i]);
+        }
+    }
     unsigned long long h_cnt[kSlabMax * 8];
     CUDA_TRY(cudaMemcpyAsync(h_cnt, sc->d_counters, sizeof(unsigned long long) * 8 * S, cudaMemcpyDeviceToHost, sc->stream));
     CUDA_TRY(cudaStreamSynchronize(sc->stream));
@@ -952,6 +1003,8 @@ NTR_API void ntr_scene_destroy(ntr_scene *sc) {
         if (fs.copied) cudaEventDestroy(fs.copied);
     }
     if (sc->h_abort) cudaFreeHost(sc->h_abort);
+    if (sc->h_stage) cudaFreeHost(sc->h_stage);
+    for (cudaEvent_t e : sc->stage_ev) if (e) cudaEventDestroy(e);
     if (sc->h_ctl) cudaFreeHost(sc->h_ctl);
     if (sc->h_cnt) cudaFreeHost(sc->h_cnt);
     if (sc->ev0) cudaEventDestroy(sc->ev0);
@@ -1047,18 +1100,21 @@ NTR_API int ntr_render(ntr_scene *sc, const ntr_image_format *fmt, void *dst, si
     }
     if ((rc = ensure((void **)&sc->d_packed, &sc->packed_cap, bytes))) return rc;
     tgt.packed = sc->d_packed;
-    if (sc->slabs && !(sc->dev.kind == NTR_SCENE_COMPOSITE && sc->any_reflective && sc->dev.max_depth > 0)) {
-        cudaPointerAttributes attr;
-        const bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-        if (pinned) {           // (a pageable destination would make every slab's copy block the host)
-            rc = run_frame_slabs(sc, fmt, static_cast<unsigned char *>(dst));
-            if (rc <= 0) return rc;
-        }
+    // a pinned (or registered) destination is written by the copy engine directly; a pageable one -- what
+    // BlockingRenderer.render is normally handed -- goes through the scene's pinned staging buffer in chunks (a plain
+    // cudaMemcpy into pageable memory would stage through the driver's bounce buffers, serially)
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const bool staged = !pinned && getenv("NTR_NO_STAGING") == nullptr;
+    if (sc->slabs && (pinned || staged) && !(sc->dev.kind == NTR_SCENE_COMPOSITE && sc->any_reflective && sc->dev.max_depth > 0)) {
+        rc = run_frame_slabs(sc, fmt, static_cast<unsigned char *>(dst), staged);
+        if (rc <= 0) return rc;
     }
     // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
     HostCopy hc{dst, (size_t)fmt->pitch, sc->d_packed, (size_t)fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel, fmt->height, false};
-    if ((rc = run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, sc->stream, &hc))) return rc;
+    if ((rc = run_frame_sync(sc, fmt->width, fmt->height, 0, 0, fmt->width, fmt->height, fmt, tgt, 0, 1, 0, sc->stream, staged ? nullptr : &hc))) return rc;
+    if (staged) return download_staged(sc, static_cast<unsigned char *>(dst), hc.dpitch, hc.row_bytes, hc.rows, sc->d_packed, sc->stream);
     if (!hc.done) {
         CUDA_TRY(cudaMemcpy2DAsync(hc.dst, hc.dpitch, hc.src, hc.spitch, hc.row_bytes, hc.rows, cudaMemcpyDeviceToHost, sc->stream));
         CUDA_TRY(cudaStreamSynchronize(sc->stream));
@@ -1548,10 +1604,18 @@ NTR_API int ntr_group_render(ntr_group *g, const ntr_image_format *fmt, void *ds
     rc = group_trace(g, fmt);
     if (rc == NTR_OK) {
         // only the pixel bytes are written, like process_pixel: the pitch padding of `dst` is left alone
-        cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)fmt->pitch, g->d_frame, (size_t)fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel,
-                                          fmt->height, cudaMemcpyDeviceToHost, g->sc[0]->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(g->sc[0]->stream);
-        if (e != cudaSuccess) rc = fail(NTR_ERR_RUNTIME, "device -> host copy failed: %s", cudaGetErrorString(e));
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!pinned) {
+            rc = download_staged(g->sc[0], static_cast<unsigned char *>(dst), (size_t)fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel,
+                                 fmt->height, g->d_frame, g->sc[0]->stream);
+        } else {
+            cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)fmt->pitch, g->d_frame, (size_t)fmt->pitch, (size_t)fmt->width * fmt->bytes_per_pixel,
+                                              fmt->height, cudaMemcpyDeviceToHost, g->sc[0]->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g->sc[0]->stream);
+            if (e != cudaSuccess) rc = fail(NTR_ERR_RUNTIME, "device -> host copy failed: %s", cudaGetErrorString(e));
+        }
     }
     g->busy.store(false);
     return rc;
