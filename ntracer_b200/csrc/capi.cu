@@ -157,7 +157,7 @@ struct ntr_scene {
     unsigned long long *h_cnt = nullptr;
     uint64_t launches = 0;
     int grid_blocks[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool warp_path = false;             // render with the warp-synchronous kernels (scenes with big leaves; NTR_WARP=0|1 overrides)
+    int warp_path = 0;                  // 1: bounce passes use the warp-synchronous kernels (scenes with big leaves), 2: every pass; NTR_WARP overrides
     const KernelSet *(*kset)(int) = nullptr;
     std::atomic<bool> busy{false};
     // begin/end frames (ntr_render_begin / ntr_render_end)
@@ -369,7 +369,13 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     f.tile_row_first = tile_row_first; f.tile_row_step = tile_row_step < 1 ? 1 : tile_row_step; f.compact = compact;
     if (fmt) fill_format(f.fmt, fmt);
 
-    int flags = sc->base_flags | (sc->instrumented ? NTR_F_COUNT : 0) | (sc->warp_path ? NTR_F_WARP : 0);
+    // Scenes with big leaves: the bounce passes run the warp-synchronous kernels (incoherent rays; lanes that run out of
+    // work help the ones parked at big leaves), the primary pass every lane for itself (the 32 rays of an 8x4 pixel block
+    // walk the same leaves: nothing to share out, and the per-lane form is the leaner code).  Measured, config 4 per
+    // pass (ms): per-lane 11.4 12.5 7.3 10.8 10.5 | warp 13.8 11.6 6.8 9.2 7.7.  NTR_WARP=0|1|2: never | bounces | all passes.
+    int flags = sc->base_flags | (sc->instrumented ? NTR_F_COUNT : 0);
+    const int primary_flags = flags | (sc->warp_path == 2 ? NTR_F_WARP : 0);
+    const int bounce_flags = flags | (sc->warp_path ? NTR_F_WARP : 0);
     const bool composite = sc->dev.kind == NTR_SCENE_COMPOSITE;
     const bool passes = composite && tgt.out_mode != NTR_OUT_IDS && sc->any_reflective && sc->dev.max_depth > 0;
     *used_passes = passes;
@@ -448,8 +454,8 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     CUDA_TRY(cudaMemsetAsync(d_ctl, 0, CTL_WORDS * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), st));
 
-    const KernelSet *ks = sc->kset(flags);
-    const int grid = grid_for(sc, flags);
+    const KernelSet *ks = sc->kset(primary_flags);
+    const int grid = grid_for(sc, primary_flags);
     const uint32_t rec4 = 2 + 2 * ((sc->dev.dim + 3) / 4);
     QueueDev q;
     memset(&q, 0, sizeof q);
@@ -529,7 +535,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
                     q.fetch_sizes = sc->fetch_sizes;
                 }
             }
-            ks->render_pass(dim3(grid), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
+            sc->kset(bounce_flags)->render_pass(dim3(grid_for(sc, bounce_flags)), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
             ++sc->launches;
             mark();
 #if NTR_FETCH_STATS
@@ -914,9 +920,10 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     if (const char *ts = getenv("NTR_TILE_SCHED")) sc->force_tile_sched = atoi(ts) != 0;
     for (uint32_t i = 0; desc->kind == NTR_SCENE_COMPOSITE && i < desc->n_nodes; ++i)
         if (desc->nodes[i].meta & NTR_LEAF_FLAG) sc->max_leaf = std::max(sc->max_leaf, desc->nodes[i].w2);
-    sc->heavy_first = sc->warp_path = sc->max_leaf >= 256;
+    sc->heavy_first = sc->max_leaf >= 256;
+    sc->warp_path = sc->max_leaf >= 256 ? 1 : 0;
     sc->adaptive_fetch = false;         // measured (round 2 call 4): fewer rays per warp from the expensive rings loses everywhere
-    if (const char *wp = getenv("NTR_WARP")) sc->warp_path = atoi(wp) != 0;
+    if (const char *wp = getenv("NTR_WARP")) sc->warp_path = std::max(0, std::min(2, atoi(wp)));
     if (const char *hf = getenv("NTR_HEAVY_FIRST")) sc->heavy_first = atoi(hf) != 0;
     if (const char *af = getenv("NTR_ADAPTIVE_FETCH")) sc->adaptive_fetch = atoi(af) != 0;
     if (const char *fs = getenv("NTR_FETCH_SIZES")) {
