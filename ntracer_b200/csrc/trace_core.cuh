@@ -1152,24 +1152,27 @@ NTR_HD bool leaf_general_chunked(const SceneDev &s, const uint4 node, const floa
 }
 
 // Per-ray axis tables of the traversal.  A k-d step needs o[axis], dir[axis] and 1/dir[axis] for a run-time axis; with
-// the vectors in registers that is a select chain per value (ncu, config 2: 7.4 % of all instructions).  With
-// NTR_SMEM_AXIS the fixed-dimension kernels keep the three vectors in a per-thread column of shared memory instead
+// the vectors in registers that is a select chain per value -- 3 x (D-1) selects plus the compares.  In 4 dimensions
+// that is cheap and beats a shared-memory table (measured, round 1: config 2 0.740 -> 0.770 ms, config 3 0.551 ->
+// 0.577 ms with the table: the shared-memory round trip sits on the node-to-node dependency chain).  In 10 dimensions
+// the chains are a THIRD of everything the kernel executes (ncu, round 2, config 5 reduced: trace_core.cuh vsel 18.9 % +
+// the axis line 13.4 % of all warp instructions, profiles/r02_c5s_dim10_ncu_summary.txt), so from NTR_SMEM_AXIS_MIN_DIM
+// dimensions on the fixed-dimension kernels keep the three vectors in a per-thread column of shared memory instead
 // (3*D floats per thread, column-major over the CTA: conflict-free for any mix of axes within a warp) and index it.
-// MEASURED (B200): slower everywhere -- config 2 0.740 -> 0.770 ms, config 3 0.551 -> 0.577 ms, config 4 opaque
-// 31.0 -> 32.7 ms: the shared-memory round trip sits on the node-to-node dependency chain, the selects do not.  Off.
-#ifndef NTR_SMEM_AXIS
-#define NTR_SMEM_AXIS 0
+#ifndef NTR_SMEM_AXIS_MIN_DIM
+#define NTR_SMEM_AXIS_MIN_DIM 9
 #endif
-#if defined(__CUDA_ARCH__) && NTR_SMEM_AXIS
+#if defined(__CUDA_ARCH__)
 #define NTR_AXIS_THREADS 128            // = kCtaThreads (kernels.cuh)
 template <int DT> __device__ __forceinline__ float *axis_slab() {
     __shared__ float slab[3 * DimCap<DT>::value * NTR_AXIS_THREADS];
     return slab + threadIdx.x;
 }
+#define NTR_AXIS_IN_SMEM(DT) (DT >= NTR_SMEM_AXIS_MIN_DIM)
 #define NTR_AXIS_SETUP(DT, D, o, dir, invdir)                                                              \
     float *axis_tab_ = nullptr;                                                                            \
-    if (DT > 0) {                                                                                          \
-        axis_tab_ = axis_slab<DT>();                                                                       \
+    if (NTR_AXIS_IN_SMEM(DT)) {                                                                            \
+        axis_tab_ = axis_slab<(NTR_AXIS_IN_SMEM(DT) ? DT : 1)>();                                          \
         _Pragma("unroll")                                                                                  \
         for (int i_ = 0; i_ < (DT > 0 ? DT : 1); ++i_) {                                                   \
             axis_tab_[i_ * NTR_AXIS_THREADS] = (o)[i_];                                                    \
@@ -1177,9 +1180,9 @@ template <int DT> __device__ __forceinline__ float *axis_slab() {
             axis_tab_[(2 * DT + i_) * NTR_AXIS_THREADS] = (invdir)[i_];                                    \
         }                                                                                                  \
     }
-#define NTR_AXIS_O(DT, o, axis) (DT > 0 ? axis_tab_[(axis) * NTR_AXIS_THREADS] : (o)[axis])
-#define NTR_AXIS_DIR(DT, dir, axis) (DT > 0 ? axis_tab_[(DT + (axis)) * NTR_AXIS_THREADS] : (dir)[axis])
-#define NTR_AXIS_INV(DT, invdir, axis) (DT > 0 ? axis_tab_[(2 * DT + (axis)) * NTR_AXIS_THREADS] : (invdir)[axis])
+#define NTR_AXIS_O(DT, o, axis) (NTR_AXIS_IN_SMEM(DT) ? axis_tab_[(axis) * NTR_AXIS_THREADS] : vsel<DT>(o, axis))
+#define NTR_AXIS_DIR(DT, dir, axis) (NTR_AXIS_IN_SMEM(DT) ? axis_tab_[(DT + (axis)) * NTR_AXIS_THREADS] : vsel<DT>(dir, axis))
+#define NTR_AXIS_INV(DT, invdir, axis) (NTR_AXIS_IN_SMEM(DT) ? axis_tab_[(2 * DT + (axis)) * NTR_AXIS_THREADS] : vsel<DT>(invdir, axis))
 #else
 #define NTR_AXIS_SETUP(DT, D, o, dir, invdir)
 #define NTR_AXIS_O(DT, o, axis) vsel<DT>(o, axis)
