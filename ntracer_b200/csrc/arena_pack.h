@@ -25,8 +25,6 @@ namespace ntr {
 
 struct ArenaLayout {
     size_t off_nodes = 0, off_refs = 0, off_simplex = 0, off_batches = 0, off_solids = 0, off_mats = 0, off_index = 0, total = 0;
-    size_t off_keys = 0, off_sparse = 0;
-    uint32_t n_keys = 0;            // distinct leaf items (= mailbox keys)
     int index_stride = 0;           // floats per leaf-index node: lo[D], hi[D], skip, item, padded to 4
     int sstride = 0, solstride = 0, lane_part = 0, batch_block = 0;
     bool any_transparent = false, any_reflective = false;
@@ -179,56 +177,12 @@ inline void pack_arena(const ntr_scene_desc *d, std::vector<unsigned char> &h, A
     L.off_batches = arena_align(L.off_simplex + (size_t)d->n_simplex * L.sstride * 4, 256);
     L.off_solids = arena_align(L.off_batches + batch_first.size() * (size_t)L.batch_block * 4, 256);
     L.off_mats = arena_align(L.off_solids + (size_t)d->n_solids * L.solstride * 4, 256);
-    // Mailbox keys: the distinct leaf items numbered densely in the order they first appear, one key per leaf-item slot.
-    // Big leaves also get their items grouped by mailbox word (key / 24): per leaf
-    //   [n_blocks] [word, mask, first entry] x n_blocks  [leaf position of every item, ordered by key]
-    // so that a traversal which has tested most of a big leaf's items already (every batch of a star polytope sits in
-    // ~80 leaves) finds the untested ones with one AND-NOT per word instead of one mailbox query per item
-    // (trace_core.cuh: leaf_general).
-    std::vector<uint32_t> keys(d->n_leaf_refs), sparse;
-    std::vector<uint32_t> node_sparse_off(d->n_nodes, 0);
-    {
-        std::unordered_map<uint32_t, uint32_t> key_of;
-        for (uint32_t i = 0; i < d->n_leaf_refs; ++i)
-            keys[i] = key_of.emplace(d->leaf_refs[i], (uint32_t)key_of.size()).first->second;
-        L.n_keys = (uint32_t)key_of.size();
-        std::vector<std::pair<uint32_t, uint32_t>> byk;
-        for (uint32_t n = 0; n < d->n_nodes && L.n_keys <= NTR_MAILBOX_MAX_KEYS; ++n) {
-            const ntr_node &nd = d->nodes[n];
-            if (!(nd.meta & NTR_LEAF_FLAG) || nd.w2 < NTR_SPARSE_LEAF_MIN) continue;
-            byk.clear();
-            for (uint32_t k = 0; k < nd.w2; ++k) byk.push_back({keys[nd.w1 + k], k});
-            std::sort(byk.begin(), byk.end());
-            node_sparse_off[n] = (uint32_t)sparse.size() + 1;
-            const size_t head = sparse.size();
-            sparse.push_back(0);
-            uint32_t n_blocks = 0;
-            for (size_t a = 0; a < byk.size();) {
-                const uint32_t word = byk[a].first / NTR_MAILBOX_BITS_PER_WORD;
-                uint32_t mask = 0;
-                size_t b = a;
-                while (b < byk.size() && byk[b].first / NTR_MAILBOX_BITS_PER_WORD == word) mask |= 1u << (byk[b++].first % NTR_MAILBOX_BITS_PER_WORD);
-                sparse.push_back(word); sparse.push_back(mask); sparse.push_back((uint32_t)a);
-                ++n_blocks;
-                a = b;
-            }
-            sparse[head] = n_blocks;
-            for (const auto &e : byk) sparse.push_back(e.second);
-        }
-    }
     L.off_index = arena_align(L.off_mats + (size_t)d->n_materials * 12 * 4, 256);
-    L.off_keys = arena_align(L.off_index + index_data.size() * 4, 256);
-    L.off_sparse = arena_align(L.off_keys + keys.size() * 4, 256);
-    L.total = arena_align(L.off_sparse + sparse.size() * 4, 256);
+    L.total = arena_align(L.off_index + index_data.size() * 4, 256);
     h.assign(L.total, 0);
-    if (!keys.empty()) memcpy(h.data() + L.off_keys, keys.data(), keys.size() * 4);
-    if (!sparse.empty()) memcpy(h.data() + L.off_sparse, sparse.data(), sparse.size() * 4);
     if (d->n_nodes) memcpy(h.data() + L.off_nodes, d->nodes, (size_t)d->n_nodes * 16);
-    for (uint32_t n = 0; n < d->n_nodes; ++n) {         // leaf nodes: w3 = offset + 1 of the word-grouped item table (0 = none)
-        if (!(d->nodes[n].meta & NTR_LEAF_FLAG)) continue;
-        const uint32_t w3 = NTR_LEAF_INDEX_MIN != 0xFFFFFFFFu ? node_index_off[n] : node_sparse_off[n];       // (the retired box index)
-        memcpy(h.data() + L.off_nodes + (size_t)n * 16 + 12, &w3, 4);
-    }
+    for (uint32_t n = 0; n < d->n_nodes; ++n)           // leaf nodes: w3 = leaf index offset (0 = none)
+        if (d->nodes[n].meta & NTR_LEAF_FLAG) memcpy(h.data() + L.off_nodes + (size_t)n * 16 + 12, &node_index_off[n], 4);
     if (!index_data.empty()) memcpy(h.data() + L.off_index, index_data.data(), index_data.size() * 4);
     {   // leaf items: {ref, float offset of the record inside its section}
         uint32_t *it = reinterpret_cast<uint32_t *>(h.data() + L.off_refs);
@@ -287,8 +241,6 @@ inline void pack_arena(const ntr_scene_desc *d, std::vector<unsigned char> &h, A
 inline void bind_arena(SceneDev &dev, const ntr_scene_desc *d, const ArenaLayout &L, const unsigned char *base) {
     dev.nodes = reinterpret_cast<const uint4 *>(base + L.off_nodes);
     dev.leaf_items = reinterpret_cast<const uint2 *>(base + L.off_refs);
-    dev.leaf_keys = reinterpret_cast<const uint32_t *>(base + L.off_keys);
-    dev.leaf_sparse = reinterpret_cast<const uint32_t *>(base + L.off_sparse);
     dev.batches = reinterpret_cast<const float *>(base + L.off_batches);
     dev.lane_part = L.lane_part;
     dev.leaf_index = reinterpret_cast<const float *>(base + L.off_index);

@@ -137,7 +137,6 @@ struct ntr_scene {
     // them out a few per warp (fetch_sizes below); NTR_HEAVY_FIRST / NTR_ADAPTIVE_FETCH = 0|1 override
     bool heavy_first = false, adaptive_fetch = false;
     uint32_t max_leaf = 0;              // items in the largest leaf of the tree
-    uint32_t n_keys = 0;                // distinct leaf items (mailbox keys)
     uint32_t *d_ring = nullptr;
     uint32_t fetch_sizes = 4u | (8u << 8) | (16u << 16);      // NTR_FETCH_SIZES=a,b,c: rays per fetch from cost rings 0, 1, 2
     bool force_tile_sched = false;      // NTR_TILE_SCHED=1: cost-sorted tile hand-out on whole frames too (heavy-tailed scenes)
@@ -281,7 +280,6 @@ int build_arena(ntr_scene *sc, const ntr_scene_desc *d) {
     CUDA_TRY(cudaMemcpy(sc->arena, h.data(), L.total, cudaMemcpyHostToDevice));
     bind_arena(sc->dev, d, L, static_cast<const unsigned char *>(sc->arena));
     sc->any_reflective = L.any_reflective;
-    sc->n_keys = L.n_keys;
     sc->base_flags = (L.any_transparent || d->n_solids) ? NTR_F_GENERAL : 0;
     return NTR_OK;
 }
@@ -956,7 +954,7 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     // the exact mailbox of scenes whose leaves overrun the bounded table (trace_core.cuh: MailboxStore): one column per
     // thread of the persistent grid, zero-initialised (generation 0 is never current)
     {
-        const uint64_t keys = sc->n_keys;
+        const uint64_t keys = (uint64_t)desc->n_simplex + desc->n_solids;
         const char *mbx = getenv("NTR_EXACT_MAILBOX");
         const bool want = mbx ? atoi(mbx) != 0 : sc->max_leaf > NTR_MAILBOX_CAP;
         if (desc->kind == NTR_SCENE_COMPOSITE && (sc->base_flags & NTR_F_GENERAL) && want && keys <= NTR_MAILBOX_MAX_KEYS) {

@@ -22,8 +22,6 @@
 // solids); bigger scenes keep the bounded table.
 #define NTR_MAILBOX_MAX_KEYS 65536
 #define NTR_MAILBOX_BITS_PER_WORD 24   // a word = generation tag (8 bits) | 24 item bits
-#define NTR_SPARSE_LEAF_MIN 64      // leaves with at least this many items carry the word-grouped item table
-#define NTR_SPARSE_CAP 32           // a leaf visit with at most this many untested items tests just those (in leaf order)
 #define NTR_STACK_CAP (NTR_MAX_TREE_DEPTH + 2)
 
 // meta word stored in the last float slot of every simplex / solid record
@@ -41,8 +39,6 @@ enum : int {
 struct SceneDev {
     const uint4 *nodes;             // ntr_node, 16 B
     const uint2 *leaf_items;        // {leaf ref (identity: (type<<30)|index), float offset of the item's record}
-    const uint32_t *leaf_keys;      // per leaf-item slot: dense number of the item among the distinct leaf items (mailbox key)
-    const uint32_t *leaf_sparse;    // big leaves: items grouped by mailbox word (arena_pack.h: build_leaf_sparse); leaf node w3 = offset + 1
     const float *simplex;           // stride sstride floats: fn[D], d, p1[D], edges[D-1][D], pad.., meta
     const float *batches;           // batch blocks (see arena_pack.h): SoA plane part + per-lane edge parts + metas
     const float *solids;            // stride solstride floats: type, inv_orientation[D*D], position[D], orientation[D*D], pad.., meta

@@ -543,11 +543,12 @@ struct MailboxStore {
     uint32_t stride;        // threads in the table
     uint32_t words;         // words per thread
     uint32_t gen;           // generation of the current traversal, 1..255
+    uint32_t solid_base;    // key of solid 0 (= number of simplex records)
     // bind to thread `tid` of the scene's table; the generation counter of the column survives between launches in the
     // word behind its bit words (a column starts all zero: generation 0 is never current)
-    NTR_HD void attach(uint32_t *table, uint32_t n_words, uint32_t n_threads, uint32_t tid) {
+    NTR_HD void attach(uint32_t *table, uint32_t n_words, uint32_t n_threads, uint32_t tid, uint32_t n_simplex) {
         col = (table && tid < n_threads) ? table + tid : nullptr;
-        stride = n_threads; words = n_words;
+        stride = n_threads; words = n_words; solid_base = n_simplex;
         gen = col ? col[(size_t)words * stride] : 0u;
     }
     NTR_HD void detach() { if (col) col[(size_t)words * stride] = gen; }
@@ -557,13 +558,13 @@ struct MailboxStore {
             gen = 1u;
         }
     }
-    // keys = SceneDev::leaf_keys: the distinct leaf items numbered densely
-    NTR_HD uint32_t tested_bits(uint32_t word) const {          // the 24 item bits of a word, 0 when it is from an older traversal
-        const uint32_t w = col[(size_t)word * stride];
-        return (w >> 24) == gen ? (w & 0xFFFFFFu) : 0u;
+    NTR_HD uint32_t key_of(uint32_t r) const { return (r >> 30) == NTR_REF_SOLID ? solid_base + (r & NTR_IDX_MASK) : (r & NTR_IDX_MASK); }
+    NTR_HD bool has(uint32_t r) const {
+        const uint32_t k = key_of(r), w = col[(size_t)(k / NTR_MAILBOX_BITS_PER_WORD) * stride];
+        return (w >> 24) == gen && ((w >> (k % NTR_MAILBOX_BITS_PER_WORD)) & 1u);
     }
-    NTR_HD bool has(uint32_t k) const { return (tested_bits(k / NTR_MAILBOX_BITS_PER_WORD) >> (k % NTR_MAILBOX_BITS_PER_WORD)) & 1u; }
-    NTR_HD void add(uint32_t k) {
+    NTR_HD void add(uint32_t r) {
+        const uint32_t k = key_of(r);
         uint32_t *p = col + (size_t)(k / NTR_MAILBOX_BITS_PER_WORD) * stride;
         const uint32_t w = *p;
         *p = ((w >> 24) == gen ? w : gen << 24) | (1u << (k % NTR_MAILBOX_BITS_PER_WORD));
@@ -589,9 +590,8 @@ struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,8
         if (big) { big->begin_traversal(); return; }
         for (int i = 0; i < NTR_MAILBOX_SLOTS; ++i) v[i] = NTR_NONE_REF;
     }
-    // r = the item's leaf ref (identity), key = its dense number (only read by the exact form)
-    NTR_HD bool has(uint32_t r, uint32_t key) const {
-        if (big) return big->has(key);
+    NTR_HD bool has(uint32_t r) const {
+        if (big) return big->has(r);
         if (n > NTR_MAILBOX_CAP || n == 0) return false;
         uint32_t h = slot_of(r);
         for (;;) {
@@ -601,8 +601,8 @@ struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,8
             h = (h + 1) & (uint32_t)(NTR_MAILBOX_SLOTS - 1);
         }
     }
-    NTR_HD void add(uint32_t r, uint32_t key) {
-        if (big) { big->add(key); return; }
+    NTR_HD void add(uint32_t r) {
+        if (big) { big->add(r); return; }
         if (n < NTR_MAILBOX_CAP) {
             uint32_t h = slot_of(r);
             while (v[h] != NTR_NONE_REF) h = (h + 1) & (uint32_t)(NTR_MAILBOX_SLOTS - 1);
@@ -895,77 +895,29 @@ NTR_HD float prim_test_general(const SceneDev &s, uint2 it, const float *o, cons
 //   the first opaque hit switches to phase 1 WITHOUT marking the item checked, so the same item is
 //   tested again (and misses its own cutoff); in phase 1 a closer opaque hit replaces o_hit;
 //   finally transparent hits of this leaf at or beyond the LAST test's result are dropped.
-// Untested items of a big leaf, in leaf order, when there are at most NTR_SPARSE_CAP of them: the leaf's items come
-// grouped by mailbox word (arena_pack.h), so one AND-NOT per word finds them -- a traversal that crosses the giant
-// leaves of a star polytope has usually tested all but a few of a leaf's 1,600 items in earlier leaves, and walking
-// the item list just to learn that was most of what its heaviest rays did.  Returns the count, or -1 when there are
-// more (the caller scans the leaf item by item).  Items the sequential scan would skip by identity (the primitive the
-// ray leaves from) are never entered in the mailbox, so they show up here and are skipped by the caller as usual.
-NTR_HD int sparse_untested(const SceneDev &s, const uint4 node, const MailboxStore &mb, unsigned short *pos) {
-    const uint32_t *sp = s.leaf_sparse + (node.w - 1);
-    const uint32_t n_blocks = ldu(sp);
-    const uint32_t *blocks = sp + 1, *entries = sp + 1 + 3 * n_blocks;
-    int n = 0;
-    for (uint32_t b = 0; b < n_blocks; ++b) {
-        const uint32_t mask = ldu(blocks + 3 * b + 1);
-        uint32_t u = mask & ~mb.tested_bits(ldu(blocks + 3 * b));
-        if (!u) continue;
-        const uint32_t first = ldu(blocks + 3 * b + 2);
-        while (u) {
-#if defined(__CUDA_ARCH__)
-            const int bit = __ffs((int)u) - 1;
-            const int rank = __popc(mask & ((1u << bit) - 1u));
-#else
-            const int bit = __builtin_ctz(u);
-            const int rank = __builtin_popcount(mask & ((1u << bit) - 1u));
-#endif
-            u &= u - 1;
-            if (n == NTR_SPARSE_CAP) return -1;
-            // insertion by leaf position: the list stays sorted
-            const unsigned short p = (unsigned short)ldu(entries + first + rank);
-            int j = n++;
-            while (j > 0 && pos[j - 1] > p) { pos[j] = pos[j - 1]; --j; }
-            pos[j] = p;
-        }
-    }
-    return n;
-}
-
 template <int DT, int FLAGS>
 NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, const float *dir, const RaySlab<DT> &rs,
                          Skip skip, HitRec &oh, GenState<DT> &g, Counters &cnt) {
     const int D = NTR_D(DT, s);
     const uint2 *items = s.leaf_items + node.y;
-    const uint32_t *keys = s.leaf_keys + node.y;
     const uint32_t size = node.z;
     const int h_start = g.th.n;
     float dist = 0;
     bool phase1 = false, retest = false;
     float P[DimCap<DT>::value], N[DimCap<DT>::value];
-    // big leaf + exact mailbox: only the untested items, when they are few (leaf positions fit 16 bits: checked at pack time)
-    unsigned short todo[NTR_SPARSE_CAP];
-    int n_todo = -1, next_todo = 0;
-    if (!NTR_USE_LEAF_INDEX && node.w && g.mb.exact() && size <= 0xFFFFu) n_todo = sparse_untested(s, node, *g.mb.big, todo);
     LeafCursor<DT> cur;
     cur.begin(s, node);
     uint32_t i = 0, last_tested = 0;
     for (;;) {
         if (!retest) {
-            if (n_todo >= 0) {
-                if (next_todo >= n_todo) break;
-                i = todo[next_todo++];
-            } else {
-                i = cur.next(s, o, rs, oh.dist);
-                if (i >= size) break;
-            }
+            i = cur.next(s, o, rs, oh.dist);
+            if (i >= size) break;
         }
         retest = false;
         const uint2 it = lditem(items + i);
         const uint32_t item = it.x;
         const bool is_batch = (item >> 30) == NTR_REF_BATCH;
-        if (!is_batch && item == skip.ref) continue;
-        const uint32_t key = g.mb.exact() ? ldu(keys + i) : 0u;
-        if (n_todo < 0 && g.mb.has(item, key)) continue;
+        if ((!is_batch && item == skip.ref) || g.mb.has(item)) continue;
         int lane;
         uint32_t wmask, meta;
         dist = prim_test_general<DT, FLAGS>(s, it, o, dir, oh.dist, skip, lane, P, N, wmask, meta, cnt);
@@ -995,7 +947,7 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
                 g.th.add(dist, item, lane);
             }
         }
-        g.mb.add(item, key);
+        g.mb.add(item);
     }
     if (!phase1) return false;
     // `dist` must be the result of the last test the reference performs.  When the index culled the tail of the
@@ -1073,12 +1025,12 @@ NTR_HD void prim_eval(const SceneDev &s, uint2 it, const float *o, const float *
 // taken earlier (with a cutoff that may have been looser, and before the mailbox may have switched itself off).
 template <int DT, int FLAGS>
 NTR_HD void replay_item(const SceneDev &s, const uint2 it, const float *o, const float *dir, Skip skip, HitRec &oh,
-                        GenState<DT> &g, Counters &cnt, bool &phase1, float &dist, ChunkEval<DT> &e, uint32_t key,
+                        GenState<DT> &g, Counters &cnt, bool &phase1, float &dist, ChunkEval<DT> &e,
                         bool mailbox_done = false /* the caller consulted and updated the mailbox for this item */) {
     const int D = NTR_D(DT, s);
     const uint32_t item = it.x;
     const bool is_batch = (item >> 30) == NTR_REF_BATCH;
-    if ((!is_batch && item == skip.ref) || (!mailbox_done && g.mb.has(item, key))) return;
+    if ((!is_batch && item == skip.ref) || (!mailbox_done && g.mb.has(item))) return;
     const bool stale_cutoff = e.dist != 0 && !(e.dist < oh.dist);
     const bool is_cube = (item >> 30) == NTR_REF_SOLID &&
                          (int)ldf(s.solids + (size_t)(item & NTR_IDX_MASK) * s.solstride) == NTR_SOLID_CUBE;
@@ -1118,7 +1070,7 @@ NTR_HD void replay_item(const SceneDev &s, const uint2 it, const float *o, const
             g.th.add(dist, item, e.lane);
         }
     }
-    if (!mailbox_done) g.mb.add(item, key);
+    if (!mailbox_done) g.mb.add(item);
 }
 
 template <int DT, int FLAGS>
@@ -1137,14 +1089,14 @@ NTR_HD bool leaf_general_chunked(const SceneDev &s, const uint4 node, const floa
         for (uint32_t j = 0; j < n; ++j) {
             const uint2 it = lditem(items + base + j);
             const bool is_batch = (it.x >> 30) == NTR_REF_BATCH;
-            const bool skipped = (!is_batch && it.x == skip.ref) || g.mb.has(it.x, ldu(s.leaf_keys + node.y + base + j));
+            const bool skipped = (!is_batch && it.x == skip.ref) || g.mb.has(it.x);
             ev[j].dist = 0; ev[j].wmask = 0; ev[j].meta = 0; ev[j].lane = -1; ev[j].geom = false;
             if (!skipped) prim_eval<DT, FLAGS>(s, it, o, dir, cutoff0, skip, ev[j], cnt);
             ev[j].skipped = skipped;
         }
         // ---- replay in leaf order ----
         for (uint32_t j = 0; j < n; ++j)
-            replay_item<DT, FLAGS>(s, lditem(items + base + j), o, dir, skip, oh, g, cnt, phase1, dist, ev[j], ldu(s.leaf_keys + node.y + base + j));
+            replay_item<DT, FLAGS>(s, lditem(items + base + j), o, dir, skip, oh, g, cnt, phase1, dist, ev[j]);
     }
     if (!phase1) return false;
     g.th.trim(dist, h_start);

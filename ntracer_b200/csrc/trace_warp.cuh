@@ -143,7 +143,6 @@ __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, ui
     Skip bskip;
     broadcast_ray<DT>(s, src, o, dir, skip, bo, bd, bskip);
     const uint2 *items = s.leaf_items + first;
-    const uint32_t *keys = s.leaf_keys + first;
     const int h_start = g.th.n;             // meaningful on the owner only
     float dist = 0;
     bool phase1 = false;
@@ -168,20 +167,20 @@ __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, ui
     NTR_UNROLL
         for (int i = 0; i < D; ++i) { e.P[i] = 0; e.N[i] = 0; }
         bool tested = false;
-        uint32_t my_key = 0;
+        uint32_t my_item = NTR_NONE_REF;
         if ((uint32_t)lane < n) {
             const uint2 it = lditem(items + base + lane);
-            my_key = exact ? ldu(keys + base + lane) : 0u;
             // the primitive the ray leaves from is skipped by identity, never evaluated
-            if (!(((it.x >> 30) != NTR_REF_BATCH) && it.x == bskip.ref) && !(exact && owner_mb.has(my_key))) {
+            if (!(((it.x >> 30) != NTR_REF_BATCH) && it.x == bskip.ref) && !(exact && owner_mb.has(it.x))) {
                 prim_eval<DT, FLAGS>(s, it, bo, bd, cutoff0, bskip, e, cnt);
                 tested = true;
+                my_item = it.x;
             }
         }
         unsigned m = __ballot_sync(kFullMask, e.dist != 0 || e.wmask != 0);        // hits and partial writes
         const unsigned tm = __ballot_sync(kFullMask, tested);
         if (exact && tm) {
-            const uint32_t key = my_key;
+            const uint32_t key = tested ? owner_mb.key_of(my_item) : 0u;
             const uint32_t word = tested ? key / NTR_MAILBOX_BITS_PER_WORD : 0x80000000u | (uint32_t)lane;    // idle lanes: a group of one
             const uint32_t bit = tested ? 1u << (key % NTR_MAILBOX_BITS_PER_WORD) : 0u;
             const unsigned peers = __match_any_sync(kFullMask, word);
@@ -208,7 +207,7 @@ __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, ui
                     for (uint32_t k = prev; k < j; ++k) {
                         ChunkEval<DT> miss;
                         miss.dist = 0; miss.wmask = 0; miss.meta = 0; miss.lane = -1; miss.skipped = false; miss.geom = true;
-                        replay_item<DT, FLAGS>(s, lditem(items + base + k), o, dir, skip, oh, g, cnt, phase1, dist, miss, 0u);
+                        replay_item<DT, FLAGS>(s, lditem(items + base + k), o, dir, skip, oh, g, cnt, phase1, dist, miss);
                     }
                 } else {
                     const unsigned gap = (j >= 32 ? 0xFFFFFFFFu : ((1u << j) - 1u)) & ~((1u << prev) - 1u);
@@ -228,7 +227,7 @@ __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, ui
                     for (int i = 0; i < D; ++i) { r.P[i] = __shfl_sync(kFullMask, e.P[i], j); r.N[i] = __shfl_sync(kFullMask, e.N[i], j); }
                 }
             }
-            if (lane == src) replay_item<DT, FLAGS>(s, lditem(items + base + j), o, dir, skip, oh, g, cnt, phase1, dist, r, 0u, exact);
+            if (lane == src) replay_item<DT, FLAGS>(s, lditem(items + base + j), o, dir, skip, oh, g, cnt, phase1, dist, r, exact);
             prev = j + 1;
             m &= m - 1;
         }

@@ -134,7 +134,7 @@ void setup(Scene &S, const ntr_scene_desc *d, const float *cam_origin, const flo
         S.dev.n_global = (int)d->n_global_lights;
         uint32_t max_leaf = 0;
         for (uint32_t i = 0; i < d->n_nodes; ++i) if (d->nodes[i].meta & NTR_LEAF_FLAG) max_leaf = std::max(max_leaf, d->nodes[i].w2);
-        const uint64_t keys = L.n_keys;
+        const uint64_t keys = (uint64_t)d->n_simplex + d->n_solids;
 #ifndef NTR_EMUL_EXACT_MAILBOX_ALWAYS
 #define NTR_EMUL_EXACT_MAILBOX_ALWAYS 0
 #endif
@@ -166,7 +166,7 @@ void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, un
     std::vector<uint32_t> qp, qpn;
     const float one[3] = {1, 1, 1};
     MailboxStore ms;
-    ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, 0);
+    ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex);
     for (int y = 0; y < h; ++y) {
         for (int x = 0; x < w; ++x) {
             const uint32_t pix = (uint32_t)y * w + x;
@@ -239,7 +239,7 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
                 warp_emu::lane = L;
                 warp_emu::warp = &W;
                 MailboxStore ms;
-                ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, (uint32_t)L);
+                ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, (uint32_t)L, S.dev.n_simplex);
                 for (size_t base = 0; base < n; base += 32) {
                     const size_t idx = base + L;
                     const bool enabled = idx < n;
@@ -326,7 +326,7 @@ void trace_t(Scene &S, uint32_t n, const float *origins, const float *dirs, floa
              int max_hits = 0, int32_t *hit_ids = nullptr, float *hit_dists = nullptr) {
     const int D = S.dev.dim;
     MailboxStore ms;
-    ms.attach((FLAGS & NTR_F_GENERAL) ? S.dev.mb_table : nullptr, S.dev.mb_words, S.dev.mb_threads, 0);
+    ms.attach((FLAGS & NTR_F_GENERAL) ? S.dev.mb_table : nullptr, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex);
     for (uint32_t i = 0; i < n; ++i) {
         Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
         GenState<DT> g;
