@@ -34,7 +34,6 @@ extern "C" {
 #define NTR_ABI_VERSION 1
 #define NTR_MAX_DIM 16          /* runtime-dimension kernels keep vectors of this many floats */
 #define NTR_MAX_CHANNELS 16     /* MAX_PIXELSIZE = 16 bytes, src/render.cpp:50 */
-#define NTR_MAX_LIGHTS 16       /* per kind; the reference has no limit, the device arena is fixed */
 #define NTR_MAX_TREE_DEPTH 62   /* traversal stack entries (reference default max depth 25, src/tracer.hpp:41) */
 
 typedef enum ntr_status {
@@ -92,7 +91,7 @@ typedef struct ntr_scene_desc {
     float fov;
     int32_t shadows;
     int32_t camera_light;
-    int32_t max_reflect_depth;
+    int32_t max_reflect_depth;      /* 0..63 (one wavefront pass per depth; more is NTR_ERR_VALUE) */
     int32_t bg_gradient_axis;
     float ambient[3], bg1[3], bg2[3], bg3[3];
     uint32_t n_point_lights;
@@ -128,6 +127,9 @@ typedef struct ntr_counters {
     uint64_t solid_tests;
     uint64_t shaded_hits;           /* base_color calls */
     uint64_t queue_overflows;       /* wavefront queue regrow events */
+    uint64_t truncated_hit_lists;   /* rays whose list of transparent hits outgrew the 16 entries the kernels keep (the
+                                       reference preallocates 10 and is undefined beyond, src/tracer.hpp:26,670-680):
+                                       their farthest layers are missing from the frame -- 0 means nothing was cut */
 } ntr_counters;
 
 typedef struct ntr_scene ntr_scene;     /* opaque: device arena + streams + queues of one scene on one GPU */

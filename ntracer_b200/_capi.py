@@ -10,7 +10,6 @@ import numpy as np
 
 NTR_MAX_DIM = 16
 NTR_MAX_CHANNELS = 16
-NTR_MAX_LIGHTS = 16
 NULL_NODE = 0xFFFFFFFF
 LEAF_FLAG = 0x80000000
 REF_SIMPLEX, REF_BATCH, REF_SOLID = 0, 1, 2
@@ -55,7 +54,7 @@ class ImageFormat(C.Structure):
 class Counters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         'primary_rays', 'reflection_rays', 'shadow_rays', 'node_steps', 'simplex_tests', 'solid_tests',
-        'shaded_hits', 'queue_overflows')]
+        'shaded_hits', 'queue_overflows', 'truncated_hit_lists')]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

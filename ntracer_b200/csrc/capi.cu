@@ -191,6 +191,8 @@ int validate_desc(const ntr_scene_desc *d, int *tree_depth_out) {
     if (d->batch_size < 1 || d->batch_size > 64) return fail(NTR_ERR_VALUE, "batch_size must be in 1..64");
     if (!d->boundary) return fail(NTR_ERR_VALUE, "composite scene needs a boundary");
     if (d->bg_gradient_axis < 0 || d->bg_gradient_axis >= d->dim) return fail(NTR_ERR_VALUE, "bg_gradient_axis out of range");
+    if (d->max_reflect_depth < 0 || d->max_reflect_depth > kMaxPasses - 1)
+        return fail(NTR_ERR_VALUE, "max_reflect_depth must be between 0 and %d (one wavefront pass per depth)", kMaxPasses - 1);
     if (d->n_nodes && !d->nodes) return fail(NTR_ERR_VALUE, "nodes is NULL");
     if (d->n_leaf_refs && !d->leaf_refs) return fail(NTR_ERR_VALUE, "leaf_refs is NULL");
     if (d->n_simplex && (!d->simplex || !d->simplex_mat)) return fail(NTR_ERR_VALUE, "simplex / simplex_mat is NULL");
@@ -628,6 +630,7 @@ int frame_collect(ntr_scene *sc, FrameJob &j, bool *again) {
     }
     sc->counters.reflection_rays = h_cnt[1]; sc->counters.shadow_rays = h_cnt[2]; sc->counters.node_steps = h_cnt[3];
     sc->counters.simplex_tests = h_cnt[4]; sc->counters.solid_tests = h_cnt[5]; sc->counters.shaded_hits = h_cnt[6];
+    sc->counters.truncated_hit_lists = h_cnt[7];
     sc->counters.queue_overflows = overflows;
     if (!j.passes || !h_ctl[CTL_OVERFLOW]) return NTR_OK;
     // a wavefront queue was too small: the counters say how many records were wanted
@@ -754,7 +757,7 @@ int run_frame_slabs(ntr_scene *sc, const ntr_image_format *fmt, unsigned char *d
     sc->counters.primary_rays = (uint64_t)fmt->width * fmt->height;
     for (int i = 0; i < S; ++i) {
         sc->counters.reflection_rays += h_cnt[i * 8 + 1]; sc->counters.shadow_rays += h_cnt[i * 8 + 2];
-        sc->counters.shaded_hits += h_cnt[i * 8 + 6];
+        sc->counters.shaded_hits += h_cnt[i * 8 + 6]; sc->counters.truncated_hit_lists += h_cnt[i * 8 + 7];
     }
     return NTR_OK;
 }
@@ -1040,6 +1043,8 @@ NTR_API int ntr_scene_set_params(ntr_scene *sc, const ntr_scene_desc *desc) {
     if (desc->kind == NTR_SCENE_COMPOSITE) {
         if (!desc->boundary) return fail(NTR_ERR_VALUE, "composite scene needs a boundary");
         if (desc->bg_gradient_axis < 0 || desc->bg_gradient_axis >= desc->dim) return fail(NTR_ERR_VALUE, "bg_gradient_axis out of range");
+        if (desc->max_reflect_depth < 0 || desc->max_reflect_depth > kMaxPasses - 1)
+            return fail(NTR_ERR_VALUE, "max_reflect_depth must be between 0 and %d (one wavefront pass per depth)", kMaxPasses - 1);
     }
     fill_params(sc->dev, desc);
     if (desc->kind == NTR_SCENE_COMPOSITE) return upload_lights(sc, desc);
@@ -1507,6 +1512,7 @@ int group_trace(ntr_group *g, const ntr_image_format *fmt) {
         g->counters.shadow_rays += sc->counters.shadow_rays; g->counters.node_steps += sc->counters.node_steps;
         g->counters.simplex_tests += sc->counters.simplex_tests; g->counters.solid_tests += sc->counters.solid_tests;
         g->counters.shaded_hits += sc->counters.shaded_hits; g->counters.queue_overflows += sc->counters.queue_overflows;
+        g->counters.truncated_hit_lists += sc->counters.truncated_hit_lists;
     }
     return NTR_OK;
 }

@@ -65,10 +65,10 @@ struct NullEmit {
 };
 
 __device__ __forceinline__ void flush_counters(const ControlDev &ctl, const Counters &cnt) {
-    unsigned long long v[6] = {cnt.reflection_rays, cnt.shadow_rays, cnt.node_steps, cnt.simplex_tests,
-                               cnt.solid_tests, cnt.shaded_hits};
+    unsigned long long v[7] = {cnt.reflection_rays, cnt.shadow_rays, cnt.node_steps, cnt.simplex_tests,
+                               cnt.solid_tests, cnt.shaded_hits, cnt.truncated};
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 0; k < 7; ++k) {
         unsigned long long x = v[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xFFFFFFFFu, x, off);

@@ -120,7 +120,7 @@ template <int DT> NTR_HD float vsel(const float *v, int i) {
 
 struct Counters {
     unsigned long long node_steps = 0, simplex_tests = 0, solid_tests = 0, shadow_rays = 0, reflection_rays = 0,
-                       shaded_hits = 0;
+                       shaded_hits = 0, truncated = 0;
 };
 
 struct Skip { uint32_t ref; int lane; };
@@ -1356,6 +1356,7 @@ NTR_HD bool light_reaches(const SceneDev &s, const float *o, const float *dir, f
     cnt.shadow_rays++;
     if (trace_occludes<DT, FLAGS>(s, o, dir, ldistance, skip, 0.0f, FLT_MAX, &hits, cnt)) return false;
     if (FLAGS & NTR_F_GENERAL) {
+        if (hits.dropped) cnt.truncated++;
         if (hits.n) {
             hits.sort_and_unique();
             for (int i = hits.n - 1; i >= 0; --i) {
@@ -1599,6 +1600,7 @@ NTR_HD void ray_color(const SceneDev &s, bool enabled, const float *o, const flo
     // shade_hit call site (keeps a single copy of the shading + shadow-traversal code in the kernel).
     int n_layers = 0;
     if (FLAGS & NTR_F_GENERAL) {
+        if (g.th.dropped) cnt.truncated++;          // the list outgrew NTR_THITS_CAP: reported, ntr_counters.truncated_hit_lists
         if (g.th.n) g.th.sort_and_unique();
         n_layers = g.th.n;
     }

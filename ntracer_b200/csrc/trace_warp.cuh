@@ -501,6 +501,7 @@ __device__ __forceinline__ bool light_reaches_warp(const SceneDev &s, bool need,
     const bool occluded = trace_occludes_warp<DT, FLAGS>(s, need, o, dir, ldistance, skip, 0.0f, FLT_MAX, &hits, cnt, done_ctr);
     if (!need || occluded) return false;
     if (FLAGS & NTR_F_GENERAL) {
+        if (hits.dropped) cnt.truncated++;
         if (hits.n) {
             hits.sort_and_unique();
             for (int i = hits.n - 1; i >= 0; --i) {
@@ -535,6 +536,7 @@ __device__ __forceinline__ void ray_color_warp(const SceneDev &s, bool enabled, 
     float w[3] = {weight[0], weight[1], weight[2]};
     int n_layers = 0;
     if (FLAGS & NTR_F_GENERAL) {
+        if (enabled && g.th.dropped) cnt.truncated++;
         if (enabled && g.th.n) g.th.sort_and_unique();
         n_layers = enabled ? g.th.n : 0;
     }

@@ -46,7 +46,7 @@ def render(sc, w, h, cam=None, generic=False, want_ids=False):
     rgb = np.zeros((h, w, 3), dtype=np.float32)
     ids = np.zeros((h, w), dtype=np.int32)
     dist = np.zeros((h, w), dtype=np.float32)
-    cnt = np.zeros(8, dtype=np.uint64)
+    cnt = np.zeros(9, dtype=np.uint64)
     lib().emul_render(C.byref(d), _p(o), _p(a), w, h, int(generic), _p(rgb), _p(ids), _p(dist), _p(cnt))
     names = [n for n, _ in _capi.Counters._fields_]
     counters = {n: int(v) for n, v in zip(names, cnt)}

@@ -159,3 +159,20 @@ def fuzz_scene(dim, seed, max_batches=24):
         sc['nodes'], sc['leaf_refs'] = nodes, np.array(refs, np.uint32)
     sc['params'] = np.array([0.8, rng.randint(0, 2), rng.randint(0, 2), rng.randint(0, 4), rng.randint(0, dim)], np.float64)
     return sc
+
+
+def stacked_layers(n_layers, opacity=0.5):
+    """n_layers big transparent triangles stacked along the view axis in front of an opaque one (3-D): every central ray
+    collects n_layers transparent hits -- beyond the 10 the reference preallocates and, from 17 on, beyond the 16 the
+    kernels keep (ntr_counters.truncated_hit_lists)."""
+    from ntracer_b200 import bulk
+    pts = np.zeros((n_layers + 1, 3, 3), np.float32)
+    for k in range(n_layers + 1):
+        z = 0.2 * k
+        pts[k] = [[-2, -2, z], [2, -2, z + 0.01 * k], [0, 2.5, z]]
+    mats = np.array([[0.3, 0.6, 1.0, 1, 1, 1, opacity, 0, 1, 8], [1, 0.5, 0.2, 1, 1, 1, 1, 0, 1, 8]], np.float32)
+    mid = np.zeros(n_layers + 1, np.int32)
+    mid[-1] = 1
+    sc = bulk.simplex_scene(pts, material_ids=mid, materials=mats, max_depth=2)
+    sc['cam_origin'] = np.array([0, 0, -4], np.float32)
+    return sc

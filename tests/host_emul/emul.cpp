@@ -200,6 +200,7 @@ void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, un
         cnt_out[0] = (unsigned long long)w * h; cnt_out[1] = cnt.reflection_rays; cnt_out[2] = cnt.shadow_rays;
         cnt_out[3] = cnt.node_steps; cnt_out[4] = cnt.simplex_tests; cnt_out[5] = cnt.solid_tests; cnt_out[6] = cnt.shaded_hits;
         cnt_out[7] = 0;
+        cnt_out[8] = cnt.truncated;
     }
 }
 
@@ -294,7 +295,7 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
         for (int L = 0; L < 32; ++L) {
             total.reflection_rays += cnts[L].reflection_rays; total.shadow_rays += cnts[L].shadow_rays;
             total.node_steps += cnts[L].node_steps; total.simplex_tests += cnts[L].simplex_tests;
-            total.solid_tests += cnts[L].solid_tests; total.shaded_hits += cnts[L].shaded_hits;
+            total.solid_tests += cnts[L].solid_tests; total.shaded_hits += cnts[L].shaded_hits; total.truncated += cnts[L].truncated;
         }
         q.swap(qn); qp.swap(qpn);
         primary = false;
@@ -304,6 +305,7 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
         cnt_out[0] = (unsigned long long)w * h; cnt_out[1] = total.reflection_rays; cnt_out[2] = total.shadow_rays;
         cnt_out[3] = total.node_steps; cnt_out[4] = total.simplex_tests; cnt_out[5] = total.solid_tests; cnt_out[6] = total.shaded_hits;
         cnt_out[7] = 0;
+        cnt_out[8] = total.truncated;
     }
 }
 #endif

@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_capi.Node) == 16
     assert C.sizeof(_capi.Channel) == 20
     assert C.sizeof(_capi.ImageFormat) == 16 + 16 * 20 + 4
-    assert C.sizeof(_capi.Counters) == 64
+    assert C.sizeof(_capi.Counters) == 72
 
 
 def test_image_format_validation_follows_reference():

@@ -360,3 +360,23 @@ def test_random_mixed_scenes_match_the_oracle():
         all_q += int(q12.sum())
     assert all_px > 30000 and bad_px <= 0.001 * all_px, (bad_px, all_px)
     assert bad_q <= 0.5 * max(all_q, 1), (bad_q, all_q)
+
+
+def test_limits_are_reported_not_silent():
+    """ntr_counters.truncated_hit_lists counts rays whose transparent-hit list outgrew the 16 entries the kernels keep; a
+    max_reflect_depth the control block cannot hold is a ValueError (the reference has neither limit)."""
+    w, h = 48, 36
+    sc = fx.stacked_layers(12)
+    with DeviceScene(sc) as ds:
+        img = ds.render_float(w, h)
+        assert ds.counters()['truncated_hit_lists'] == 0
+        assert fx.lsb_stats(img, ol.render_float(sc, w, h))[0] <= 0.001
+    sc = fx.stacked_layers(20)
+    with DeviceScene(sc) as ds:
+        ds.render_float(w, h)
+        assert ds.counters()['truncated_hit_lists'] > 0
+        deep = dict(sc, params=np.array([0.8, 0, 1, 64, 1], np.float64))
+        with pytest.raises(ValueError):
+            ds.set_params(deep)
+    with pytest.raises(ValueError):
+        DeviceScene(deep)

@@ -101,3 +101,17 @@ def test_batched_soup_every_fixed_dimension_and_generic(dim):
         assert cnt_o[k] == cnt[k], (dim, k)
     g, _ = el.render(sc, w, h, generic=True)
     assert np.abs(a - g).max() <= 2e-6
+
+
+def test_truncated_hit_lists_are_reported_and_too_deep_reflection_is_rejected():
+    """Limits that would change the picture are not silent: rays with more transparent layers than the kernels' lists hold
+    (16; the reference itself is undefined beyond 10) are counted in ntr_counters.truncated_hit_lists."""
+    w, h = 24, 18
+    sc = fx.stacked_layers(12)
+    a, mask, cnt_o = ol.render_float(sc, w, h, with_mask=True, with_counters=True)
+    b, cnt_e = el.render(sc, w, h)
+    assert cnt_e['truncated_hit_lists'] == 0 and np.abs(a - b).max() <= 2e-6      # 12 layers: beyond the reference's 10, fine here
+    assert (mask & 1).any()                                                        # ... and the oracle says so
+    sc = fx.stacked_layers(20)
+    b, cnt_e = el.render(sc, w, h)
+    assert cnt_e['truncated_hit_lists'] > 0
