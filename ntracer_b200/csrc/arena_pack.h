@@ -25,88 +25,11 @@ namespace ntr {
 
 struct ArenaLayout {
     size_t off_nodes = 0, off_refs = 0, off_simplex = 0, off_batches = 0, off_solids = 0, off_mats = 0, off_index = 0, total = 0;
-    int index_stride = 0;           // floats per leaf-index node: lo[D], hi[D], skip, item, padded to 4
     int sstride = 0, solstride = 0, lane_part = 0, batch_block = 0;
     bool any_transparent = false, any_reflective = false;
 };
 
 inline size_t arena_align(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// Leaves with at least this many items get an in-order bounding-box index.  Measured (host emulation, 192x108):
-// bit-identical images for opaque scenes, but on {5/2,3,3} it only removes 30 % of the simplex tests (the reference's
-// leaf order is not spatially coherent and star-polytope cells have fat 4-D boxes) and the box tests cost more than
-// they save, so it is OFF by default (build with -DNTR_LEAF_INDEX_MIN=12 -DNTR_USE_LEAF_INDEX=1 to experiment).
-#ifndef NTR_LEAF_INDEX_MIN
-#define NTR_LEAF_INDEX_MIN 0xFFFFFFFFu
-#endif
-
-// Axis-aligned bounds of the region one simplex record accepts: the vertices are p1 and p1 + v_j with
-// edge_normal_i . v_j = -delta_ij and face_normal . v_j = 0 (checked against Triangle.from_points for D = 3..6);
-// returns false for degenerate records (the caller then never culls them).
-inline bool simplex_bounds(int D, const float *rec, double *lo, double *hi) {
-    const float *fn = rec, *p1 = rec + D + 1, *edges = rec + 2 * D + 1;
-    double M[NTR_MAXD][2 * NTR_MAXD];
-    for (int r = 0; r < D; ++r) {
-        const float *row = r < D - 1 ? edges + (size_t)r * D : fn;
-        for (int c = 0; c < D; ++c) { M[r][c] = row[c]; M[r][D + c] = r == c ? 1.0 : 0.0; }
-    }
-    for (int c = 0; c < D; ++c) {                        // Gauss-Jordan with partial pivoting
-        int piv = c;
-        for (int r = c + 1; r < D; ++r) if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
-        if (!(fabs(M[piv][c]) > 1e-30)) return false;
-        if (piv != c) for (int k = 0; k < 2 * D; ++k) std::swap(M[piv][k], M[c][k]);
-        const double inv = 1.0 / M[c][c];
-        for (int k = 0; k < 2 * D; ++k) M[c][k] *= inv;
-        for (int r = 0; r < D; ++r) {
-            if (r == c) continue;
-            const double f = M[r][c];
-            if (f != 0) for (int k = 0; k < 2 * D; ++k) M[r][k] -= f * M[c][k];
-        }
-    }
-    for (int i = 0; i < D; ++i) { lo[i] = hi[i] = p1[i]; }
-    for (int j = 0; j < D - 1; ++j) {
-        for (int i = 0; i < D; ++i) {
-            const double v = p1[i] - M[i][D + j];        // p1 + v_j, v_j = -(column j of M^-1)
-            if (!(v == v) || fabs(v) > 1e30) return false;
-            if (v < lo[i]) lo[i] = v;
-            if (v > hi[i]) hi[i] = v;
-        }
-    }
-    return true;
-}
-
-struct ItemBox { float lo[NTR_MAXD], hi[NTR_MAXD]; };
-
-// Pre-order, in-order-visiting bounding-box index over the items of ONE leaf (DESIGN.md section 4 "leaf index"):
-// node = {lo[D], hi[D], skip, item}; children follow their parent, `skip` is the index of the first node after the
-// subtree, item >= 0 marks a single leaf item.  Walking it front to back and jumping to `skip` whenever the ray
-// misses a box visits the surviving items in their ORIGINAL leaf order, which is what the reference's sequential
-// leaf loop (and its first-tested-wins tie rule) needs.
-inline void build_leaf_index(int D, int stride, const std::vector<ItemBox> &boxes, uint32_t a, uint32_t b,
-                             std::vector<float> &out, uint32_t base) {
-    const size_t me = out.size();
-    out.resize(me + stride, 0.0f);
-    if (b - a == 1) {
-        for (int i = 0; i < D; ++i) { out[me + i] = boxes[a].lo[i]; out[me + D + i] = boxes[a].hi[i]; }
-        const uint32_t skip = (uint32_t)((out.size() - base) / stride);
-        memcpy(&out[me + 2 * D], &skip, 4);
-        const int32_t item = (int32_t)a;
-        memcpy(&out[me + 2 * D + 1], &item, 4);
-        return;
-    }
-    const uint32_t mid = a + (b - a) / 2;
-    build_leaf_index(D, stride, boxes, a, mid, out, base);
-    build_leaf_index(D, stride, boxes, mid, b, out, base);
-    for (int i = 0; i < D; ++i) {
-        float lo = boxes[a].lo[i], hi = boxes[a].hi[i];
-        for (uint32_t k = a + 1; k < b; ++k) { lo = std::min(lo, boxes[k].lo[i]); hi = std::max(hi, boxes[k].hi[i]); }
-        out[me + i] = lo; out[me + D + i] = hi;
-    }
-    const uint32_t skip = (uint32_t)((out.size() - base) / stride);
-    memcpy(&out[me + 2 * D], &skip, 4);
-    const int32_t item = -1;
-    memcpy(&out[me + 2 * D + 1], &item, 4);
-}
 
 inline void pack_arena(const ntr_scene_desc *d, std::vector<unsigned char> &h, ArenaLayout &L) {
     const int D = d->dim;
@@ -125,52 +48,6 @@ inline void pack_arena(const ntr_scene_desc *d, std::vector<unsigned char> &h, A
         if ((r >> 30) == NTR_REF_BATCH && batch_slot.emplace(r, (uint32_t)batch_first.size()).second)
             batch_first.push_back(r & NTR_IDX_MASK);
     }
-    // leaf indices for big leaves
-    L.index_stride = (2 * D + 2 + 3) / 4 * 4;
-    std::vector<float> index_data;
-    std::vector<uint32_t> node_index_off(d->n_nodes, 0);          // float4 offset + 1 into the index section, 0 = none
-    {
-        std::unordered_map<uint32_t, ItemBox> box_of;
-        auto item_box = [&](uint32_t r) -> const ItemBox & {
-            auto it = box_of.find(r);
-            if (it != box_of.end()) return it->second;
-            ItemBox bx;
-            for (int i = 0; i < D; ++i) { bx.lo[i] = -3.0e38f; bx.hi[i] = 3.0e38f; }      // never culled
-            const uint32_t kind = r >> 30, idx = r & NTR_IDX_MASK;
-            if (kind != NTR_REF_SOLID) {
-                const int lanes = kind == NTR_REF_BATCH ? B : 1;
-                double lo[NTR_MAXD], hi[NTR_MAXD], tlo[NTR_MAXD], thi[NTR_MAXD];
-                bool ok = true;
-                for (int l = 0; l < lanes && ok; ++l) {
-                    ok = simplex_bounds(D, d->simplex + (size_t)(idx + l) * sin, tlo, thi);
-                    for (int i = 0; i < D && ok; ++i) {
-                        if (l == 0) { lo[i] = tlo[i]; hi[i] = thi[i]; }
-                        else { lo[i] = std::min(lo[i], tlo[i]); hi[i] = std::max(hi[i], thi[i]); }
-                    }
-                }
-                if (ok) {
-                    // the simplex test accepts points up to ROUNDING_FUZZ (barycentric) outside: pad generously
-                    double scale = 1e-3;
-                    for (int i = 0; i < D; ++i) scale = std::max(scale, std::max(fabs(lo[i]), fabs(hi[i])));
-                    for (int i = 0; i < D; ++i) {
-                        const double pad = 1e-4 * scale + 1e-4 * (hi[i] - lo[i]);
-                        bx.lo[i] = (float)(lo[i] - pad);
-                        bx.hi[i] = (float)(hi[i] + pad);
-                    }
-                }
-            }
-            return box_of.emplace(r, bx).first->second;
-        };
-        for (uint32_t n = 0; n < d->n_nodes; ++n) {
-            const ntr_node &nd = d->nodes[n];
-            if (!(nd.meta & NTR_LEAF_FLAG) || nd.w2 < NTR_LEAF_INDEX_MIN) continue;
-            std::vector<ItemBox> boxes(nd.w2);
-            for (uint32_t k = 0; k < nd.w2; ++k) boxes[k] = item_box(d->leaf_refs[nd.w1 + k]);
-            const uint32_t base = (uint32_t)index_data.size();
-            node_index_off[n] = base / 4 + 1;
-            build_leaf_index(D, L.index_stride, boxes, 0, nd.w2, index_data, base);
-        }
-    }
     L.off_nodes = 0;
     L.off_refs = arena_align(L.off_nodes + (size_t)d->n_nodes * 16, 256);
     L.off_simplex = arena_align(L.off_refs + (size_t)d->n_leaf_refs * 8, 256);
@@ -178,12 +55,9 @@ inline void pack_arena(const ntr_scene_desc *d, std::vector<unsigned char> &h, A
     L.off_solids = arena_align(L.off_batches + batch_first.size() * (size_t)L.batch_block * 4, 256);
     L.off_mats = arena_align(L.off_solids + (size_t)d->n_solids * L.solstride * 4, 256);
     L.off_index = arena_align(L.off_mats + (size_t)d->n_materials * 12 * 4, 256);
-    L.total = arena_align(L.off_index + index_data.size() * 4, 256);
+    L.total = L.off_index;
     h.assign(L.total, 0);
     if (d->n_nodes) memcpy(h.data() + L.off_nodes, d->nodes, (size_t)d->n_nodes * 16);
-    for (uint32_t n = 0; n < d->n_nodes; ++n)           // leaf nodes: w3 = leaf index offset (0 = none)
-        if (d->nodes[n].meta & NTR_LEAF_FLAG) memcpy(h.data() + L.off_nodes + (size_t)n * 16 + 12, &node_index_off[n], 4);
-    if (!index_data.empty()) memcpy(h.data() + L.off_index, index_data.data(), index_data.size() * 4);
     {   // leaf items: {ref, float offset of the record inside its section}
         uint32_t *it = reinterpret_cast<uint32_t *>(h.data() + L.off_refs);
         for (uint32_t i = 0; i < d->n_leaf_refs; ++i) {
@@ -243,8 +117,6 @@ inline void bind_arena(SceneDev &dev, const ntr_scene_desc *d, const ArenaLayout
     dev.leaf_items = reinterpret_cast<const uint2 *>(base + L.off_refs);
     dev.batches = reinterpret_cast<const float *>(base + L.off_batches);
     dev.lane_part = L.lane_part;
-    dev.leaf_index = reinterpret_cast<const float *>(base + L.off_index);
-    dev.index_stride = L.index_stride;
     dev.simplex = reinterpret_cast<const float *>(base + L.off_simplex);
     dev.solids = reinterpret_cast<const float *>(base + L.off_solids);
     dev.materials = reinterpret_cast<const float *>(base + L.off_mats);

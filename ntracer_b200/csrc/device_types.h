@@ -43,7 +43,6 @@ struct SceneDev {
     const float *batches;           // batch blocks (see arena_pack.h): SoA plane part + per-lane edge parts + metas
     const float *solids;            // stride solstride floats: type, inv_orientation[D*D], position[D], orientation[D*D], pad.., meta
     const float *materials;         // 12 floats per material (10 used)
-    const float *leaf_index;        // in-order bounding-box indices of big leaves (arena_pack.h); leaf node w3 = offset/4 + 1
     const float *point_lights;      // stride D+3
     const float *global_lights;     // stride D+3
     uint32_t *mb_table;             // exact mailbox: mb_words words per thread, word w of thread t at [w * mb_threads + t] (nullptr: none)
@@ -51,7 +50,6 @@ struct SceneDev {
     uint32_t root;
     uint32_t n_simplex;
     int dim, batch, sstride, solstride;
-    int index_stride;               // floats per leaf-index node
     int lane_part;                  // floats per lane in a batch block's stage-2 part: D*D rounded up to 4
     int kind;
     int n_point, n_global;

@@ -85,13 +85,6 @@ NTR_HD float rcp_approx(float x) {
     return 1.0f / x;
 #endif
 }
-NTR_HD void prefetch_l1(const void *p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
 NTR_HD float u2f(uint32_t u) {
 #if defined(__CUDA_ARCH__)
     return __uint_as_float(u);
@@ -197,12 +190,8 @@ NTR_HD float simplex_single(const SceneDev &s, uint32_t off, const float *o, con
 }
 
 // Edge part of one batch lane (tracer.hpp:567-579): lower edge bound only, then the area sum.  The record is loaded
-// into registers by load(); issuing those loads BEFORE the exact division of the plane test (NTR_EARLY_EDGE_LOAD) was
-// tried and rejected.
-#ifndef NTR_EARLY_EDGE_LOAD
-#define NTR_EARLY_EDGE_LOAD 0      // measured: issuing the loads before the division is SLOWER (config 2 0.746 -> 0.82 ms,
-                                   // config 4 opaque 31.1 -> 34.5 ms): lanes rejected by the exact t test waste them
-#endif
+// into registers by load() AFTER the exact division of the plane test (issuing the loads before it was measured slower,
+// round 1: config 2 0.746 -> 0.82 ms -- lanes rejected by the exact t test waste them).
 template <int DT> struct EdgeRec {
     static constexpr int LP = DT > 0 ? (DT * DT + 3) / 4 * 4 : 4;
     static constexpr bool STAGED = DT > 0 && DT <= 8;          // see SimplexRec
@@ -286,14 +275,9 @@ NTR_HD float batch_test(const SceneDev &s, uint32_t off, const float *o, const f
             if (den[k] == 0) continue;
             // mask = denom != 0 && t >= 0 (:562-565); t[i] && t[i] < min_t (:586)
             EdgeRec<DT> er;
-#if NTR_EARLY_EDGE_LOAD
-            er.load(edges + (g + k) * LPART);       // in flight while the division below completes
-#endif
             const float t = num[k] / den[k];
             if (!(t >= 0) || t == 0 || !(t < min_t)) continue;
-#if !NTR_EARLY_EDGE_LOAD
             er.load(edges + (g + k) * LPART);
-#endif
             if (!batch_lane_edges<DT>(s, er, o, dir, t)) continue;
             min_t = t;
             r_index = g + k;
@@ -302,67 +286,6 @@ NTR_HD float batch_test(const SceneDev &s, uint32_t off, const float *o, const f
     if (r_index == -1) return 0;
     index = r_index;
     meta = f2u(ldf(edges + B * LPART + r_index));
-    return min_t;
-}
-
-// The same test split in two for 4-lane batches, so that the plane parts of TWO consecutive leaf items can be issued
-// back to back (independent loads and FFMA chains -> twice the instruction- and memory-level parallelism of a single
-// warp; ncu: the kernel is latency bound, issue slots 43 % busy).  Exactness: the plane part of the second item is
-// computed with the cutoff from BEFORE the first item's result, which is looser; the finish step re-checks every lane
-// against the cutoff current at that moment (`t < min_t`), which is precisely what the sequential scan does.
-struct BatchPlane { float num[4], den[4]; unsigned viable; };
-
-template <int DT>
-NTR_HD BatchPlane batch_plane4(const SceneDev &s, uint32_t off, const float *o, const float *dir, int index, float cutoff) {
-    const int D = NTR_D(DT, s);
-    const float *blk = s.batches + off;
-    float den[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};
-    NTR_UNROLL
-    for (int i = 0; i < D; ++i) {
-        const float4 f = ld4(blk + i * 4);
-        den[0] += f.x * dir[i]; den[1] += f.y * dir[i]; den[2] += f.z * dir[i]; den[3] += f.w * dir[i];
-        od[0] += f.x * o[i]; od[1] += f.y * o[i]; od[2] += f.z * o[i]; od[3] += f.w * o[i];
-    }
-    const float4 dd = ld4(blk + D * 4);
-    const float dv[4] = {dd.x, dd.y, dd.z, dd.w};
-    BatchPlane r;
-    r.viable = 0;
-    const float cut = cutoff * 1.000001f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        r.num[k] = -(od[k] + dv[k]);
-        r.den[k] = den[k];
-        const float ta = r.num[k] * rcp_approx(den[k]);
-        const bool reject = (fabsf(den[k]) > 1e-30f) & ((ta < 0) | (ta > cut));
-        r.viable |= ((reject | (k == index)) ? 0u : 1u) << k;
-    }
-    return r;
-}
-
-template <int DT>
-NTR_HD float batch_finish4(const SceneDev &s, uint32_t off, const BatchPlane &p, const float *o, const float *dir,
-                           int &index, float cutoff, uint32_t &meta) {
-    if (!p.viable) return 0;
-    const int D = NTR_D(DT, s);
-    const int LPART = DT > 0 ? (DT * DT + 3) / 4 * 4 : s.lane_part;
-    const float *edges = s.batches + off + (D + 1) * 4;
-    float min_t = cutoff;
-    int r_index = -1;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (!(p.viable & (1u << k))) continue;
-        if (p.den[k] == 0) continue;
-        EdgeRec<DT> er;
-        er.load(edges + k * LPART);
-        const float t = p.num[k] / p.den[k];
-        if (!(t >= 0) || t == 0 || !(t < min_t)) continue;
-        if (!batch_lane_edges<DT>(s, er, o, dir, t)) continue;
-        min_t = t;
-        r_index = k;
-    }
-    if (r_index == -1) return 0;
-    index = r_index;
-    meta = f2u(ldf(edges + 4 * LPART + r_index));
     return min_t;
 }
 
@@ -618,86 +541,13 @@ template <int DT> struct GenState {
     Mailbox mb;
 };
 
-// ---- leaf index ---------------------------------------------------------------------------------------
-// Per-ray constants of the slab test.
+// Per-ray constants of the traversal.
 template <int DT> struct RaySlab {
     float invdir[DimCap<DT>::value];
-    uint32_t zmask;                     // axes with direction == 0 (tested by containment instead of a slab)
     NTR_HD void init(const SceneDev &s, const float *dir) {
         const int D = NTR_D(DT, s);
-        zmask = 0;
     NTR_UNROLL
-        for (int i = 0; i < D; ++i) { invdir[i] = 1 / dir[i]; zmask |= (dir[i] == 0 ? 1u : 0u) << i; }   // tracer.hpp:1174
-    }
-};
-
-// Walks the items of a leaf in their original order.  Big leaves carry an in-order bounding-box index
-// (arena_pack.h: build_leaf_index): subtrees whose (padded) box the ray segment (0, cutoff) misses are jumped over.
-// Skipping an item is only ever done when its test would have returned 0 (a miss), which has no side effect for
-// simplex items, so the sequential semantics of the reference's leaf loop are preserved.
-#ifndef NTR_USE_LEAF_INDEX
-#define NTR_USE_LEAF_INDEX 0      // see arena_pack.h: measured not to pay off on the benchmark scenes
-#endif
-template <int DT> struct LeafCursor {
-    const float *idx;
-    uint32_t i, n_nodes, size;
-    NTR_HD void begin(const SceneDev &s, const uint4 node) {
-        size = node.z;
-        i = 0;
-        idx = (NTR_USE_LEAF_INDEX && node.w) ? s.leaf_index + (size_t)(node.w - 1) * 4 : nullptr;
-        n_nodes = 2 * size - 1;
-    }
-    NTR_HD uint32_t next(const SceneDev &s, const float *o, const RaySlab<DT> &rs, float cutoff) {
-#if !NTR_USE_LEAF_INDEX
-        return i < size ? i++ : size;
-#else
-        if (!idx) return i < size ? i++ : size;
-        const int D = NTR_D(DT, s);
-        const int stride = DT > 0 ? (2 * DT + 2 + 3) / 4 * 4 : s.index_stride;
-        while (i < n_nodes) {
-            const float *nd = idx + (size_t)i * stride;
-            float tmin = 0.0f, tmax = cutoff;
-            bool out = false;
-            if (DT > 0) {
-                float r[(2 * (DT > 0 ? DT : 1) + 2 + 3) / 4 * 4];
-    NTR_UNROLL
-                for (int k = 0; k < stride / 4; ++k) {
-                    const float4 v = ld4(nd + 4 * k);
-                    r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
-                }
-    NTR_UNROLL
-                for (int a = 0; a < D; ++a) {
-                    const float lo = r[a], hi = r[D + a];
-                    if (rs.zmask & (1u << a)) { out |= (o[a] < lo) | (o[a] > hi); }
-                    else {
-                        const float t1 = (lo - o[a]) * rs.invdir[a], t2 = (hi - o[a]) * rs.invdir[a];
-                        tmin = fmaxf(tmin, fminf(t1, t2));
-                        tmax = fminf(tmax, fmaxf(t1, t2));
-                    }
-                }
-                const uint32_t skip = f2u(r[2 * D]);
-                const int item = (int)f2u(r[2 * D + 1]);
-                if (out || tmin > tmax) { i = skip; continue; }
-                ++i;
-                if (item >= 0) return (uint32_t)item;
-            } else {
-                for (int a = 0; a < D; ++a) {
-                    const float lo = ldf(nd + a), hi = ldf(nd + D + a);
-                    if (rs.zmask & (1u << a)) { out |= (o[a] < lo) | (o[a] > hi); }
-                    else {
-                        const float t1 = (lo - o[a]) * rs.invdir[a], t2 = (hi - o[a]) * rs.invdir[a];
-                        tmin = fmaxf(tmin, fminf(t1, t2));
-                        tmax = fminf(tmax, fmaxf(t1, t2));
-                    }
-                }
-                if (out || tmin > tmax) { i = f2u(ldf(nd + 2 * D)); continue; }
-                const int item = (int)f2u(ldf(nd + 2 * D + 1));
-                ++i;
-                if (item >= 0) return (uint32_t)item;
-            }
-        }
-        return size;
-#endif
+        for (int i = 0; i < D; ++i) invdir[i] = 1 / dir[i];      // tracer.hpp:1174
     }
 };
 
@@ -710,54 +560,16 @@ template <int DT> struct LeafCursor {
 // most recently tested batch refs, kept as a shift register (0 = disabled).  Measured on config 2: 8 entries
 // remove 35 % of the simplex tests, 16 remove 42 % (the reference's unbounded list removes 39 %); 8 entries at 64
 // registers / 8 CTAs per SM beat 16 entries at 80 registers / 6 CTAs (config 2 -3.5 %, config 4 opaque -10 %).
-#ifndef NTR_PREFETCH_NEXT_ITEM
-#define NTR_PREFETCH_NEXT_ITEM 0
-#endif
-#ifndef NTR_PAIR_BATCHES
-#define NTR_PAIR_BATCHES 0      // leaf_opaque testing two batch items per iteration (see batch_plane4): exact, but measured
-                                // slower on B200 (config 4 opaque 34.6 -> 38.7 ms, config 2 unchanged): off
-#endif
+// (Measured and dropped, round 1 / round 2: testing two batch items per iteration, 34.6 -> 38.7 ms on config 4 opaque;
+// prefetching the next item's record; a direct-mapped per-ray table for single simplexes in local memory, config 5
+// reduced 23.2 -> 23.7 ms with 64 entries, 24.9 ms with 256.)
 #ifndef NTR_MINI_MAILBOX
 #define NTR_MINI_MAILBOX 8
 #endif
-// Optional mailbox for SINGLE simplexes (leaf items that are not batches: scenes from bulk.simplex_scene, config 5).
-// The register mailbox above is useless there (76 items per leaf on the 1 M soup), and without any mailbox the kernels
-// re-test a simplex in every leaf it was duplicated into: 12,500 tests per ray against the 4,591 the reference
-// algorithm performs with its unbounded list (oracle counters).  NTR_SINGLE_MAILBOX = N (a power of two) keeps a
-// direct-mapped table of the N most recently tested ids per ray in local memory; a false negative only costs a
-// repeated test.  Exact for the same reason as the batch mailbox.  Host emulation, 200 k ten-dimensional simplexes,
-// tests per ray: none 2,859 | 64 entries 2,319 | 256 entries 1,727 | 1,024 entries 1,487 | unbounded (oracle) 1,395,
-// images identical.  Default 0 (off): written at the end of round 1 when no GPU time was left -- whether the
-// local-memory traffic (N*4 bytes per thread) costs less than the tests it saves is still to be measured.
-#ifndef NTR_SINGLE_MAILBOX
-#define NTR_SINGLE_MAILBOX 0
-#endif
-#if NTR_SINGLE_MAILBOX > 0
-struct SingleMailbox {
-    static_assert((NTR_SINGLE_MAILBOX & (NTR_SINGLE_MAILBOX - 1)) == 0, "NTR_SINGLE_MAILBOX must be a power of two");
-    uint32_t v[NTR_SINGLE_MAILBOX];
-    NTR_HD void clear() {
-        for (int i = 0; i < NTR_SINGLE_MAILBOX; ++i) v[i] = NTR_NONE_REF;
-    }
-    NTR_HD bool test_and_set(uint32_t r) {
-        const uint32_t h = ((r * 2654435761u) >> 16) & (uint32_t)(NTR_SINGLE_MAILBOX - 1);       // Fibonacci hash, middle bits
-        if (v[h] == r) return true;
-        v[h] = r;
-        return false;
-    }
-};
-#endif
-
 struct MiniMailbox {
-#if NTR_SINGLE_MAILBOX > 0
-    SingleMailbox single;
-#endif
 #if NTR_MINI_MAILBOX > 0
     uint32_t v[NTR_MINI_MAILBOX];       // most recent first; constant indices only, so it lives in registers
     NTR_HD void clear() {
-#if NTR_SINGLE_MAILBOX > 0
-        single.clear();
-#endif
 #pragma unroll
         for (int i = 0; i < NTR_MINI_MAILBOX; ++i) v[i] = NTR_NONE_REF;
     }
@@ -773,11 +585,7 @@ struct MiniMailbox {
         return f;
     }
 #else
-    NTR_HD void clear() {
-#if NTR_SINGLE_MAILBOX > 0
-        single.clear();
-#endif
-    }
+    NTR_HD void clear() {}
     NTR_HD bool test_and_set(uint32_t) { return false; }
 #endif
 };
@@ -788,63 +596,8 @@ NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, con
     const uint2 *items = s.leaf_items + node.y;
     const uint32_t size = node.z;
     bool hit = false;
-#if !NTR_USE_LEAF_INDEX && NTR_PAIR_BATCHES
-    if (DT > 0) {
-        // two items per iteration: both plane parts first, then the finishes in leaf order
-        uint32_t i = 0;
-        while (i < size) {
-            const uint2 a = lditem(items + i);
-            const bool a_batch = (a.x >> 30) == NTR_REF_BATCH;
-            if (a_batch && i + 1 < size) {
-                const uint2 b = lditem(items + i + 1);
-                if ((b.x >> 30) == NTR_REF_BATCH) {
-                    const bool ta = !mm.test_and_set(a.x), tb = !mm.test_and_set(b.x);
-                    int ia = skip.ref == a.x ? skip.lane : -1, ib = skip.ref == b.x ? skip.lane : -1;
-                    BatchPlane pa, pb;
-                    pa.viable = pb.viable = 0;
-                    if (ta) pa = batch_plane4<DT>(s, a.y, o, dir, ia, oh.dist);
-                    if (tb) pb = batch_plane4<DT>(s, b.y, o, dir, ib, oh.dist);
-                    if (FLAGS & NTR_F_COUNT) cnt.simplex_tests += 4 * ((ta ? 1 : 0) + (tb ? 1 : 0));
-                    uint32_t meta;
-                    float dist = batch_finish4<DT>(s, a.y, pa, o, dir, ia, oh.dist, meta);
-                    if (dist) { oh.dist = dist; oh.ref = a.x; oh.lane = ia; hit = true; }
-                    dist = batch_finish4<DT>(s, b.y, pb, o, dir, ib, oh.dist, meta);
-                    if (dist) { oh.dist = dist; oh.ref = b.x; oh.lane = ib; hit = true; }
-                    i += 2;
-                    continue;
-                }
-            }
-            uint32_t meta;
-            if (a_batch) {
-                if (!mm.test_and_set(a.x)) {
-                    int index = skip.ref == a.x ? skip.lane : -1;
-                    const float dist = batch_test<DT, FLAGS>(s, a.y, o, dir, index, oh.dist, meta, cnt);
-                    if (dist) { oh.dist = dist; oh.ref = a.x; oh.lane = index; hit = true; }
-                }
-            } else if (a.x != skip.ref) {
-                if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
-                const float dist = simplex_single<DT>(s, a.y, o, dir, oh.dist, meta);
-                if (dist) { oh.dist = dist; oh.ref = a.x; oh.lane = -1; hit = true; }
-            }
-            ++i;
-        }
-        return hit;
-    }
-#endif
-    LeafCursor<DT> cur;
-    cur.begin(s, node);
-    for (;;) {
-        const uint32_t i = cur.next(s, o, rs, oh.dist);
-        if (i >= size) break;
+    for (uint32_t i = 0; i < size; ++i) {
         const uint2 it = lditem(items + i);
-#if NTR_PREFETCH_NEXT_ITEM
-        // the traversal is latency bound (ncu: long-scoreboard stalls dominate): start fetching the next item's
-        // record while this one is being tested
-        if (i + 1 < size) {
-            const uint2 nx = lditem(items + i + 1);
-            prefetch_l1(((nx.x >> 30) == NTR_REF_BATCH ? s.batches : s.simplex) + nx.y);
-        }
-#endif
         const uint32_t item = it.x;
         uint32_t meta;
         if ((item >> 30) == NTR_REF_BATCH) {
@@ -853,9 +606,6 @@ NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, con
             float dist = batch_test<DT, FLAGS>(s, it.y, o, dir, index, oh.dist, meta, cnt);
             if (dist) { oh.dist = dist; oh.ref = item; oh.lane = index; hit = true; }
         } else if (item != skip.ref) {
-#if NTR_SINGLE_MAILBOX > 0
-            if (mm.single.test_and_set(item)) continue;
-#endif
             if (FLAGS & NTR_F_COUNT) cnt.simplex_tests++;
             float dist = simplex_single<DT>(s, it.y, o, dir, oh.dist, meta);
             if (dist) { oh.dist = dist; oh.ref = item; oh.lane = -1; hit = true; }
@@ -905,13 +655,11 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
     float dist = 0;
     bool phase1 = false, retest = false;
     float P[DimCap<DT>::value], N[DimCap<DT>::value];
-    LeafCursor<DT> cur;
-    cur.begin(s, node);
-    uint32_t i = 0, last_tested = 0;
+    uint32_t i = 0, next = 0;
     for (;;) {
         if (!retest) {
-            i = cur.next(s, o, rs, oh.dist);
-            if (i >= size) break;
+            if (next >= size) break;
+            i = next++;
         }
         retest = false;
         const uint2 it = lditem(items + i);
@@ -921,7 +669,6 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
         int lane;
         uint32_t wmask, meta;
         dist = prim_test_general<DT, FLAGS>(s, it, o, dir, oh.dist, skip, lane, P, N, wmask, meta, cnt);
-        last_tested = i;
         if (!phase1) {
             if (wmask) {
     NTR_UNROLL
@@ -950,10 +697,7 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
         g.mb.add(item);
     }
     if (!phase1) return false;
-    // `dist` must be the result of the last test the reference performs.  When the index culled the tail of the
-    // leaf, those items would have been tested and missed (0).
-    if (cur.idx && last_tested + 1 < size) dist = 0;
-    g.th.trim(dist, h_start);
+    g.th.trim(dist, h_start);           // `dist`: the result of the last test (Q3)
     return true;
 }
 
@@ -1241,11 +985,7 @@ NTR_HD bool leaf_occludes(const SceneDev &s, const uint4 node, const float *o, c
                           float ldistance, Skip skip, HitList *hits, Counters &cnt) {
     const uint2 *items = s.leaf_items + node.y;
     const uint32_t size = node.z;
-    LeafCursor<DT> cur;
-    cur.begin(s, node);
-    for (;;) {
-        const uint32_t i = cur.next(s, o, rs, ldistance);
-        if (i >= size) break;
+    for (uint32_t i = 0; i < size; ++i) {
         const uint2 it = lditem(items + i);
         const uint32_t item = it.x, off = it.y;
         const uint32_t kind = item >> 30;
