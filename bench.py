@@ -234,7 +234,14 @@ def kernel_name(sc, dim):
     """The kernel that dominates a frame of this scene (one render_pass_kernel instantiation per dimension and variant)."""
     fixed = 3 <= dim <= 10 and not int(os.environ.get('NTR_FORCE_GENERIC', '0') or 0)
     general = int(sc['kind']) == 1 and (bool(np.any(np.asarray(sc['materials'])[:, 6] < 1)) or len(sc['solids']) > 0)
-    return 'render_pass_kernel<%d,%d>' % (dim if fixed else 0, 1 if general else 0)
+    name = 'render_pass_kernel<%d,%d>' % (dim if fixed else 0, 1 if general else 0)
+    if int(sc['kind']) == 1 and len(sc['nodes']):
+        nodes = np.asarray(sc['nodes']).reshape(-1, 4)
+        leaves = (nodes[:, 0] & 0x80000000) != 0
+        if leaves.any() and int(nodes[leaves, 2].max()) >= 256:
+            # scenes with big leaves: the bounce passes run the warp-synchronous instantiation (flag bit 2, capi.cu)
+            name += ' (primary pass) + render_pass_kernel<%d,%d> (bounce passes)' % (dim if fixed else 0, (1 if general else 0) | 4)
+    return name
 
 
 def measured_traffic(config, kernel):
@@ -242,7 +249,7 @@ def measured_traffic(config, kernel):
     capture of this workload (profiles/r02_traffic.json, written by tools/ncu_traffic.py); None when there is none."""
     try:
         t = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))[config]
-        if t['kernel'] == kernel:
+        if t['kernel'].split(',')[0] == kernel.split(',')[0]:           # same kernel family (dimension)
             return t
     except Exception:
         pass
