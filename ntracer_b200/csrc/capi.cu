@@ -957,24 +957,15 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     // the exact mailbox of scenes whose leaves overrun the bounded table (trace_core.cuh: MailboxStore): one column per
     // thread of the persistent grid, zero-initialised (generation 0 is never current)
     {
-        // General variant: the exact table IS the semantics (the oracle's unbounded list).  Opaque variant: a mailbox can
-        // only save tests (a re-tested primitive misses its own cutoff), so the table is an optimisation there -- the
-        // 1 M-simplex soup of config 5 tests 12,500 simplexes per ray without it, 4,591 with it.  Bounded by a byte budget
-        // (NTR_MAILBOX_MAX_BYTES, default 32 GB of the 180): one bit per item and thread.
         const uint64_t keys = (uint64_t)desc->n_simplex + desc->n_solids;
         const char *mbx = getenv("NTR_EXACT_MAILBOX");
         const bool want = mbx ? atoi(mbx) != 0 : sc->max_leaf > NTR_MAILBOX_CAP;
-        int blocks = 0;
-        for (int f = 0; f < 8; ++f) if ((f & NTR_F_GENERAL) == (sc->base_flags & NTR_F_GENERAL)) blocks = std::max(blocks, grid_for(sc, f));
-        const uint64_t words = (keys + NTR_MAILBOX_BITS_PER_WORD - 1) / NTR_MAILBOX_BITS_PER_WORD;
-        const uint64_t need = (words + 1) * (uint64_t)blocks * kCtaThreads * sizeof(uint32_t);
-        const char *mbb = getenv("NTR_MAILBOX_MAX_BYTES");
-        const uint64_t budget = mbb ? strtoull(mbb, nullptr, 10) : (32ull << 30);
-        const bool fits = (sc->base_flags & NTR_F_GENERAL) ? keys <= NTR_MAILBOX_MAX_KEYS : need <= budget;
-        if (desc->kind == NTR_SCENE_COMPOSITE && want && keys > 0 && fits) {
+        if (desc->kind == NTR_SCENE_COMPOSITE && (sc->base_flags & NTR_F_GENERAL) && want && keys <= NTR_MAILBOX_MAX_KEYS) {
+            int blocks = 0;
+            for (int f = 0; f < 8; ++f) if ((f & NTR_F_GENERAL) == (sc->base_flags & NTR_F_GENERAL)) blocks = std::max(blocks, grid_for(sc, f));
             sc->dev.mb_threads = (uint32_t)blocks * kCtaThreads;
-            sc->dev.mb_words = (uint32_t)words;
-            const size_t bytes = (size_t)need;
+            sc->dev.mb_words = (uint32_t)((keys + NTR_MAILBOX_BITS_PER_WORD - 1) / NTR_MAILBOX_BITS_PER_WORD);
+            const size_t bytes = (size_t)(sc->dev.mb_words + 1) * sc->dev.mb_threads * sizeof(uint32_t);
             if (cudaMalloc(&sc->dev.mb_table, bytes) != cudaSuccess) {
                 cudaGetLastError();
                 return bail(fail(NTR_ERR_MEMORY, "out of device memory for the mailbox table (%zu bytes)", bytes));

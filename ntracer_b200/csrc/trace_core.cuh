@@ -494,9 +494,6 @@ struct MailboxStore {
     }
 };
 
-NTR_HD bool big_has(const MailboxStore *mb, uint32_t ref) { return mb->has(ref); }
-NTR_HD void big_add(MailboxStore *mb, uint32_t ref) { mb->add(ref); }
-
 struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,832-834
     // The reference's list is defined up to 20 entries (quick_list growth copies bytes, tracer.hpp:670-680: beyond
     // that has() scans uninitialised slots).  This one is exact up to NTR_MAILBOX_CAP entries and then switches itself
@@ -569,9 +566,7 @@ template <int DT> struct RaySlab {
 #ifndef NTR_MINI_MAILBOX
 #define NTR_MINI_MAILBOX 8
 #endif
-struct MailboxStore;
 struct MiniMailbox {
-    MailboxStore *big = nullptr;        // scenes with big leaves: the exact per-thread bitset answers instead (see MailboxStore)
 #if NTR_MINI_MAILBOX > 0
     uint32_t v[NTR_MINI_MAILBOX];       // most recent first; constant indices only, so it lives in registers
     NTR_HD void clear() {
@@ -595,9 +590,6 @@ struct MiniMailbox {
 #endif
 };
 
-NTR_HD bool big_has(const MailboxStore *mb, uint32_t ref);
-NTR_HD void big_add(MailboxStore *mb, uint32_t ref);
-
 template <int DT, int FLAGS>
 NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, const float *dir, const RaySlab<DT> &rs,
                         Skip skip, HitRec &oh, MiniMailbox &mm, Counters &cnt) {
@@ -608,12 +600,8 @@ NTR_HD bool leaf_opaque(const SceneDev &s, const uint4 node, const float *o, con
         const uint2 it = lditem(items + i);
         const uint32_t item = it.x;
         uint32_t meta;
-        if (mm.big && item != skip.ref) {           // (the primitive the ray leaves from stays out of the mailbox: its other lanes count)
-            if (big_has(mm.big, item)) continue;
-            big_add(mm.big, item);
-        }
         if ((item >> 30) == NTR_REF_BATCH) {
-            if (!mm.big && mm.test_and_set(item)) continue;
+            if (mm.test_and_set(item)) continue;
             int index = skip.ref == item ? skip.lane : -1;
             float dist = batch_test<DT, FLAGS>(s, it.y, o, dir, index, oh.dist, meta, cnt);
             if (dist) { oh.dist = dist; oh.ref = item; oh.lane = index; hit = true; }
@@ -922,12 +910,7 @@ NTR_HD bool trace_nearest(const SceneDev &s, const float *o, const float *dir, S
     int sp = 0;
     uint32_t node = s.root;
     MiniMailbox mm;
-    if (FLAGS & NTR_F_GENERAL) { g->mb.clear(); }
-    else {
-        mm.clear();
-        mm.big = g ? g->mb.big : nullptr;
-        if (mm.big) mm.big->begin_traversal();
-    }
+    if (FLAGS & NTR_F_GENERAL) { g->mb.clear(); } else { mm.clear(); }
     for (;;) {
         // ---- descend to a leaf (or fall off the tree) ----
         bool result = false;

@@ -254,12 +254,7 @@ __device__ __forceinline__ bool trace_nearest_warp(const SceneDev &s, bool enabl
     int sp = 0;
     uint32_t node = s.root;
     MiniMailbox mm;
-    if (FLAGS & NTR_F_GENERAL) { g.mb.clear(); }
-    else {
-        mm.clear();
-        mm.big = g.mb.big;
-        if (mm.big) mm.big->begin_traversal();
-    }
+    if (FLAGS & NTR_F_GENERAL) { g.mb.clear(); } else { mm.clear(); }
     int state = enabled ? NTR_S_DESCEND : NTR_S_DONE;
     bool result = false, ret = false;
     uint4 leaf = make_uint4(0u, 0u, 0u, 0u);

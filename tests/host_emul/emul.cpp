@@ -138,7 +138,7 @@ void setup(Scene &S, const ntr_scene_desc *d, const float *cam_origin, const flo
 #ifndef NTR_EMUL_EXACT_MAILBOX_ALWAYS
 #define NTR_EMUL_EXACT_MAILBOX_ALWAYS 0
 #endif
-        if ((max_leaf > NTR_MAILBOX_CAP || NTR_EMUL_EXACT_MAILBOX_ALWAYS) && keys > 0 && keys <= 4 * NTR_MAILBOX_MAX_KEYS) {
+        if ((S.flags & NTR_F_GENERAL) && (max_leaf > NTR_MAILBOX_CAP || NTR_EMUL_EXACT_MAILBOX_ALWAYS) && keys <= NTR_MAILBOX_MAX_KEYS) {
             S.dev.mb_threads = 32;
             S.dev.mb_words = (uint32_t)((keys + NTR_MAILBOX_BITS_PER_WORD - 1) / NTR_MAILBOX_BITS_PER_WORD);
             S.mailbox.assign((size_t)(S.dev.mb_words + 1) * S.dev.mb_threads, 0u);
@@ -328,7 +328,7 @@ void trace_t(Scene &S, uint32_t n, const float *origins, const float *dirs, floa
              int max_hits = 0, int32_t *hit_ids = nullptr, float *hit_dists = nullptr) {
     const int D = S.dev.dim;
     MailboxStore ms;
-    ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex);
+    ms.attach((FLAGS & NTR_F_GENERAL) ? S.dev.mb_table : nullptr, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex);
     for (uint32_t i = 0; i < n; ++i) {
         Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
         GenState<DT> g;
