@@ -111,6 +111,20 @@ inline void pack_arena(const ntr_scene_desc *d, std::vector<unsigned char> &h, A
         memcpy(mt + (size_t)i * 12, d->materials + (size_t)i * 10, sizeof(float) * 10);
 }
 
+// Mailbox keys (trace_core.cuh: MailboxStore) are record indices; a tree whose simplex items are all aligned 4-lane
+// batches (what the reference's SSE builds produce) uses one key in four.  Returns 2 when the record indices of the
+// leaf items stay distinct after dropping two bits -- the table then needs a quarter of the words -- else 0.
+inline uint32_t mailbox_key_shift(const ntr_scene_desc *d) {
+    std::unordered_map<uint32_t, uint32_t> owner;          // index >> 2  ->  the one leaf ref allowed to map there
+    for (uint32_t i = 0; i < d->n_leaf_refs; ++i) {
+        const uint32_t r = d->leaf_refs[i];
+        if ((r >> 30) == NTR_REF_SOLID) continue;
+        const auto it = owner.emplace((r & NTR_IDX_MASK) >> 2, r);
+        if (!it.second && it.first->second != r) return 0;
+    }
+    return 2;
+}
+
 // Points a SceneDev at an arena that lives at `base` (device or, in the test harness, host memory).
 inline void bind_arena(SceneDev &dev, const ntr_scene_desc *d, const ArenaLayout &L, const unsigned char *base) {
     dev.nodes = reinterpret_cast<const uint4 *>(base + L.off_nodes);

@@ -964,7 +964,9 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
             int blocks = 0;
             for (int f = 0; f < 8; ++f) if ((f & NTR_F_GENERAL) == (sc->base_flags & NTR_F_GENERAL)) blocks = std::max(blocks, grid_for(sc, f));
             sc->dev.mb_threads = (uint32_t)blocks * kCtaThreads;
-            sc->dev.mb_words = (uint32_t)((keys + NTR_MAILBOX_BITS_PER_WORD - 1) / NTR_MAILBOX_BITS_PER_WORD);
+            sc->dev.mb_shift = mailbox_key_shift(desc);
+            const uint64_t nk = ((uint64_t)desc->n_simplex >> sc->dev.mb_shift) + 1 + desc->n_solids;
+            sc->dev.mb_words = (uint32_t)((nk + NTR_MAILBOX_BITS_PER_WORD - 1) / NTR_MAILBOX_BITS_PER_WORD);
             const size_t bytes = (size_t)(sc->dev.mb_words + 1) * sc->dev.mb_threads * sizeof(uint32_t);
             if (cudaMalloc(&sc->dev.mb_table, bytes) != cudaSuccess) {
                 cudaGetLastError();

@@ -47,6 +47,8 @@ struct SceneDev {
     const float *global_lights;     // stride D+3
     uint32_t *mb_table;             // exact mailbox: mb_words words per thread, word w of thread t at [w * mb_threads + t] (nullptr: none)
     uint32_t mb_words, mb_threads;
+    uint32_t mb_shift;              // mailbox key of a simplex / batch item = record index >> mb_shift (2 when the leaf items' record
+                                    // indices stay distinct after dropping two bits: a tree of aligned 4-lane batches), solids follow
     uint32_t root;
     uint32_t n_simplex;
     int dim, batch, sstride, solstride;

@@ -152,7 +152,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
     }
     uint32_t fetches = 0;
     MailboxStore ms;                    // this thread's column of the exact mailbox (scenes with big leaves), if any
-    ms.attach((FLAGS & NTR_F_GENERAL) ? s.mb_table : nullptr, s.mb_words, s.mb_threads, blockIdx.x * blockDim.x + threadIdx.x, s.n_simplex);
+    ms.attach((FLAGS & NTR_F_GENERAL) ? s.mb_table : nullptr, s.mb_words, s.mb_threads, blockIdx.x * blockDim.x + threadIdx.x, s.n_simplex, s.mb_shift);
     for (;;) {
         // ---------------- fetch: an 8x4 pixel block of a tile (primary) or up to 32 queued bounces ----------------
         uint32_t b = 0, take = 32;
@@ -332,7 +332,7 @@ trace_rays_kernel(const __grid_constant__ SceneDev s, uint32_t n, const float *o
     constexpr int CAP = DimCap<DT>::value;
     const int D = NTR_D(DT, s);
     MailboxStore ms;
-    ms.attach((FLAGS & NTR_F_GENERAL) ? s.mb_table : nullptr, s.mb_words, s.mb_threads, blockIdx.x * blockDim.x + threadIdx.x, s.n_simplex);
+    ms.attach((FLAGS & NTR_F_GENERAL) ? s.mb_table : nullptr, s.mb_words, s.mb_threads, blockIdx.x * blockDim.x + threadIdx.x, s.n_simplex, s.mb_shift);
     // grid-stride: the host never launches more threads than the mailbox table has columns
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float o[CAP], dir[CAP];

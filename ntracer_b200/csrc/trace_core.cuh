@@ -466,12 +466,13 @@ struct MailboxStore {
     uint32_t stride;        // threads in the table
     uint32_t words;         // words per thread
     uint32_t gen;           // generation of the current traversal, 1..255
-    uint32_t solid_base;    // key of solid 0 (= number of simplex records)
+    uint32_t solid_base;    // key of solid 0
+    uint32_t shift;         // SceneDev::mb_shift
     // bind to thread `tid` of the scene's table; the generation counter of the column survives between launches in the
     // word behind its bit words (a column starts all zero: generation 0 is never current)
-    NTR_HD void attach(uint32_t *table, uint32_t n_words, uint32_t n_threads, uint32_t tid, uint32_t n_simplex) {
+    NTR_HD void attach(uint32_t *table, uint32_t n_words, uint32_t n_threads, uint32_t tid, uint32_t n_simplex, uint32_t key_shift) {
         col = (table && tid < n_threads) ? table + tid : nullptr;
-        stride = n_threads; words = n_words; solid_base = n_simplex;
+        stride = n_threads; words = n_words; shift = key_shift; solid_base = (n_simplex >> key_shift) + 1;
         gen = col ? col[(size_t)words * stride] : 0u;
     }
     NTR_HD void detach() { if (col) col[(size_t)words * stride] = gen; }
@@ -481,7 +482,7 @@ struct MailboxStore {
             gen = 1u;
         }
     }
-    NTR_HD uint32_t key_of(uint32_t r) const { return (r >> 30) == NTR_REF_SOLID ? solid_base + (r & NTR_IDX_MASK) : (r & NTR_IDX_MASK); }
+    NTR_HD uint32_t key_of(uint32_t r) const { return (r >> 30) == NTR_REF_SOLID ? solid_base + (r & NTR_IDX_MASK) : (r & NTR_IDX_MASK) >> shift; }
     NTR_HD bool has(uint32_t r) const {
         const uint32_t k = key_of(r), w = col[(size_t)(k / NTR_MAILBOX_BITS_PER_WORD) * stride];
         return (w >> 24) == gen && ((w >> (k % NTR_MAILBOX_BITS_PER_WORD)) & 1u);

@@ -140,7 +140,9 @@ void setup(Scene &S, const ntr_scene_desc *d, const float *cam_origin, const flo
 #endif
         if ((S.flags & NTR_F_GENERAL) && (max_leaf > NTR_MAILBOX_CAP || NTR_EMUL_EXACT_MAILBOX_ALWAYS) && keys <= NTR_MAILBOX_MAX_KEYS) {
             S.dev.mb_threads = 32;
-            S.dev.mb_words = (uint32_t)((keys + NTR_MAILBOX_BITS_PER_WORD - 1) / NTR_MAILBOX_BITS_PER_WORD);
+            S.dev.mb_shift = mailbox_key_shift(d);
+            const uint64_t nk = ((uint64_t)d->n_simplex >> S.dev.mb_shift) + 1 + d->n_solids;
+            S.dev.mb_words = (uint32_t)((nk + NTR_MAILBOX_BITS_PER_WORD - 1) / NTR_MAILBOX_BITS_PER_WORD);
             S.mailbox.assign((size_t)(S.dev.mb_words + 1) * S.dev.mb_threads, 0u);
             S.dev.mb_table = S.mailbox.data();
         }
@@ -166,7 +168,7 @@ void render_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dists, un
     std::vector<uint32_t> qp, qpn;
     const float one[3] = {1, 1, 1};
     MailboxStore ms;
-    ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex);
+    ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex, S.dev.mb_shift);
     for (int y = 0; y < h; ++y) {
         for (int x = 0; x < w; ++x) {
             const uint32_t pix = (uint32_t)y * w + x;
@@ -240,7 +242,7 @@ void render_warp_t(Scene &S, int w, int h, float *rgb, int32_t *ids, float *dist
                 warp_emu::lane = L;
                 warp_emu::warp = &W;
                 MailboxStore ms;
-                ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, (uint32_t)L, S.dev.n_simplex);
+                ms.attach(S.dev.mb_table, S.dev.mb_words, S.dev.mb_threads, (uint32_t)L, S.dev.n_simplex, S.dev.mb_shift);
                 for (size_t base = 0; base < n; base += 32) {
                     const size_t idx = base + L;
                     const bool enabled = idx < n;
@@ -328,7 +330,7 @@ void trace_t(Scene &S, uint32_t n, const float *origins, const float *dirs, floa
              int max_hits = 0, int32_t *hit_ids = nullptr, float *hit_dists = nullptr) {
     const int D = S.dev.dim;
     MailboxStore ms;
-    ms.attach((FLAGS & NTR_F_GENERAL) ? S.dev.mb_table : nullptr, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex);
+    ms.attach((FLAGS & NTR_F_GENERAL) ? S.dev.mb_table : nullptr, S.dev.mb_words, S.dev.mb_threads, 0, S.dev.n_simplex, S.dev.mb_shift);
     for (uint32_t i = 0; i < n; ++i) {
         Skip skip = {skip_ref ? skip_ref[i] : NTR_NONE_REF, skip_lane ? skip_lane[i] : -1};
         GenState<DT> g;
