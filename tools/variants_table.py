@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""Collects every tools/quick.py measurement of the round (gpurun_out/r02*/q_*.json) into profiles/r02_variants.md."""
+import glob
+import json
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CALLS = {
+    'r02': ('call 1', 'round-1 kernels as they were: baseline, the round-1 cooperative variant (tail only), 80/96-register builds, direct-mapped single-simplex tables (sm64/sm256)'),
+    'r02b': ('call 2', 'first warp-synchronous path (parking at every big leaf, warp-uniform shading) + open-addressing mailbox: w80/w96 = register budgets, lm32/lm96 = leaf threshold, oh8 = overhead term, nocoop = never park'),
+    'r02c': ('call 3', 'INVALID for bounce passes: the abort flag (mapped host memory) was polled on the first fetch of every warp; kept for the record'),
+    'r02d': ('call 4', 'p0 = every lane for itself, w1 = warp nearest-hit traversal + per-lane shading, w2 = + warp-uniform shading, w1r = w1 at 80 registers; noaf = no adaptive fetch, nohf = no heavy-first order, fABC = rays per fetch from cost rings 0/1/2; *s = fetch-duration statistics build'),
+    'r02e': ('call 5', 'wXmY: X = NTR_WARP (0 per lane, 1 warp form), Y = NTR_EXACT_MAILBOX; def = defaults of that commit (warp form for every pass of big-leaf scenes)'),
+    'r02g': ('call 7', 'word-grouped item tables + sparse scan of big leaves (reverted): w0/w1/w2 = NTR_WARP'),
+    'r02h': ('call 8', 'shared-memory axis tables from 9 dimensions on (noaxis = without)'),
+    'r02i': ('call 9', 'exact mailbox table for opaque scenes as well (reverted; nomb = without)'),
+    'r02j': ('call 10', 'quarter-size mailbox table (keys >> 2): the shipped code'),
+    'r02k': ('call 11', 'thresholds of the cooperative leaves on the shipped code: md = NTR_COOP_MIN_DONE, lm = NTR_COOP_LEAF_MIN, cc = NTR_COOP_CHUNK_COST'),
+}
+
+
+def main():
+    out = ['# Round 2: every A/B measurement (`tools/quick.py`, device ms per frame, median of 5 after 3 warm-up frames, L2 flushed)\n',
+           '`_w8` / `_w4` / `_w2` = one GPU rendering only the tile rows rank 0 of 8 / 4 / 2 would own (what bounds the N-GPU frame).',
+           'Configs: c2 = {5,3,3} 1080p shadows; c3 = 6-D solids 1080p; c4 = {5/2,3,3} 4K reflections + transparency; c4o = its opaque',
+           'variant; c4b = {5/2,5,3} 4K; c5s = 10-D soup, 16 k simplexes, 4K; c5 = 1 M simplexes.  Round-1 values: c2 0.745, c3 0.536,',
+           'c4 57.6, c4o 31.1, c5s 23.3, c5 1320 ms; c4_w8 25.5 ms.\n']
+    for d, (call, what) in CALLS.items():
+        files = sorted(glob.glob(os.path.join(ROOT, 'gpurun_out', d, 'q_*.json')))
+        if not files:
+            continue
+        out.append('## %s (`gpurun_out/%s/`)\n\n%s\n' % (call, d, what))
+        out.append('| run | ms (median) | ms (min) |\n|---|---|---|')
+        for f in files:
+            try:
+                j = json.load(open(f))
+            except Exception:
+                continue
+            name = os.path.basename(f)[2:-5]
+            out.append('| %s | %.3f | %.3f |' % (name, j['ms_median'], j['ms_min']))
+        passes = []
+        for f in sorted(glob.glob(os.path.join(ROOT, 'gpurun_out', d, 'q_c4*.err'))):
+            lines = [l for l in open(f, errors='replace').read().splitlines() if l.startswith('ntr pass ms')]
+            if lines:
+                passes.append('`%s`: %s' % (os.path.basename(f)[2:-4], lines[-1][len('ntr pass ms:'):].strip()))
+        if passes:
+            out.append('\nper-pass ms (primary, bounces 1-4) and rays per bounce pass, config 4:\n')
+            out += ['* ' + p for p in passes]
+        out.append('')
+    open(os.path.join(ROOT, 'profiles', 'r02_variants.md'), 'w').write('\n'.join(out) + '\n')
+
+
+if __name__ == '__main__':
+    main()
