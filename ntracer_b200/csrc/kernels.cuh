@@ -36,13 +36,22 @@ template <int DT> struct QueueEmit {
         const int leader = __ffs(mask) - 1;
         const int lane = threadIdx.x & 31;
         uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(q.out_count, (uint32_t)__popc(mask));
+        if (lane == leader) {
+            const uint32_t n = (uint32_t)__popc(mask);
+            base = atomicAdd(q.out_merged ? q.m_tail : q.out_count, n);
+            if (q.out_merged) {         // the rays that fit count as pending until a consumer has finished them
+                const uint32_t fit = base >= q.capacity ? 0u : min(n, q.capacity - base);
+                if (fit) atomicAdd(q.m_pending, fit);
+            }
+        }
         base = __shfl_sync(mask, base, leader);
         const uint32_t idx = base + (uint32_t)__popc(mask & lanemask_lt());
         if (idx >= q.capacity) { *ctl.overflow = 1u; return; }
         float4 *rec = q.out + (size_t)idx * q.rec4;
-        rec[0] = make_float4(__uint_as_float(pixel), __uint_as_float(b.skip.ref),
-                             __int_as_float((b.skip.lane & 0xFFFF) | (b.depth << 16)), 0.0f);
+        const float4 head = make_float4(__uint_as_float(pixel), __uint_as_float(b.skip.ref),
+                                        __int_as_float((b.skip.lane & 0xFFFF) | (b.depth << 16)),
+                                        __uint_as_float(q.out_merged ? q.epoch : 0u));
+        if (!q.out_merged) rec[0] = head;
         rec[1] = make_float4(b.w[0], b.w[1], b.w[2], 0.0f);
         constexpr int CAP = DimCap<DT>::value;
         const int D4 = (int)(q.rec4 - 2) / 2;       // float4s per vector
@@ -57,6 +66,10 @@ template <int DT> struct QueueEmit {
                 rec[2 + k] = vo;
                 rec[2 + D4 + k] = vd;
             }
+        }
+        if (q.out_merged) {             // publish: the tagged head word goes last, behind a fence
+            __threadfence();
+            __stcg(rec, head);
         }
     }
 };
@@ -146,17 +159,52 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                             ? (f.tiles_y - f.tile_row_first + f.tile_row_step - 1) / f.tile_row_step : 0;
     uint32_t total = (uint32_t)my_rows * (uint32_t)f.tiles_x * NTR_BLOCKS_PER_TILE;
     const int D4 = (int)(q.rec4 - 2) / 2;
-    if (!primary) {
+    if (!primary && !q.in_merged) {
         total = *q.in_count;
         if (total > q.capacity) total = q.capacity;
     }
     uint32_t fetches = 0;
+    // merged bounce kernel: the 32 queue slots this warp owns, which of them it has processed, and how long it has waited
+    uint32_t m_base = 0, m_done = 0xFFFFFFFFu, m_spins = 0;
     MailboxStore ms;                    // this thread's column of the exact mailbox (scenes with big leaves), if any
     ms.attach((FLAGS & NTR_F_GENERAL) ? s.mb_table : nullptr, s.mb_words, s.mb_threads, blockIdx.x * blockDim.x + threadIdx.x, s.n_simplex, s.mb_shift);
     for (;;) {
         // ---------------- fetch: an 8x4 pixel block of a tile (primary) or up to 32 queued bounces ----------------
         uint32_t b = 0, take = 32;
-        if (lane == 0) {
+        bool m_ready = false;
+        if (!primary && q.in_merged) {
+            // ---- one launch for every remaining depth: the queue grows while it is consumed ----
+            // A warp owns 32 consecutive slots and processes whichever of them are published (tag word == epoch), as
+            // they come -- a ready ray is never held back by an unfilled neighbour, so the rays that produce the next
+            // ones always make progress.  Nothing ready: if no ray is in flight anywhere (m_pending == 0) nothing will
+            // ever be appended again (a published ray in this warp's range would still count as pending), so the warp
+            // is finished; otherwise it naps and looks again.
+            if (m_done == 0xFFFFFFFFu) {
+                if (lane == 0) m_base = atomicAdd(q.in_cursor, 32u);
+                m_base = __shfl_sync(0xFFFFFFFFu, m_base, 0);
+                m_done = 0;
+            }
+            const uint32_t tail = min(*(volatile uint32_t *)q.m_tail, q.capacity);
+            const uint32_t slot = m_base + (uint32_t)lane;
+            if (!((m_done >> lane) & 1u) && slot < tail)
+                m_ready = ((volatile uint32_t *)(q.in + (size_t)slot * q.rec4))[3] == q.epoch;
+            const unsigned rm = __ballot_sync(0xFFFFFFFFu, m_ready);
+            if (!rm) {
+                uint32_t stop = 0;
+                if (lane == 0) {
+                    if (*(volatile uint32_t *)q.m_pending == 0) stop = 1;
+                    else if ((++m_spins & 63u) == 0 && *ctl.abort_flag) stop = 1;
+                    else if (m_spins > (1u << 24)) { stop = 1; *ctl.overflow = 2u; }       // stalled: reported, never a hang
+                }
+                if (__shfl_sync(0xFFFFFFFFu, stop, 0)) break;
+                __nanosleep(200);
+                continue;
+            }
+            __threadfence();            // the records behind the tags just seen are read after this point
+            m_done |= rm;
+            b = m_base;
+            m_spins = 0;
+        } else if (lane == 0) {
             if (primary) b = atomicAdd(ctl.tile_cursor, 1u);
             else {
                 if (q.ring_start) {
@@ -171,9 +219,11 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                 b = atomicAdd(q.in_cursor, take);
             }
         }
-        b = __shfl_sync(0xFFFFFFFFu, b, 0);
-        take = __shfl_sync(0xFFFFFFFFu, take, 0);
-        if (b >= total) break;
+        if (primary || !q.in_merged) {
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            take = __shfl_sync(0xFFFFFFFFu, take, 0);
+            if (b >= total) break;
+        }
         // renderer::state poll (reference render.cpp:412).  The flag lives in mapped host memory, so only every
         // 512th block / every 64th fetch of a warp looks at it (ncu: at every 64th block the PCIe read was 2.9 % of all
         // stall samples); whoever sees it pushes the cursor past the end for everybody.
@@ -183,7 +233,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
 #endif
         // (bounce passes: the fetch whose range crosses a multiple of 8192 rays looks, whatever its size)
         if ((primary ? (b & 511u) == 0 : (b & 8191u) < take) && *ctl.abort_flag) {
-            if (lane == 0) atomicAdd(primary ? ctl.tile_cursor : q.in_cursor, 0x40000000u);
+            if (lane == 0 && (primary || !q.in_merged)) atomicAdd(primary ? ctl.tile_cursor : q.in_cursor, 0x40000000u);
             break;
         }
         float o[CAP], dir[CAP];
@@ -224,9 +274,10 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
             }
         } else {
             const uint32_t idx = b + lane;
-            if ((uint32_t)lane < take && idx < total) {
+            if (q.in_merged ? m_ready : ((uint32_t)lane < take && idx < total)) {
+                // (merged queue: the records were written by other SMs during this launch -- read them past L1)
                 const float4 *rec = q.in + (size_t)((q.in_perm && idx < q.n_sorted) ? __ldg(q.in_perm + idx) : idx) * q.rec4;
-                const float4 h = rec[0], wv = rec[1];
+                const float4 h = q.in_merged ? __ldcg(rec) : rec[0], wv = q.in_merged ? __ldcg(rec + 1) : rec[1];
                 pix = __float_as_uint(h.x);
                 skip.ref = __float_as_uint(h.y);
                 const int ld = __float_as_int(h.z);
@@ -236,7 +287,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
 #pragma unroll
                 for (int k = 0; k < (CAP + 3) / 4; ++k) {
                     if (k < D4) {
-                        const float4 vo = rec[2 + k], vd = rec[2 + D4 + k];
+                        const float4 vo = q.in_merged ? __ldcg(rec + 2 + k) : rec[2 + k], vd = q.in_merged ? __ldcg(rec + 2 + D4 + k) : rec[2 + D4 + k];
                         if (4 * k + 0 < CAP) { o[4 * k + 0] = vo.x; dir[4 * k + 0] = vd.x; }
                         if (4 * k + 1 < CAP) { o[4 * k + 1] = vo.y; dir[4 * k + 1] = vd.y; }
                         if (4 * k + 2 < CAP) { o[4 * k + 2] = vo.z; dir[4 * k + 2] = vd.z; }
@@ -283,6 +334,10 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                 atomicAdd(f.accum + (size_t)pix * 3 + 0, acc[0]);
                 atomicAdd(f.accum + (size_t)pix * 3 + 1, acc[1]);
                 atomicAdd(f.accum + (size_t)pix * 3 + 2, acc[2]);
+            }
+            if (q.in_merged) {          // these rays are complete (their own bounces were counted when they were emitted)
+                const unsigned fin = __ballot_sync(0xFFFFFFFFu, active);
+                if (lane == 0 && fin) atomicSub(q.m_pending, (uint32_t)__popc(fin));
             }
             continue;
         }

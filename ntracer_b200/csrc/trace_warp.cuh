@@ -36,7 +36,8 @@ namespace ntr {
 #define NTR_COOP_OVERHEAD 3         // cost of serving one parked ray (broadcast + fold), in units of one item test
 #endif
 #ifndef NTR_COOP_CHUNK_COST
-#define NTR_COOP_CHUNK_COST 2       // cost of one cooperative 32-item chunk (test + votes + fold), in units of one item test
+#define NTR_COOP_CHUNK_COST 3       // cost of one cooperative 32-item chunk (test + votes + fold), in units of one item test
+                                    // (measured, config 4: 1 -> 45.6 ms, 2 -> 44.0, 3 -> 43.5; the other thresholds move it by < 1 %)
 #endif
 #ifndef NTR_COOP_MIN_DONE
 #define NTR_COOP_MIN_DONE 16        // a ray parks at a big leaf only while at least this many lanes of its warp have nothing

@@ -123,6 +123,21 @@ def test_stream_pinned_destination_ticket_rules_and_abort():
         t4 = ds.render_begin(fmt, pinned[0].numpy())            # the next frame starts clean
         ds.render_end(t4)
         assert np.array_equal(pinned[0].numpy(), ref)
+        # ... also in the steady state of the pipelined loop, where a frame is always open: one abort
+        # word per frame -- the abort hits a and b, c is begun afterwards and must come out whole
+        for p in pinned:
+            p.fill_(0xAB)
+        ta = ds.render_begin(fmt, pinned[0].numpy())
+        tb = ds.render_begin(fmt, pinned[1].numpy())
+        ds.abort()
+        with pytest.raises(_capi.AbortedError):
+            ds.render_end(ta)
+        tc = ds.render_begin(fmt, pinned[2].numpy())            # b is still open
+        with pytest.raises(_capi.AbortedError):
+            ds.render_end(tb)
+        ds.render_end(tc)
+        assert np.array_equal(pinned[2].numpy(), ref)
+        assert np.array_equal(ds.render(fmt, np.full(fmt.pitch * h, 0xAB, np.uint8)), ref)     # a synchronous call does not care either
 
 
 def _rotation_golden():
