@@ -52,8 +52,9 @@ constexpr int kMaxPasses = 64;          // upper bound on max_reflect_depth hand
 // control block layout (uint32 words)
 constexpr int kSlabMax = 4;
 enum { CTL_TILE_CURSOR = 0, CTL_OVERFLOW = 1, CTL_COUNT0 = 2, CTL_CURSOR0 = CTL_COUNT0 + kMaxPasses + 1,
-       CTL_M_TAIL = CTL_CURSOR0 + kMaxPasses + 1, CTL_M_PENDING, CTL_M_HEAD,        // the merged bounce queue
-       CTL_WORDS = CTL_M_HEAD + 1 };
+       // the merged bounce queue: polled by waiting warps while busy warps update it, a 128-byte line per word
+       CTL_M_TAIL = (CTL_CURSOR0 + kMaxPasses + 1 + 31) / 32 * 32, CTL_M_PENDING = CTL_M_TAIL + 32, CTL_M_HEAD = CTL_M_PENDING + 32,
+       CTL_M_IDLE = CTL_M_HEAD + 32, CTL_WORDS = CTL_M_IDLE + 32 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -479,6 +480,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     q.out_merged = d0 == 1;
     q.m_tail = d_ctl + CTL_M_TAIL;
     q.m_pending = d_ctl + CTL_M_PENDING;
+    q.m_idle = d_ctl + CTL_M_IDLE;
     q.epoch = sc->epoch;
     q.out_count = d_ctl + CTL_COUNT0 + 1;
     q.in_count = q.in_cursor = nullptr;

@@ -114,6 +114,7 @@ struct QueueDev {
     // the same launch consumes it; a record is published by its tag word (rec[0].w == epoch, written last).
     uint32_t *m_tail;               // records reserved by producers so far (out_merged: the queue `out` is this one)
     uint32_t *m_pending;            // rays emitted and not yet completed: 0 = nothing more will ever be appended
+    uint32_t *m_idle;               // warps polling the empty queue
     uint32_t epoch;                 // tag of this frame's records (never 0)
     int out_merged;                 // emit into the merged queue (tagged records, m_tail / m_pending accounting)
     int in_merged;                  // this launch consumes the merged queue (in == out, in_cursor = head)

@@ -128,6 +128,12 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 #ifndef NTR_MIN_CTAS
 #define NTR_MIN_CTAS 8
 #endif
+#ifndef NTR_MERGE_NAP_MAX
+#define NTR_MERGE_NAP_MAX 25600     // ns: longest pause between two looks of an idle warp at the merged queue
+#endif
+#ifndef NTR_MERGE_IDLE_MIN
+#define NTR_MERGE_IDLE_MIN 64       // idle warps that always stay with the merged queue
+#endif
 #ifndef NTR_FETCH_STATS
 #define NTR_FETCH_STATS 0          // diagnostic: per-fetch durations (see ControlDev::fetch_stats); never in the shipped build
 #endif
@@ -165,7 +171,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
     }
     uint32_t fetches = 0;
     // merged bounce kernel: the 32 queue slots this warp owns, which of them it has processed, and how long it has waited
-    uint32_t m_base = 0, m_done = 0xFFFFFFFFu, m_spins = 0;
+    uint32_t m_base = 0, m_done = 0xFFFFFFFFu, m_spins = 0, m_idle = 0;
     MailboxStore ms;                    // this thread's column of the exact mailbox (scenes with big leaves), if any
     ms.attach((FLAGS & NTR_F_GENERAL) ? s.mb_table : nullptr, s.mb_words, s.mb_threads, blockIdx.x * blockDim.x + threadIdx.x, s.n_simplex, s.mb_shift);
     for (;;) {
@@ -174,31 +180,72 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
         bool m_ready = false;
         if (!primary && q.in_merged) {
             // ---- one launch for every remaining depth: the queue grows while it is consumed ----
-            // A warp owns 32 consecutive slots and processes whichever of them are published (tag word == epoch), as
-            // they come -- a ready ray is never held back by an unfilled neighbour, so the rays that produce the next
-            // ones always make progress.  Nothing ready: if no ray is in flight anywhere (m_pending == 0) nothing will
-            // ever be appended again (a published ray in this warp's range would still count as pending), so the warp
-            // is finished; otherwise it naps and looks again.
+            // m_tail = slots reserved by producers (published a moment later: tag word == epoch), in_cursor = slots
+            // reserved by consumers, m_pending = rays emitted and not yet completed (queued + being traced); each of
+            // the three has a cache line of its own (capi.cu) because waiting warps poll them while busy warps update them.
+            // A free warp reserves the next 32 slots when at least one of them is taken (the check is not atomic with the
+            // reservation, so a range may still lie beyond the tail) and traces them when the whole range is filled --
+            // 32 rays together, not as they trickle in.  A range that is only partly filled is traced when nothing else
+            // is in flight anywhere (pending == the rays waiting in it: ranges fill in order, so it is the last one and
+            // no more can come before these are traced).  With nothing queued a warp idles, polling ever more slowly;
+            // only as many warps idle as the rays in flight can feed (each emits at most two), the others leave.
             if (m_done == 0xFFFFFFFFu) {
-                if (lane == 0) m_base = atomicAdd(q.in_cursor, 32u);
+                uint32_t got = 0;           // 0 = nothing queued: idle, 1 = range reserved, 2 = finished
+                if (lane == 0) {
+                    const uint32_t head = *(volatile uint32_t *)q.in_cursor, tail = min(*(volatile uint32_t *)q.m_tail, q.capacity);
+                    if (tail > head) {
+                        m_base = atomicAdd(q.in_cursor, 32u);
+                        got = 1;
+                        if (m_idle) { atomicSub(q.m_idle, 1u); m_idle = 0; }
+                    } else {
+                        const uint32_t pending = *(volatile uint32_t *)q.m_pending;
+                        if (pending == 0) got = 2;
+                        else if (!m_idle) {
+                            if (atomicAdd(q.m_idle, 1u) >= pending / 16u + NTR_MERGE_IDLE_MIN) { atomicSub(q.m_idle, 1u); got = 2; }
+                            else m_idle = 1;
+                        }
+                        if (got == 0) {
+                            if ((++m_spins & 63u) == 0 && *ctl.abort_flag) got = 2;
+                            else if (m_spins > (1u << 20)) { got = 2; *ctl.overflow = 2u; }     // stalled: reported, never a hang
+                        }
+                    }
+                }
+                got = __shfl_sync(0xFFFFFFFFu, got, 0);
+                if (got == 2) break;
+                if (got == 0) {
+                    m_spins = __shfl_sync(0xFFFFFFFFu, m_spins, 0);
+                    __nanosleep(min(400u << min(m_spins, 8u), (uint32_t)NTR_MERGE_NAP_MAX));
+                    continue;
+                }
                 m_base = __shfl_sync(0xFFFFFFFFu, m_base, 0);
                 m_done = 0;
+                m_spins = 0;
             }
             const uint32_t tail = min(*(volatile uint32_t *)q.m_tail, q.capacity);
             const uint32_t slot = m_base + (uint32_t)lane;
-            if (!((m_done >> lane) & 1u) && slot < tail)
-                m_ready = ((volatile uint32_t *)(q.in + (size_t)slot * q.rec4))[3] == q.epoch;
-            const unsigned rm = __ballot_sync(0xFFFFFFFFu, m_ready);
-            if (!rm) {
-                uint32_t stop = 0;
+            const bool want = !((m_done >> lane) & 1u) && slot < tail;
+            if (want) m_ready = ((volatile uint32_t *)(q.in + (size_t)slot * q.rec4))[3] == q.epoch;
+            const unsigned wm = __ballot_sync(0xFFFFFFFFu, want), rm = __ballot_sync(0xFFFFFFFFu, m_ready);
+            uint32_t go = (wm && rm == wm) ? 1u : 0u;
+            if (!go || tail < m_base + 32u) {
                 if (lane == 0) {
-                    if (*(volatile uint32_t *)q.m_pending == 0) stop = 1;
-                    else if ((++m_spins & 63u) == 0 && *ctl.abort_flag) stop = 1;
-                    else if (m_spins > (1u << 24)) { stop = 1; *ctl.overflow = 2u; }       // stalled: reported, never a hang
+                    const uint32_t pending = *(volatile uint32_t *)q.m_pending;
+                    if (go) go = pending == (uint32_t)__popc(rm) ? 1u : 0u;
+                    if (!go) {
+                        if (pending == 0) go = 2;                                   // nothing queued or traced anywhere: finished
+                        else if ((++m_spins & 63u) == 0 && *ctl.abort_flag) go = 2;
+                        else if (m_spins > (1u << 20)) { go = 2; *ctl.overflow = 2u; }
+                    }
                 }
-                if (__shfl_sync(0xFFFFFFFFu, stop, 0)) break;
-                __nanosleep(200);
-                continue;
+                go = __shfl_sync(0xFFFFFFFFu, go, 0);
+                if (go == 2) break;
+                if (go == 0) {
+                    m_ready = false;
+                    m_spins = __shfl_sync(0xFFFFFFFFu, m_spins, 0);
+                    // a range that is filling is watched closely, one that lies beyond the tail as slowly as idle warps do
+                    __nanosleep(tail > m_base ? 400u : min(400u << min(m_spins, 8u), (uint32_t)NTR_MERGE_NAP_MAX));
+                    continue;
+                }
             }
             __threadfence();            // the records behind the tags just seen are read after this point
             m_done |= rm;
