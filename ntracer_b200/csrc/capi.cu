@@ -52,9 +52,7 @@ constexpr int kMaxPasses = 64;          // upper bound on max_reflect_depth hand
 // control block layout (uint32 words)
 constexpr int kSlabMax = 4;
 enum { CTL_TILE_CURSOR = 0, CTL_OVERFLOW = 1, CTL_COUNT0 = 2, CTL_CURSOR0 = CTL_COUNT0 + kMaxPasses + 1,
-       // the merged bounce queue: polled by waiting warps while busy warps update it, a 128-byte line per word
-       CTL_M_TAIL = (CTL_CURSOR0 + kMaxPasses + 1 + 31) / 32 * 32, CTL_M_PENDING = CTL_M_TAIL + 32, CTL_M_HEAD = CTL_M_PENDING + 32,
-       CTL_M_IDLE = CTL_M_HEAD + 32, CTL_WORDS = CTL_M_IDLE + 32 };
+       CTL_WORDS = CTL_CURSOR0 + kMaxPasses + 1 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -112,13 +110,7 @@ struct ntr_scene {
     float *d_accum = nullptr; size_t accum_cap = 0;
     unsigned char *d_packed = nullptr; size_t packed_cap = 0;
     int32_t *d_ids = nullptr; float *d_dists = nullptr; size_t ids_cap = 0;
-    float4 *d_queue[3] = {nullptr, nullptr, nullptr};      // [0], [1]: ping-pong of the per-depth passes; [2]: the merged queue
-    // One launch for every bounce depth from merge_from on (0 = a launch per depth): the queue is consumed while it grows,
-    // so idle warps go on with the next depth's rays instead of waiting for the slowest warp of this one.  No re-binning
-    // of those rays.  Default: sharded renders (a share of the frame per GPU: its passes are too small to fill the
-    // machine and end in long tails) merge from depth 1, whole frames keep a sorted launch per depth.  NTR_MERGE_FROM=d.
-    int merge_from = -1;                // -1 = by the rule above
-    uint32_t epoch = 0;                 // tag of the current frame's records in the merged queue
+    float4 *d_queue[2] = {nullptr, nullptr};
     uint32_t queue_capacity = 0;
     void *d_scratch = nullptr; size_t scratch_cap = 0;
     // cost-sorted tile schedule (valid for one window / interleave geometry at a time)
@@ -305,11 +297,10 @@ int ensure(void **p, size_t *cap, size_t need) {
 
 int ensure_queues(ntr_scene *sc, uint32_t capacity) {
     if (sc->queue_capacity >= capacity && sc->d_queue[0]) return NTR_OK;
-    for (int i = 0; i < 3; ++i) if (sc->d_queue[i]) { cudaFree(sc->d_queue[i]); sc->d_queue[i] = nullptr; }
+    for (int i = 0; i < 2; ++i) if (sc->d_queue[i]) { cudaFree(sc->d_queue[i]); sc->d_queue[i] = nullptr; }
     sc->queue_capacity = 0;
     const uint32_t rec4 = 2 + 2 * ((sc->dev.dim + 3) / 4);
-    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaMalloc(&sc->d_queue[i], (size_t)capacity * rec4 * sizeof(float4)));
-    CUDA_TRY(cudaMemset(sc->d_queue[2], 0, (size_t)capacity * rec4 * sizeof(float4)));          // no record carries a tag yet
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaMalloc(&sc->d_queue[i], (size_t)capacity * rec4 * sizeof(float4)));
     sc->queue_capacity = capacity;
     return NTR_OK;
 }
@@ -471,17 +462,8 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     QueueDev q;
     memset(&q, 0, sizeof q);
     q.capacity = sc->queue_capacity; q.rec4 = rec4;
-    // bounce depths from d0 on share one launch (see ntr_scene::merge_from); d0 > max_depth: a launch per depth
-    int d0 = sc->merge_from >= 0 ? sc->merge_from : (f.tile_row_step > 1 ? 1 : 0);
-    if (d0 <= 0 || !passes) d0 = kMaxPasses + 8;
-    if (++sc->epoch == 0) sc->epoch = 1;
     q.in = nullptr;
-    q.out = d0 == 1 ? sc->d_queue[2] : sc->d_queue[0];
-    q.out_merged = d0 == 1;
-    q.m_tail = d_ctl + CTL_M_TAIL;
-    q.m_pending = d_ctl + CTL_M_PENDING;
-    q.m_idle = d_ctl + CTL_M_IDLE;
-    q.epoch = sc->epoch;
+    q.out = sc->d_queue[0];
     q.out_count = d_ctl + CTL_COUNT0 + 1;
     q.in_count = q.in_cursor = nullptr;
     auto mark = [&]() {
@@ -507,21 +489,8 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     }
     if (passes) {
         for (int depth = 1; depth <= sc->dev.max_depth; ++depth) {
-            if (depth >= d0) {
-                // every remaining depth in one launch: the merged queue is read and appended to at the same time
-                q.in = q.out = sc->d_queue[2];
-                q.in_merged = q.out_merged = 1;
-                q.in_count = q.out_count = nullptr;
-                q.in_cursor = d_ctl + CTL_M_HEAD;
-                q.in_perm = nullptr; q.n_sorted = 0; q.ring_start = nullptr;
-                sc->kset(bounce_flags)->render_pass(dim3(grid_for(sc, bounce_flags)), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
-                ++sc->launches;
-                mark();
-                break;
-            }
             q.in = sc->d_queue[(depth - 1) & 1];
-            q.out = depth + 1 == d0 ? sc->d_queue[2] : sc->d_queue[depth & 1];
-            q.out_merged = depth + 1 == d0;
+            q.out = sc->d_queue[depth & 1];
             q.in_count = d_ctl + CTL_COUNT0 + depth;
             q.out_count = d_ctl + CTL_COUNT0 + depth + 1;
             q.in_cursor = d_ctl + CTL_CURSOR0 + depth;
@@ -636,7 +605,6 @@ int frame_collect(ntr_scene *sc, FrameJob &j, bool *again) {
         cudaEventElapsedTime(&ms, sc->pass_ev[1], sc->pass_ev[sc->n_pass_ev - 1]);
         uint64_t rays = 0;
         for (int d = 1; d <= sc->dev.max_depth && d <= kMaxPasses; ++d) rays += std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
-        rays += std::min(h_ctl[CTL_M_TAIL], sc->queue_capacity);
         if (rays > 0) sc->pass_ns_per_ray = ms * 1e6f / (float)rays;
     }
     if (j.passes) for (int d = 1; d <= kMaxPasses; ++d) sc->prev_pass_count[d] = std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
@@ -649,7 +617,6 @@ int frame_collect(ntr_scene *sc, FrameJob &j, bool *again) {
         }
         fprintf(stderr, "  rays:");
         for (int d = 1; d <= sc->dev.max_depth + 1 && d <= kMaxPasses; ++d) fprintf(stderr, " %u", h_ctl[CTL_COUNT0 + d]);
-        if (h_ctl[CTL_M_TAIL]) fprintf(stderr, "  merged: %u", h_ctl[CTL_M_TAIL]);
         fprintf(stderr, "\n");
     }
     if (sc->h_abort[sc->abort_idx]) return fail(NTR_ERR_ABORTED, "render aborted");
@@ -669,8 +636,6 @@ int frame_collect(ntr_scene *sc, FrameJob &j, bool *again) {
     // a wavefront queue was too small: the counters say how many records were wanted
     uint32_t need = 0;
     for (int d = 1; d <= kMaxPasses; ++d) need = std::max(need, h_ctl[CTL_COUNT0 + d]);
-    need = std::max(need, h_ctl[CTL_M_TAIL]);
-    if (h_ctl[CTL_OVERFLOW] == 2u) return fail(NTR_ERR_RUNTIME, "the merged bounce queue stalled (rays pending, none published)");
     sc->counters.queue_overflows = overflows + 1;
     int rc = ensure_queues(sc, (uint32_t)std::min<uint64_t>((uint64_t)need * 2 + 1024, 0x7FFFFFFFu));
     if (rc) return rc;
@@ -962,7 +927,6 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->warp_path = sc->max_leaf >= 256 ? 1 : 0;
     sc->adaptive_fetch = false;         // measured (round 2 call 4): fewer rays per warp from the expensive rings loses everywhere
     if (const char *wp = getenv("NTR_WARP")) sc->warp_path = std::max(0, std::min(2, atoi(wp)));
-    if (const char *mf = getenv("NTR_MERGE_FROM")) sc->merge_from = std::max(0, atoi(mf));
     if (const char *hf = getenv("NTR_HEAVY_FIRST")) sc->heavy_first = atoi(hf) != 0;
     if (const char *af = getenv("NTR_ADAPTIVE_FETCH")) sc->adaptive_fetch = atoi(af) != 0;
     if (const char *fs = getenv("NTR_FETCH_SIZES")) {
@@ -1035,7 +999,7 @@ NTR_API void ntr_scene_destroy(ntr_scene *sc) {
     if (sc->stream) cudaStreamSynchronize(sc->stream);
     cudaFree(sc->arena); cudaFree(sc->d_lights); cudaFree(sc->d_ctl); cudaFree(sc->d_counters); cudaFree(sc->dev.mb_table);
     cudaFree(sc->d_accum); cudaFree(sc->d_packed); cudaFree(sc->d_ids); cudaFree(sc->d_dists);
-    cudaFree(sc->d_queue[0]); cudaFree(sc->d_queue[1]); cudaFree(sc->d_queue[2]); cudaFree(sc->d_scratch);
+    cudaFree(sc->d_queue[0]); cudaFree(sc->d_queue[1]); cudaFree(sc->d_scratch);
     cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order); cudaFree(sc->d_ring);
     cudaFree(sc->d_keys[0]); cudaFree(sc->d_keys[1]); cudaFree(sc->d_perm[0]); cudaFree(sc->d_perm[1]); cudaFree(sc->d_sort_tmp);
     if (sc->copy_stream) { cudaStreamSynchronize(sc->copy_stream); cudaStreamDestroy(sc->copy_stream); }

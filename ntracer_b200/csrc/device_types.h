@@ -110,14 +110,6 @@ struct QueueDev {
     const uint32_t *ring_start;     // optional (sorted, heavy-first passes): first sorted index of cost ring 1, 2, 3 at [1..3];
                                     // warps take fewer rays per fetch from the expensive rings (kernels.cuh)
     uint32_t fetch_sizes;           // rays per fetch from rings 0, 1, 2 (one byte each; ring 3 and unsorted passes: 32)
-    // The merged bounce kernel (one launch for every remaining depth, kernels.cuh): rays are appended to `out` while
-    // the same launch consumes it; a record is published by its tag word (rec[0].w == epoch, written last).
-    uint32_t *m_tail;               // records reserved by producers so far (out_merged: the queue `out` is this one)
-    uint32_t *m_pending;            // rays emitted and not yet completed: 0 = nothing more will ever be appended
-    uint32_t *m_idle;               // warps polling the empty queue
-    uint32_t epoch;                 // tag of this frame's records (never 0)
-    int out_merged;                 // emit into the merged queue (tagged records, m_tail / m_pending accounting)
-    int in_merged;                  // this launch consumes the merged queue (in == out, in_cursor = head)
     uint32_t capacity;              // in records
     uint32_t rec4;                  // record size in float4 units
 };

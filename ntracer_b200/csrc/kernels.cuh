@@ -36,22 +36,13 @@ template <int DT> struct QueueEmit {
         const int leader = __ffs(mask) - 1;
         const int lane = threadIdx.x & 31;
         uint32_t base = 0;
-        if (lane == leader) {
-            const uint32_t n = (uint32_t)__popc(mask);
-            base = atomicAdd(q.out_merged ? q.m_tail : q.out_count, n);
-            if (q.out_merged) {         // the rays that fit count as pending until a consumer has finished them
-                const uint32_t fit = base >= q.capacity ? 0u : min(n, q.capacity - base);
-                if (fit) atomicAdd(q.m_pending, fit);
-            }
-        }
+        if (lane == leader) base = atomicAdd(q.out_count, (uint32_t)__popc(mask));
         base = __shfl_sync(mask, base, leader);
         const uint32_t idx = base + (uint32_t)__popc(mask & lanemask_lt());
         if (idx >= q.capacity) { *ctl.overflow = 1u; return; }
         float4 *rec = q.out + (size_t)idx * q.rec4;
-        const float4 head = make_float4(__uint_as_float(pixel), __uint_as_float(b.skip.ref),
-                                        __int_as_float((b.skip.lane & 0xFFFF) | (b.depth << 16)),
-                                        __uint_as_float(q.out_merged ? q.epoch : 0u));
-        if (!q.out_merged) rec[0] = head;
+        rec[0] = make_float4(__uint_as_float(pixel), __uint_as_float(b.skip.ref),
+                             __int_as_float((b.skip.lane & 0xFFFF) | (b.depth << 16)), 0.0f);
         rec[1] = make_float4(b.w[0], b.w[1], b.w[2], 0.0f);
         constexpr int CAP = DimCap<DT>::value;
         const int D4 = (int)(q.rec4 - 2) / 2;       // float4s per vector
@@ -66,10 +57,6 @@ template <int DT> struct QueueEmit {
                 rec[2 + k] = vo;
                 rec[2 + D4 + k] = vd;
             }
-        }
-        if (q.out_merged) {             // publish: the tagged head word goes last, behind a fence
-            __threadfence();
-            __stcg(rec, head);
         }
     }
 };
@@ -128,12 +115,6 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 #ifndef NTR_MIN_CTAS
 #define NTR_MIN_CTAS 8
 #endif
-#ifndef NTR_MERGE_NAP_MAX
-#define NTR_MERGE_NAP_MAX 25600     // ns: longest pause between two looks of an idle warp at the merged queue
-#endif
-#ifndef NTR_MERGE_IDLE_MIN
-#define NTR_MERGE_IDLE_MIN 64       // idle warps that always stay with the merged queue
-#endif
 #ifndef NTR_FETCH_STATS
 #define NTR_FETCH_STATS 0          // diagnostic: per-fetch durations (see ControlDev::fetch_stats); never in the shipped build
 #endif
@@ -165,93 +146,17 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                             ? (f.tiles_y - f.tile_row_first + f.tile_row_step - 1) / f.tile_row_step : 0;
     uint32_t total = (uint32_t)my_rows * (uint32_t)f.tiles_x * NTR_BLOCKS_PER_TILE;
     const int D4 = (int)(q.rec4 - 2) / 2;
-    if (!primary && !q.in_merged) {
+    if (!primary) {
         total = *q.in_count;
         if (total > q.capacity) total = q.capacity;
     }
     uint32_t fetches = 0;
-    // merged bounce kernel: the 32 queue slots this warp owns, which of them it has processed, and how long it has waited
-    uint32_t m_base = 0, m_done = 0xFFFFFFFFu, m_spins = 0, m_idle = 0;
     MailboxStore ms;                    // this thread's column of the exact mailbox (scenes with big leaves), if any
     ms.attach((FLAGS & NTR_F_GENERAL) ? s.mb_table : nullptr, s.mb_words, s.mb_threads, blockIdx.x * blockDim.x + threadIdx.x, s.n_simplex, s.mb_shift);
     for (;;) {
         // ---------------- fetch: an 8x4 pixel block of a tile (primary) or up to 32 queued bounces ----------------
         uint32_t b = 0, take = 32;
-        bool m_ready = false;
-        if (!primary && q.in_merged) {
-            // ---- one launch for every remaining depth: the queue grows while it is consumed ----
-            // m_tail = slots reserved by producers (published a moment later: tag word == epoch), in_cursor = slots
-            // reserved by consumers, m_pending = rays emitted and not yet completed (queued + being traced); each of
-            // the three has a cache line of its own (capi.cu) because waiting warps poll them while busy warps update them.
-            // A free warp reserves the next 32 slots when at least one of them is taken (the check is not atomic with the
-            // reservation, so a range may still lie beyond the tail) and traces them when the whole range is filled --
-            // 32 rays together, not as they trickle in.  A range that is only partly filled is traced when nothing else
-            // is in flight anywhere (pending == the rays waiting in it: ranges fill in order, so it is the last one and
-            // no more can come before these are traced).  With nothing queued a warp idles, polling ever more slowly;
-            // only as many warps idle as the rays in flight can feed (each emits at most two), the others leave.
-            if (m_done == 0xFFFFFFFFu) {
-                uint32_t got = 0;           // 0 = nothing queued: idle, 1 = range reserved, 2 = finished
-                if (lane == 0) {
-                    const uint32_t head = *(volatile uint32_t *)q.in_cursor, tail = min(*(volatile uint32_t *)q.m_tail, q.capacity);
-                    if (tail > head) {
-                        m_base = atomicAdd(q.in_cursor, 32u);
-                        got = 1;
-                        if (m_idle) { atomicSub(q.m_idle, 1u); m_idle = 0; }
-                    } else {
-                        const uint32_t pending = *(volatile uint32_t *)q.m_pending;
-                        if (pending == 0) got = 2;
-                        else if (!m_idle) {
-                            if (atomicAdd(q.m_idle, 1u) >= pending / 16u + NTR_MERGE_IDLE_MIN) { atomicSub(q.m_idle, 1u); got = 2; }
-                            else m_idle = 1;
-                        }
-                        if (got == 0) {
-                            if ((++m_spins & 63u) == 0 && *ctl.abort_flag) got = 2;
-                            else if (m_spins > (1u << 20)) { got = 2; *ctl.overflow = 2u; }     // stalled: reported, never a hang
-                        }
-                    }
-                }
-                got = __shfl_sync(0xFFFFFFFFu, got, 0);
-                if (got == 2) break;
-                if (got == 0) {
-                    m_spins = __shfl_sync(0xFFFFFFFFu, m_spins, 0);
-                    __nanosleep(min(400u << min(m_spins, 8u), (uint32_t)NTR_MERGE_NAP_MAX));
-                    continue;
-                }
-                m_base = __shfl_sync(0xFFFFFFFFu, m_base, 0);
-                m_done = 0;
-                m_spins = 0;
-            }
-            const uint32_t tail = min(*(volatile uint32_t *)q.m_tail, q.capacity);
-            const uint32_t slot = m_base + (uint32_t)lane;
-            const bool want = !((m_done >> lane) & 1u) && slot < tail;
-            if (want) m_ready = ((volatile uint32_t *)(q.in + (size_t)slot * q.rec4))[3] == q.epoch;
-            const unsigned wm = __ballot_sync(0xFFFFFFFFu, want), rm = __ballot_sync(0xFFFFFFFFu, m_ready);
-            uint32_t go = (wm && rm == wm) ? 1u : 0u;
-            if (!go || tail < m_base + 32u) {
-                if (lane == 0) {
-                    const uint32_t pending = *(volatile uint32_t *)q.m_pending;
-                    if (go) go = pending == (uint32_t)__popc(rm) ? 1u : 0u;
-                    if (!go) {
-                        if (pending == 0) go = 2;                                   // nothing queued or traced anywhere: finished
-                        else if ((++m_spins & 63u) == 0 && *ctl.abort_flag) go = 2;
-                        else if (m_spins > (1u << 20)) { go = 2; *ctl.overflow = 2u; }
-                    }
-                }
-                go = __shfl_sync(0xFFFFFFFFu, go, 0);
-                if (go == 2) break;
-                if (go == 0) {
-                    m_ready = false;
-                    m_spins = __shfl_sync(0xFFFFFFFFu, m_spins, 0);
-                    // a range that is filling is watched closely, one that lies beyond the tail as slowly as idle warps do
-                    __nanosleep(tail > m_base ? 400u : min(400u << min(m_spins, 8u), (uint32_t)NTR_MERGE_NAP_MAX));
-                    continue;
-                }
-            }
-            __threadfence();            // the records behind the tags just seen are read after this point
-            m_done |= rm;
-            b = m_base;
-            m_spins = 0;
-        } else if (lane == 0) {
+        if (lane == 0) {
             if (primary) b = atomicAdd(ctl.tile_cursor, 1u);
             else {
                 if (q.ring_start) {
@@ -266,11 +171,9 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                 b = atomicAdd(q.in_cursor, take);
             }
         }
-        if (primary || !q.in_merged) {
-            b = __shfl_sync(0xFFFFFFFFu, b, 0);
-            take = __shfl_sync(0xFFFFFFFFu, take, 0);
-            if (b >= total) break;
-        }
+        b = __shfl_sync(0xFFFFFFFFu, b, 0);
+        take = __shfl_sync(0xFFFFFFFFu, take, 0);
+        if (b >= total) break;
         // renderer::state poll (reference render.cpp:412).  The flag lives in mapped host memory, so only every
         // 512th block / every 64th fetch of a warp looks at it (ncu: at every 64th block the PCIe read was 2.9 % of all
         // stall samples); whoever sees it pushes the cursor past the end for everybody.
@@ -280,7 +183,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
 #endif
         // (bounce passes: the fetch whose range crosses a multiple of 8192 rays looks, whatever its size)
         if ((primary ? (b & 511u) == 0 : (b & 8191u) < take) && *ctl.abort_flag) {
-            if (lane == 0 && (primary || !q.in_merged)) atomicAdd(primary ? ctl.tile_cursor : q.in_cursor, 0x40000000u);
+            if (lane == 0) atomicAdd(primary ? ctl.tile_cursor : q.in_cursor, 0x40000000u);
             break;
         }
         float o[CAP], dir[CAP];
@@ -321,10 +224,9 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
             }
         } else {
             const uint32_t idx = b + lane;
-            if (q.in_merged ? m_ready : ((uint32_t)lane < take && idx < total)) {
-                // (merged queue: the records were written by other SMs during this launch -- read them past L1)
+            if ((uint32_t)lane < take && idx < total) {
                 const float4 *rec = q.in + (size_t)((q.in_perm && idx < q.n_sorted) ? __ldg(q.in_perm + idx) : idx) * q.rec4;
-                const float4 h = q.in_merged ? __ldcg(rec) : rec[0], wv = q.in_merged ? __ldcg(rec + 1) : rec[1];
+                const float4 h = rec[0], wv = rec[1];
                 pix = __float_as_uint(h.x);
                 skip.ref = __float_as_uint(h.y);
                 const int ld = __float_as_int(h.z);
@@ -334,7 +236,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
 #pragma unroll
                 for (int k = 0; k < (CAP + 3) / 4; ++k) {
                     if (k < D4) {
-                        const float4 vo = q.in_merged ? __ldcg(rec + 2 + k) : rec[2 + k], vd = q.in_merged ? __ldcg(rec + 2 + D4 + k) : rec[2 + D4 + k];
+                        const float4 vo = rec[2 + k], vd = rec[2 + D4 + k];
                         if (4 * k + 0 < CAP) { o[4 * k + 0] = vo.x; dir[4 * k + 0] = vd.x; }
                         if (4 * k + 1 < CAP) { o[4 * k + 1] = vo.y; dir[4 * k + 1] = vd.y; }
                         if (4 * k + 2 < CAP) { o[4 * k + 2] = vo.z; dir[4 * k + 2] = vd.z; }
@@ -381,10 +283,6 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
                 atomicAdd(f.accum + (size_t)pix * 3 + 0, acc[0]);
                 atomicAdd(f.accum + (size_t)pix * 3 + 1, acc[1]);
                 atomicAdd(f.accum + (size_t)pix * 3 + 2, acc[2]);
-            }
-            if (q.in_merged) {          // these rays are complete (their own bounces were counted when they were emitted)
-                const unsigned fin = __ballot_sync(0xFFFFFFFFu, active);
-                if (lane == 0 && fin) atomicSub(q.m_pending, (uint32_t)__popc(fin));
             }
             continue;
         }
