@@ -139,6 +139,7 @@ struct ntr_scene {
     uint32_t max_leaf = 0;              // items in the largest leaf of the tree
     uint32_t *d_ring = nullptr;
     uint32_t fetch_sizes = 4u | (8u << 8) | (16u << 16);      // NTR_FETCH_SIZES=a,b,c: rays per fetch from cost rings 0, 1, 2
+    bool no_tile_sched = false;         // NTR_TILE_SCHED=0: row-major tile order always
     bool force_tile_sched = false;      // NTR_TILE_SCHED=1: cost-sorted tile hand-out on whole frames too (heavy-tailed scenes)
     bool zero_copy = false;             // NTR_ZEROCOPY=1: ntr_render stores single-pass frames straight into pinned destinations
     uint32_t queue_init = 0;            // NTR_QUEUE_INIT: initial queue capacity override (tests force the regrow path)
@@ -410,8 +411,11 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     const long long key = ((((long long)win_w * 65536 + win_h) * 64 + tile_row_first) * 64 + f.tile_row_step) * 4 + x0 % 2 * 2 + y0 % 2;
     // measured: the cost-sorted schedule pays when the frame is sharded over GPUs (8 GPUs, config 2: strip render
     // 0.258 -> 0.203 ms) -- each rank then has only ~2 blocks per warp and the tail matters -- but costs ~8 % on a
-    // whole frame on one GPU (loss of row-major locality + the cost bookkeeping), so it is used for sharded renders only
-    const bool use_sched = n_tiles >= 64 && composite && tgt.out_mode != NTR_OUT_IDS && (f.tile_row_step > 1 || sc->force_tile_sched);
+    // whole frame on one GPU (loss of row-major locality + the cost bookkeeping), so it is used for sharded renders --
+    // and for whole frames of scenes with giant leaves, whose few blocks through the centre cost 10-90x the mean
+    // (config 4: primary pass 11.2-11.6 -> 10.4 ms, frame 43.3 -> 42.4 ms, calls 17 and 20)
+    const bool use_sched = n_tiles >= 64 && composite && tgt.out_mode != NTR_OUT_IDS && !sc->no_tile_sched &&
+                           (f.tile_row_step > 1 || sc->force_tile_sched || sc->max_leaf >= 256);
     if (use_sched) {
         if (sc->tile_cap < n_tiles) {
             cudaFree(sc->d_tile_cost); cudaFree(sc->d_tile_order);
@@ -920,7 +924,7 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->sort_rays = getenv("NTR_NO_RAY_SORT") == nullptr;
     if (const char *zc = getenv("NTR_ZEROCOPY")) sc->zero_copy = atoi(zc) != 0;
     sc->slabs = getenv("NTR_NO_SLABS") == nullptr;
-    if (const char *ts = getenv("NTR_TILE_SCHED")) sc->force_tile_sched = atoi(ts) != 0;
+    if (const char *ts = getenv("NTR_TILE_SCHED")) { sc->force_tile_sched = atoi(ts) != 0; sc->no_tile_sched = atoi(ts) == 0; }
     for (uint32_t i = 0; desc->kind == NTR_SCENE_COMPOSITE && i < desc->n_nodes; ++i)
         if (desc->nodes[i].meta & NTR_LEAF_FLAG) sc->max_leaf = std::max(sc->max_leaf, desc->nodes[i].w2);
     sc->heavy_first = sc->max_leaf >= 256;

@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--world', type=int, default=1)
     ap.add_argument('--size', default=None, help='WxH override')
     ap.add_argument('--check', action='store_true')
+    ap.add_argument('--param', action='append', default=[], help='index=value: overwrite an entry of the scene params (1 = shadows, 3 = max depth)')
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -36,6 +37,11 @@ def main():
     if args.size:
         w, h = [int(v) for v in args.size.split('x')]
     sc, g = bench.load_fixture(fixture)
+    if args.param:
+        sc = dict(sc, params=np.array(sc['params'], dtype=np.float64))
+        for kv in args.param:
+            k, v = kv.split('=')
+            sc['params'][int(k)] = float(v)
     ds = DeviceScene(sc, 0)
     fmt = _capi.make_image_format(w, h, _capi.RGB8)
     rows = ((h + 31) // 32 + args.world - 1) // args.world * 32

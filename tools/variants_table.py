@@ -17,6 +17,14 @@ CALLS = {
     'r02i': ('call 9', 'exact mailbox table for opaque scenes as well (reverted; nomb = without)'),
     'r02j': ('call 10', 'quarter-size mailbox table (keys >> 2): the shipped code'),
     'r02k': ('call 11', 'thresholds of the cooperative leaves on the shipped code: md = NTR_COOP_MIN_DONE, lm = NTR_COOP_LEAF_MIN, cc = NTR_COOP_CHUNK_COST'),
+    'r02l': ('call 12', 'one launch for every bounce depth, first version (mN = NTR_MERGE_FROM=N; profiles/r02_merged_queue.md)'),
+    'r02m': ('call 13', 'merged bounce launch, second version'),
+    'r02n': ('call 14', 'merged bounce launch, third version'),
+    'r02o': ('call 15', 'merged bounce launch, fourth version (nap6/nap100 = longest pause of an idle warp 6.4 / 102 us, idle8 = 8 idle warps stay); removed afterwards'),
+    'r02q': ('call 17', 'primary pass split in two launches: tiles costing more than hN mean tiles traced one 8x1 pixel row per warp by the warp-synchronous kernel, the rest beside it on a second stream; sched = NTR_TILE_SCHED=1 on a whole frame (h0_sched = the cost-sorted tile order alone).  Not kept'),
+    'r02r': ('call 18', 'where the heaviest 8x4 blocks of a 1/8 share spend their time: noshadow = shadows off, depth0 = no bounces, *_stats = per-fetch durations (NTR_FETCH_STATS).  The longest block (8-9 M cycles = the whole primary pass of the share) is nearest-hit traversal alone: shadows off changes it by 2 %'),
+    'r02s': ('call 19', 'software prefetch (prefetch.global.L1) of the batch record pfN items ahead in leaves of 32 items or more: +8..10 % everywhere, the longest block gets longer too -- the tail is bound by instructions, not by fetch latency.  Not kept'),
+    'r02t': ('call 20', 'split primary pass with finer units: hN = cost factor, uM = pixels of a block per warp in the heavy tiles.  Even one ray per warp with 31 lanes helping does not shorten the primary pass of the share.  Not kept'),
 }
 
 
