@@ -1535,7 +1535,9 @@ NTR_API int ntr_group_create(const ntr_scene_desc *desc, int n, const int *devic
         cudaGetLastError();
         return fail(NTR_ERR_NO_DEVICE, "no CUDA device available: ntracer_b200 renders on sm_100a only and has no CPU fallback");
     }
-    if (n < 0 || n > ndev) return fail(NTR_ERR_VALUE, "the box has %d device(s), %d asked for", ndev, n);
+    // a device may be listed more than once: each entry is a chain of passes of its own over its share of the tile rows,
+    // and the chains of one device run side by side (one chain's tail beside the other's bulk)
+    if (n < 0 || (!devices && n > ndev) || n > 64) return fail(NTR_ERR_VALUE, "the box has %d device(s), %d asked for", ndev, n);
     if (n == 0) n = ndev;
     ntr_group *g = new (std::nothrow) ntr_group();
     if (!g) return fail(NTR_ERR_MEMORY, "out of memory");
@@ -1543,7 +1545,6 @@ NTR_API int ntr_group_create(const ntr_scene_desc *desc, int n, const int *devic
     for (int i = 0; i < n; ++i) {
         const int d = devices ? devices[i] : i;
         if (d < 0 || d >= ndev) return bail(fail(NTR_ERR_VALUE, "device %d out of range", d));
-        for (int k : g->dev) if (k == d) return bail(fail(NTR_ERR_VALUE, "device %d listed twice", d));
         ntr_scene *sc = nullptr;
         const int rc = ntr_scene_create(desc, d, &sc);
         if (rc) return bail(rc);
@@ -1553,6 +1554,7 @@ NTR_API int ntr_group_create(const ntr_scene_desc *desc, int n, const int *devic
     // every device stores into the frame buffer of dev[0]
     for (int i = 1; i < n; ++i) {
         int can = 0;
+        if (g->dev[i] == g->dev[0]) continue;
         if (cudaDeviceCanAccessPeer(&can, g->dev[i], g->dev[0]) != cudaSuccess || !can)
             return bail(fail(NTR_ERR_RUNTIME, "device %d cannot access the memory of device %d (no peer access)", g->dev[i], g->dev[0]));
         cudaSetDevice(g->dev[i]);

@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--world', type=int, default=1)
     ap.add_argument('--size', default=None, help='WxH override')
     ap.add_argument('--check', action='store_true')
+    ap.add_argument('--chains', default=None, help='device list of a group, e.g. 0,0 = two chains on GPU 0 (ntr_group_*)')
     ap.add_argument('--param', action='append', default=[], help='index=value: overwrite an entry of the scene params (1 = shadows, 3 = max depth)')
     args = ap.parse_args()
     import numpy as np
@@ -42,6 +43,24 @@ def main():
         for kv in args.param:
             k, v = kv.split('=')
             sc['params'][int(k)] = float(v)
+    if args.chains:
+        from ntracer_b200.backend import DeviceGroup
+        grp = DeviceGroup(sc, devices=[int(d) for d in args.chains.split(',')])
+        fmt = _capi.make_image_format(w, h, _capi.RGB8)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+        ms = []
+        for i in range(args.frames + 3):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ptr = grp.render_device(fmt)
+            if i >= 3:
+                ms.append(grp.last_kernel_ms())
+        import ctypes
+        host = np.zeros(fmt.pitch * h, np.uint8)
+        grp.render(fmt, host)
+        print(json.dumps({'config': args.config, 'chains': args.chains, 'w': w, 'h': h, 'ms_median': statistics.median(ms), 'ms_min': min(ms),
+                          'ms': [round(v, 3) for v in ms], 'counters': grp.counters(), 'frame_md5': hashlib.md5(host.tobytes()).hexdigest()}), flush=True)
+        return
     ds = DeviceScene(sc, 0)
     fmt = _capi.make_image_format(w, h, _capi.RGB8)
     rows = ((h + 31) // 32 + args.world - 1) // args.world * 32

@@ -25,6 +25,8 @@ CALLS = {
     'r02r': ('call 18', 'where the heaviest 8x4 blocks of a 1/8 share spend their time: noshadow = shadows off, depth0 = no bounces, *_stats = per-fetch durations (NTR_FETCH_STATS).  The longest block (8-9 M cycles = the whole primary pass of the share) is nearest-hit traversal alone: shadows off changes it by 2 %'),
     'r02s': ('call 19', 'software prefetch (prefetch.global.L1) of the batch record pfN items ahead in leaves of 32 items or more: +8..10 % everywhere, the longest block gets longer too -- the tail is bound by instructions, not by fetch latency.  Not kept'),
     'r02t': ('call 20', 'split primary pass with finer units: hN = cost factor, uM = pixels of a block per warp in the heavy tiles.  Even one ray per warp with 31 lanes helping does not shorten the primary pass of the share.  Not kept'),
+    'r02u': ('call 21', 'settled code (def) against a single copy of the exact division + edge part of the batch test (el = NTR_EDGE_LOOP=1: 6 % fewer SASS instructions, +10 % time on config 2: the dynamic lane select costs more than the copies).  Not kept'),
+    'r02v': ('call 22', 'chN = N chains of passes on ONE GPU (ntr_group_create with the device listed N times: each chain renders its interleaved tile rows with queues and launches of its own, so one chain\'s tail runs beside another\'s bulk): config 4 42.3 -> 40.4 ms with 3-4 chains, everything else flat or worse'),
 }
 
 
