@@ -52,6 +52,7 @@ class Color:
     def __truediv__(self, b): return self._bin(b, lambda x, y: x / y)
     __div__ = __truediv__
     def apply(self, f): return Color(f(self.r), f(self.g), f(self.b))
+    def __reduce__(self): return (_color_unpickle, (_encode_floats(tuple(self)),))       # render.cpp:1094-1101
 
 
 class Material:
@@ -77,10 +78,113 @@ class Material:
                          self.opacity, self.reflectivity, self.specular_intensity, self.specular_exp], np.float32)
 
     def __eq__(self, b): return isinstance(b, Material) and bool(np.all(self._row() == b._row()))
+    def __reduce__(self): return (_material_unpickle, (_encode_floats(self._row()),))     # render.cpp:1197-1208
     def __hash__(self): return id(self)
     def __repr__(self):
         return 'Material(%r,%r,%r,%r,%r,%r)' % (tuple(self.color), self.opacity, self.reflectivity, self.specular_intensity,
                                                 self.specular_exp, tuple(self.specular))
+
+
+# ---- the reference's pickle encodings (src/render.cpp:1391-1657, 1698-1746) ------------------------------------------
+# Every picklable value type reduces to (render._<type>_unpickle, args) with its floats as big-endian IEEE-754 bytes;
+# the functions below take exactly the arguments the reference's take and fail the same way, so a pickle written by
+# either side names the same functions with the same payload (ntracer_b200.compat maps the module names).
+def _encode_floats(values):
+    return np.asarray(values, dtype='>f4').tobytes()
+
+
+def _decode_floats(data, count, what):
+    if not isinstance(data, (bytes, bytearray)):
+        raise TypeError('object is not an instance of bytes')
+    if len(data) != 4 * count:
+        raise ValueError('%s data is malformed' % what)
+    return np.frombuffer(bytes(data), dtype='>f4').astype(np.float32)
+
+
+def _check_args(args, n, name):
+    if len(args) != n:
+        raise TypeError('%s takes exactly %d arguments' % (name, n))
+
+
+def _color_unpickle(data):
+    return Color(*_decode_floats(data, 3, 'color'))
+
+
+def _material_unpickle(data):
+    v = [float(x) for x in _decode_floats(data, 10, 'material')]
+    m = Material(v[0:3], 1, 0, v[8], v[9], v[3:6])
+    object.__setattr__(m, 'opacity', v[6])          # stored as they are: the reference's unpickle does not clamp
+    object.__setattr__(m, 'reflectivity', v[7])
+    return m
+
+
+def _vector_unpickle(*args):
+    from . import tracern
+    _check_args(args, 2, '_vector_unpickle')
+    dim = tracern._check_dimension(args[0])
+    return tracern.Vector._wrap(_decode_floats(args[1], dim, 'vector'))
+
+
+def _matrix_unpickle(*args):
+    from . import tracern
+    _check_args(args, 2, '_matrix_unpickle')
+    dim = tracern._check_dimension(args[0])
+    return tracern.Matrix._wrap(_decode_floats(args[1], dim * dim, 'matrix').reshape(dim, dim))
+
+
+def _triangle_unpickle(*args):
+    from . import tracern
+    _check_args(args, 3, '_triangle_unpickle')
+    dim = tracern._check_dimension(args[0])
+    rows = _decode_floats(args[1], dim * (dim + 1), 'triangle').reshape(dim + 1, dim)        # p1, face_normal, edge normals
+    if not isinstance(args[2], Material):
+        raise TypeError('object is not an instance of Material')
+    V = tracern.Vector._wrap
+    return tracern.Triangle(V(rows[0]), V(rows[1]), [V(r) for r in rows[2:]], args[2])           # d is recomputed, like triangle_extra
+
+
+def _triangle_batch_unpickle(*args):
+    from . import tracern
+    if len(args) < 3:
+        raise TypeError('wrong number of arguments')
+    dim = tracern._check_dimension(args[1])
+    B = tracern.BATCH_SIZE
+    if int(args[0]) != B:
+        raise TypeError('The TriangleBatch instance was pickled with a different batch size. It cannot be loaded here.')
+    if len(args) != 3 + B:
+        raise TypeError('wrong number of arguments')
+    rows = _decode_floats(args[2], B * dim * (dim + 1), 'triangle batch').reshape(dim + 1, dim, B)    # [row][coordinate][lane]
+    for m in args[3:]:
+        if not isinstance(m, Material):
+            raise TypeError('object is not an instance of Material')
+    V = tracern.Vector._wrap
+    return tracern.TriangleBatch([tracern.Triangle(V(rows[0, :, k]), V(rows[1, :, k]), [V(rows[2 + e, :, k]) for e in range(dim - 1)],
+                                                   args[3 + k]) for k in range(B)])
+
+
+def _solid_unpickle(*args):
+    from . import tracern
+    _check_args(args, 3, '_solid_unpickle')
+    dim = tracern._check_dimension(args[0])
+    data = args[1]
+    if not isinstance(data, (bytes, bytearray)):
+        raise TypeError('object is not an instance of bytes')
+    if len(data) != 4 * dim * (dim + 1) + 1:
+        raise ValueError('solid data is malformed')
+    if data[0] not in (tracern.CUBE, tracern.SPHERE):
+        raise ValueError('solid data is corrupt')
+    if not isinstance(args[2], Material):
+        raise TypeError('object is not an instance of Material')
+    vals = _decode_floats(data[1:], dim * (dim + 1), 'solid')
+    return tracern.Solid(int(data[0]), tracern.Vector._wrap(vals[dim * dim:]), tracern.Matrix._wrap(vals[:dim * dim].reshape(dim, dim)), args[2])
+
+
+def _aabb_unpickle(*args):
+    from . import tracern
+    _check_args(args, 2, '_aabb_unpickle')
+    dim = tracern._check_dimension(args[0])
+    vals = _decode_floats(args[1], 2 * dim, 'AABB')
+    return tracern.AABB(dim, tracern.Vector._wrap(vals[:dim]), tracern.Vector._wrap(vals[dim:]))
 
 
 class Channel:

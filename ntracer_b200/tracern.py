@@ -14,7 +14,8 @@ import numpy as np
 
 from . import _capi
 from .backend import DeviceGroup, DeviceScene, FLT_MAX
-from .render import Color, LockedError, Material, Scene, _color_tuple
+from . import render as _render
+from .render import Color, LockedError, Material, Scene, _color_tuple, _encode_floats
 
 BATCH_SIZE = 4      # lanes of a TriangleBatch; the reference's SSE build has v_real::size == 4
 CUBE, SPHERE = 1, 2
@@ -27,6 +28,7 @@ def _check_dimension(d):
         raise ValueError('dimension cannot be smaller than 3')
     if d > _capi.NTR_MAX_DIM:
         raise ValueError('dimension cannot be greater than %d' % _capi.NTR_MAX_DIM)
+    return int(d)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -99,6 +101,7 @@ class Vector:
     def __neg__(self): return Vector._wrap(-self._v)
     def __abs__(self): return self.absolute()
     def __eq__(self, b): return isinstance(b, Vector) and b._v.size == self._v.size and bool(np.all(self._v == b._v))
+    def __reduce__(self): return (_render._vector_unpickle, (self.dimension, _encode_floats(self._v)))       # ntracer_body.hpp:2016-2020
     def __ne__(self, b): return not self.__eq__(b)
 
     def square(self): return float(np.dot(self._v, self._v))
@@ -155,6 +158,7 @@ class Matrix:
     def __len__(self): return int(self._m.shape[0])
     def __getitem__(self, i): return Vector._wrap(self._m[i].copy())
     def __eq__(self, b): return isinstance(b, Matrix) and self._m.shape == b._m.shape and bool(np.all(self._m == b._m))
+    def __reduce__(self): return (_render._matrix_unpickle, (self.dimension, _encode_floats(self._m.ravel())))  # :2347-2351
     def __repr__(self): return 'Matrix(%d,%r)' % (self.dimension, self.values)
 
     def __mul__(self, b):
@@ -282,6 +286,9 @@ class AABB:
         self.end = Vector(dimension, [FLT_MAX] * dimension) if end is None else _as_vector(end, dimension)
 
     dimension = property(lambda self: self.start.dimension)
+
+    def __reduce__(self):                       # ntracer_body.hpp:2559-2563
+        return (_render._aabb_unpickle, (self.dimension, _encode_floats(np.concatenate([self.start._v, self.end._v]))))
 
     def left(self, axis, split):
         return AABB(self.dimension, self.start, self.end.set_c(axis, split))
@@ -478,6 +485,13 @@ class Triangle(Primitive):
 
     dimension = property(lambda self: self.p1.dimension)
 
+    def _rows(self):
+        """p1, face_normal, edge normals: the rows of the reference's pickle payload (ntracer_body.hpp:1217-1232)"""
+        return np.stack([self.p1._v, self.face_normal._v] + [e._v for e in self.edge_normals])
+
+    def __reduce__(self):
+        return (_render._triangle_unpickle, (self.dimension, _encode_floats(self._rows().ravel()), self.material))
+
     def _twin(self):
         return Triangle(self.p1, self.face_normal, self.edge_normals, _PROBE_MATERIAL)
 
@@ -525,6 +539,10 @@ class TriangleBatch(PrimitiveBatch):
     def __len__(self): return BATCH_SIZE
     def __getitem__(self, i): return self._t[i]
 
+    def __reduce__(self):                       # [row][coordinate][lane], then the lanes' materials (render.cpp:1722-1732)
+        rows = np.stack([t._rows() for t in self._t], axis=-1)
+        return (_render._triangle_batch_unpickle, (BATCH_SIZE, self.dimension, _encode_floats(rows.ravel())) + tuple(t.material for t in self._t))
+
     def _twin(self):
         return TriangleBatch([t._twin() for t in self._t])
 
@@ -545,6 +563,10 @@ class Solid(Primitive):
         self.material = material
 
     dimension = property(lambda self: self.position.dimension)
+
+    def __reduce__(self):                       # type byte, orientation, position (render.cpp:1733-1743)
+        data = bytes([self.type]) + _encode_floats(self.orientation._m.ravel()) + _encode_floats(self.position._v)
+        return (_render._solid_unpickle, (self.dimension, data, self.material))
 
     def _twin(self):
         return Solid(self.type, self.position, self.orientation, _PROBE_MATERIAL)
