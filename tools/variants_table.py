@@ -27,6 +27,7 @@ CALLS = {
     'r02t': ('call 20', 'split primary pass with finer units: hN = cost factor, uM = pixels of a block per warp in the heavy tiles.  Even one ray per warp with 31 lanes helping does not shorten the primary pass of the share.  Not kept'),
     'r02u': ('call 21', 'settled code (def) against a single copy of the exact division + edge part of the batch test (el = NTR_EDGE_LOOP=1: 6 % fewer SASS instructions, +10 % time on config 2: the dynamic lane select costs more than the copies).  Not kept'),
     'r02v': ('call 22', 'chN = N chains of passes on ONE GPU (ntr_group_create with the device listed N times: each chain renders its interleaved tile rows with queues and launches of its own, so one chain\'s tail runs beside another\'s bulk): config 4 42.3 -> 40.4 ms with 3-4 chains, everything else flat or worse'),
+    'r02w': ('call 23', 'primary pass of opaque scenes as a tracing launch (nearest hits into a buffer) + a shading launch of the same kernel (split = NTR_SPLIT_SHADE=1; frames identical, 5 GPU tests): no gain on config 2 (0.786 vs 0.779 ms; the stage switch itself cost the fused path 4 %), worse on shares and on the opaque star polytope.  Not kept -- halving the instructions each launch executes does not buy back the second launch, the hit buffer and the second tail'),
 }
 
 
