@@ -157,7 +157,16 @@ struct ntr_scene {
     uint32_t *h_ctl = nullptr;              // pinned read-back of the control block and the counters (frame_readback)
     unsigned long long *h_cnt = nullptr;
     uint64_t launches = 0;
-    int grid_blocks[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int grid_blocks[16] = {};
+    // NTR_F_WIDE builds (96 registers, 5 CTAs per SM) per pass: which of the two builds a pass runs is MEASURED -- the second
+    // frame of a view runs the ordinary build everywhere, the third the wide one, from the fourth on every pass runs the one
+    // that was faster by more than 3 % (pass times from the events the frame records anyway).  NTR_WIDE=0|1: never | always.
+    int wide_mode = -1;
+    long long tune_key = -1;            // the view the measurements belong to (frame size and interleave, like sched_key)
+    int tune_frames = 0;                // frames of that view rendered so far
+    int tune_slot = -1;                 // what this frame's pass times are recorded as: 0 ordinary, 1 wide, -1 not at all
+    uint32_t wide_mask = 0;             // passes (bit 0 = primary, bit d = bounce depth d) that run the wide build
+    float tune_ms[2][kMaxPasses + 2] = {};
     int warp_path = 0;                  // 1: bounce passes use the warp-synchronous kernels (scenes with big leaves), 2: every pass; NTR_WARP overrides
     const KernelSet *(*kset)(int) = nullptr;
     std::atomic<bool> busy{false};
@@ -460,8 +469,23 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     CUDA_TRY(cudaMemsetAsync(d_ctl, 0, CTL_WORDS * sizeof(uint32_t), st));
     CUDA_TRY(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), st));
 
-    const KernelSet *ks = sc->kset(primary_flags);
-    const int grid = grid_for(sc, primary_flags);
+    // passes that end in a few long rays (the late bounce passes of a frame, every pass of a share of a sharded frame)
+    // run the 96-register build of scenes with giant leaves: see kernels.cuh, NTR_F_WIDE
+    const bool wide_ok = sc->wide_mode != 0 && composite && passes && (flags & NTR_F_GENERAL) && sc->dev.dim <= 5 && sc->max_leaf >= 256;
+    uint32_t wide_now = 0;
+    sc->tune_slot = -1;
+    if (wide_ok && sc->wide_mode == 1) wide_now = 0xFFFFFFFFu;
+    else if (wide_ok) {
+        if (sc->tune_key != key) { sc->tune_key = key; sc->tune_frames = 0; sc->wide_mask = 0; }
+        const int n = sc->tune_frames++;
+        if (n == 1) sc->tune_slot = 0;
+        else if (n == 2) { sc->tune_slot = 1; wide_now = 0xFFFFFFFFu; }
+        else if (n > 2) wide_now = sc->wide_mask;
+    }
+    auto wide_for = [&](int pass) { return (wide_now >> pass) & 1u ? (int)NTR_F_WIDE : 0; };
+    const int pflags = primary_flags | wide_for(0);
+    const KernelSet *ks = sc->kset(pflags);
+    const int grid = grid_for(sc, pflags);
     const uint32_t rec4 = 2 + 2 * ((sc->dev.dim + 3) / 4);
     QueueDev q;
     memset(&q, 0, sizeof q);
@@ -541,7 +565,8 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
                     q.fetch_sizes = sc->fetch_sizes;
                 }
             }
-            sc->kset(bounce_flags)->render_pass(dim3(grid_for(sc, bounce_flags)), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
+            const int bf = bounce_flags | wide_for(depth < 32 ? depth : 31);
+            sc->kset(bf)->render_pass(dim3(grid_for(sc, bf)), dim3(kCtaThreads), st, sc->dev, sc->cam, f, q, ctl);
             ++sc->launches;
             mark();
 #if NTR_FETCH_STATS
@@ -612,6 +637,16 @@ int frame_collect(ntr_scene *sc, FrameJob &j, bool *again) {
         if (rays > 0) sc->pass_ns_per_ray = ms * 1e6f / (float)rays;
     }
     if (j.passes) for (int d = 1; d <= kMaxPasses; ++d) sc->prev_pass_count[d] = std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
+    if (j.passes && sc->tune_slot >= 0 && sc->n_pass_ev > 1 && !h_ctl[CTL_OVERFLOW]) {
+        // the build auto-tuner of frame_submit: this frame was a measurement
+        for (int i = 0; i + 1 < sc->n_pass_ev && i < kMaxPasses + 2; ++i) cudaEventElapsedTime(&sc->tune_ms[sc->tune_slot][i], sc->pass_ev[i], sc->pass_ev[i + 1]);
+        if (sc->tune_slot == 1) {
+            sc->wide_mask = 0;
+            for (int i = 0; i + 1 < sc->n_pass_ev && i < 32; ++i)
+                if (sc->tune_ms[1][i] < 0.97f * sc->tune_ms[0][i]) sc->wide_mask |= 1u << i;
+            if (sc->pass_timing) fprintf(stderr, "ntr wide builds: pass mask 0x%x\n", sc->wide_mask);
+        }
+    }
     if (sc->pass_timing && sc->n_pass_ev > 1) {
         fprintf(stderr, "ntr pass ms:");
         for (int i = 0; i + 1 < sc->n_pass_ev; ++i) {
@@ -924,6 +959,7 @@ NTR_API int ntr_scene_create(const ntr_scene_desc *desc, int device, ntr_scene *
     sc->sort_rays = getenv("NTR_NO_RAY_SORT") == nullptr;
     if (const char *zc = getenv("NTR_ZEROCOPY")) sc->zero_copy = atoi(zc) != 0;
     sc->slabs = getenv("NTR_NO_SLABS") == nullptr;
+    if (const char *wb = getenv("NTR_WIDE")) sc->wide_mode = atoi(wb) != 0;
     if (const char *ts = getenv("NTR_TILE_SCHED")) { sc->force_tile_sched = atoi(ts) != 0; sc->no_tile_sched = atoi(ts) == 0; }
     for (uint32_t i = 0; desc->kind == NTR_SCENE_COMPOSITE && i < desc->n_nodes; ++i)
         if (desc->nodes[i].meta & NTR_LEAF_FLAG) sc->max_leaf = std::max(sc->max_leaf, desc->nodes[i].w2);

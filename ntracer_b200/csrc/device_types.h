@@ -32,8 +32,10 @@ enum : int {
     NTR_F_GENERAL = 1,      // scene has transparent materials and/or solids: mailbox, transparent-hit list,
                             // explicit normal mirroring (reference quirks)
     NTR_F_COUNT = 2,        // instrumented: node/primitive counters (never used for timing)
-    NTR_F_WARP = 4          // render_pass_kernel only: the warp-synchronous per-ray path (trace_warp.cuh), chosen for scenes
+    NTR_F_WARP = 4,         // render_pass_kernel only: the warp-synchronous per-ray path (trace_warp.cuh), chosen for scenes
                             // with big leaves; otherwise every lane traces for itself (trace_core.cuh)
+    NTR_F_WIDE = 8          // render_pass_kernel only, general variant in 3..5 dimensions: 96 registers / 5 CTAs per SM instead of
+                            // 64 / 8 -- no spills, fewer warps: the build for passes that end in a few long rays (kernels.cuh)
 };
 
 struct SceneDev {

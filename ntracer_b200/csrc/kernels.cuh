@@ -125,9 +125,18 @@ __device__ __forceinline__ void store_block_packed(const FrameDev &f, unsigned c
 #ifndef NTR_MIN_CTAS_MID
 #define NTR_MIN_CTAS_MID 6         // dimensions 6..8; measured on config 3 (6-D): 8 -> 0.550 ms, 6 -> 0.536 ms
 #endif
-template <int DT> struct MinCtas { static constexpr int value = DT > 8 ? NTR_MIN_CTAS_HI : (DT >= 6 ? NTR_MIN_CTAS_MID : NTR_MIN_CTAS); };
+// NTR_F_WIDE: measured on config 4 (call 25) with the whole 4-D family at 8 / 7 / 6 / 5 CTAs per SM: the full frame wants
+// occupancy (42.6 / 43.6 / 45.5 / 47.4 ms) but its two last bounce passes (0.9 M and 0.6 M rays) and every pass of a 1/8
+// share are decided by a few long rays and want registers (share: 15.2 / 14.9 / 15.0 / 14.4 ms), so both builds exist and
+// the host picks per pass (capi.cu: wide_below).
+#ifndef NTR_MIN_CTAS_WIDE
+#define NTR_MIN_CTAS_WIDE 5
+#endif
+template <int DT, int FLAGS = 0> struct MinCtas {
+    static constexpr int value = (FLAGS & NTR_F_WIDE) ? NTR_MIN_CTAS_WIDE : DT > 8 ? NTR_MIN_CTAS_HI : (DT >= 6 ? NTR_MIN_CTAS_MID : NTR_MIN_CTAS);
+};
 template <int DT, int FLAGS>
-__global__ void __launch_bounds__(kCtaThreads, MinCtas<DT>::value)
+__global__ void __launch_bounds__(kCtaThreads, MinCtas<DT, FLAGS>::value)
 render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ CameraDev cam,
                    const __grid_constant__ FrameDev f, const __grid_constant__ QueueDev q,
                    const __grid_constant__ ControlDev ctl) {
@@ -253,7 +262,7 @@ render_pass_kernel(const __grid_constant__ SceneDev s, const __grid_constant__ C
         // warp-synchronous form (trace_warp.cuh: all 32 lanes enter, `active` says who has a ray; rays park at big leaves
         // and the warp splits them over its lanes when enough lanes are idle) wins where single rays walk leaves of
         // hundreds of items (config 4: 58.4 -> 49.9 ms, its 1/8-frame share 26.3 -> 19.9 ms).
-        constexpr int RF = FLAGS & ~NTR_F_WARP;     // the per-ray code knows nothing of the switch
+        constexpr int RF = FLAGS & ~(NTR_F_WARP | NTR_F_WIDE);      // the per-ray code knows nothing of the switches
         if constexpr ((FLAGS & NTR_F_WARP) != 0) {
             if (s.kind != NTR_SCENE_BOX) {          // warp-uniform
                 if (!active) {
@@ -417,12 +426,12 @@ template <int DT, int FLAGS> struct Launch {
     }
     // the ray hooks have no warp form: both render variants share them
     static KernelSet get() {
-        return KernelSet{&render_pass, &Launch<DT, FLAGS & ~NTR_F_WARP>::trace_rays, &Launch<DT, FLAGS & ~NTR_F_WARP>::occludes_rays,
-                         &max_blocks_per_sm};
+        return KernelSet{&render_pass, &Launch<DT, FLAGS & 3>::trace_rays, &Launch<DT, FLAGS & 3>::occludes_rays, &max_blocks_per_sm};
     }
 };
 
-// defined in kern_d*.cu: variant index = FLAGS (0..7)
+// defined in kern_d*.cu: variant index = FLAGS (0..15; NTR_F_WIDE builds exist for the general variant in 3..5 dimensions,
+// everywhere else the index falls back to the build without it)
 const KernelSet *kernel_set_d3(int flags);
 const KernelSet *kernel_set_d4(int flags);
 const KernelSet *kernel_set_d5(int flags);
@@ -438,6 +447,16 @@ const KernelSet *kernel_set_dn(int flags);
         static const KernelSet sets[8] = {Launch<DT, 0>::get(), Launch<DT, 1>::get(), Launch<DT, 2>::get(), \
                                           Launch<DT, 3>::get(), Launch<DT, 4>::get(), Launch<DT, 5>::get(), \
                                           Launch<DT, 6>::get(), Launch<DT, 7>::get()};                  \
+        return &sets[flags & 7];                                                                        \
+    }
+#define NTR_INSTANTIATE_DIM_WIDE(NAME, DT)                                                              \
+    const KernelSet *NAME(int flags) {                                                                  \
+        static const KernelSet sets[8] = {Launch<DT, 0>::get(), Launch<DT, 1>::get(), Launch<DT, 2>::get(), \
+                                          Launch<DT, 3>::get(), Launch<DT, 4>::get(), Launch<DT, 5>::get(), \
+                                          Launch<DT, 6>::get(), Launch<DT, 7>::get()};                  \
+        static const KernelSet wide[4] = {Launch<DT, 1 | NTR_F_WIDE>::get(), Launch<DT, 3 | NTR_F_WIDE>::get(), \
+                                          Launch<DT, 5 | NTR_F_WIDE>::get(), Launch<DT, 7 | NTR_F_WIDE>::get()}; \
+        if ((flags & NTR_F_WIDE) && (flags & NTR_F_GENERAL)) return &wide[(flags & 7) >> 1];          \
         return &sets[flags & 7];                                                                        \
     }
 

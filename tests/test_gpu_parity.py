@@ -203,6 +203,26 @@ def test_interleaved_tile_rows_compose_the_frame():
         assert np.abs(out - full).max() <= 1       # float atomics in a different order: at most 1 LSB
 
 
+def test_wide_register_build_renders_the_same_frame(monkeypatch):
+    """Scenes with giant leaves have a second build of the general 3..5-D kernels (96 registers, NTR_F_WIDE) that the host
+    tries on the third frame of a view and keeps for the passes it was faster on (capi.cu: wide_mode).  Whatever it picks,
+    the picture is the same: five frames of one view (ordinary, measured, wide, tuned, tuned) and a forced-wide frame."""
+    sc, g = fx.load('ggs120')
+    sc = fx.variant(sc, g, 'refl_transp')
+    fmt = _capi.make_image_format(320, 200, _capi.RGB8)
+    with DeviceScene(sc) as ds:
+        frames = [ds.render(fmt).astype(np.int32) for _ in range(5)]
+        counters = ds.counters()
+    for fr in frames[1:]:
+        assert np.abs(fr - frames[0]).max() <= 1                # float atomics of the bounce passes: at most 1 LSB
+    monkeypatch.setenv('NTR_WIDE', '1')
+    with DeviceScene(sc) as ds:
+        forced = ds.render(fmt).astype(np.int32)
+        assert np.abs(forced - frames[0]).max() <= 1
+        c = ds.counters()
+        assert (c['reflection_rays'], c['shadow_rays']) == (counters['reflection_rays'], counters['shadow_rays'])
+
+
 def test_full_size_properties_config2():
     """BASELINE config 2 at 1920x1080: windowed single-pixel evaluation equals the frame, the packed frame
     equals packing the float frame, counters are consistent, and a sample of rows matches the oracle."""

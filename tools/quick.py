@@ -24,6 +24,7 @@ def main():
     ap.add_argument('config')
     ap.add_argument('--frames', type=int, default=5)
     ap.add_argument('--world', type=int, default=1)
+    ap.add_argument('--rank', type=int, default=0, help='which of the --world shares to render')
     ap.add_argument('--size', default=None, help='WxH override')
     ap.add_argument('--check', action='store_true')
     ap.add_argument('--chains', default=None, help='device list of a group, e.g. 0,0 = two chains on GPU 0 (ntr_group_*)')
@@ -71,11 +72,11 @@ def main():
     for i in range(args.frames + 3):
         flush.zero_()
         torch.cuda.synchronize()
-        ds.render_device(fmt, buf.data_ptr(), buf.numel(), st.cuda_stream, 0, args.world, args.world > 1)
+        ds.render_device(fmt, buf.data_ptr(), buf.numel(), st.cuda_stream, args.rank, args.world, args.world > 1)
         st.synchronize()
         if i >= 3:
             ms.append(ds.last_kernel_ms())
-    out = {'config': args.config, 'lib': os.environ.get('NTR_B200_LIB', 'default'), 'w': w, 'h': h, 'world': args.world,
+    out = {'config': args.config, 'lib': os.environ.get('NTR_B200_LIB', 'default'), 'w': w, 'h': h, 'world': args.world, 'rank': args.rank,
            'ms_median': statistics.median(ms), 'ms_min': min(ms), 'ms': [round(v, 3) for v in ms],
            'counters': ds.counters(), 'frame_md5': hashlib.md5(buf.cpu().numpy().tobytes()).hexdigest()}
     if args.check:
