@@ -241,9 +241,6 @@ def kernel_name(sc, dim):
         if leaves.any() and int(nodes[leaves, 2].max()) >= 256:
             # scenes with big leaves: the bounce passes run the warp-synchronous instantiation (flag bit 2, capi.cu)
             name += ' (primary pass) + render_pass_kernel<%d,%d> (bounce passes)' % (dim if fixed else 0, (1 if general else 0) | 4)
-            if general and fixed and dim <= 5 and os.environ.get('NTR_WIDE', '1') != '0':
-                # ... or its 96-register build (flag bit 3) for the passes that measured faster with it (capi.cu: wide_mode)
-                name += ' / <%d,%d> (passes that measured faster at 96 registers)' % (dim, 1 | 4 | 8)
     return name
 
 

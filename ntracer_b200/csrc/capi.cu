@@ -158,15 +158,12 @@ struct ntr_scene {
     unsigned long long *h_cnt = nullptr;
     uint64_t launches = 0;
     int grid_blocks[16] = {};
-    // NTR_F_WIDE builds (96 registers, 5 CTAs per SM) per pass: which of the two builds a pass runs is MEASURED -- the second
-    // frame of a view runs the ordinary build everywhere, the third the wide one, from the fourth on every pass runs the one
-    // that was faster by more than 3 % (pass times from the events the frame records anyway).  NTR_WIDE=0|1: never | always.
+    // NTR_F_WIDE builds (96 registers, 5 CTAs per SM): for frames sharded over 4 or more GPUs, whose passes all end in a few
+    // long rays (measured, config 4: 1/4 share 20.9 -> 19.9 ms, 1/8 share 15.2 -> 14.4 ms; 1/2 share and whole frames lose
+    // 2..12 %).  Picking the build per pass from pass times measured on the second and third frame of a view gained another
+    // 0.7 % on whole frames when it measured right and lost 4 % when one noisy sample misled it (calls 27, 28): not kept.
+    // NTR_WIDE=0|1: never | always.
     int wide_mode = -1;
-    long long tune_key = -1;            // the view the measurements belong to (frame size and interleave, like sched_key)
-    int tune_frames = 0;                // frames of that view rendered so far
-    int tune_slot = -1;                 // what this frame's pass times are recorded as: 0 ordinary, 1 wide, -1 not at all
-    uint32_t wide_mask = 0;             // passes (bit 0 = primary, bit d = bounce depth d) that run the wide build
-    float tune_ms[2][kMaxPasses + 2] = {};
     int warp_path = 0;                  // 1: bounce passes use the warp-synchronous kernels (scenes with big leaves), 2: every pass; NTR_WARP overrides
     const KernelSet *(*kset)(int) = nullptr;
     std::atomic<bool> busy{false};
@@ -472,16 +469,7 @@ int enqueue_frame(ntr_scene *sc, cudaStream_t st, int width, int height, int x0,
     // passes that end in a few long rays (the late bounce passes of a frame, every pass of a share of a sharded frame)
     // run the 96-register build of scenes with giant leaves: see kernels.cuh, NTR_F_WIDE
     const bool wide_ok = sc->wide_mode != 0 && composite && passes && (flags & NTR_F_GENERAL) && sc->dev.dim <= 5 && sc->max_leaf >= 256;
-    uint32_t wide_now = 0;
-    sc->tune_slot = -1;
-    if (wide_ok && sc->wide_mode == 1) wide_now = 0xFFFFFFFFu;
-    else if (wide_ok) {
-        if (sc->tune_key != key) { sc->tune_key = key; sc->tune_frames = 0; sc->wide_mask = 0; }
-        const int n = sc->tune_frames++;
-        if (n == 1) sc->tune_slot = 0;
-        else if (n == 2) { sc->tune_slot = 1; wide_now = 0xFFFFFFFFu; }
-        else if (n > 2) wide_now = sc->wide_mask;
-    }
+    const uint32_t wide_now = wide_ok && (sc->wide_mode == 1 || f.tile_row_step >= 4) ? 0xFFFFFFFFu : 0u;
     auto wide_for = [&](int pass) { return (wide_now >> pass) & 1u ? (int)NTR_F_WIDE : 0; };
     const int pflags = primary_flags | wide_for(0);
     const KernelSet *ks = sc->kset(pflags);
@@ -637,16 +625,6 @@ int frame_collect(ntr_scene *sc, FrameJob &j, bool *again) {
         if (rays > 0) sc->pass_ns_per_ray = ms * 1e6f / (float)rays;
     }
     if (j.passes) for (int d = 1; d <= kMaxPasses; ++d) sc->prev_pass_count[d] = std::min(h_ctl[CTL_COUNT0 + d], sc->queue_capacity);
-    if (j.passes && sc->tune_slot >= 0 && sc->n_pass_ev > 1 && !h_ctl[CTL_OVERFLOW]) {
-        // the build auto-tuner of frame_submit: this frame was a measurement
-        for (int i = 0; i + 1 < sc->n_pass_ev && i < kMaxPasses + 2; ++i) cudaEventElapsedTime(&sc->tune_ms[sc->tune_slot][i], sc->pass_ev[i], sc->pass_ev[i + 1]);
-        if (sc->tune_slot == 1) {
-            sc->wide_mask = 0;
-            for (int i = 0; i + 1 < sc->n_pass_ev && i < 32; ++i)
-                if (sc->tune_ms[1][i] < 0.97f * sc->tune_ms[0][i]) sc->wide_mask |= 1u << i;
-            if (sc->pass_timing) fprintf(stderr, "ntr wide builds: pass mask 0x%x\n", sc->wide_mask);
-        }
-    }
     if (sc->pass_timing && sc->n_pass_ev > 1) {
         fprintf(stderr, "ntr pass ms:");
         for (int i = 0; i + 1 < sc->n_pass_ev; ++i) {

@@ -482,14 +482,19 @@ struct MailboxStore {
             gen = 1u;
         }
     }
-    NTR_HD uint32_t key_of(uint32_t r) const { return (r >> 30) == NTR_REF_SOLID ? solid_base + (r & NTR_IDX_MASK) : (r & NTR_IDX_MASK) >> shift; }
-    NTR_HD bool has(uint32_t r) const {
-        const uint32_t k = key_of(r), w = col[(size_t)(k / NTR_MAILBOX_BITS_PER_WORD) * stride];
+    // The queries take the table's geometry from the scene constants (kernel parameters: constant-bank operands) and the
+    // column / generation by value: ncu, config 4, showed this descriptor being re-read from local memory field by field
+    // on every item of every leaf (a fifth of the kernel's local-memory instructions).
+    NTR_HD static uint32_t key_of(const SceneDev &s, uint32_t r) {
+        return (r >> 30) == NTR_REF_SOLID ? (s.n_simplex >> s.mb_shift) + 1u + (r & NTR_IDX_MASK) : (r & NTR_IDX_MASK) >> s.mb_shift;
+    }
+    NTR_HD static bool has(const SceneDev &s, const uint32_t *col, uint32_t gen, uint32_t r) {
+        const uint32_t k = key_of(s, r), w = col[(size_t)(k / NTR_MAILBOX_BITS_PER_WORD) * s.mb_threads];
         return (w >> 24) == gen && ((w >> (k % NTR_MAILBOX_BITS_PER_WORD)) & 1u);
     }
-    NTR_HD void add(uint32_t r) {
-        const uint32_t k = key_of(r);
-        uint32_t *p = col + (size_t)(k / NTR_MAILBOX_BITS_PER_WORD) * stride;
+    NTR_HD static void add(const SceneDev &s, uint32_t *col, uint32_t gen, uint32_t r) {
+        const uint32_t k = key_of(s, r);
+        uint32_t *p = col + (size_t)(k / NTR_MAILBOX_BITS_PER_WORD) * s.mb_threads;
         const uint32_t w = *p;
         *p = ((w >> 24) == gen ? w : gen << 24) | (1u << (k % NTR_MAILBOX_BITS_PER_WORD));
     }
@@ -506,16 +511,18 @@ struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,8
     uint32_t v[NTR_MAILBOX_SLOTS];      // NTR_NONE_REF = empty slot (no item ref has both type bits set)
     int n;
     MailboxStore *big;                  // set: the exact per-thread bitset replaces the table (scenes with big leaves)
+    uint32_t *col;                      // ... its column and the generation of the traversal in progress, by value
+    uint32_t gen;
     static_assert((NTR_MAILBOX_SLOTS & (NTR_MAILBOX_SLOTS - 1)) == 0 && NTR_MAILBOX_SLOTS > NTR_MAILBOX_CAP, "mailbox table size");
     NTR_HD static uint32_t slot_of(uint32_t r) { return (r * 2654435761u) >> 16 & (uint32_t)(NTR_MAILBOX_SLOTS - 1); }
     NTR_HD bool exact() const { return big != nullptr; }
     NTR_HD void clear() {
         n = 0;
-        if (big) { big->begin_traversal(); return; }
+        if (big) { big->begin_traversal(); col = big->col; gen = big->gen; return; }
         for (int i = 0; i < NTR_MAILBOX_SLOTS; ++i) v[i] = NTR_NONE_REF;
     }
-    NTR_HD bool has(uint32_t r) const {
-        if (big) return big->has(r);
+    NTR_HD bool has(const SceneDev &s, uint32_t r) const {
+        if (big) return MailboxStore::has(s, col, gen, r);
         if (n > NTR_MAILBOX_CAP || n == 0) return false;
         uint32_t h = slot_of(r);
         for (;;) {
@@ -525,8 +532,8 @@ struct Mailbox {                        // prim_list `checked`, tracer.hpp:782,8
             h = (h + 1) & (uint32_t)(NTR_MAILBOX_SLOTS - 1);
         }
     }
-    NTR_HD void add(uint32_t r) {
-        if (big) { big->add(r); return; }
+    NTR_HD void add(const SceneDev &s, uint32_t r) {
+        if (big) { MailboxStore::add(s, col, gen, r); return; }
         if (n < NTR_MAILBOX_CAP) {
             uint32_t h = slot_of(r);
             while (v[h] != NTR_NONE_REF) h = (h + 1) & (uint32_t)(NTR_MAILBOX_SLOTS - 1);
@@ -666,7 +673,7 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
         const uint2 it = lditem(items + i);
         const uint32_t item = it.x;
         const bool is_batch = (item >> 30) == NTR_REF_BATCH;
-        if ((!is_batch && item == skip.ref) || g.mb.has(item)) continue;
+        if ((!is_batch && item == skip.ref) || g.mb.has(s, item)) continue;
         int lane;
         uint32_t wmask, meta;
         dist = prim_test_general<DT, FLAGS>(s, it, o, dir, oh.dist, skip, lane, P, N, wmask, meta, cnt);
@@ -695,7 +702,7 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
                 g.th.add(dist, item, lane);
             }
         }
-        g.mb.add(item);
+        g.mb.add(s, item);
     }
     if (!phase1) return false;
     g.th.trim(dist, h_start);           // `dist`: the result of the last test (Q3)
@@ -775,7 +782,7 @@ NTR_HD void replay_item(const SceneDev &s, const uint2 it, const float *o, const
     const int D = NTR_D(DT, s);
     const uint32_t item = it.x;
     const bool is_batch = (item >> 30) == NTR_REF_BATCH;
-    if ((!is_batch && item == skip.ref) || (!mailbox_done && g.mb.has(item))) return;
+    if ((!is_batch && item == skip.ref) || (!mailbox_done && g.mb.has(s, item))) return;
     const bool stale_cutoff = e.dist != 0 && !(e.dist < oh.dist);
     const bool is_cube = (item >> 30) == NTR_REF_SOLID &&
                          (int)ldf(s.solids + (size_t)(item & NTR_IDX_MASK) * s.solstride) == NTR_SOLID_CUBE;
@@ -815,7 +822,7 @@ NTR_HD void replay_item(const SceneDev &s, const uint2 it, const float *o, const
             g.th.add(dist, item, e.lane);
         }
     }
-    if (!mailbox_done) g.mb.add(item);
+    if (!mailbox_done) g.mb.add(s, item);
 }
 
 template <int DT, int FLAGS>
@@ -834,7 +841,7 @@ NTR_HD bool leaf_general_chunked(const SceneDev &s, const uint4 node, const floa
         for (uint32_t j = 0; j < n; ++j) {
             const uint2 it = lditem(items + base + j);
             const bool is_batch = (it.x >> 30) == NTR_REF_BATCH;
-            const bool skipped = (!is_batch && it.x == skip.ref) || g.mb.has(it.x);
+            const bool skipped = (!is_batch && it.x == skip.ref) || g.mb.has(s, it.x);
             ev[j].dist = 0; ev[j].wmask = 0; ev[j].meta = 0; ev[j].lane = -1; ev[j].geom = false;
             if (!skipped) prim_eval<DT, FLAGS>(s, it, o, dir, cutoff0, skip, ev[j], cnt);
             ev[j].skipped = skipped;

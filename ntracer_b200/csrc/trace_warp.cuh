@@ -172,7 +172,7 @@ __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, ui
         if ((uint32_t)lane < n) {
             const uint2 it = lditem(items + base + lane);
             // the primitive the ray leaves from is skipped by identity, never evaluated
-            if (!(((it.x >> 30) != NTR_REF_BATCH) && it.x == bskip.ref) && !(exact && owner_mb.has(it.x))) {
+            if (!(((it.x >> 30) != NTR_REF_BATCH) && it.x == bskip.ref) && !(exact && MailboxStore::has(s, owner_mb.col, owner_mb.gen, it.x))) {
                 prim_eval<DT, FLAGS>(s, it, bo, bd, cutoff0, bskip, e, cnt);
                 tested = true;
                 my_item = it.x;
@@ -181,7 +181,7 @@ __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, ui
         unsigned m = __ballot_sync(kFullMask, e.dist != 0 || e.wmask != 0);        // hits and partial writes
         const unsigned tm = __ballot_sync(kFullMask, tested);
         if (exact && tm) {
-            const uint32_t key = tested ? owner_mb.key_of(my_item) : 0u;
+            const uint32_t key = tested ? MailboxStore::key_of(s, my_item) : 0u;
             const uint32_t word = tested ? key / NTR_MAILBOX_BITS_PER_WORD : 0x80000000u | (uint32_t)lane;    // idle lanes: a group of one
             const uint32_t bit = tested ? 1u << (key % NTR_MAILBOX_BITS_PER_WORD) : 0u;
             const unsigned peers = __match_any_sync(kFullMask, word);
@@ -194,7 +194,7 @@ __device__ __forceinline__ bool coop_leaf_general(const SceneDev &s, int src, ui
                 bits |= __shfl_sync(kFullMask, bit, j);
             }
             if (tested && lane == __ffs(peers) - 1) {
-                uint32_t *p = owner_mb.col + (size_t)word * owner_mb.stride;
+                uint32_t *p = owner_mb.col + (size_t)word * s.mb_threads;
                 const uint32_t w = *p;
                 *p = ((w >> 24) == owner_mb.gen ? w : owner_mb.gen << 24) | bits;
             }

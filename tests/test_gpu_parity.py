@@ -204,21 +204,29 @@ def test_interleaved_tile_rows_compose_the_frame():
 
 
 def test_wide_register_build_renders_the_same_frame(monkeypatch):
-    """Scenes with giant leaves have a second build of the general 3..5-D kernels (96 registers, NTR_F_WIDE) that the host
-    tries on the third frame of a view and keeps for the passes it was faster on (capi.cu: wide_mode).  Whatever it picks,
-    the picture is the same: five frames of one view (ordinary, measured, wide, tuned, tuned) and a forced-wide frame."""
+    """Scenes with giant leaves have a second build of the general 3..5-D kernels (96 registers, NTR_F_WIDE) that renders
+    the shares of frames sharded over 4 or more GPUs (capi.cu: wide_mode).  Same code at another register budget: the
+    picture is the same -- a share of 4 against the whole frame, and a whole frame with the build forced."""
+    import torch
     sc, g = fx.load('ggs120')
     sc = fx.variant(sc, g, 'refl_transp')
-    fmt = _capi.make_image_format(320, 200, _capi.RGB8)
+    w, h = 320, 200
+    fmt = _capi.make_image_format(w, h, _capi.RGB8)
     with DeviceScene(sc) as ds:
-        frames = [ds.render(fmt).astype(np.int32) for _ in range(5)]
+        whole = ds.render(fmt).astype(np.int32).reshape(h, fmt.pitch)
         counters = ds.counters()
-    for fr in frames[1:]:
-        assert np.abs(fr - frames[0]).max() <= 1                # float atomics of the bounce passes: at most 1 LSB
+        rows = [ty for ty in range((h + 31) // 32) if ty % 4 == 1]
+        strip = torch.zeros(len(rows) * 32 * fmt.pitch, dtype=torch.uint8, device='cuda')
+        ds.render_device(fmt, strip.data_ptr(), strip.numel(), 0, 1, 4, True)           # rank 1 of 4: the wide build
+        torch.cuda.synchronize()
+        s = strip.cpu().numpy().reshape(len(rows) * 32, fmt.pitch).astype(np.int32)
+        for k, ty in enumerate(rows):
+            n = min(32, h - ty * 32)
+            assert np.abs(s[k * 32:k * 32 + n] - whole[ty * 32:ty * 32 + n]).max() <= 1   # float atomics of the bounce passes
     monkeypatch.setenv('NTR_WIDE', '1')
     with DeviceScene(sc) as ds:
-        forced = ds.render(fmt).astype(np.int32)
-        assert np.abs(forced - frames[0]).max() <= 1
+        forced = ds.render(fmt).astype(np.int32).reshape(h, fmt.pitch)
+        assert np.abs(forced - whole).max() <= 1
         c = ds.counters()
         assert (c['reflection_rays'], c['shadow_rays']) == (counters['reflection_rays'], counters['shadow_rays'])
 

@@ -30,7 +30,8 @@ CALLS = {
     'r02w': ('call 23', 'primary pass of opaque scenes as a tracing launch (nearest hits into a buffer) + a shading launch of the same kernel (split = NTR_SPLIT_SHADE=1; frames identical, 5 GPU tests): no gain on config 2 (0.786 vs 0.779 ms; the stage switch itself cost the fused path 4 %), worse on shares and on the opaque star polytope.  Not kept -- halving the instructions each launch executes does not buy back the second launch, the hit buffer and the second tail'),
     'r02y': ('call 25', 'register budgets of the whole 3..5-D family on the settled code: cN = NTR_MIN_CTAS=N (8 -> 64 registers, 7 -> 72, 6 -> 80, 5 -> 96): whole frames want occupancy, shares and late bounce passes want registers; rKof8 = the share of rank K of 8 (13.9 .. 17.3 ms: what the 8-GPU frame waits for is its slowest rank)'),
     'r02z': ('call 26', 'both builds in one library (NTR_F_WIDE), the wide one for passes below wbN rays / pixels: no ray count separates the passes that gain from the ones that lose (0.64 M first bounces of a half frame lose, 0.62 M fourth bounces of a whole frame gain)'),
-    'r02za': ('call 27', 'the build picked per pass by MEASUREMENT (wauto: frame 2 of a view ordinary, frame 3 wide, then the faster one per pass) against never (w0) and always (w1): config 4 whole 42.4 -> 42.1, 1/4 share 20.9 -> 19.9, 1/8 share 15.2 -> 14.5 ms.  Shipped'),
+    'r02za': ('call 27', 'the build picked per pass by MEASUREMENT (wauto: frame 2 of a view ordinary, frame 3 wide, then the faster one per pass) against never (w0) and always (w1): config 4 whole 42.4 -> 42.1, 1/4 share 20.9 -> 19.9, 1/8 share 15.2 -> 14.5 ms -- but see call 28'),
+    'r02zb': ('call 28', 'new = mailbox queries with the table geometry from the scene constants and column / generation by value, base = the descriptor behind a pointer (both with the wide build for shares of 4 or more GPUs only: the per-pass tuner of call 27 picked the wide build for the first bounce pass of a whole frame in the first run of this call, 44.2 ms, and was dropped)'),
 }
 
 
