@@ -661,15 +661,9 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
     const uint32_t size = node.z;
     const int h_start = g.th.n;
     float dist = 0;
-    bool phase1 = false, retest = false;
+    bool phase1 = false;
     float P[DimCap<DT>::value], N[DimCap<DT>::value];
-    uint32_t i = 0, next = 0;
-    for (;;) {
-        if (!retest) {
-            if (next >= size) break;
-            i = next++;
-        }
-        retest = false;
+    for (uint32_t i = 0; i < size; ++i) {
         const uint2 it = lditem(items + i);
         const uint32_t item = it.x;
         const bool is_batch = (item >> 30) == NTR_REF_BATCH;
@@ -688,10 +682,18 @@ NTR_HD bool leaf_general(const SceneDev &s, const uint4 node, const float *o, co
                 if (meta & NTR_META_OPAQUE) {
                     oh.dist = dist; oh.ref = item; oh.lane = lane;
                     phase1 = true;
-                    retest = true;      // `goto hit` re-tests this item (tracer.hpp:1008,1041)
-                    continue;           // ... and skips checked.add
+                    // `goto hit` tests this item once more before it is marked checked (tracer.hpp:1008,1041).  With the
+                    // cutoff now at its own distance that test can only miss (the comparison is strict, the arithmetic the
+                    // same) and a miss in phase 1 writes nothing: what it leaves behind is the last-test result 0 (Q13)
+                    // and its count.
+                    dist = 0;
+                    if (FLAGS & NTR_F_COUNT) {
+                        if ((item >> 30) == NTR_REF_SOLID) cnt.solid_tests++;
+                        else cnt.simplex_tests += is_batch ? (uint32_t)(((DT > 0 ? 4 : s.batch) + 3) / 4 * 4) : 1u;
+                    }
+                } else {
+                    g.th.add(dist, item, lane);
                 }
-                g.th.add(dist, item, lane);
             }
         } else if (dist) {
             if (meta & NTR_META_OPAQUE) {
