@@ -32,6 +32,9 @@ CALLS = {
     'r02z': ('call 26', 'both builds in one library (NTR_F_WIDE), the wide one for passes below wbN rays / pixels: no ray count separates the passes that gain from the ones that lose (0.64 M first bounces of a half frame lose, 0.62 M fourth bounces of a whole frame gain)'),
     'r02za': ('call 27', 'the build picked per pass by MEASUREMENT (wauto: frame 2 of a view ordinary, frame 3 wide, then the faster one per pass) against never (w0) and always (w1): config 4 whole 42.4 -> 42.1, 1/4 share 20.9 -> 19.9, 1/8 share 15.2 -> 14.5 ms -- but see call 28'),
     'r02zb': ('call 28', 'new = mailbox queries with the table geometry from the scene constants and column / generation by value, base = the descriptor behind a pointer (both with the wide build for shares of 4 or more GPUs only: the per-pass tuner of call 27 picked the wide build for the first bounce pass of a whole frame in the first run of this call, 44.2 ms, and was dropped)'),
+    'r02zc': ('call 29', 'leaf_general without the executed re-test of the first opaque hit (new) against with it (base).  Kept'),
+    'r02zd': ('call 30', 'tag mailbox for opaque single-simplex scenes, per-thread table in device memory (tN slots, pN software-pipelined, d20 = tree depth 20): tests halved, config 5 30 % slower.  Not kept'),
+    'r02ze': ('call 31', 'tag mailbox, per-warp table in dynamic shared memory (tN entries), software prefetch of single-simplex records (pfK): thread-level tests -40 %, config 5 2 % slower, prefetch 5 % slower.  Not kept'),
 }
 
 
