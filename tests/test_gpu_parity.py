@@ -408,3 +408,47 @@ def test_limits_are_reported_not_silent():
             ds.set_params(deep)
     with pytest.raises(ValueError):
         DeviceScene(deep)
+
+
+def _empty_composite(sc):
+    e = dict(sc)
+    e['nodes'] = np.zeros((0, 4), np.uint32)
+    e['leaf_refs'] = np.zeros(0, np.uint32)
+    e['root'] = np.int64(0xFFFFFFFF)
+    e['simplex'] = np.zeros((0, sc['simplex'].shape[1]), np.float32)
+    e['simplex_mat'] = np.zeros(0, np.int32)
+    return e
+
+
+def test_tiny_and_ragged_frames_and_the_empty_scene():
+    """Edge cases of the tile queue and the packer: frames smaller than one 8x4 block, one pixel, widths and heights that
+    end inside a block and inside a 32-pixel tile, one-block-high strips -- float image and packed bytes against the
+    oracle (packer bit-exact on the oracle's own floats, <= 1 LSB on the device's) -- and a CompositeScene without any
+    primitive (no tree: every ray gets the background gradient, composite_scene::ray_color's miss branch)."""
+    sc, g = fx.load('cell120')
+    sc = fx.variant(sc, g, 'shadows')
+    box, _ = fx.load('box4')
+    with DeviceScene(sc) as ds, DeviceScene(box) as db:
+        for w, h in ((1, 1), (3, 2), (8, 4), (9, 5), (31, 33), (33, 31), (257, 3), (2, 130)):
+            for scene, dev in ((sc, ds), (box, db)):
+                o = ol.render_float(scene, w, h)
+                fl = dev.render_float(w, h)
+                assert fl.shape == o.shape
+                bad, mx = fx.lsb_stats(fl, o)
+                assert bad * w * h <= max(1, 0.001 * w * h), (w, h, bad, mx)
+                for pitch_pad in (0, 5):
+                    fmt = _capi.make_image_format(w, h, _capi.RGB8, w * 3 + pitch_pad)
+                    dest = np.full(fmt.pitch * h, 0xA5, np.uint8)
+                    img = dev.render(fmt, dest).reshape(h, fmt.pitch)
+                    assert np.array_equal(ol.pack(fmt, fl).reshape(h, fmt.pitch)[:, :w * 3], img[:, :w * 3]), (w, h)
+                    assert (img[:, w * 3:] == 0xA5).all()          # padding bytes are never written
+    e = _empty_composite(sc)
+    with DeviceScene(e) as de:
+        for w, h in ((64, 36), (5, 3)):
+            o = ol.render_float(e, w, h)
+            fl = de.render_float(w, h)
+            assert np.abs(fl - o).max() <= 2e-6
+            ids, dist = de.primary_hit_ids(w, h)
+            assert (ids == -1).all()
+        ids, dist, nt = de.trace_rays(np.zeros((4, 4), np.float32), np.ones((4, 4), np.float32))
+        assert (ids == -1).all() and (nt == 0).all()

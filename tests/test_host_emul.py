@@ -115,3 +115,25 @@ def test_truncated_hit_lists_are_reported_and_too_deep_reflection_is_rejected():
     sc = fx.stacked_layers(20)
     b, cnt_e = el.render(sc, w, h)
     assert cnt_e['truncated_hit_lists'] > 0
+
+
+def test_tiny_and_ragged_frames_and_the_empty_scene():
+    """CPU twin of the GPU edge-case test: frames of one pixel / smaller than a block / ending inside a block, and a
+    CompositeScene without primitives (no tree: background gradient only), per-ray device code against the oracle."""
+    sc, g = fx.load('cell120')
+    sc = fx.variant(sc, g, 'shadows')
+    for w, h in ((1, 1), (3, 2), (9, 5), (33, 31), (257, 3)):
+        a = ol.render_float(sc, w, h)
+        b, _ = el.render(sc, w, h)
+        assert a.shape == b.shape == (h, w, 3) and np.abs(a - b).max() <= 2e-6
+    e = dict(sc)
+    e['nodes'] = np.zeros((0, 4), np.uint32)
+    e['leaf_refs'] = np.zeros(0, np.uint32)
+    e['root'] = np.int64(0xFFFFFFFF)
+    e['simplex'] = np.zeros((0, sc['simplex'].shape[1]), np.float32)
+    e['simplex_mat'] = np.zeros(0, np.int32)
+    a = ol.render_float(e, 32, 18)
+    b, ids, dist, cnt = el.render(e, 32, 18, want_ids=True)
+    assert np.abs(a - b).max() <= 2e-6 and (ids == -1).all()
+    assert cnt['simplex_tests'] == 0 and cnt['shaded_hits'] == 0
+    assert np.ptp(a.reshape(-1, 3), axis=0).max() > 0.05             # the gradient, not a constant
