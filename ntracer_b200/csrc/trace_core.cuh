@@ -119,6 +119,10 @@ struct Counters {
 struct Skip { uint32_t ref; int lane; };
 struct HitRec { float dist; uint32_t ref; int lane; };
 
+#ifndef NTR_BIG_SIMPLEX_PIPE
+#define NTR_BIG_SIMPLEX_PIPE 1      // above 8 dimensions: simplex_single_big (vector loads, next edge requested ahead)
+#endif
+
 // ---- simplex records -------------------------------------------------------------------------------
 // Register-staged view of one simplex record: stage 1 brings face_normal and d (enough for the plane
 // test), stage 2 the rest.  DT == 0 reads through the pointer instead.
@@ -158,11 +162,77 @@ template <> struct SimplexRec<0> {
     NTR_HD uint32_t meta(int sstride) const { return f2u(ldf(g + sstride - 1)); }
 };
 
+// The single-simplex test above 8 dimensions, where the record (>= 92 floats) is not staged in registers as a whole.
+// ncu, config 5 (1 M ten-dimensional simplexes, `profiles/r02_c5_ncu_full_summary.txt`): 68 % of the stall samples are
+// long-scoreboard waits and 43 % of all samples sit on the edge loop, which read its 10 coefficients with scalar loads
+// AFTER the previous edge's early-exit branch -- one trip to L1/L2 per edge on the dependency chain (the lanes of a warp
+// are at different leaf items, so these are 20 different records per load instruction: L1 hit rate 59 %).  Here the
+// record is read as aligned float4s: face normal, d and p1 in one batch (p1 no longer waits for the t test), and the
+// float4s of edge e+1 are requested before edge e is evaluated.  Same arithmetic in the same order as simplex_single.
+template <int DT>
+NTR_HD float simplex_single_big(const SceneDev &s, uint32_t off, const float *o, const float *dir, float cutoff,
+                                uint32_t &meta) {
+    constexpr int D = DT;
+    constexpr int S = (((DT + 1) * DT + 1) + 3) / 4 * 4;
+    constexpr int E0 = 2 * D + 1;                   // first float of edge 0
+    constexpr int NA = (E0 + 3) / 4;                // float4s that hold face_normal, d, p1
+    constexpr int NW = (D + 2) / 4 + 1;             // float4s an edge of D floats can span
+    const float *rec = s.simplex + off;
+    float a[4 * NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        const float4 v = ld4(rec + 4 * k);
+        a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+    }
+    float denom = 0, od = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) { denom += a[i] * dir[i]; od += a[i] * o[i]; }
+    if (denom == 0) return 0;
+    const float t = -(od + a[D]) / denom;
+    if (t <= 0 || t >= cutoff) return 0;
+    float pside[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) pside[i] = a[D + 1 + i] - (o[i] + t * dir[i]);
+    float cur[4 * NW], nxt[4 * NW];
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        if (E0 / 4 + k <= (E0 + D - 1) / 4) {
+            const float4 v = ld4(rec + 4 * (E0 / 4 + k));
+            cur[4 * k] = v.x; cur[4 * k + 1] = v.y; cur[4 * k + 2] = v.z; cur[4 * k + 3] = v.w;
+        }
+    }
+    float tot = 0;
+#pragma unroll
+    for (int e = 0; e < D - 1; ++e) {
+        if (e + 1 < D - 1) {
+            const int f0 = E0 + (e + 1) * D, q0 = f0 / 4, q1 = (f0 + D - 1) / 4;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                if (q0 + k <= q1) {
+                    const float4 v = ld4(rec + 4 * (q0 + k));
+                    nxt[4 * k] = v.x; nxt[4 * k + 1] = v.y; nxt[4 * k + 2] = v.z; nxt[4 * k + 3] = v.w;
+                }
+            }
+        }
+        const int base = (E0 + e * D) & 3;
+        float area = 0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) area += cur[base + i] * pside[i];
+        if (area < -NTR_FUZZ || area > (1 + NTR_FUZZ)) return 0;
+        tot += area;
+#pragma unroll
+        for (int k = 0; k < 4 * NW; ++k) cur[k] = nxt[k];
+    }
+    if (tot <= (1 + NTR_FUZZ)) { meta = f2u(ldf(rec + S - 1)); return t; }
+    return 0;
+}
+
 // triangle::intersects (tracer.hpp:411-440): the single-primitive n-simplex test.  (The approximate-quotient pre-filter of
 // batch_test was tried here too: config 5 got 3-4 % SLOWER -- one division per record is cheap next to the loads.)
 template <int DT>
 NTR_HD float simplex_single(const SceneDev &s, uint32_t off, const float *o, const float *dir, float cutoff,
                             uint32_t &meta) {
+    if constexpr (DT > 8 && NTR_BIG_SIMPLEX_PIPE) return simplex_single_big<DT>(s, off, o, dir, cutoff, meta);
     const int D = NTR_D(DT, s);
     SimplexRec<DT> R;
     R.stage1(s.simplex + off);

@@ -35,6 +35,7 @@ CALLS = {
     'r02zc': ('call 29', 'leaf_general without the executed re-test of the first opaque hit (new) against with it (base).  Kept'),
     'r02zd': ('call 30', 'tag mailbox for opaque single-simplex scenes, per-thread table in device memory (tN slots, pN software-pipelined, d20 = tree depth 20): tests halved, config 5 30 % slower.  Not kept'),
     'r02ze': ('call 31', 'tag mailbox, per-warp table in dynamic shared memory (tN entries), software prefetch of single-simplex records (pfK): thread-level tests -40 %, config 5 2 % slower, prefetch 5 % slower.  Not kept'),
+    'r02zf': ('call 32', 'single-simplex test above 8 dimensions with aligned float4 loads and the next edge requested ahead (new) against scalar loads behind the early-exit branches (base): config 5 -1.8 %, config 5 reduced -1.1 %.  Kept'),
 }
 
 
