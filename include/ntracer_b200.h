@@ -275,6 +275,20 @@ NTR_API int ntr_simplex_from_points(int dim, uint32_t n, const float *points, fl
 NTR_API int ntr_build_kdtree(int dim, uint32_t n, const float *lo, const float *hi, int max_depth, int split_threshold,
                              float traversal_cost, float intersection_cost, ntr_node **nodes_out, uint32_t *n_nodes_out,
                              uint32_t **refs_out, uint32_t *n_refs_out, uint32_t *root_out, float *boundary_out);
+/* The same tree build with the simplexes behind the items, so that an item is listed only in the cells its geometry
+ * can touch -- what the reference's builder achieves with its exact primitive / box overlap tests
+ * (src/tracer.hpp:1465-1675, used by split_kdtree :2284-2354) and bounding boxes alone cannot.  Item i owns simplexes
+ * item_first[i] .. item_first[i+1]-1 (item_first: n + 1 entries, [0] = 0; an item with none, e.g. a solid, is kept by its
+ * bounds); per simplex: bounds s_lo / s_hi (n_simplex x D) and its record (s_records: n_simplex x ((D+1)*D+1), the
+ * ntr_scene_desc.simplex layout).  A cell is dropped for a simplex when a separating axis exists among the box axes,
+ * the face normal and the D facet directions (the barycentric functions of the ray test, src/tracer.hpp:411-440, are
+ * affine: their ranges over the cell come from its extreme corners); conservative by a relative margin.
+ * item_first == NULL: ntr_build_kdtree. */
+NTR_API int ntr_build_kdtree_culled(int dim, uint32_t n, const float *lo, const float *hi, const uint32_t *item_first,
+                                    uint32_t n_simplex, const float *s_lo, const float *s_hi, const float *s_records,
+                                    int max_depth, int split_threshold, float traversal_cost, float intersection_cost,
+                                    ntr_node **nodes_out, uint32_t *n_nodes_out, uint32_t **refs_out, uint32_t *n_refs_out,
+                                    uint32_t *root_out, float *boundary_out);
 NTR_API void ntr_free(void *p);
 /* Batch grouping ahead of the tree build (group_primitives, src/tracer.hpp:2395-2427: triangles are packed into
  * triangle_batch items of v_real::size lanes).  order_out receives a permutation of the n items (bounds lo/hi: n x D)

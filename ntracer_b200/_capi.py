@@ -216,6 +216,8 @@ def load():
         'ntr_simplex_from_points': (C.c_int, [i32, u32, vp, vp]),
         'ntr_build_kdtree': (C.c_int, [i32, u32, vp, vp, i32, i32, C.c_float, C.c_float, C.POINTER(vp), C.POINTER(u32),
                                        C.POINTER(vp), C.POINTER(u32), C.POINTER(u32), vp]),
+        'ntr_build_kdtree_culled': (C.c_int, [i32, u32, vp, vp, vp, u32, vp, vp, vp, i32, i32, C.c_float, C.c_float, C.POINTER(vp),
+                                              C.POINTER(u32), C.POINTER(vp), C.POINTER(u32), C.POINTER(u32), vp]),
         'ntr_free': (None, [vp]),
         'ntr_group_items': (C.c_int, [i32, u32, vp, vp, i32, vp]),
         'ntr_group_create': (C.c_int, [C.POINTER(SceneDesc), i32, vp, C.POINTER(vp)]),
@@ -250,7 +252,7 @@ EXPORTED_SYMBOLS = (
     'ntr_render_end', 'ntr_render_float',
     'ntr_calculate_color', 'ntr_primary_hit_ids', 'ntr_trace_rays', 'ntr_trace_rays_hits', 'ntr_occludes_rays', 'ntr_abort',
     'ntr_get_counters', 'ntr_set_instrumented', 'ntr_last_kernel_ms', 'ntr_launch_count',
-    'ntr_measure_fp32_peak', 'ntr_simplex_from_points', 'ntr_build_kdtree', 'ntr_free', 'ntr_group_items',
+    'ntr_measure_fp32_peak', 'ntr_simplex_from_points', 'ntr_build_kdtree', 'ntr_build_kdtree_culled', 'ntr_free', 'ntr_group_items',
     'ntr_group_create', 'ntr_group_destroy', 'ntr_group_size', 'ntr_group_set_camera', 'ntr_group_set_params',
     'ntr_group_render', 'ntr_group_render_device', 'ntr_group_abort', 'ntr_group_get_counters',
     'ntr_group_last_kernel_ms', 'ntr_group_launch_count',

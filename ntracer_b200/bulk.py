@@ -22,8 +22,12 @@ def simplex_records(points):
     return rec
 
 
-def build_kdtree(lo, hi, max_depth=0, split_threshold=0, traversal_cost=-1.0, intersection_cost=-1.0):
-    """lo, hi: float32 [n, D] item bounds -> (nodes uint32 [m,4], item indices per leaf uint32 [k], root, boundary [2,D])"""
+def build_kdtree(lo, hi, max_depth=0, split_threshold=0, traversal_cost=-1.0, intersection_cost=-1.0, cull=None):
+    """lo, hi: float32 [n, D] item bounds -> (nodes uint32 [m,4], item indices per leaf uint32 [k], root, boundary [2,D])
+
+    cull = (item_first uint32 [n+1], s_lo [m, D], s_hi [m, D], records [m, (D+1)*D+1]): the simplexes behind the items
+    (item i owns simplexes item_first[i] .. item_first[i+1]-1; bounds and record of each) -- an item is then listed only
+    in the cells one of its simplexes can touch (ntr_build_kdtree_culled)."""
     lo = np.ascontiguousarray(lo, dtype=np.float32)
     hi = np.ascontiguousarray(hi, dtype=np.float32)
     n, d = lo.shape
@@ -35,10 +39,23 @@ def build_kdtree(lo, hi, max_depth=0, split_threshold=0, traversal_cost=-1.0, in
     nodes_p, refs_p = C.c_void_p(), C.c_void_p()
     n_nodes, n_refs, root = C.c_uint32(), C.c_uint32(), C.c_uint32()
     boundary = np.zeros((2, d), dtype=np.float32)
-    _capi.check(lib.ntr_build_kdtree(d, n, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), int(max_depth),
-                                     int(split_threshold), float(traversal_cost), float(intersection_cost),
-                                     C.byref(nodes_p), C.byref(n_nodes), C.byref(refs_p), C.byref(n_refs), C.byref(root),
-                                     boundary.ctypes.data_as(C.c_void_p)))
+    if cull is not None:
+        first = np.ascontiguousarray(cull[0], dtype=np.uint32)
+        s_lo, s_hi, s_pl = (np.ascontiguousarray(a, dtype=np.float32) for a in cull[1:])
+        m = s_lo.shape[0] if s_lo.ndim == 2 else 0
+        if first.shape != (n + 1,) or s_lo.shape != (m, d) or s_hi.shape != (m, d) or s_pl.shape != (m, (d + 1) * d + 1):
+            raise ValueError('cull = (item_first [n+1], s_lo [m,D], s_hi [m,D], records [m,(D+1)*D+1])')
+        _capi.check(lib.ntr_build_kdtree_culled(d, n, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p),
+                                                first.ctypes.data_as(C.c_void_p), m, s_lo.ctypes.data_as(C.c_void_p),
+                                                s_hi.ctypes.data_as(C.c_void_p), s_pl.ctypes.data_as(C.c_void_p), int(max_depth),
+                                                int(split_threshold), C.c_float(traversal_cost), C.c_float(intersection_cost),
+                                                C.byref(nodes_p), C.byref(n_nodes), C.byref(refs_p), C.byref(n_refs), C.byref(root),
+                                                boundary.ctypes.data_as(C.c_void_p)))
+    else:
+        _capi.check(lib.ntr_build_kdtree(d, n, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), int(max_depth),
+                                         int(split_threshold), float(traversal_cost), float(intersection_cost),
+                                         C.byref(nodes_p), C.byref(n_nodes), C.byref(refs_p), C.byref(n_refs), C.byref(root),
+                                         boundary.ctypes.data_as(C.c_void_p)))
     try:
         nodes = np.ctypeslib.as_array(C.cast(nodes_p, C.POINTER(C.c_uint32)), shape=(max(n_nodes.value, 1) * 4,))[:n_nodes.value * 4].copy().reshape(-1, 4)
         refs = np.ctypeslib.as_array(C.cast(refs_p, C.POINTER(C.c_uint32)), shape=(max(n_refs.value, 1),))[:n_refs.value].copy()
@@ -60,7 +77,7 @@ def group_items(lo, hi, group=4):
     return order
 
 
-def batched_tree(lo, hi, batch=4, **tree_kw):
+def batched_tree(lo, hi, batch=4, records=None, **tree_kw):
     """Groups n simplexes into batches of `batch` and builds the tree over the ITEMS (batches + left-over singles), the
     way build_kdtree does in the reference's SIMD builds (src/tracer.hpp:2431-2455).
     -> (order [n]: new position -> old simplex index, nodes, leaf refs ((1<<30)|first record for batches), root, boundary)"""
@@ -72,7 +89,12 @@ def batched_tree(lo, hi, batch=4, **tree_kw):
     ihi = np.concatenate([hi[:nb * batch].reshape(nb, batch, -1).max(axis=1), hi[nb * batch:]]) if nb else hi
     item_ref = np.concatenate([(1 << 30) | (np.arange(nb, dtype=np.uint32) * batch),
                                np.arange(nb * batch, n, dtype=np.uint32)]).astype(np.uint32)
-    nodes, items, root, boundary = build_kdtree(ilo, ihi, **tree_kw)
+    cull = None
+    if records is not None:
+        # (records: [n, (D+1)*D+1] in the ORIGINAL order) item k < nb owns simplexes k*batch .. (k+1)*batch-1
+        first = np.concatenate([np.arange(nb + 1, dtype=np.uint32) * batch, nb * batch + 1 + np.arange(n - nb * batch, dtype=np.uint32)])
+        cull = (first, lo, hi, np.asarray(records, np.float32)[order])
+    nodes, items, root, boundary = build_kdtree(ilo, ihi, cull=cull, **tree_kw)
     nodes = nodes.copy()
     refs = item_ref[items]
     # the reference keeps the batches of a leaf in front of its single primitives (tracer.hpp:1142-1150) and stores
@@ -87,9 +109,10 @@ def batched_tree(lo, hi, batch=4, **tree_kw):
     return order, nodes, refs, root, boundary
 
 
-def simplex_scene(points, material_ids=None, materials=None, batch=1, **tree_kw):
+def simplex_scene(points, material_ids=None, materials=None, batch=1, cull=False, **tree_kw):
     """Flat CompositeScene dict for n simplexes given by their vertices (float32 [n, D, D]).  batch = 4 packs them into
-    4-lane batch items first (the layout the tuned batch test of the kernels works on)."""
+    4-lane batch items first (the layout the tuned batch test of the kernels works on).  cull = True: the tree lists a
+    simplex only in the cells it can touch (ntr_build_kdtree_culled) instead of every cell its box overlaps."""
     pts = np.ascontiguousarray(points, dtype=np.float32)
     n, d, _ = pts.shape
     rec = simplex_records(pts)
@@ -98,10 +121,10 @@ def simplex_scene(points, material_ids=None, materials=None, batch=1, **tree_kw)
         material_ids = np.zeros(n, dtype=np.int32)
     material_ids = np.ascontiguousarray(material_ids, dtype=np.int32)
     if batch > 1:
-        order, nodes, refs, root, boundary = batched_tree(lo, hi, batch, **tree_kw)
+        order, nodes, refs, root, boundary = batched_tree(lo, hi, batch, records=rec if cull else None, **tree_kw)
         rec, material_ids = rec[order], material_ids[order]
     else:
-        nodes, refs, root, boundary = build_kdtree(lo, hi, **tree_kw)
+        nodes, refs, root, boundary = build_kdtree(lo, hi, cull=(np.arange(n + 1, dtype=np.uint32), lo, hi, rec) if cull else None, **tree_kw)
     if materials is None:
         materials = np.array([[1, 0.5, 0.5, 1, 1, 1, 1, 0, 1, 8]], dtype=np.float32)      # Material((1,0.5,0.5))
     cam_axes = np.eye(d, dtype=np.float32)

@@ -67,6 +67,78 @@ struct Builder {
     int max_depth, split_threshold;
     double c_trav, c_isect;
     static constexpr int kBins = 32;
+    // optional (ntr_build_kdtree_culled): the simplexes behind every item -- item i owns simplexes
+    // item_first[i] .. item_first[i+1]-1, each with its own bounds and its record (face_normal[D], d, p1[D],
+    // edge_normals[D-1][D]) -- so that an item is handed to a child cell only if one of its simplexes can touch the cell.
+    // A simplex is the part of its hyperplane where the D barycentric functions the ray test evaluates (area_i =
+    // edge_normal_i . (p1 - x) >= 0 for i = 1..D-1 and 1 - sum area_i >= 0, tracer.hpp:411-440) are non-negative; all of
+    // them and the plane function are affine, so their ranges over a box come from the box's extreme corners.  The cell
+    // cannot touch the simplex if its bounds miss the cell, or the plane function has one sign on the whole cell, or one
+    // barycentric function is negative on the whole cell: necessary conditions only (separating axes: the box axes, the
+    // normal, the D facet directions), each with a relative margin, so an item whose geometry meets the cell is never
+    // dropped.  Items without simplexes (solids) are kept by their bounds alone.
+    const uint32_t *item_first = nullptr;
+    const float *s_lo = nullptr, *s_hi = nullptr, *s_rec = nullptr;
+
+    // range of  c + sum_k g[k] * x[k]  over the box, and a magnitude for the rounding margin
+    static void affine_range(int D, const float *g, double c, const double *blo, const double *bhi, double &mn, double &mx, double &mag) {
+        mn = mx = c;
+        mag = fabs(c);
+        for (int k = 0; k < D; ++k) {
+            const double x0 = (double)g[k] * blo[k], x1 = (double)g[k] * bhi[k];
+            mn += std::min(x0, x1);
+            mx += std::max(x0, x1);
+            mag += std::max(fabs(x0), fabs(x1));
+        }
+    }
+
+    bool touches(uint32_t item, const double *blo, const double *bhi) const {
+        if (!item_first) return true;
+        const uint32_t a = item_first[item], b = item_first[item + 1];
+        if (a == b) return true;
+        const size_t S = (size_t)(D + 1) * D + 1;
+        double gsum[NTR_MAX_DIM];
+        for (uint32_t s = a; s < b; ++s) {
+            const float *l = s_lo + (size_t)s * D, *h = s_hi + (size_t)s * D, *rec = s_rec + (size_t)s * S;
+            bool in = true;
+            for (int k = 0; k < D && in; ++k) {
+                const double tol = 1e-6 * (fabs(blo[k]) + fabs(bhi[k]) + 1e-30);
+                if ((double)l[k] > bhi[k] + tol || (double)h[k] < blo[k] - tol) in = false;
+            }
+            if (!in) continue;
+            double mn, mx, mag;
+            affine_range(D, rec, (double)rec[D], blo, bhi, mn, mx, mag);            // the hyperplane: normal . x + d
+            if (mn > 1e-5 * mag || mx < -1e-5 * mag) continue;
+            // area_i(x) = e_i . p1 - e_i . x; all of them >= 0 and their sum <= 1 on the simplex
+            const float *p1 = rec + D + 1;
+            double csum = 0;
+            for (int k = 0; k < D; ++k) gsum[k] = 0;
+            for (int i = 0; i < D - 1 && in; ++i) {
+                const float *e = rec + 2 * D + 1 + (size_t)i * D;
+                double c = 0;
+                for (int k = 0; k < D; ++k) { c += (double)e[k] * (double)p1[k]; gsum[k] += e[k]; }
+                csum += c;
+                // range of e . x over the box; area = c - e . x
+                double emn, emx, emag;
+                affine_range(D, e, 0.0, blo, bhi, emn, emx, emag);
+                const double eps = 1e-5 * (emag + fabs(c)) + 1e-5;
+                if (c - emn < -eps) in = false;           // the largest area on the cell is negative
+                if (c - emx > 1 + eps) in = false;        // the smallest area on the cell is above 1
+            }
+            if (!in) continue;
+            {   // sum of the areas <= 1
+                double emn = 0, emag = 0;
+                for (int k = 0; k < D; ++k) {
+                    const double x0 = gsum[k] * blo[k], x1 = gsum[k] * bhi[k];
+                    emn += std::max(x0, x1);              // largest gsum . x  ->  smallest sum of areas
+                    emag += std::max(fabs(x0), fabs(x1));
+                }
+                if (csum - emn > 1 + 1e-5 * (emag + fabs(csum)) + 1e-5) continue;
+            }
+            return true;
+        }
+        return false;
+    }
 
     struct Node { uint32_t meta, w1, w2, w3; std::vector<uint32_t> items; };
     // subtrees are built into private vectors and spliced together afterwards
@@ -98,6 +170,8 @@ struct Builder {
         int best_axis = -1;
         double best_split = 0;
         std::vector<uint32_t> hl(kBins + 1), hh(kBins + 1);
+        double ax_cost[NTR_MAX_DIM], ax_split[NTR_MAX_DIM];
+        for (int ax = 0; ax < D; ++ax) { ax_cost[ax] = 1e300; ax_split[ax] = 0; }
         for (int ax = 0; ax < D; ++ax) {
             if (!(ext[ax] > 0)) continue;
             std::fill(hl.begin(), hl.end(), 0u);
@@ -130,25 +204,61 @@ struct Builder {
                 if (cost < best_cost && (n_left < n || n_right < n)) {
                     best_cost = cost; best_axis = ax; best_split = nlo[ax] + w;
                 }
+                if (cost < ax_cost[ax]) { ax_cost[ax] = cost; ax_split[ax] = nlo[ax] + w; }
+            }
+        }
+        if (item_first) {
+            // With the simplexes at hand the counts of the sweep (bounding boxes) overestimate what the children will
+            // hold, and the sweep gives up splitting too early.  Re-evaluate a few candidate planes -- per axis the
+            // sweep's best and the spatial median -- with the children's real contents and take the cheapest.
+            best_cost = c_isect * (double)n;
+            best_axis = -1;
+            double l_hi[NTR_MAX_DIM], r_lo[NTR_MAX_DIM], e2[NTR_MAX_DIM];
+            for (int ax = 0; ax < D; ++ax) {
+                if (!(ext[ax] > 0)) continue;
+                for (int cand = 0; cand < 2; ++cand) {
+                    const double sp = cand == 0 ? ax_split[ax] : nlo[ax] + 0.5 * ext[ax];
+                    if (cand == 0 && !(ax_cost[ax] < 1e300)) continue;
+                    const float split = (float)sp;
+                    if (!((double)split > nlo[ax] && (double)split < nhi[ax])) continue;
+                    memcpy(l_hi, nhi, sizeof(double) * D);
+                    memcpy(r_lo, nlo, sizeof(double) * D);
+                    l_hi[ax] = split; r_lo[ax] = split;
+                    size_t nl = 0, nr = 0;
+                    for (uint32_t i : idx) {
+                        const float a = lo[(size_t)i * D + ax], b = hi[(size_t)i * D + ax];
+                        const bool flat = a == split && b == split;
+                        if ((a < split || flat) && touches(i, nlo, l_hi)) ++nl;
+                        if ((b > split || flat) && touches(i, r_lo, nhi)) ++nr;
+                    }
+                    if (nl == n && nr == n) continue;
+                    memcpy(e2, ext, sizeof(double) * D);
+                    e2[ax] = (double)split - nlo[ax];
+                    const double al = area(e2);
+                    e2[ax] = nhi[ax] - (double)split;
+                    const double ar = area(e2);
+                    const double cost = c_trav + c_isect * (al * (double)nl + ar * (double)nr) / parent_area;
+                    if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = split; }
+                }
             }
         }
         if (best_axis < 0) return make_leaf();
         const float split = (float)best_split;
         std::vector<uint32_t> li, ri;
         li.reserve(n); ri.reserve(n);
-        for (uint32_t i : idx) {
-            const float a = lo[(size_t)i * D + best_axis], b = hi[(size_t)i * D + best_axis];
-            const bool flat = a == split && b == split;
-            if (a < split || flat) li.push_back(i);
-            if (b > split || flat) ri.push_back(i);
-        }
-        if (li.size() == n && ri.size() == n) return make_leaf();
-        std::vector<uint32_t>().swap(idx);                  // free before recursing
         double l_hi[NTR_MAX_DIM], r_lo[NTR_MAX_DIM];
         memcpy(l_hi, nhi, sizeof(double) * D);
         memcpy(r_lo, nlo, sizeof(double) * D);
         l_hi[best_axis] = split;
         r_lo[best_axis] = split;
+        for (uint32_t i : idx) {
+            const float a = lo[(size_t)i * D + best_axis], b = hi[(size_t)i * D + best_axis];
+            const bool flat = a == split && b == split;
+            if ((a < split || flat) && touches(i, nlo, l_hi)) li.push_back(i);
+            if ((b > split || flat) && touches(i, r_lo, nhi)) ri.push_back(i);
+        }
+        if (li.size() == n && ri.size() == n) return make_leaf();
+        std::vector<uint32_t>().swap(idx);                  // free before recursing
         const uint32_t me = (uint32_t)t.nodes.size();
         uint32_t bits;
         memcpy(&bits, &split, 4);
@@ -263,6 +373,29 @@ NTR_API int ntr_group_items(int dim, uint32_t n, const float *lo, const float *h
 NTR_API int ntr_build_kdtree(int dim, uint32_t n, const float *lo, const float *hi, int max_depth, int split_threshold,
                              float traversal_cost, float intersection_cost, ntr_node **nodes_out, uint32_t *n_nodes_out,
                              uint32_t **refs_out, uint32_t *n_refs_out, uint32_t *root_out, float *boundary_out) {
+    return ntr_build_kdtree_culled(dim, n, lo, hi, nullptr, 0, nullptr, nullptr, nullptr, max_depth, split_threshold, traversal_cost,
+                                   intersection_cost, nodes_out, n_nodes_out, refs_out, n_refs_out, root_out, boundary_out);
+}
+
+// The same with the simplexes behind the items (see Builder::touches): what the reference's builder does with its exact
+// overlap tests (src/tracer.hpp:1465-1675, 2284-2354), here as separating axes: bounds, hyperplane, facet directions.
+NTR_API int ntr_build_kdtree_culled(int dim, uint32_t n, const float *lo, const float *hi, const uint32_t *item_first,
+                                    uint32_t n_simplex, const float *s_lo, const float *s_hi, const float *s_records,
+                                    int max_depth, int split_threshold, float traversal_cost, float intersection_cost,
+                                    ntr_node **nodes_out, uint32_t *n_nodes_out, uint32_t **refs_out, uint32_t *n_refs_out,
+                                    uint32_t *root_out, float *boundary_out) {
+    if (item_first) {
+        if (n_simplex && (!s_lo || !s_hi || !s_records)) return ntr_fail(NTR_ERR_VALUE, "simplex bounds / records are NULL");
+        if (item_first[0] != 0) return ntr_fail(NTR_ERR_VALUE, "item_first[0] must be 0");
+        for (uint32_t k = 0; k < n; ++k)
+            if (item_first[k + 1] < item_first[k] || item_first[k + 1] > n_simplex)
+                return ntr_fail(NTR_ERR_VALUE, "item_first is not a non-decreasing sequence within the simplex count");
+        if (dim >= 3 && dim <= NTR_MAX_DIM)
+            for (size_t k = 0; k < (size_t)n_simplex * ((size_t)(dim + 1) * dim + 1); ++k) {
+                if (!(s_records[k] > -3e38f && s_records[k] < 3e38f))
+                    return ntr_fail(NTR_ERR_VALUE, "simplex %zu: record holds NaN or infinity", k / ((size_t)(dim + 1) * dim + 1));
+            }
+    }
     if (dim < 3 || dim > NTR_MAX_DIM) return ntr_fail(NTR_ERR_VALUE, "dimension must be between 3 and %d", NTR_MAX_DIM);
     if (!nodes_out || !refs_out || !n_nodes_out || !n_refs_out || !root_out || !boundary_out) return ntr_fail(NTR_ERR_VALUE, "NULL output argument");
     if (n && (!lo || !hi)) return ntr_fail(NTR_ERR_VALUE, "item bounds are NULL");
@@ -272,6 +405,7 @@ NTR_API int ntr_build_kdtree(int dim, uint32_t n, const float *lo, const float *
             return ntr_fail(NTR_ERR_VALUE, "item %zu: bounds are NaN, infinite or inverted", k / D);
     Builder b;
     b.D = D; b.lo = lo; b.hi = hi;
+    b.item_first = item_first; b.s_lo = s_lo; b.s_hi = s_hi; b.s_rec = s_records;
     b.max_depth = max_depth > 0 ? std::min(max_depth, NTR_MAX_TREE_DEPTH - 2) : 25;
     b.split_threshold = split_threshold > 0 ? split_threshold : 2;
     b.c_trav = traversal_cost >= 0 ? traversal_cost : 1.0;

@@ -1134,8 +1134,8 @@ def screen_coord_to_ray(cam, x, y, w, h, fov):
 def build_kdtree(primitives, extra_threads=-1, *, max_depth=None, split_threshold=None, traversal_cost=None,
                  intersection_cost=None, update_primitives=False):
     """-> (AABB, KDNode).  The tree comes from this backend's native host-side builder (csrc/builder.cpp,
-    ntr_group_items + ntr_build_kdtree: triangles grouped into TriangleBatch items, then a binned SAH over the items'
-    bounding boxes).  It is NOT the reference's builder (src/tracer.hpp:1930-2455): colours and hit ids do not depend on
+    ntr_group_items + ntr_build_kdtree_culled: triangles grouped into TriangleBatch items, then a binned SAH over the
+    items' bounding boxes whose candidate planes are re-evaluated with the cells' real contents).  It is NOT the reference's builder (src/tracer.hpp:1930-2455): colours and hit ids do not depend on
     the tree, except with shadows on."""
     from . import bulk
     protos = list(primitives)
@@ -1155,6 +1155,7 @@ def build_kdtree(primitives, extra_threads=-1, *, max_depth=None, split_threshol
     prims = [p.primitive for p in protos]
     tri = [i for i, q in enumerate(prims) if isinstance(q, Triangle)]
     items, ilo, ihi = [], [], []
+    owned = []          # per item: the prototypes of its simplexes (none for a solid)
     if BATCH_SIZE > 1 and len(tri) >= BATCH_SIZE:
         order = bulk.group_items(lo[tri], hi[tri], BATCH_SIZE)
         nb = len(tri) // BATCH_SIZE
@@ -1163,6 +1164,7 @@ def build_kdtree(primitives, extra_threads=-1, *, max_depth=None, split_threshol
             items.append(TriangleBatch([prims[j] for j in members]))
             ilo.append(lo[members].min(axis=0))
             ihi.append(hi[members].max(axis=0))
+            owned.append(members)
         single = [tri[int(j)] for j in order[nb * BATCH_SIZE:]] + [i for i, q in enumerate(prims) if not isinstance(q, Triangle)]
     else:
         single = list(range(len(prims)))
@@ -1170,9 +1172,20 @@ def build_kdtree(primitives, extra_threads=-1, *, max_depth=None, split_threshol
         items.append(prims[j])
         ilo.append(lo[j])
         ihi.append(hi[j])
+        owned.append([j] if isinstance(prims[j], Triangle) else [])
+    # The simplexes behind the items go to the builder too, so that -- like the reference's builder with its exact
+    # overlap tests (src/tracer.hpp:1465-1675) -- an item is listed only in the cells its geometry can touch
+    # (ntr_build_kdtree_culled; a rebuilt {5,3,3} scene then costs the reference algorithm the same number of simplex
+    # tests per frame as on the reference's own tree, against 2.2 x with bounding boxes alone).
+    flat = [j for m in owned for j in m]
+    first = np.cumsum([0] + [len(m) for m in owned]).astype(np.uint32)
+    recs = np.zeros((len(flat), (d + 1) * d + 1), np.float32)
+    for k, j in enumerate(flat):
+        recs[k] = prims[j]._row()
+    cull = (first, lo[flat].reshape(-1, d), hi[flat].reshape(-1, d), recs) if flat else None
     nodes, refs, root, boundary = bulk.build_kdtree(np.stack(ilo), np.stack(ihi), max_depth or 0, split_threshold or 0,
                                                     -1.0 if traversal_cost is None else traversal_cost,
-                                                    -1.0 if intersection_cost is None else intersection_cost)
+                                                    -1.0 if intersection_cost is None else intersection_cost, cull=cull)
     # children always follow their parent in the node array, so a reverse sweep builds the objects bottom-up
     objs = [None] * len(nodes)
     for i in range(len(nodes) - 1, -1, -1):

@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 
 from ntracer_b200 import NTracer, Material, bulk, _capi
+from tests import emul_lib as el
+from tests import fixtures as fx
 from tests import oracle_lib as ol
 
 
@@ -169,3 +171,108 @@ def test_batched_scene_renders_like_the_single_simplex_scene():
     assert np.array_equal(ol.render_float(a, 96, 54), ol.render_float(b, 96, 54))
     ids_a, _ = ol.primary_hit_ids(a, 96, 54)
     assert (ids_a >= 0).mean() > 0.2
+
+
+def _leaf_of(nodes, root, x):
+    k = root
+    while True:
+        meta, a, b, c = (int(v) for v in nodes[k])
+        if meta & 0x80000000:
+            return k
+        split = float(np.array([a], np.uint32).view(np.float32)[0])
+        k = b if x[meta] < split else c
+        if k == 0xFFFFFFFF:
+            return None
+
+
+@pytest.mark.parametrize('dim,n', [(3, 400), (4, 600), (6, 300), (10, 200)])
+def test_culled_tree_never_drops_a_simplex_from_a_cell_it_touches(dim, n):
+    """ntr_build_kdtree_culled lists an item only in the cells one of its simplexes can touch (separating axes: bounds,
+    face normal, facet directions -- what the reference's builder does with its exact overlap tests,
+    src/tracer.hpp:1465-1675).  Conservative: every point OF a simplex lies in a leaf that lists the simplex (random
+    barycentric samples, vertices and facet centres included); and, for the flat simplexes of 3 and 4 dimensions, much
+    smaller than the tree over bounding boxes."""
+    from ntracer_b200 import bulk
+    rng = np.random.RandomState(dim)
+    pts = bulk.soup(dim, n, seed=dim, spread=0.3)
+    rec = bulk.simplex_records(pts)
+    lo, hi = pts.min(axis=1), pts.max(axis=1)
+    plain = bulk.build_kdtree(lo, hi, max_depth=18)
+    nodes, refs, root, boundary = bulk.build_kdtree(lo, hi, max_depth=18, cull=(np.arange(n + 1, dtype=np.uint32), lo, hi, rec))
+    if dim <= 4:
+        assert len(refs) < 0.85 * len(plain[1])
+    lam = rng.dirichlet(np.ones(dim) * 0.5, size=(n, 24)).astype(np.float64)          # 24 samples per simplex, corners favoured
+    lam[:, 0] = np.eye(dim)[rng.randint(0, dim, n)]                                    # a vertex
+    lam[:, 1] = (1 - np.eye(dim)[rng.randint(0, dim, n)]) / (dim - 1)                  # a facet centre
+    missing = 0
+    for s in range(n):
+        for x in lam[s] @ pts[s].astype(np.float64):
+            leaf = _leaf_of(nodes, root, x)
+            if leaf is None or s not in refs[int(nodes[leaf, 1]):int(nodes[leaf, 1]) + int(nodes[leaf, 2])]:
+                # a sample within rounding of a split plane may sit on the other side of it: the neighbour must list it then
+                near = False
+                k = root
+                while k != 0xFFFFFFFF and not (int(nodes[k, 0]) & 0x80000000):
+                    split = float(np.array([int(nodes[k, 1])], np.uint32).view(np.float32)[0])
+                    if abs(x[int(nodes[k, 0])] - split) < 1e-5:
+                        near = True
+                    k = int(nodes[k, 2]) if x[int(nodes[k, 0])] < split else int(nodes[k, 3])
+                missing += not near
+    assert missing == 0
+
+
+def test_culled_tree_renders_the_same_picture():
+    """Scenes built with and without the culling, single simplexes and 4-lane batches: the oracle's hit ids and distances
+    are identical, the lit picture is the same, shadows included (an occluder is found in whichever cell the shadow ray
+    meets it), and the culled tree costs fewer simplex tests."""
+    from ntracer_b200 import bulk
+    w, h = 96, 54
+    for dim, n, batch in ((4, 500, 1), (4, 500, 4), (7, 240, 4)):
+        pts = bulk.soup(dim, n, seed=3 + dim, spread=0.3)
+        out = []
+        for cull in (False, True):
+            sc = bulk.simplex_scene(pts, batch=batch, cull=cull, max_depth=16)
+            sc['cam_origin'] = np.array([0, 0, -3] + [0] * (dim - 3), np.float32)
+            sc['point_lights'] = np.array([[2, 3, -4] + [0] * (dim - 3) + [1, 1, 1]], np.float32)
+            sc['params'] = np.array([0.8, 1, 1, 4, 1], dtype=np.float64)                   # shadows on
+            img, cnt = ol.render_float(sc, w, h, with_counters=True)
+            ids, dist = ol.primary_hit_ids(sc, w, h)
+            out.append((sc, img, cnt, ids, dist))
+        (s0, i0, c0, id0, d0), (s1, i1, c1, id1, d1) = out
+        assert (id0 >= 0).sum() > 50
+        assert np.array_equal(id0 >= 0, id1 >= 0) and np.array_equal(d0, d1)
+        bad, mx = fx.lsb_stats(i1, i0)
+        assert bad <= 0.001, (dim, batch, bad, mx)
+        assert c1['simplex_tests'] < c0['simplex_tests'], (dim, batch, c1['simplex_tests'], c0['simplex_tests'])
+        e, _ = el.render(s1, w, h)
+        assert np.abs(e - i1).max() <= 2e-6                                              # the device code on the culled tree
+
+
+def test_rebuilt_120_cell_costs_what_the_reference_tree_costs():
+    """The {5,3,3} fixture rebuilt from its own simplexes through this repo's grouping and builder (what
+    build_composite_scene does) against the tree the reference built: same hits, the shadowed picture within the parity
+    bound (the only tree-dependent part), and no more simplex tests per frame than on the
+    reference's tree (2.2 x with bounding boxes alone)."""
+    from ntracer_b200 import bulk
+    sc, g = fx.load('cell120')
+    sc = fx.variant(sc, g, 'shadows')
+    D, rec = int(sc['dim']), sc['simplex']
+    n = rec.shape[0]
+    p1 = rec[:, D + 1:2 * D + 1].astype(np.float64)
+    E = rec[:, 2 * D + 1:2 * D + 1 + (D - 1) * D].reshape(n, D - 1, D).astype(np.float64)
+    pts = np.zeros((n, D, D))
+    pts[:, 0] = p1
+    for k in range(n):
+        pts[k, 1:] = p1[k] - np.linalg.pinv(E[k]).T        # edge_normal_i . (p1 - p_j) = delta_ij (tracer.hpp:454-461)
+    pts = pts.astype(np.float32)
+    assert np.abs(bulk.simplex_records(pts) - rec).max() <= 1e-4
+    b = bulk.simplex_scene(pts, material_ids=sc['simplex_mat'], materials=sc['materials'], batch=4, cull=True)
+    for k in ('params', 'ambient', 'bg1', 'bg2', 'bg3', 'point_lights', 'global_lights', 'cam_origin', 'cam_axes'):
+        b[k] = sc[k]
+    w, h = 240, 135
+    ia, ca = ol.render_float(sc, w, h, with_counters=True)
+    ib, cb = ol.render_float(b, w, h, with_counters=True)
+    bad, mx = fx.lsb_stats(ib, ia)
+    assert bad <= 0.001, (bad, mx)
+    assert cb['shadow_rays'] == ca['shadow_rays']
+    assert cb['simplex_tests'] <= 1.05 * ca['simplex_tests'] and cb['node_steps'] <= 1.05 * ca['node_steps']
