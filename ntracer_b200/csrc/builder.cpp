@@ -67,6 +67,7 @@ struct Builder {
     int max_depth, split_threshold;
     double c_trav, c_isect;
     static constexpr int kBins = 32;
+    static constexpr int kForceSplit = 128;     // culled builds: cells with at least this many items are split regardless
     // optional (ntr_build_kdtree_culled): the simplexes behind every item -- item i owns simplexes
     // item_first[i] .. item_first[i+1]-1, each with its own bounds and its record (face_normal[D], d, p1[D],
     // edge_normals[D-1][D]) -- so that an item is handed to a child cell only if one of its simplexes can touch the cell.
@@ -213,6 +214,12 @@ struct Builder {
             // sweep's best and the spatial median -- with the children's real contents and take the cheapest.
             best_cost = c_isect * (double)n;
             best_axis = -1;
+            // A cell that still holds hundreds of items is split even when no plane pays by the greedy estimate (the centre
+            // of a star polytope: every plane through it leaves most of the big simplexes on both sides, and only several
+            // levels further down do the cells get small enough to lose them): at the cheapest plane that sends fewer than
+            // all items to each side.  Leaves of that size are what a frame's slowest rays walk.
+            double forced_cost = 1e300, forced_split = 0;
+            int forced_axis = -1;
             double l_hi[NTR_MAX_DIM], r_lo[NTR_MAX_DIM], e2[NTR_MAX_DIM];
             for (int ax = 0; ax < D; ++ax) {
                 if (!(ext[ax] > 0)) continue;
@@ -239,8 +246,10 @@ struct Builder {
                     const double ar = area(e2);
                     const double cost = c_trav + c_isect * (al * (double)nl + ar * (double)nr) / parent_area;
                     if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = split; }
+                    if (cost < forced_cost && nl < n && nr < n) { forced_cost = cost; forced_axis = ax; forced_split = split; }
                 }
             }
+            if (best_axis < 0 && n >= (size_t)kForceSplit && forced_axis >= 0) { best_axis = forced_axis; best_split = forced_split; }
         }
         if (best_axis < 0) return make_leaf();
         const float split = (float)best_split;

@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--check', action='store_true')
     ap.add_argument('--chains', default=None, help='device list of a group, e.g. 0,0 = two chains on GPU 0 (ntr_group_*)')
     ap.add_argument('--param', action='append', default=[], help='index=value: overwrite an entry of the scene params (1 = shadows, 3 = max depth)')
+    ap.add_argument('--scene-npz', default=None, help='a flat scene dict saved with numpy.savez to render instead of the config\'s fixture (same frame size)')
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -39,6 +40,9 @@ def main():
     if args.size:
         w, h = [int(v) for v in args.size.split('x')]
     sc, g = bench.load_fixture(fixture)
+    if args.scene_npz:
+        z = np.load(args.scene_npz)
+        sc = {k: z[k] for k in z.files}
     if args.param:
         sc = dict(sc, params=np.array(sc['params'], dtype=np.float64))
         for kv in args.param:
